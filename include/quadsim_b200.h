@@ -1,0 +1,149 @@
+/* quadsim_b200.h -- C ABI of the B200-native batched QuadSim environment library (libquadsim_b200.so).
+ *
+ * The reference (sd196821/QuadSim) is pure Python and has NO FFI/plugin boundary; its boundary for this hot
+ * path is the gym / stable-baselines VecEnv protocol.  Each entry point below names the
+ * reference interface it stands in for.  All `file:line` citations are into the reference tree.
+ *
+ * Conventions
+ *   - plain C types only; `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
+ *   - every call returns QS_OK (0) or a negative qs_status and never throws; qs_last_error() (thread-local)
+ *     gives the message;
+ *   - "device pointer" arguments are caller-owned, contiguous, in the handle's dtype (float for QS_F32, double
+ *     for QS_F64); all work is enqueued on the caller's stream, with no hidden synchronisation on the step path;
+ *   - a handle is bound to one CUDA device, owns all persistent per-env state, and is not thread-safe.
+ */
+#ifndef QUADSIM_B200_H
+#define QUADSIM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QS_ABI_VERSION 1
+
+typedef enum {
+  QS_OK = 0,
+  QS_ERR_INVALID = -1,    /* bad argument / configuration */
+  QS_ERR_CUDA = -2,       /* a CUDA runtime call failed (message has the CUDA error string) */
+  QS_ERR_NO_DEVICE = -3,  /* no usable CUDA device: the library has no CPU fallback */
+  QS_ERR_ALLOC = -4
+} qs_status;
+
+/* gym ids registered by gym-docking/gym_docking/__init__.py:3-21 */
+typedef enum {
+  QS_HOVER = 0,   /* 'hovering-v0'  HoveringEnv        gym_docking/envs/hovering_env.py:10-95 */
+  QS_DOCK_V0 = 1, /* 'docking-v0'   DockingEnv         gym_docking/envs/docking_env.py:12-254 */
+  QS_DOCK_V2 = 2  /* 'docking-v2'   MovingDockingEnv   gym_docking/envs/moving_docking_env.py:12-219 */
+} qs_env_kind;
+
+typedef enum { QS_F32 = 0, QS_F64 = 1 } qs_dtype;
+
+/* Initial-state randomisation (Philox4x32-10, key = seed, counter = (env_id lo, env_id hi, episode, stream)).
+ * The reference has the docking jitter commented out (docking_env.py:34) and samples the hover / docking-v1 init
+ * once at construction (hovering_env.py:23-24, imitating_docking_env.py:34). */
+typedef enum {
+  QS_RAND_NONE = 0,    /* reference docking-v0/v2 behaviour: fixed initial state */
+  QS_RAND_EPISODE = 1, /* new jitter every episode (north-star auto-reset) */
+  QS_RAND_ONCE = 2     /* one jitter per env for its lifetime (hovering-v0 / docking-v1 behaviour) */
+} qs_randomize;
+
+/* bits of info_out (per env, per step); 'flag_docking' and 'done_overlimit' are the reference's info keys
+ * (docking_env.py:226-229) */
+enum { QS_INFO_DONE = 1, QS_INFO_OVERLIMIT = 2, QS_INFO_DOCKING = 4, QS_INFO_OVERTIME = 8 };
+
+typedef struct qs_env qs_env_t;
+
+typedef struct {
+  int32_t env_kind;   /* qs_env_kind */
+  int32_t dtype;      /* qs_dtype */
+  int64_t n_envs;     /* envs owned by this handle (one handle per GPU / rank) */
+  uint64_t seed;      /* Philox key */
+  uint64_t env_id0;   /* global id of this handle's env 0 (rank * n_envs): trajectories do not depend on the GPU count */
+  int32_t randomize;  /* qs_randomize */
+  int32_t device;     /* CUDA device ordinal */
+  double half_width;  /* jitter half-width; <= 0 selects the default (0.5 docking, 1.0 hover position) */
+  int32_t auto_reset; /* 1: stable-baselines VecEnv semantics (done envs re-seat inside the step);
+                         0: plain gym.Env semantics (state stays terminal until qs_reset) */
+  int32_t reserved;
+} qs_config_t;
+
+/* Device pointers to array-of-struct views of the per-env state: ALWAYS float64 (t/episode: int32), whatever the handle's
+ * dtype, so that export -> import is bit-transparent (the fp32 layout keeps positions relative to a fixed origin; the
+ * conversion to world coordinates is exact in float64).  NULL members are skipped.  Used for parity injection and for
+ * env checkpoint/restore.
+ * Fields mirror the reference objects: env.chaser.state / env.target.state (quadrotor.py:26), Drone.u (:33),
+ * env.target_state_des[6:10] (docking_env.py:60-64), env.last_shaping (:27), env.t (:22). */
+typedef struct {
+  void* chaser;        /* [N,13]  (hover: the single drone) */
+  void* target;        /* [N,13]  docking only */
+  void* u_chaser;      /* [N,4]   previous limited command (one-step latency) */
+  void* u_target;      /* [N,4]   docking only */
+  void* des_q;         /* [N,4]   docking only */
+  void* last_shaping;  /* [N]     docking only */
+  void* ep_return;     /* [N] */
+  int32_t* t;          /* [N]     steps taken in the current episode */
+  int32_t* episode;    /* [N]     episode index (Philox counter word 2) */
+} qs_state_arrays_t;
+
+int qs_abi_version(void);
+const char* qs_last_error(void);
+
+/* gym.make(id) / SubprocVecEnv([...]*n)  (run_moving_docking_ppo2.py:65-67): build n_envs environments. */
+int qs_create(qs_env_t** out, const qs_config_t* cfg);
+int qs_destroy(qs_env_t* env);
+/* observation_space.shape[0]: 12 for docking (docking_env.py:85-95), 13 for hover (hovering_env.py:36-40). */
+int qs_obs_dim(const qs_env_t* env);
+int64_t qs_num_envs(const qs_env_t* env);
+/* env.seed(seed)  (docking_env.py:252-254; the reference never reads it -- here it re-keys Philox). */
+int qs_seed(qs_env_t* env, uint64_t seed);
+
+/* VecEnv.reset() -> obs[N,obs_dim]  (docking_env.py:233-244, hovering_env.py:80-82).  Every env that has stepped in
+ * its current episode starts its next episode; envs that have not stepped stay (idempotent). */
+int qs_reset(qs_env_t* env, void* obs_out, void* stream);
+
+/* VecEnv.step(actions[N,4]) -> obs[N,obs_dim], reward[N], done[N]  (rl_baselines/ppo2/ppo2.py:482;
+ * docking_env.py:104-231, moving_docking_env.py:111-192, hovering_env.py:47-78) with the stable-baselines worker's
+ * auto-reset: for done envs obs is the reset observation while reward/done are the terminal step's. */
+int qs_step(qs_env_t* env, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out, void* stream);
+/* As qs_step, plus the per-step info the reference returns: info_out[N] bitmask (QS_INFO_*), terminal_obs[N,obs_dim]
+ * (the pre-reset observation, SB's info['terminal_observation']).  Either may be NULL. */
+int qs_step_ex(qs_env_t* env, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out,
+               uint8_t* info_out, void* terminal_obs_out, void* stream);
+/* Same step for HOST buffers (what a numpy VecEnv caller holds): copies actions in, steps, copies results out, chunked
+ * over internal streams so H2D, kernel and D2H overlap.  Blocking.  Buffers should come from qs_host_alloc (pinned). */
+int qs_step_host(qs_env_t* env, const void* actions_host, void* obs_host, void* reward_host, uint8_t* done_host);
+int qs_host_alloc(void** out, uint64_t bytes);
+int qs_host_free(void* p);
+
+/* env.chaser.state / env.target.state / ... read and write access (parity injection, checkpoint/restore). */
+int qs_export_state(qs_env_t* env, const qs_state_arrays_t* dst, void* stream);
+int qs_import_state(qs_env_t* env, const qs_state_arrays_t* src, void* stream);
+
+/* Episode statistics accumulated on the device since the previous call:
+ * [sum of episode returns, sum of episode lengths, episodes finished, docked env-steps, env-steps with a non-finite
+ * observation or reward].  Synchronises `stream`.  The reference logs these through SB's Monitor/ep_info
+ * (rl_baselines/ppo2/ppo2.py:494-497). */
+int qs_get_stats(qs_env_t* env, double stats[5], void* stream);
+
+/* Leaf functions of the reference on device arrays of n rows (dtype as given), for function-level parity tests and
+ * for callers that use utils/transform.py, Drone or controller directly.  Unused pointers are NULL. */
+typedef enum {
+  QS_FN_QUAT2EULER = 0, /* utils/transform.py:94-120    in0 q[n,4]                     -> out0 euler[n,3] */
+  QS_FN_EULER2QUAT = 1, /* utils/transform.py:123-136   in0 euler[n,3]                 -> out0 q[n,4] */
+  QS_FN_QUAT2ROT = 2,   /* utils/transform.py:4-20      in0 q[n,4]                     -> out0 R[n,9] */
+  QS_FN_ROT2EULER = 3,  /* utils/transform.py:23-46     in0 R[n,9]                     -> out0 euler[n,3] */
+  QS_FN_U_LIMIT = 4,    /* quadrotor.py:171-187         in0 u[n,4]                     -> out0 u[n,4] */
+  QS_FN_DRONE_STEP = 5, /* quadrotor.py:126-144         in0 state[n,13] in1 u_prev[n,4] in2 u_cmd[n,4] -> out0 state, out1 u_prev */
+  QS_FN_PID = 6,        /* PIDController.py:179-185     in0 des[n,13] in1 now[n,13]    -> out0 u[n,4], out1 des_q[n,4] */
+  QS_FN_VEL_CTRL = 7,   /* PIDController.py:106-141     in0 des[n,13] in1 now[n,13]    -> out0 u[n,4], out1 des_q[n,4] */
+  QS_FN_STATE2REL = 8,  /* docking_env.py:257-295       in0 chaser[n,13] in1 target[n,13] -> out0 rel[n,12] */
+  QS_FN_PHILOX = 9      /* in0 uint32 ctr[n,4], in1 uint32 key[n,2] -> out0 uint32[n,4] (dtype ignored) */
+} qs_fn;
+int qs_fn_apply(int fn, int dtype, int64_t n, const void* in0, const void* in1, const void* in2, void* out0,
+                void* out1, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -29,7 +29,7 @@ def build(force=False):
 
 class _Config(C.Structure):
     _fields_ = [("kind", C.c_int), ("n_envs", C.c_int64), ("seed", C.c_uint64), ("env_id0", C.c_uint64),
-                ("randomize", C.c_int), ("half_width", C.c_double)]
+                ("randomize", C.c_int), ("half_width", C.c_double), ("auto_reset", C.c_int)]
 
 
 _lib = None
@@ -165,11 +165,11 @@ _FIELDS = {"chaser": (0, 13, np.float64), "target": (1, 13, np.float64), "u_c": 
 class OracleVecEnv:
     """Batched fp64 CPU environment with stable-baselines auto-reset semantics."""
 
-    def __init__(self, kind, n_envs, seed=0, env_id0=0, randomize=RAND_NONE, half_width=0.0, nthreads=1):
+    def __init__(self, kind, n_envs, seed=0, env_id0=0, randomize=RAND_NONE, half_width=0.0, nthreads=1, auto_reset=True):
         if isinstance(kind, str):
             kind = KINDS[kind]
         self.kind, self.n, self.nthreads = kind, int(n_envs), int(nthreads)
-        cfg = _Config(kind, self.n, seed, env_id0, randomize, half_width)
+        cfg = _Config(kind, self.n, seed, env_id0, randomize, half_width, int(auto_reset))
         self._h = lib().qo_vec_create(C.byref(cfg))
         self.obs_dim = lib().qo_vec_obs_dim(self._h)
 

@@ -443,7 +443,7 @@ static void dock_step_one(qo_vec* v, int64_t i, const double* a, double* obs, do
   for (int k = 0; k < 12; k++) finite = finite && isfinite(rel[k]);
   acc->nnonfinite += !finite;
   if (term_obs) memcpy(term_obs, rel, sizeof rel);
-  if (dn) { /* SB VecEnv worker auto-reset */
+  if (dn && v->cfg.auto_reset) { /* SB VecEnv worker auto-reset */
     acc->ret += v->ep_return[i]; acc->len += (double)v->t[i]; acc->neps += 1;
     v->episode[i] += 1;
     env_seat(v, i, obs);
@@ -485,7 +485,7 @@ static void hover_step_one(qo_vec* v, int64_t i, const double* a, double* obs, d
   for (int k = 0; k < 13; k++) finite = finite && isfinite(s[k]);
   acc->nnonfinite += !finite;
   if (term_obs) memcpy(term_obs, s, 13 * sizeof(double));
-  if (dn) {
+  if (dn && v->cfg.auto_reset) {
     acc->ret += v->ep_return[i]; acc->len += (double)v->t[i]; acc->neps += 1;
     v->episode[i] += 1;
     env_seat(v, i, obs);

@@ -1,0 +1,84 @@
+"""ctypes binding of libquadsim_b200.so (C ABI: include/quadsim_b200.h).
+
+The library is the product: if it cannot be loaded this module raises -- there is no Python/CPU fallback.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+OK = 0
+HOVER, DOCK_V0, DOCK_V2 = 0, 1, 2
+F32, F64 = 0, 1
+RAND_NONE, RAND_EPISODE, RAND_ONCE = 0, 1, 2
+INFO_DONE, INFO_OVERLIMIT, INFO_DOCKING, INFO_OVERTIME = 1, 2, 4, 8
+(FN_QUAT2EULER, FN_EULER2QUAT, FN_QUAT2ROT, FN_ROT2EULER, FN_U_LIMIT, FN_DRONE_STEP, FN_PID, FN_VEL_CTRL,
+ FN_STATE2REL, FN_PHILOX) = range(10)
+ABI_VERSION = 1
+
+# every symbol include/quadsim_b200.h declares (tests check the built library exports all of them)
+SYMBOLS = ["qs_abi_version", "qs_last_error", "qs_create", "qs_destroy", "qs_obs_dim", "qs_num_envs", "qs_seed",
+           "qs_reset", "qs_step", "qs_step_ex", "qs_step_host", "qs_host_alloc", "qs_host_free", "qs_export_state",
+           "qs_import_state", "qs_get_stats", "qs_fn_apply"]
+
+
+class Config(C.Structure):
+    _fields_ = [("env_kind", C.c_int32), ("dtype", C.c_int32), ("n_envs", C.c_int64), ("seed", C.c_uint64),
+                ("env_id0", C.c_uint64), ("randomize", C.c_int32), ("device", C.c_int32), ("half_width", C.c_double),
+                ("auto_reset", C.c_int32), ("reserved", C.c_int32)]
+
+
+class StateArrays(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("chaser", "target", "u_chaser", "u_target", "des_q", "last_shaping",
+                                          "ep_return", "t", "episode")]
+
+
+class QuadSimError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load (building first if the in-tree .so is missing or stale and nvcc is present)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not _build.up_to_date():
+        try:
+            path = _build.build()
+        except Exception as exc:  # no nvcc on this box: use the shipped .so if there is one
+            if not os.path.exists(path):
+                raise QuadSimError("libquadsim_b200.so is not built and cannot be built here (%s); run "
+                                   "`python -m quadsim_b200.build`. There is no CPU fallback." % exc) from exc
+    L = C.CDLL(path)
+    vp, i64, u64 = C.c_void_p, C.c_int64, C.c_uint64
+    L.qs_abi_version.restype = C.c_int
+    L.qs_last_error.restype = C.c_char_p
+    L.qs_create.argtypes = [C.POINTER(vp), C.POINTER(Config)]
+    L.qs_destroy.argtypes = [vp]
+    L.qs_obs_dim.argtypes = [vp]
+    L.qs_num_envs.argtypes = [vp]
+    L.qs_num_envs.restype = i64
+    L.qs_seed.argtypes = [vp, u64]
+    L.qs_reset.argtypes = [vp, vp, vp]
+    L.qs_step.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.qs_step_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.qs_step_host.argtypes = [vp, vp, vp, vp, vp]
+    L.qs_host_alloc.argtypes = [C.POINTER(vp), u64]
+    L.qs_host_free.argtypes = [vp]
+    L.qs_export_state.argtypes = [vp, C.POINTER(StateArrays), vp]
+    L.qs_import_state.argtypes = [vp, C.POINTER(StateArrays), vp]
+    L.qs_get_stats.argtypes = [vp, C.POINTER(C.c_double), vp]
+    L.qs_fn_apply.argtypes = [C.c_int, C.c_int, i64, vp, vp, vp, vp, vp, vp]
+    if L.qs_abi_version() != ABI_VERSION:
+        raise QuadSimError("libquadsim_b200.so ABI %d != expected %d; rebuild" % (L.qs_abi_version(), ABI_VERSION))
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != OK:
+        raise QuadSimError("quadsim_b200 error %d: %s" % (rc, load().qs_last_error().decode()))

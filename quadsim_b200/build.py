@@ -1,0 +1,56 @@
+"""Build libquadsim_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m quadsim_b200.build [--force] [--verbose]
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "_lib")
+LIB_PATH = os.path.join(LIB_DIR, "libquadsim_b200.so")
+SOURCES = [os.path.join(CSRC, "qs_lib.cu")]
+DEPS = SOURCES + [os.path.join(CSRC, "qs_core.cuh"), os.path.join(ROOT, "include", "quadsim_b200.h"), os.path.abspath(__file__)]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+]
+
+
+def find_nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: quadsim_b200 needs the CUDA toolkit to build its library")
+
+
+def up_to_date():
+    return os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in DEPS)
+
+
+def build(force=False, verbose=False, extra_flags=()):
+    """Compile the CUDA library if it is missing or older than its sources; returns its path."""
+    if not force and up_to_date():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    # g++ from the system: the image exports CC/CXX pointing at a toolchain nvcc does not need
+    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(ROOT, "include"), "-o", LIB_PATH] + SOURCES
+    if os.path.exists("/usr/bin/g++"):
+        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    log = os.path.join(LIB_DIR, "build.log")
+    with open(log, "w") as f:
+        f.write(" ".join(cmd) + "\n" + res.stdout)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed (exit %d); see %s" % (res.returncode, log))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

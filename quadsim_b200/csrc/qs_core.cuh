@@ -1,0 +1,566 @@
+// qs_core.cuh -- per-environment arithmetic of the QuadSim hot path, written once for fp32 and fp64.
+//
+// Every function cites the reference code (sd196821/QuadSim, file:line) whose behaviour it reproduces; the
+// semantics are the ones SURVEY.md section 0.1 / Appendix A pin down by running the reference:
+//   Q1  Drone.step == one explicit Euler step with the RHS frozen at (state, u_prev)   quadrotor.py:115-134
+//   Q2  the new command is stored AFTER integrating (one step of control latency)       quadrotor.py:132-142
+//   Q3  "quat2rot" uses an elementwise square: unit diagonal, 6 off-diagonals            quadrotor.py:243
+//   Q4  the controller's desired quaternion persists across steps and episodes          PIDController.py:100-102
+//   Q5  docking-v2's derivative term is identically zero                                moving_docking_env.py:117,126
+//
+// Two arithmetic modes:
+//   T = double : literal -- follows the reference's formulas step by step (parity <= 1e-9, flags bit-exact).
+//   T = float  : "fast"  -- algebraically identical shortcuts that remove transcendentals from the common path
+//                (threshold tests on sines/tangents instead of angles, rsqrt normalisation, sin/cos of an
+//                atan2 taken from its arguments).  Parity bar: 1e-4 * max(1, |ref|).  -DQS_LITERAL32 turns the
+//                shortcuts off for A/B accuracy checks.
+//
+// The header also compiles as plain C++ (tests/host_harness.cpp) so tolerances can be explored without a
+// GPU; that build is test-only and never loaded by the package.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define QS_HD __host__ __device__ __forceinline__
+#else
+#define QS_HD inline
+#endif
+
+namespace qs {
+
+// ---- physical constants: dynamics/quadrotor.py:10-63 ; gains: controller/PIDController.py:10-44 ----
+template <typename T> struct K {
+  static constexpr T dt = T(0.02), g = T(9.81), mass = T(0.18), L = T(0.086);
+  static constexpr T I0 = T(0.00025), I1 = T(0.000232), I2 = T(0.0003738);
+  static constexpr T lam = T(1.5e-9 / 6.11e-8);
+  static constexpr T mg = T(0.18 * 9.81);
+  static constexpr T pi = T(3.141592653589793);
+  static constexpr T d85 = T(85 * 3.141592653589793 / 180), d175 = T(175 * 3.141592653589793 / 180),
+                     d10 = T(10 * 3.141592653589793 / 180);
+  static constexpr T kp_roll = T(-10), kp_pitch = T(-10), kp_yaw = T(-9.5);
+  static constexpr T kd_roll = T(5.1), kd_pitch = T(5.1), kd_yaw = T(4.0);
+  static constexpr T kp_x = T(-1), kp_y = T(-1), kp_z = T(50), kd_x = T(-1.65), kd_y = T(-1.65), kd_z = T(8);
+  static constexpr T kp_vx = T(-0.7), kp_vy = T(-0.7), kp_vz = T(1);
+};
+
+template <typename T> struct is_f32 { static constexpr bool value = false; };
+template <> struct is_f32<float> { static constexpr bool value = true; };
+#ifdef QS_LITERAL32
+template <typename T> constexpr bool kFast = false;
+#else
+template <typename T> constexpr bool kFast = is_f32<T>::value;
+#endif
+
+// ---- scalar math wrappers ----
+QS_HD float m_sqrt(float x) { return sqrtf(x); }
+QS_HD double m_sqrt(double x) { return sqrt(x); }
+QS_HD float m_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+QS_HD double m_rsqrt(double x) { return 1.0 / sqrt(x); }
+QS_HD float m_abs(float x) { return fabsf(x); }
+QS_HD double m_abs(double x) { return fabs(x); }
+QS_HD float m_asin(float x) { return asinf(x); }
+QS_HD double m_asin(double x) { return asin(x); }
+QS_HD float m_atan2(float y, float x) { return atan2f(y, x); }
+QS_HD double m_atan2(double y, double x) { return atan2(y, x); }
+QS_HD float m_tan(float x) { return tanf(x); }
+QS_HD double m_tan(double x) { return tan(x); }
+QS_HD void m_sincos(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+  sincosf(x, s, c);
+#else
+  *s = sinf(x); *c = cosf(x);
+#endif
+}
+QS_HD void m_sincos(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+  sincos(x, s, c);
+#else
+  *s = sin(x); *c = cos(x);
+#endif
+}
+QS_HD float m_min(float a, float b) { return fminf(a, b); }
+QS_HD double m_min(double a, double b) { return fmin(a, b); }
+QS_HD float m_max(float a, float b) { return fmaxf(a, b); }
+QS_HD double m_max(double a, double b) { return fmax(a, b); }
+template <typename T> QS_HD T m_sign(T x) { return T((x > T(0)) - (x < T(0))); }
+template <typename T> QS_HD bool m_finite(T x) { return (x - x) == T(0); }
+template <typename T> QS_HD T norm3(T x, T y, T z) { return m_sqrt(x * x + y * y + z * z); }
+
+template <typename T> struct Euler { T phi, theta, psi; };
+template <typename T> struct Quat { T w, x, y, z; };
+
+// One quadrotor: state[13] (quadrotor.py:26) + the previous, already limited command u (Q2).
+template <typename T> struct Drone {
+  T px, py, pz, vx, vy, vz, q0, q1, q2, q3, wx, wy, wz;
+  T u0, u1, u2, u3;
+};
+
+// The six off-diagonal entries of the reference's "rotation matrix" (diagonal is exactly 1, Q3).
+template <typename T> struct Rot { T r01, r02, r10, r12, r20, r21; };
+
+// utils/transform.py:94-120  quat2euler (un-normalised quaternion in, Z-X-Y angles out)
+template <typename T> QS_HD Euler<T> quat2euler(T w, T x, T y, T z) {
+  T r10 = T(2) * (x * y - w * z);
+  T r11 = w * w - x * x + y * y - z * z;
+  T r12 = T(2) * (w * x + y * z);
+  T r02 = T(2) * (x * z - w * y);
+  T r22 = w * w - x * x - y * y + z * z;
+  Euler<T> e;
+  e.psi = m_atan2(-r10, r11);
+  if (r12 < T(1)) {
+    if (r12 < T(-1)) { e.phi = -K<T>::pi / T(2); e.theta = T(0); }
+    else { e.phi = m_asin(r12); e.theta = m_atan2(-r02, r22); }
+  } else { e.phi = K<T>::pi / T(2); e.theta = T(0); }
+  return e;
+}
+
+// utils/transform.py:123-136  euler2quat
+template <typename T> QS_HD Quat<T> euler2quat(T roll, T pitch, T yaw) {
+  T cy, sy, cp, sp, cr, sr;
+  m_sincos(yaw * T(0.5), &sy, &cy);
+  m_sincos(pitch * T(0.5), &sp, &cp);
+  m_sincos(roll * T(0.5), &sr, &cr);
+  Quat<T> q;
+  q.w = cr * cp * cy - sr * sp * sy;
+  q.x = sr * cp * cy - cr * sp * sy;
+  q.y = sr * cp * sy + cr * sp * cy;
+  q.z = cr * cp * sy + sr * sp * cy;
+  return q;
+}
+
+// utils/transform.py:4-20 == dynamics/quadrotor.py:226-245 (Q3): R = I + 2*h.*h + 2*q0*h with
+// h01=-n3 h02=n2 h12=-n1 h10=n3 h20=-n2 h21=n1, n = q/|q| and q0 RAW.
+template <typename T> QS_HD Rot<T> quat2rot(T q0, T q1, T q2, T q3) {
+  T n1, n2, n3;
+  T ss = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
+  if (kFast<T>) { T inv = m_rsqrt(ss); n1 = q1 * inv; n2 = q2 * inv; n3 = q3 * inv; }
+  else { T n = m_sqrt(ss); n1 = q1 / n; n2 = q2 / n; n3 = q3 / n; }
+  T w2 = T(2) * q0;
+  Rot<T> R;
+  R.r01 = (T(2) * n3) * n3 - w2 * n3;
+  R.r10 = (T(2) * n3) * n3 + w2 * n3;
+  R.r02 = (T(2) * n2) * n2 + w2 * n2;
+  R.r20 = (T(2) * n2) * n2 - w2 * n2;
+  R.r12 = (T(2) * n1) * n1 - w2 * n1;
+  R.r21 = (T(2) * n1) * n1 + w2 * n1;
+  return R;
+}
+
+// utils/transform.py:23-46  rot2euler on (R12, R10, R11, R02, R22)
+template <typename T> QS_HD Euler<T> rot2euler(T r12, T r10, T r11, T r02, T r22) {
+  Euler<T> e;
+  e.psi = m_atan2(-r10, r11);
+  if (r12 < T(1)) {
+    if (r12 < T(-1)) { e.phi = -K<T>::pi / T(2); e.theta = T(0); }
+    else { e.phi = m_asin(r12); e.theta = m_atan2(-r02, r22); }
+  } else { e.phi = K<T>::pi / T(2); e.theta = T(0); }
+  return e;
+}
+
+// dynamics/quadrotor.py:171-187  u_limit: per-rotor thrust A@[F,Mx,My] clamped to [0, F_max/4 = m*g], Mz untouched
+template <typename T> QS_HD void u_limit(T F, T Mx, T My, T Mz, T& o0, T& o1, T& o2, T& o3) {
+  const T hl = T(0.5 / 0.086), L = K<T>::L, fmax = K<T>::mg;
+  T p0 = T(0.25) * F - hl * My;
+  T p1 = T(0.25) * F + hl * Mx;
+  T p2 = T(0.25) * F + hl * My;
+  T p3 = T(0.25) * F - hl * Mx;
+  p0 = m_max(m_min(p0, fmax), T(0));
+  p1 = m_max(m_min(p1, fmax), T(0));
+  p2 = m_max(m_min(p2, fmax), T(0));
+  p3 = m_max(m_min(p3, fmax), T(0));
+  o0 = ((p0 + p1) + p2) + p3;
+  o1 = L * p1 - L * p3;
+  o2 = L * p2 - L * p0;
+  o3 = Mz;
+}
+
+// rotor thrusts -> [F, Mx, My, Mz]: rotor2control, dynamics/quadrotor.py:56-59
+template <typename T> QS_HD void rotor2control(T f0, T f1, T f2, T f3, T& F, T& Mx, T& My, T& Mz) {
+  const T L = K<T>::L, lam = K<T>::lam;
+  F = ((f0 + f1) + f2) + f3;
+  Mx = L * f1 - L * f3;
+  My = L * f2 - L * f0;
+  Mz = ((lam * f0 - lam * f1) + lam * f2) - lam * f3;
+}
+
+// dynamics/quadrotor.py:126-144  Drone.step(u_cmd): Euler step with frozen RHS df(state, u_prev) (:80-113),
+// attitude_limit (:146-168), then u_prev <- u_limit(u_cmd).  Returns true if the attitude clamp fired.
+template <typename T> QS_HD bool drone_step(Drone<T>& d, T c0, T c1, T c2, T c3) {
+  using C = K<T>;
+  const T dt = C::dt;
+  // --- df: quadrotor.py:80-113 ---
+  T ss = d.q0 * d.q0 + d.q1 * d.q1 + d.q2 * d.q2 + d.q3 * d.q3;
+  T n1, n2;
+  if (kFast<T>) { T inv = m_rsqrt(ss); n1 = d.q1 * inv; n2 = d.q2 * inv; }
+  else { T n = m_sqrt(ss); n1 = d.q1 / n; n2 = d.q2 / n; }
+  T w2 = T(2) * d.q0;
+  T r20 = (T(2) * n2) * n2 - w2 * n2, r21 = (T(2) * n1) * n1 + w2 * n1;
+  const T inv_m = T(1.0) / C::mass;
+  T ax = inv_m * (r20 * d.u0), ay = inv_m * (r21 * d.u0), az = inv_m * (d.u0 - C::mg);
+  T e2 = T(2) * (T(1) - ss);  // K_quat * e_quat, quadrotor.py:96-97
+  T sk0 = -d.wx * d.q1 - d.wy * d.q2 - d.wz * d.q3;  // q_sk @ q, quadrotor.py:98-103
+  T sk1 = d.wx * d.q0 - d.wy * d.q2 + d.wz * d.q3;
+  T sk2 = d.wy * d.q0 + d.wz * d.q1 - d.wx * d.q3;
+  T sk3 = d.wz * d.q0 - d.wy * d.q1 + d.wx * d.q2;
+  T dq0 = T(-0.5) * sk0 + e2 * d.q0, dq1 = T(-0.5) * sk1 + e2 * d.q1;
+  T dq2 = T(-0.5) * sk2 + e2 * d.q2, dq3 = T(-0.5) * sk3 + e2 * d.q3;
+  // inv(I) @ (I@u[1:] - w x (I w)), quadrotor.py:83,105
+  T Iw0 = C::I0 * d.wx, Iw1 = C::I1 * d.wy, Iw2 = C::I2 * d.wz;
+  T aw0 = (T(1) / C::I0) * (C::I0 * d.u1 - (d.wy * Iw2 - d.wz * Iw1));
+  T aw1 = (T(1) / C::I1) * (C::I1 * d.u2 - (d.wz * Iw0 - d.wx * Iw2));
+  T aw2 = (T(1) / C::I2) * (C::I2 * d.u3 - (d.wx * Iw1 - d.wy * Iw0));
+  // --- y = s + dt * f (Q1) ---
+  d.px += dt * d.vx; d.py += dt * d.vy; d.pz += dt * d.vz;
+  d.vx += dt * ax; d.vy += dt * ay; d.vz += dt * az;
+  d.q0 += dt * dq0; d.q1 += dt * dq1; d.q2 += dt * dq2; d.q3 += dt * dq3;
+  d.wx += dt * aw0; d.wy += dt * aw1; d.wz += dt * aw2;
+  // --- attitude_limit: quadrotor.py:146-168 ---
+  bool clamp = false;
+  if (kFast<T>) {
+    // |phi|>=85deg <=> |r12|>=sin85 ; |theta|>=85deg <=> not(r22>0 && |r02|<r22*tan85) ;
+    // |psi|>=175deg <=> r11<0 && |r10|<=|r11|*tan5  -- no transcendental unless the clamp fires
+    T w = d.q0, x = d.q1, y = d.q2, z = d.q3;
+    T r10 = T(2) * (x * y - w * z), r11 = w * w - x * x + y * y - z * z, r12 = T(2) * (w * x + y * z);
+    T r02 = T(2) * (x * z - w * y), r22 = w * w - x * x - y * y + z * z;
+    const T s85 = T(0.99619469809174555), t85 = T(11.430052302761343), t5 = T(0.087488663525924007);
+    bool in_phi = m_abs(r12) < s85;
+    bool in_theta = (r22 > T(0)) && (m_abs(r02) < r22 * t85);
+    bool in_psi = !((r11 < T(0)) && (m_abs(r10) <= -r11 * t5));
+    clamp = !(in_phi && in_theta && in_psi);
+    if (!(r12 < T(1)) || r12 < T(-1)) clamp = true;  // phi = +-90deg branch: theta forced to 0
+  } else {
+    clamp = true;
+  }
+  if (clamp) {
+    Euler<T> e = quat2euler(d.q0, d.q1, d.q2, d.q3);
+    T r = e.phi, p = e.theta, y = e.psi;
+    bool flag = false;
+    Quat<T> lim = {d.q0, d.q1, d.q2, d.q3};
+    if (m_abs(r) >= C::d85) { lim = euler2quat(m_sign(r) * C::d85, p, y); flag = true; }
+    if (m_abs(p) >= C::d85) { lim = euler2quat(r, m_sign(p) * C::d85, y); flag = true; }
+    if (m_abs(y) >= C::d175) { lim = euler2quat(r, p, m_sign(y) * C::d175); flag = true; }
+    if (m_abs(r) <= C::d85 && m_abs(p) <= C::d85 && m_abs(y) <= C::d175) flag = false;
+    clamp = flag;
+    if (flag) {
+      d.q0 = lim.w; d.q1 = lim.x; d.q2 = lim.y; d.q3 = lim.z;
+      d.wx = T(0); d.wy = T(0); d.wz = T(0);
+    }
+  }
+  // --- u_prev <- u_limit(u_cmd) (Q2) ---
+  u_limit(c0, c1, c2, c3, d.u0, d.u1, d.u2, d.u3);
+  return clamp;
+}
+
+// Shared tail of hover_controller (PIDController.py:87-104) and vel_controller (:119-134) followed by
+// attitude_controller (:52-74): acc_des -> u = [F, M].  des_q is read (psi_des) and OVERWRITTEN (Q4).
+template <typename T> QS_HD void acc2cmd(T ax, T ay, T az, Quat<T>& dq, const Drone<T>& now, T& F, T& M0, T& M1, T& M2) {
+  using C = K<T>;
+  F = C::mass * C::g + C::mass * az;
+  T phi_d, theta_d, psi_d;
+  {
+    // psi_des = quat2euler(des_q)[2]
+    T w = dq.w, x = dq.x, y = dq.y, z = dq.z;
+    T r10 = T(2) * (x * y - w * z), r11 = w * w - x * x + y * y - z * z;
+    psi_d = m_atan2(-r10, r11);
+  }
+  T sp, cp;
+  m_sincos(psi_d, &sp, &cp);
+  phi_d = (ax * sp - ay * cp) / C::g;
+  theta_d = (ax * cp + ay * sp) / C::g;
+  dq = euler2quat(phi_d, theta_d, psi_d);
+  // attitude_controller re-extracts the desired angles from the quaternion it was just given
+  Euler<T> ed;
+  if (kFast<T> && m_abs(phi_d) < T(1.5) && m_abs(theta_d) < T(3.1)) {
+    ed.phi = phi_d; ed.theta = theta_d; ed.psi = psi_d;  // quat2euler(euler2quat(.)) == identity on this range
+  } else {
+    ed = quat2euler(dq.w, dq.x, dq.y, dq.z);
+  }
+  Euler<T> en = quat2euler(now.q0, now.q1, now.q2, now.q3);
+  // des rates: des[10]=des[11]=0 (written), des[12]=0 (never set)
+  M0 = C::kp_roll * (ed.phi - en.phi) + C::kd_roll * (T(0) - now.wx);
+  M1 = C::kp_pitch * (ed.theta - en.theta) + C::kd_pitch * (T(0) - now.wy);
+  M2 = C::kp_yaw * (ed.psi - en.psi) + C::kd_yaw * (T(0) - now.wz);
+}
+
+// controller/PIDController.py:179-185  PID(des, now) with des pos/vel given explicitly
+template <typename T> QS_HD void pid(T dpx, T dpy, T dpz, T dvx, T dvy, T dvz, Quat<T>& dq, const Drone<T>& now,
+                                     T& F, T& M0, T& M1, T& M2) {
+  using C = K<T>;
+  T ax = C::kp_x * (dpx - now.px) + C::kd_x * (dvx - now.vx);
+  T ay = C::kp_y * (dpy - now.py) + C::kd_y * (dvy - now.vy);
+  T az = C::kp_z * (dpz - now.pz) + C::kd_z * (dvz - now.vz);
+  acc2cmd(ax, ay, az, dq, now, F, M0, M1, M2);
+}
+
+// controller/PIDController.py:106-141  vel_controller(des, now, last) with last == now (Q5): the kd_v* terms vanish
+template <typename T> QS_HD void vel_controller(T dvx, T dvy, T dvz, Quat<T>& dq, const Drone<T>& now, T& F, T& M0,
+                                                T& M1, T& M2) {
+  using C = K<T>;
+  T ax = C::kp_vx * (dvx - now.vx);
+  T ay = C::kp_vy * (dvy - now.vy);
+  T az = C::kp_vz * (dvz - now.vz);
+  acc2cmd(ax, ay, az, dq, now, F, M0, M1, M2);
+}
+
+// gym_docking/envs/docking_env.py:257-295 state2rel, with get_dock_port_state (quadrotor.py:213-224) folded in for
+// the ports the envs use: chaser [+0.1,0,0] (docking_env.py:38), target [-0.1,0,0] (:51).
+// c = chaser (drone A), t = target (drone B).  rel = [dp(3), dv(3), euler(3), euler rates(3)].
+template <typename T> QS_HD void state2rel(const Drone<T>& c, const Drone<T>& t, T rel[12]) {
+  Rot<T> A = quat2rot(c.q0, c.q1, c.q2, c.q3);  // R_I2A
+  Rot<T> B = quat2rot(t.q0, t.q1, t.q2, t.q3);  // R_I2B
+  // dock ports: r = R^T @ [d,0,0] = d * (1, R01, R02); pos = p + r; vel = v + w x r
+  const T dc = T(0.1), dt_ = T(-0.1);
+  T rc0 = dc, rc1 = A.r01 * dc, rc2 = A.r02 * dc;
+  T rt0 = dt_, rt1 = B.r01 * dt_, rt2 = B.r02 * dt_;
+  if (kFast<T>) {
+    // difference the two ~50 m positions first, then add the +-0.1 m lever arms
+    rel[0] = (t.px - c.px) + (rt0 - rc0);
+    rel[1] = (t.py - c.py) + (rt1 - rc1);
+    rel[2] = (t.pz - c.pz) + (rt2 - rc2);
+  } else {
+    rel[0] = (t.px + rt0) - (c.px + rc0);
+    rel[1] = (t.py + rt1) - (c.py + rc1);
+    rel[2] = (t.pz + rt2) - (c.pz + rc2);
+  }
+  T vc0 = c.vx + (-c.wz * rc1 + c.wy * rc2), vc1 = c.vy + (c.wz * rc0 - c.wx * rc2), vc2 = c.vz + (-c.wy * rc0 + c.wx * rc1);
+  T vt0 = t.vx + (-t.wz * rt1 + t.wy * rt2), vt1 = t.vy + (t.wz * rt0 - t.wx * rt2), vt2 = t.vz + (-t.wy * rt0 + t.wx * rt1);
+  rel[3] = vt0 - vc0; rel[4] = vt1 - vc1; rel[5] = vt2 - vc2;
+  // R_A2B = R_I2B @ R_I2A^T  (unit diagonals)
+  T ab00 = T(1) + B.r01 * A.r01 + B.r02 * A.r02;
+  T ab01 = A.r10 + B.r01 + B.r02 * A.r12;
+  T ab02 = A.r20 + B.r01 * A.r21 + B.r02;
+  T ab10 = B.r10 + A.r01 + B.r12 * A.r02;
+  T ab11 = B.r10 * A.r10 + T(1) + B.r12 * A.r12;
+  T ab12 = B.r10 * A.r20 + A.r21 + B.r12;
+  T ab20 = B.r20 + B.r21 * A.r01 + A.r02;
+  T ab21 = B.r20 * A.r10 + B.r21 + A.r12;
+  T ab22 = B.r20 * A.r20 + B.r21 * A.r21 + T(1);
+  Euler<T> e = rot2euler(ab12, ab10, ab11, ab02, ab22);
+  rel[6] = e.phi; rel[7] = e.theta; rel[8] = e.psi;
+  // rel_A2B_inB = R_I2B @ w_B - (R_A2B @ R_I2A) @ w_A ; evaluated as R_A2B @ (R_I2A @ w_A)
+  T b0 = t.wx + B.r01 * t.wy + B.r02 * t.wz;
+  T b1 = B.r10 * t.wx + t.wy + B.r12 * t.wz;
+  T b2 = B.r20 * t.wx + B.r21 * t.wy + t.wz;
+  T a0 = c.wx + A.r01 * c.wy + A.r02 * c.wz;
+  T a1 = A.r10 * c.wx + c.wy + A.r12 * c.wz;
+  T a2 = A.r20 * c.wx + A.r21 * c.wy + c.wz;
+  T p = b0 - (ab00 * a0 + ab01 * a1 + ab02 * a2);
+  T q = b1 - (ab10 * a0 + ab11 * a1 + ab12 * a2);
+  T r = b2 - (ab20 * a0 + ab21 * a1 + ab22 * a2);
+  T st, ct, tphi, icphi, cphi = T(1);
+  if (kFast<T> && ab12 < T(1) && ab12 > T(-1)) {
+    // theta = atan2(-ab02, ab22), phi = asin(ab12): their sin/cos/tan follow from the arguments
+    T h = m_rsqrt(ab02 * ab02 + ab22 * ab22);
+    st = -ab02 * h; ct = ab22 * h;
+    icphi = m_rsqrt((T(1) - ab12) * (T(1) + ab12));
+    tphi = ab12 * icphi;
+    if (!(ab02 * ab02 + ab22 * ab22 > T(0))) { st = T(0); ct = T(1); }  // atan2(0,0) = 0
+  } else {
+    m_sincos(e.theta, &st, &ct);
+    tphi = m_tan(e.phi);
+    T sphi;
+    m_sincos(e.phi, &sphi, &cphi);
+    icphi = T(0);
+  }
+  T rc_ps = r * ct - p * st;
+  rel[9] = p * ct + r * st;
+  rel[10] = q - tphi * rc_ps;
+  rel[11] = (icphi != T(0)) ? rc_ps * icphi : rc_ps / cphi;
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11).  Not in the reference: the north star's counter-based per-env RNG
+// for the randomised auto-reset (docking_env.py:34 has the distribution commented out). ----
+struct U4 { uint32_t x, y, z, w; };
+QS_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c.x, p1 = (uint64_t)0xCD9E8D57u * c.z;
+    U4 n;
+    n.x = (uint32_t)(p1 >> 32) ^ c.y ^ k0; n.y = (uint32_t)p1;
+    n.z = (uint32_t)(p0 >> 32) ^ c.w ^ k1; n.w = (uint32_t)p0;
+    c = n;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// exact fp32 ops (no FMA contraction) so host oracle, fp32 kernel and fp64 kernel all get the same bits
+QS_HD float f_mul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  volatile float r = a * b; return r;
+#endif
+}
+QS_HD float f_add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  volatile float r = a + b; return r;
+#endif
+}
+// jitter_i = ((x_i >> 8) * 2^-24 - 0.5) * scale, all in fp32
+QS_HD void philox_jitter3(uint64_t seed, uint64_t env_id, uint32_t episode, uint32_t stream, float scale, float j[3]) {
+  U4 c = {(uint32_t)env_id, (uint32_t)(env_id >> 32), episode, stream};
+  U4 x = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float s = 5.9604644775390625e-08f;
+  j[0] = f_mul(f_add(f_mul((float)(x.x >> 8), s), -0.5f), scale);
+  j[1] = f_mul(f_add(f_mul((float)(x.y >> 8), s), -0.5f), scale);
+  j[2] = f_mul(f_add(f_mul((float)(x.z >> 8), s), -0.5f), scale);
+}
+
+// =========================================================================================================
+// Environment level: one env's step / (re)seat in registers.  The CUDA kernels (qs_lib.cu) are load -> these -> store.
+// =========================================================================================================
+constexpr int kHover = 0, kDockV0 = 1, kDockV2 = 2;                 // == qs_env_kind
+constexpr int kRandNone = 0, kRandEpisode = 1, kRandOnce = 2;       // == qs_randomize
+constexpr int kInfoDone = 1, kInfoOverlimit = 2, kInfoDocking = 4, kInfoOvertime = 8;  // == QS_INFO_*
+
+struct RngCfg { uint64_t seed, env_id0; int randomize; float jitter_scale; };
+
+// Docking positions are ~50 m from the world origin (y = -50) while everything the env computes from them is a
+// difference of a few metres.  The fp32 path therefore keeps both drones' positions RELATIVE to the fixed point
+// O = (10,-50,5) (target start == docking-v0 set-point, docking_env.py:47,59): the dynamics are translation invariant, so
+// this is the same trajectory with ~10x smaller position rounding.  The fp64 path stays in world coordinates
+// (literal).  State export/import (always float64) converts, exactly, at the boundary.
+template <typename T> struct Origin { static constexpr T x = T(0), y = T(0), z = T(0); };
+#ifndef QS_LITERAL32
+template <> struct Origin<float> { static constexpr float x = 10.f, y = -50.f, z = 5.f; };
+#endif
+
+template <typename T> struct DockEnv {
+  Drone<T> c, t;        // chaser (drone A), target (drone B)
+  Quat<T> dq;           // target_state_des[6:10] (Q4)
+  T last_shaping, ep_return;
+  int32_t tt, episode;  // env.t ; Philox counter word 2
+};
+template <typename T> struct HoverEnv {
+  Drone<T> d;
+  T ep_return;
+  int32_t tt, episode;
+};
+template <typename T> struct StepOut {
+  T reward;
+  bool done, docking, overlimit, overtime, nonfinite;
+  QS_HD int info() const { return (done ? kInfoDone : 0) | (overlimit ? kInfoOverlimit : 0) | (docking ? kInfoDocking : 0) | (overtime ? kInfoOvertime : 0); }
+};
+
+template <typename T> QS_HD Drone<T> drone_at(T x, T y, T z) {
+  return Drone<T>{x, y, z, T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
+}
+
+// env.reset(): Drone.reset x2 (quadrotor.py:65-78: state <- ini, u <- 0) and docking_env.py:233-244 (t, shaping <- 0).
+// target_state_des (dq) is NOT re-initialised (Q4).  Chaser ini [8,-50,5] + Philox jitter U(-hw,hw)^3 (the distribution
+// commented out at docking_env.py:34), target ini [10,-50,5].  obs = state2rel of the seated states, which for identity
+// attitudes and zero rates is (dp, 0, ..., 0).
+template <typename T> QS_HD void dock_env_seat(DockEnv<T>& e, const RngCfg& rng, int64_t i, T obs[12]) {
+  float j[3] = {0.f, 0.f, 0.f};
+  if (rng.randomize != kRandNone)
+    philox_jitter3(rng.seed, rng.env_id0 + (uint64_t)i, rng.randomize == kRandOnce ? 0u : (uint32_t)e.episode, 0u, rng.jitter_scale, j);
+  using O = Origin<T>;  // the fp32 subtractions below are exact (result has fewer significant bits than the minuend)
+  e.c = drone_at<T>(T(f_add(8.f, j[0])) - O::x, T(f_add(-50.f, j[1])) - O::y, T(f_add(5.f, j[2])) - O::z);
+  e.t = drone_at<T>(T(10) - O::x, T(-50) - O::y, T(5) - O::z);
+  e.tt = 0; e.last_shaping = T(0); e.ep_return = T(0);
+  if (kFast<T>) obs[0] = (e.t.px - e.c.px) + T(-0.2);
+  else obs[0] = (e.t.px + T(-0.1)) - (e.c.px + T(0.1));
+  obs[1] = e.t.py - e.c.py; obs[2] = e.t.pz - e.c.pz;
+#pragma unroll
+  for (int k = 3; k < 12; k++) obs[k] = T(0);
+}
+
+// gym_docking/envs/docking_env.py:104-231 (KIND = kDockV0) / moving_docking_env.py:111-192 (KIND = kDockV2).
+// rel = the step's observation (terminal observation if done); the caller applies the auto-reset.
+template <typename T, int KIND> QS_HD void dock_env_step(DockEnv<T>& e, const T act[4], T rel[12], StepOut<T>& o) {
+  using C = K<T>;
+  e.tt += 1;  // docking_env.py:108
+  // chaser command: rotor2control @ (action_std * a + action_mean), action_std = action_mean = m*g/2 (docking_env.py:98-99,115)
+  const T half = T(1.0 * 0.18 * 9.81 / 2.0);
+  T uc0, uc1, uc2, uc3;
+  rotor2control(half * act[0] + half, half * act[1] + half, half * act[2] + half, half * act[3] + half, uc0, uc1, uc2, uc3);
+  // target command from the target state BEFORE stepping (docking_env.py:119 / moving_docking_env.py:126)
+  T ut0, ut1, ut2, ut3;
+  using O = Origin<T>;
+  if (KIND == kDockV0) pid(T(10) - O::x, T(-50) - O::y, T(5) - O::z, T(0), T(0), T(0), e.dq, e.t, ut0, ut1, ut2, ut3);  // des: docking_env.py:60-64
+  else vel_controller(T(0.2), T(0), T(0), e.dq, e.t, ut0, ut1, ut2, ut3);                         // des vel: moving_docking_env.py:62-66
+  drone_step(e.t, ut0, ut1, ut2, ut3);  // docking_env.py:120
+  drone_step(e.c, uc0, uc1, uc2, uc3);  // docking_env.py:121
+  state2rel(e.c, e.t, rel);             // docking_env.py:124-127
+  // flags: docking_env.py:130-152 / moving_docking_env.py:137-157
+  const T radius = KIND == kDockV0 ? T(3) : T(10);
+  T np_ = norm3(rel[0], rel[1], rel[2]), nv = norm3(rel[3], rel[4], rel[5]);
+  o.docking = (np_ < T(0.1)) && (nv < T(0.1)) && (m_abs(rel[6]) < C::d10) && (m_abs(rel[7]) < C::d10) && (m_abs(rel[8]) < C::d10);
+  o.overlimit = (np_ >= radius) || (e.c.pz <= T(0.1 - (double)O::z));
+  o.overtime = e.tt >= 600;
+  o.done = o.overlimit || o.overtime;
+  // shaping / reward: docking_env.py:215-222 / moving_docking_env.py:176-183
+  T na = m_sqrt(act[0] * act[0] + act[1] * act[1] + act[2] * act[2] + act[3] * act[3]);
+  T shaping;
+  if (kFast<T>) {
+    shaping = -(T(10) / radius) * np_ - nv - T(10.0 / 3.141592653589793) * norm3(rel[6], rel[7], rel[8]) -
+              norm3(rel[9], rel[10], rel[11]) - T(0.1) * na + (o.docking ? T(1) : T(0));
+  } else {
+    shaping = T(-10) * norm3(rel[0] / radius, rel[1] / radius, rel[2] / radius) - T(1) * nv -
+              T(10) * norm3(rel[6] / C::pi, rel[7] / C::pi, rel[8] / C::pi) - T(1) * norm3(rel[9], rel[10], rel[11]) -
+              T(0.1) * na + T(1) * (o.docking ? T(1) : T(0));
+  }
+  o.reward = shaping - e.last_shaping;
+  e.last_shaping = shaping;
+  e.ep_return += o.reward;
+  T fsum = m_abs(o.reward);
+#pragma unroll
+  for (int k = 0; k < 12; k++) fsum += m_abs(rel[k]);
+  o.nonfinite = !m_finite(fsum);
+}
+
+template <typename T> QS_HD void drone_to_obs13(const Drone<T>& d, T o[13]) {
+  o[0] = d.px; o[1] = d.py; o[2] = d.pz; o[3] = d.vx; o[4] = d.vy; o[5] = d.vz;
+  o[6] = d.q0; o[7] = d.q1; o[8] = d.q2; o[9] = d.q3; o[10] = d.wx; o[11] = d.wy; o[12] = d.wz;
+}
+
+// hover (re)seat: hovering_env.py:23-29, :80-82 -- pos [0,0,5] + U(-hw,hw)^3, euler U(-0.2,0.2)^3, zero rates, u <- 0
+template <typename T> QS_HD void hover_env_seat(HoverEnv<T>& e, const RngCfg& rng, int64_t i, T obs[13]) {
+  float jp[3] = {0.f, 0.f, 0.f}, je[3] = {0.f, 0.f, 0.f};
+  if (rng.randomize != kRandNone) {
+    uint32_t ep = rng.randomize == kRandOnce ? 0u : (uint32_t)e.episode;
+    philox_jitter3(rng.seed, rng.env_id0 + (uint64_t)i, ep, 0u, rng.jitter_scale, jp);
+    philox_jitter3(rng.seed, rng.env_id0 + (uint64_t)i, ep, 1u, 0.4f, je);
+  }
+  Quat<T> q = euler2quat(T(je[0]), T(je[1]), T(je[2]));
+  e.d = drone_at<T>(T(f_add(0.f, jp[0])), T(f_add(0.f, jp[1])), T(f_add(5.f, jp[2])));
+  e.d.q0 = q.w; e.d.q1 = q.x; e.d.q2 = q.y; e.d.q3 = q.z;
+  e.tt = 0; e.ep_return = T(0);
+  drone_to_obs13(e.d, obs);
+}
+
+// hovering-v0 step: gym_docking/envs/hovering_env.py:47-78
+template <typename T> QS_HD void hover_env_step(HoverEnv<T>& e, const T act[4], T obs[13], StepOut<T>& o) {
+  Drone<T>& d = e.d;
+  e.tt += 1;
+  const T amax = T(1.0 * 0.18 * 9.81);  // action_max = m*g per rotor, hovering_env.py:42
+  T u0, u1, u2, u3;
+  rotor2control(amax * act[0], amax * act[1], amax * act[2], amax * act[3], u0, u1, u2, u3);  // :51
+  drone_step(d, u0, u1, u2, u3);                                                               // :52
+  // errors w.r.t. state_des = [0,0,5, 0.., q=identity, 0..] (hovering_env.py:31-35, :57-60); quat2euler(identity) = 0
+  Euler<T> en = quat2euler(d.q0, d.q1, d.q2, d.q3);
+  T pe = norm3(T(0) - d.px, T(0) - d.py, T(5) - d.pz), ve = norm3(d.vx, d.vy, d.vz);
+  T ae = norm3(en.phi, en.theta, en.psi), we = norm3(d.wx, d.wy, d.wz);
+  T r_thre = (pe < T(0.1) && ve < T(0.1)) ? T(1) : T(0);                                      // :62-66
+  o.done = (norm3(d.px, d.py, d.pz) > T(100)) || (ve > T(100));                                // :68
+  o.overlimit = o.done; o.overtime = false; o.docking = r_thre > T(0);
+  o.reward = o.done ? T(-0.1) : (r_thre + T(0.1) - T(0.01) * pe - T(0.001) * ve - T(0.01) * ae - T(0.001) * we);  // :70-76
+  e.ep_return += o.reward;
+  drone_to_obs13(d, obs);
+  T fsum = m_abs(o.reward);
+#pragma unroll
+  for (int k = 0; k < 13; k++) fsum += m_abs(obs[k]);
+  o.nonfinite = !m_finite(fsum);
+}
+
+}  // namespace qs

@@ -1,0 +1,686 @@
+// qs_lib.cu -- CUDA kernels (sm_100a) and the C ABI of libquadsim_b200.so (include/quadsim_b200.h).
+//
+// One thread per environment.  Persistent per-env state lives in HBM as structure-of-arrays of 16-byte rows
+// (float4 for fp32, double2 for fp64) so every load/store instruction of a warp covers one contiguous 512-byte
+// span; the whole step (target controller -> 2x Drone.step -> dock ports -> state2rel -> flags/shaping/reward ->
+// auto-reset with Philox) runs in registers between one set of loads and one set of stores.
+//
+// There is NO CPU fallback: qs_create fails with QS_ERR_NO_DEVICE when no CUDA device is usable.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/quadsim_b200.h"
+#include "qs_core.cuh"
+
+namespace {
+
+using namespace qs;
+
+constexpr int kBlock = 128;        // threads per CTA (4 warps); grid = ceil(n / 128)
+constexpr int kStatWords = 8;      // doubles per warp statistics slot (5 used), 64-byte stride
+constexpr int64_t kHostChunk = 1 << 17;  // envs per pipelined chunk in qs_step_host
+constexpr int kHostStreams = 4;
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define QS_CUDA(call)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return fail(QS_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// HBM layout.  A "row" is 16 bytes per env: Row<float>::V = float4 (4 words), Row<double>::V = double2 (2 words).
+// Row r of env i sits at rows[r * stride + i].  Word order (docking, 44 words; fp64 stores the first 42):
+//    0- 3  chaser p.xyz, w.x      4- 7  chaser v.xyz, w.y     8-11  chaser q      12-15  chaser u_prev
+//   16-19  target p.xyz, w.x     20-23  target v.xyz, w.y    24-27  target q      28-31  target u_prev
+//   32-35  des_q                 36-39  chaser w.z, target w.z, last_shaping, ep_return
+//   40-43  t (int), episode (uint), spare, spare
+// Hover (20 words): 0-15 as the chaser above; 16-19 = w.z, ep_return, t (int), episode (uint).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T> struct Row;
+template <> struct Row<float> { using V = float4; static constexpr int W = 4; };
+template <> struct Row<double> { using V = double2; static constexpr int W = 2; };
+
+template <typename T> constexpr int dock_words() { return is_f32<T>::value ? 44 : 42; }
+constexpr int kHoverWords = 20;
+
+__device__ __forceinline__ void unpack(const float4& v, float* w) { w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+__device__ __forceinline__ void unpack(const double2& v, double* w) { w[0] = v.x; w[1] = v.y; }
+__device__ __forceinline__ float4 pack(const float* w) { return make_float4(w[0], w[1], w[2], w[3]); }
+__device__ __forceinline__ double2 pack(const double* w) { return make_double2(w[0], w[1]); }
+
+template <typename T, int NW> __device__ __forceinline__ void load_words(const void* base, int64_t stride, int64_t i, T (&w)[NW]) {
+  using V = typename Row<T>::V;
+  constexpr int W = Row<T>::W;
+  const V* rows = reinterpret_cast<const V*>(base);
+#pragma unroll
+  for (int r = 0; r < NW / W; r++) unpack(rows[r * stride + i], &w[r * W]);
+}
+template <typename T, int NW> __device__ __forceinline__ void store_words(void* base, int64_t stride, int64_t i, const T (&w)[NW]) {
+  using V = typename Row<T>::V;
+  constexpr int W = Row<T>::W;
+  V* rows = reinterpret_cast<V*>(base);
+#pragma unroll
+  for (int r = 0; r < NW / W; r++) rows[r * stride + i] = pack(&w[r * W]);
+}
+
+__device__ __forceinline__ int32_t word_to_int(float x) { return __float_as_int(x); }
+__device__ __forceinline__ int32_t word_to_int(double x) { return (int32_t)__double_as_longlong(x); }
+template <typename T> __device__ __forceinline__ T int_to_word(int32_t v);
+template <> __device__ __forceinline__ float int_to_word<float>(int32_t v) { return __int_as_float(v); }
+template <> __device__ __forceinline__ double int_to_word<double>(int32_t v) { return __longlong_as_double((long long)v); }
+
+// row-major [N, C] outputs written as 16-byte vectors (C*sizeof(T) is a multiple of 16 for C in {4, 12})
+template <typename T, int C> __device__ __forceinline__ void store_row(void* base, int64_t i, const T* v) {
+  using V = typename Row<T>::V;
+  constexpr int W = Row<T>::W;
+  static_assert(C % W == 0, "row width must be a whole number of 16-byte vectors");
+  V* p = reinterpret_cast<V*>(reinterpret_cast<T*>(base) + i * C);
+#pragma unroll
+  for (int k = 0; k < C / W; k++) p[k] = pack(&v[k * W]);
+}
+template <typename T> __device__ __forceinline__ void load_action(const void* base, int64_t i, T a[4]) {
+  using V = typename Row<T>::V;
+  constexpr int W = Row<T>::W;
+  const V* p = reinterpret_cast<const V*>(reinterpret_cast<const T*>(base) + i * 4);
+#pragma unroll
+  for (int k = 0; k < 4 / W; k++) unpack(__ldg(p + k), &a[k * W]);
+}
+
+struct StepArgs {
+  void* state;
+  int64_t stride;   // envs per row (n_envs rounded up)
+  int64_t first, n; // this launch covers envs [first, first + n)
+  const void* actions;
+  void* obs;
+  void* reward;
+  uint8_t* done;
+  uint8_t* info;      // may be null
+  void* term_obs;     // may be null
+  double* warp_stats; // [ceil(N/32)][kStatWords]
+  RngCfg rng;
+  int auto_reset;
+};
+
+// Per-warp statistics: deterministic (fixed lane order), no atomics.  Slot = global warp index of the env range, so
+// concurrent chunk launches (qs_step_host) never share a slot.
+__device__ __forceinline__ void warp_stats_update(double* warp_stats, int64_t i, unsigned mask, bool done, bool docking,
+                                                  bool nonfinite, double ep_ret, int ep_len) {
+  unsigned bd = __ballot_sync(mask, done), bk = __ballot_sync(mask, docking), bn = __ballot_sync(mask, nonfinite);
+  if ((bd | bk | bn) == 0) return;
+  double sret = 0.0, slen = 0.0;
+  for (unsigned m = bd; m; m &= m - 1) {
+    int l = __ffs(m) - 1;
+    sret += __shfl_sync(mask, ep_ret, l);
+    slen += (double)__shfl_sync(mask, ep_len, l);
+  }
+  if ((threadIdx.x & 31) == (__ffs(mask) - 1)) {
+    double* s = warp_stats + (i >> 5) * kStatWords;
+    if (bd) { s[0] += sret; s[1] += slen; s[2] += (double)__popc(bd); }
+    if (bk) s[3] += (double)__popc(bk);
+    if (bn) s[4] += (double)__popc(bn);
+  }
+}
+
+// word <-> struct mapping of the row layout above
+template <typename T, int NW> __device__ __forceinline__ void words_to_dock(const T (&w)[NW], DockEnv<T>& e) {
+  e.c = Drone<T>{w[0], w[1], w[2], w[4], w[5], w[6], w[8], w[9], w[10], w[11], w[3], w[7], w[36], w[12], w[13], w[14], w[15]};
+  e.t = Drone<T>{w[16], w[17], w[18], w[20], w[21], w[22], w[24], w[25], w[26], w[27], w[19], w[23], w[37], w[28], w[29], w[30], w[31]};
+  e.dq = Quat<T>{w[32], w[33], w[34], w[35]};
+  e.last_shaping = w[38]; e.ep_return = w[39];
+  e.tt = word_to_int(w[40]); e.episode = word_to_int(w[41]);
+}
+template <typename T, int NW> __device__ __forceinline__ void dock_to_words(const DockEnv<T>& e, T (&w)[NW]) {
+  const Drone<T>&c = e.c, &t = e.t;
+  w[0] = c.px; w[1] = c.py; w[2] = c.pz; w[3] = c.wx; w[4] = c.vx; w[5] = c.vy; w[6] = c.vz; w[7] = c.wy;
+  w[8] = c.q0; w[9] = c.q1; w[10] = c.q2; w[11] = c.q3; w[12] = c.u0; w[13] = c.u1; w[14] = c.u2; w[15] = c.u3;
+  w[16] = t.px; w[17] = t.py; w[18] = t.pz; w[19] = t.wx; w[20] = t.vx; w[21] = t.vy; w[22] = t.vz; w[23] = t.wy;
+  w[24] = t.q0; w[25] = t.q1; w[26] = t.q2; w[27] = t.q3; w[28] = t.u0; w[29] = t.u1; w[30] = t.u2; w[31] = t.u3;
+  w[32] = e.dq.w; w[33] = e.dq.x; w[34] = e.dq.y; w[35] = e.dq.z;
+  w[36] = c.wz; w[37] = t.wz; w[38] = e.last_shaping; w[39] = e.ep_return;
+  w[40] = int_to_word<T>(e.tt); w[41] = int_to_word<T>(e.episode);
+  if (NW > 42) { w[NW - 2] = T(0); w[NW - 1] = T(0); }
+}
+template <typename T> __device__ __forceinline__ void words_to_hover(const T (&w)[kHoverWords], HoverEnv<T>& e) {
+  e.d = Drone<T>{w[0], w[1], w[2], w[4], w[5], w[6], w[8], w[9], w[10], w[11], w[3], w[7], w[16], w[12], w[13], w[14], w[15]};
+  e.ep_return = w[17]; e.tt = word_to_int(w[18]); e.episode = word_to_int(w[19]);
+}
+template <typename T> __device__ __forceinline__ void hover_to_words(const HoverEnv<T>& e, T (&w)[kHoverWords]) {
+  const Drone<T>& d = e.d;
+  w[0] = d.px; w[1] = d.py; w[2] = d.pz; w[3] = d.wx; w[4] = d.vx; w[5] = d.vy; w[6] = d.vz; w[7] = d.wy;
+  w[8] = d.q0; w[9] = d.q1; w[10] = d.q2; w[11] = d.q3; w[12] = d.u0; w[13] = d.u1; w[14] = d.u2; w[15] = d.u3;
+  w[16] = d.wz; w[17] = e.ep_return; w[18] = int_to_word<T>(e.tt); w[19] = int_to_word<T>(e.episode);
+}
+template <typename T> __device__ __forceinline__ void store_obs13(void* base, int64_t i, const T* v) {
+  T* o = reinterpret_cast<T*>(base) + i * 13;
+#pragma unroll
+  for (int k = 0; k < 13; k++) o[k] = v[k];
+}
+
+// =========================================================================================================
+// Fused docking step: gym_docking/envs/docking_env.py:104-231 (KIND = QS_DOCK_V0) and
+// moving_docking_env.py:111-192 (KIND = QS_DOCK_V2) + the stable-baselines worker's auto-reset.
+// The arithmetic is qs::dock_env_step / dock_env_seat (qs_core.cuh); this kernel is load -> step -> store.
+// =========================================================================================================
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kBlock) dock_step_kernel(const StepArgs a) {
+  constexpr int NW = dock_words<T>();
+  const int64_t i = a.first + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const bool active = i < a.first + a.n;
+  const unsigned mask = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+
+  T w[NW];
+  load_words<T, NW>(a.state, a.stride, i, w);
+  T act[4];
+  load_action<T>(a.actions, i, act);
+  DockEnv<T> e;
+  words_to_dock<T, NW>(w, e);
+
+  T rel[12];
+  StepOut<T> o;
+  dock_env_step<T, KIND>(e, act, rel, o);
+
+  reinterpret_cast<T*>(a.reward)[i] = o.reward;
+  a.done[i] = o.done ? 1 : 0;
+  if (a.info) a.info[i] = (uint8_t)o.info();
+  if (a.term_obs) store_row<T, 12>(a.term_obs, i, rel);
+  const double stat_ret = (double)e.ep_return;
+  const int stat_len = e.tt;
+  if (o.done && a.auto_reset) {
+    e.episode += 1;
+    dock_env_seat<T>(e, a.rng, i, rel);
+  }
+  store_row<T, 12>(a.obs, i, rel);
+  dock_to_words<T, NW>(e, w);
+  store_words<T, NW>(a.state, a.stride, i, w);
+  warp_stats_update(a.warp_stats, i, mask, o.done, o.docking, o.nonfinite, stat_ret, stat_len);
+}
+
+// =========================================================================================================
+// hovering-v0 step: gym_docking/envs/hovering_env.py:47-78 + auto-reset to the per-env initial state (:80-82)
+// =========================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kBlock) hover_step_kernel(const StepArgs a) {
+  const int64_t i = a.first + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const bool active = i < a.first + a.n;
+  const unsigned mask = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  T w[kHoverWords];
+  load_words<T, kHoverWords>(a.state, a.stride, i, w);
+  T act[4];
+  load_action<T>(a.actions, i, act);
+  HoverEnv<T> e;
+  words_to_hover<T>(w, e);
+  T obs[13];
+  StepOut<T> o;
+  hover_env_step<T>(e, act, obs, o);
+  reinterpret_cast<T*>(a.reward)[i] = o.reward;
+  a.done[i] = o.done ? 1 : 0;
+  if (a.info) a.info[i] = (uint8_t)o.info();
+  if (a.term_obs) store_obs13<T>(a.term_obs, i, obs);
+  const double stat_ret = (double)e.ep_return;
+  const int stat_len = e.tt;
+  if (o.done && a.auto_reset) {
+    e.episode += 1;
+    hover_env_seat<T>(e, a.rng, i, obs);
+  }
+  store_obs13<T>(a.obs, i, obs);
+  hover_to_words<T>(e, w);
+  store_words<T, kHoverWords>(a.state, a.stride, i, w);
+  warp_stats_update(a.warp_stats, i, mask, o.done, o.docking, o.nonfinite, stat_ret, stat_len);
+}
+
+// =========================================================================================================
+// construct / reset kernels (VecEnv.reset(): docking_env.py:233-244, hovering_env.py:80-82)
+//   mode 0: construct -- episode 0, des_q = identity (docking_env.py:60-63), u = 0
+//   mode 1: reset()   -- envs with t != 0 start their next episode; des_q survives (Q4)
+// =========================================================================================================
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kBlock) seat_kernel(const StepArgs a, int mode) {
+  const int64_t i = a.first + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= a.first + a.n) return;
+  if (KIND == QS_HOVER) {
+    T w[kHoverWords];
+    HoverEnv<T> e;
+    e.episode = 0;
+    if (mode == 1) {
+      load_words<T, kHoverWords>(a.state, a.stride, i, w);
+      words_to_hover<T>(w, e);
+      e.episode += e.tt != 0 ? 1 : 0;
+    }
+    T obs[13];
+    hover_env_seat<T>(e, a.rng, i, obs);
+    hover_to_words<T>(e, w);
+    store_words<T, kHoverWords>(a.state, a.stride, i, w);
+    if (a.obs) store_obs13<T>(a.obs, i, obs);
+  } else {
+    constexpr int NW = dock_words<T>();
+    T w[NW];
+    DockEnv<T> e;
+    e.episode = 0;
+    e.dq = Quat<T>{T(1), T(0), T(0), T(0)};
+    if (mode == 1) {
+      load_words<T, NW>(a.state, a.stride, i, w);
+      words_to_dock<T, NW>(w, e);
+      e.episode += e.tt != 0 ? 1 : 0;
+    }
+    T obs[12];
+    dock_env_seat<T>(e, a.rng, i, obs);
+    dock_to_words<T, NW>(e, w);
+    store_words<T, NW>(a.state, a.stride, i, w);
+    if (a.obs) store_row<T, 12>(a.obs, i, obs);
+  }
+}
+
+// =========================================================================================================
+// state export / import (array-of-struct views <-> row layout)
+// =========================================================================================================
+struct StateArrays { void *chaser, *target, *uc, *ut, *desq, *last_shaping, *ep_return; int32_t *t, *episode; };
+
+template <typename T, bool HOVER, bool IMPORT>
+__global__ void __launch_bounds__(kBlock) state_io_kernel(void* state, int64_t stride, int64_t n, StateArrays s) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  constexpr int NW = HOVER ? kHoverWords : dock_words<T>();
+  T w[NW];
+  load_words<T, NW>(state, stride, i, w);
+  // word index of state[k] (k = 0..12) relative to a drone's base word; positions (k < 3) are stored relative to Origin<T>
+  const int sidx[13] = {0, 1, 2, 4, 5, 6, 8, 9, 10, 11, 3, 7, -1};
+  const double org[3] = {HOVER ? 0.0 : (double)Origin<T>::x, HOVER ? 0.0 : (double)Origin<T>::y, HOVER ? 0.0 : (double)Origin<T>::z};
+  double* ch = reinterpret_cast<double*>(s.chaser);
+  double* tg = reinterpret_cast<double*>(s.target);
+  double* uc = reinterpret_cast<double*>(s.uc);
+  double* ut = reinterpret_cast<double*>(s.ut);
+  double* dq = reinterpret_cast<double*>(s.desq);
+  double* ls = reinterpret_cast<double*>(s.last_shaping);
+  double* er = reinterpret_cast<double*>(s.ep_return);
+  constexpr int WZ_C = HOVER ? 16 : 36, WZ_T = 37, ER = HOVER ? 17 : 39, TT = HOVER ? 18 : 40, EP = HOVER ? 19 : 41;
+#pragma unroll
+  for (int k = 0; k < 13; k++) {
+    const double o = k < 3 ? org[k] : 0.0;
+    const int wc = k == 12 ? WZ_C : sidx[k];
+    if (ch) { if (IMPORT) w[wc] = (T)(ch[i * 13 + k] - o); else ch[i * 13 + k] = (double)w[wc] + o; }
+    if (!HOVER && tg) {
+      const int wt = k == 12 ? WZ_T : 16 + sidx[k];
+      if (IMPORT) w[wt] = (T)(tg[i * 13 + k] - o); else tg[i * 13 + k] = (double)w[wt] + o;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (uc) { if (IMPORT) w[12 + k] = (T)uc[i * 4 + k]; else uc[i * 4 + k] = (double)w[12 + k]; }
+    if (!HOVER && ut) { if (IMPORT) w[28 + k] = (T)ut[i * 4 + k]; else ut[i * 4 + k] = (double)w[28 + k]; }
+    if (!HOVER && dq) { if (IMPORT) w[32 + k] = (T)dq[i * 4 + k]; else dq[i * 4 + k] = (double)w[32 + k]; }
+  }
+  if (!HOVER && ls) { if (IMPORT) w[38] = (T)ls[i]; else ls[i] = (double)w[38]; }
+  if (er) { if (IMPORT) w[ER] = (T)er[i]; else er[i] = (double)w[ER]; }
+  if (s.t) { if (IMPORT) w[TT] = int_to_word<T>(s.t[i]); else s.t[i] = word_to_int(w[TT]); }
+  if (s.episode) { if (IMPORT) w[EP] = int_to_word<T>(s.episode[i]); else s.episode[i] = word_to_int(w[EP]); }
+  if (IMPORT) store_words<T, NW>(state, stride, i, w);
+}
+
+// statistics: fixed-order reduction of the per-warp slots, then clear them
+__global__ void __launch_bounds__(1024) stats_reduce_kernel(double* warp_stats, int64_t n_slots, double* out) {
+  __shared__ double sm[5][1024];
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (int64_t s = threadIdx.x; s < n_slots; s += 1024) {
+    double* p = warp_stats + s * kStatWords;
+#pragma unroll
+    for (int k = 0; k < 5; k++) { acc[k] += p[k]; p[k] = 0.0; }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; k++) sm[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  for (int off = 512; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 5) out[threadIdx.x] = sm[threadIdx.x][0];
+}
+
+// =========================================================================================================
+// leaf-function kernels (array-of-struct in/out; same device functions as the fused kernels)
+// =========================================================================================================
+template <typename T> __device__ __forceinline__ Drone<T> load_state13(const T* s, const T* u) {
+  Drone<T> d = {s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], s[9], s[10], s[11], s[12], T(0), T(0), T(0), T(0)};
+  if (u) { d.u0 = u[0]; d.u1 = u[1]; d.u2 = u[2]; d.u3 = u[3]; }
+  return d;
+}
+
+template <typename T>
+__global__ void fn_kernel(int fn, int64_t n, const T* in0, const T* in1, const T* in2, T* out0, T* out1) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  switch (fn) {
+    case QS_FN_QUAT2EULER: {
+      Euler<T> e = quat2euler(in0[4 * i], in0[4 * i + 1], in0[4 * i + 2], in0[4 * i + 3]);
+      out0[3 * i] = e.phi; out0[3 * i + 1] = e.theta; out0[3 * i + 2] = e.psi;
+    } break;
+    case QS_FN_EULER2QUAT: {
+      Quat<T> q = euler2quat(in0[3 * i], in0[3 * i + 1], in0[3 * i + 2]);
+      out0[4 * i] = q.w; out0[4 * i + 1] = q.x; out0[4 * i + 2] = q.y; out0[4 * i + 3] = q.z;
+    } break;
+    case QS_FN_QUAT2ROT: {
+      Rot<T> R = quat2rot(in0[4 * i], in0[4 * i + 1], in0[4 * i + 2], in0[4 * i + 3]);
+      T* o = out0 + 9 * i;
+      o[0] = T(1); o[1] = R.r01; o[2] = R.r02; o[3] = R.r10; o[4] = T(1); o[5] = R.r12; o[6] = R.r20; o[7] = R.r21; o[8] = T(1);
+    } break;
+    case QS_FN_ROT2EULER: {
+      const T* R = in0 + 9 * i;
+      Euler<T> e = rot2euler(R[5], R[3], R[4], R[2], R[8]);
+      out0[3 * i] = e.phi; out0[3 * i + 1] = e.theta; out0[3 * i + 2] = e.psi;
+    } break;
+    case QS_FN_U_LIMIT: {
+      u_limit(in0[4 * i], in0[4 * i + 1], in0[4 * i + 2], in0[4 * i + 3], out0[4 * i], out0[4 * i + 1], out0[4 * i + 2], out0[4 * i + 3]);
+    } break;
+    case QS_FN_DRONE_STEP: {
+      Drone<T> d = load_state13(in0 + 13 * i, in1 + 4 * i);
+      drone_step(d, in2[4 * i], in2[4 * i + 1], in2[4 * i + 2], in2[4 * i + 3]);
+      drone_to_obs13(d, out0 + 13 * i);
+      out1[4 * i] = d.u0; out1[4 * i + 1] = d.u1; out1[4 * i + 2] = d.u2; out1[4 * i + 3] = d.u3;
+    } break;
+    case QS_FN_PID:
+    case QS_FN_VEL_CTRL: {
+      const T* des = in0 + 13 * i;
+      Drone<T> now = load_state13(in1 + 13 * i, (const T*)nullptr);
+      Quat<T> dq = {des[6], des[7], des[8], des[9]};
+      T F, M0, M1, M2;
+      if (fn == QS_FN_PID) pid(des[0], des[1], des[2], des[3], des[4], des[5], dq, now, F, M0, M1, M2);
+      else vel_controller(des[3], des[4], des[5], dq, now, F, M0, M1, M2);
+      out0[4 * i] = F; out0[4 * i + 1] = M0; out0[4 * i + 2] = M1; out0[4 * i + 3] = M2;
+      out1[4 * i] = dq.w; out1[4 * i + 1] = dq.x; out1[4 * i + 2] = dq.y; out1[4 * i + 3] = dq.z;
+    } break;
+    case QS_FN_STATE2REL: {
+      Drone<T> c = load_state13(in0 + 13 * i, (const T*)nullptr), t = load_state13(in1 + 13 * i, (const T*)nullptr);
+      T rel[12];
+      state2rel(c, t, rel);
+#pragma unroll
+      for (int k = 0; k < 12; k++) out0[12 * i + k] = rel[k];
+    } break;
+    default: break;
+  }
+}
+
+__global__ void philox_kernel(int64_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  U4 c = {ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3]};
+  U4 r = philox4x32_10(c, key[2 * i], key[2 * i + 1]);
+  out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+
+}  // namespace
+
+// =========================================================================================================
+// host side
+// =========================================================================================================
+struct qs_env {
+  qs_config_t cfg;
+  int obs_dim;
+  int n_rows;
+  int64_t stride;
+  size_t esize;
+  void* state = nullptr;
+  double* warp_stats = nullptr;
+  int64_t n_slots = 0;
+  double* stats_dev = nullptr;
+  double* stats_host = nullptr;  // pinned
+  float jitter_scale;
+  // qs_step_host pipeline
+  cudaStream_t hstreams[kHostStreams] = {};
+  void *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
+  uint8_t* h_done = nullptr;
+};
+
+namespace {
+
+StepArgs make_args(qs_env* e, int64_t first, int64_t n) {
+  StepArgs a;
+  memset(&a, 0, sizeof a);
+  a.state = e->state; a.stride = e->stride; a.first = first; a.n = n;
+  a.warp_stats = e->warp_stats;
+  a.rng = RngCfg{e->cfg.seed, e->cfg.env_id0, e->cfg.randomize, e->jitter_scale};
+  a.auto_reset = e->cfg.auto_reset;
+  return a;
+}
+
+template <typename T> int launch_step_t(qs_env* e, const StepArgs& a, cudaStream_t st) {
+  const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
+  switch (e->cfg.env_kind) {
+    case QS_HOVER: hover_step_kernel<T><<<grid, kBlock, 0, st>>>(a); break;
+    case QS_DOCK_V0: dock_step_kernel<T, QS_DOCK_V0><<<grid, kBlock, 0, st>>>(a); break;
+    default: dock_step_kernel<T, QS_DOCK_V2><<<grid, kBlock, 0, st>>>(a); break;
+  }
+  QS_CUDA(cudaGetLastError());
+  return QS_OK;
+}
+int launch_step(qs_env* e, const StepArgs& a, cudaStream_t st) {
+  if (a.n <= 0) return QS_OK;
+  return e->cfg.dtype == QS_F32 ? launch_step_t<float>(e, a, st) : launch_step_t<double>(e, a, st);
+}
+
+template <typename T> int launch_seat_t(qs_env* e, const StepArgs& a, int mode, cudaStream_t st) {
+  const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
+  switch (e->cfg.env_kind) {
+    case QS_HOVER: seat_kernel<T, QS_HOVER><<<grid, kBlock, 0, st>>>(a, mode); break;
+    case QS_DOCK_V0: seat_kernel<T, QS_DOCK_V0><<<grid, kBlock, 0, st>>>(a, mode); break;
+    default: seat_kernel<T, QS_DOCK_V2><<<grid, kBlock, 0, st>>>(a, mode); break;
+  }
+  QS_CUDA(cudaGetLastError());
+  return QS_OK;
+}
+int launch_seat(qs_env* e, void* obs, int mode, cudaStream_t st) {
+  StepArgs a = make_args(e, 0, e->cfg.n_envs);
+  a.obs = obs;
+  return e->cfg.dtype == QS_F32 ? launch_seat_t<float>(e, a, mode, st) : launch_seat_t<double>(e, a, mode, st);
+}
+
+template <typename T, bool IMPORT> int launch_state_io(qs_env* e, const qs_state_arrays_t* s, cudaStream_t st) {
+  StateArrays sa = {s->chaser, s->target, s->u_chaser, s->u_target, s->des_q, s->last_shaping, s->ep_return, s->t, s->episode};
+  const unsigned grid = (unsigned)((e->cfg.n_envs + kBlock - 1) / kBlock);
+  if (e->cfg.env_kind == QS_HOVER) state_io_kernel<T, true, IMPORT><<<grid, kBlock, 0, st>>>(e->state, e->stride, e->cfg.n_envs, sa);
+  else state_io_kernel<T, false, IMPORT><<<grid, kBlock, 0, st>>>(e->state, e->stride, e->cfg.n_envs, sa);
+  QS_CUDA(cudaGetLastError());
+  return QS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qs_abi_version(void) { return QS_ABI_VERSION; }
+const char* qs_last_error(void) { return g_err; }
+
+int qs_create(qs_env_t** out, const qs_config_t* cfg) {
+  if (!out || !cfg) return fail(QS_ERR_INVALID, "qs_create: null argument");
+  *out = nullptr;
+  if (cfg->env_kind < QS_HOVER || cfg->env_kind > QS_DOCK_V2) return fail(QS_ERR_INVALID, "qs_create: unknown env_kind %d", cfg->env_kind);
+  if (cfg->dtype != QS_F32 && cfg->dtype != QS_F64) return fail(QS_ERR_INVALID, "qs_create: unknown dtype %d", cfg->dtype);
+  if (cfg->n_envs <= 0) return fail(QS_ERR_INVALID, "qs_create: n_envs must be positive (got %lld)", (long long)cfg->n_envs);
+  if (cfg->randomize < QS_RAND_NONE || cfg->randomize > QS_RAND_ONCE) return fail(QS_ERR_INVALID, "qs_create: unknown randomize mode %d", cfg->randomize);
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(QS_ERR_NO_DEVICE, "qs_create: no CUDA device (%s); quadsim_b200 has no CPU fallback", ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(QS_ERR_INVALID, "qs_create: device %d out of range [0,%d)", cfg->device, ndev);
+  DeviceGuard g(cfg->device);
+  if (!g.ok) return fail(QS_ERR_CUDA, "qs_create: cannot select device %d", cfg->device);
+  qs_env* e = new (std::nothrow) qs_env();
+  if (!e) return fail(QS_ERR_ALLOC, "qs_create: out of host memory");
+  e->cfg = *cfg;
+  if (e->cfg.half_width <= 0) e->cfg.half_width = cfg->env_kind == QS_HOVER ? 1.0 : 0.5;
+  e->jitter_scale = (float)(2.0 * e->cfg.half_width);
+  e->obs_dim = cfg->env_kind == QS_HOVER ? 13 : 12;
+  e->esize = cfg->dtype == QS_F32 ? 4 : 8;
+  const int words = cfg->env_kind == QS_HOVER ? kHoverWords : (cfg->dtype == QS_F32 ? 44 : 42);
+  e->n_rows = words / (cfg->dtype == QS_F32 ? 4 : 2);
+  e->stride = (cfg->n_envs + kBlock - 1) / kBlock * kBlock;
+  e->n_slots = e->stride / 32;
+  cudaError_t err;
+  if ((err = cudaMalloc(&e->state, (size_t)e->n_rows * e->stride * 16)) != cudaSuccess ||
+      (err = cudaMalloc(&e->warp_stats, (size_t)e->n_slots * kStatWords * sizeof(double))) != cudaSuccess ||
+      (err = cudaMalloc(&e->stats_dev, 8 * sizeof(double))) != cudaSuccess ||
+      (err = cudaMallocHost(&e->stats_host, 8 * sizeof(double))) != cudaSuccess ||
+      (err = cudaMemset(e->state, 0, (size_t)e->n_rows * e->stride * 16)) != cudaSuccess ||
+      (err = cudaMemset(e->warp_stats, 0, (size_t)e->n_slots * kStatWords * sizeof(double))) != cudaSuccess) {
+    int rc = fail(QS_ERR_ALLOC, "qs_create: device allocation failed: %s", cudaGetErrorString(err));
+    qs_destroy(e);
+    return rc;
+  }
+  int rc = launch_seat(e, nullptr, 0, 0);
+  if (rc != QS_OK) { qs_destroy(e); return rc; }
+  if ((err = cudaStreamSynchronize(0)) != cudaSuccess) {
+    rc = fail(QS_ERR_CUDA, "qs_create: init kernel failed: %s", cudaGetErrorString(err));
+    qs_destroy(e);
+    return rc;
+  }
+  *out = e;
+  return QS_OK;
+}
+
+int qs_destroy(qs_env_t* e) {
+  if (!e) return QS_OK;
+  DeviceGuard g(e->cfg.device);
+  for (auto& s : e->hstreams) if (s) cudaStreamDestroy(s);
+  cudaFree(e->h_act); cudaFree(e->h_obs); cudaFree(e->h_rew); cudaFree(e->h_done);
+  cudaFree(e->state); cudaFree(e->warp_stats); cudaFree(e->stats_dev);
+  if (e->stats_host) cudaFreeHost(e->stats_host);
+  delete e;
+  return QS_OK;
+}
+
+int qs_obs_dim(const qs_env_t* e) { return e ? e->obs_dim : fail(QS_ERR_INVALID, "null handle"); }
+int64_t qs_num_envs(const qs_env_t* e) { return e ? e->cfg.n_envs : (int64_t)fail(QS_ERR_INVALID, "null handle"); }
+
+int qs_seed(qs_env_t* e, uint64_t seed) {
+  if (!e) return fail(QS_ERR_INVALID, "null handle");
+  e->cfg.seed = seed;
+  return QS_OK;
+}
+
+int qs_reset(qs_env_t* e, void* obs_out, void* stream) {
+  if (!e || !obs_out) return fail(QS_ERR_INVALID, "qs_reset: null argument");
+  DeviceGuard g(e->cfg.device);
+  return launch_seat(e, obs_out, 1, (cudaStream_t)stream);
+}
+
+int qs_step_ex(qs_env_t* e, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out, uint8_t* info_out,
+               void* terminal_obs_out, void* stream) {
+  if (!e || !actions || !obs_out || !reward_out || !done_out) return fail(QS_ERR_INVALID, "qs_step: null argument");
+  DeviceGuard g(e->cfg.device);
+  StepArgs a = make_args(e, 0, e->cfg.n_envs);
+  a.actions = actions; a.obs = obs_out; a.reward = reward_out; a.done = done_out; a.info = info_out; a.term_obs = terminal_obs_out;
+  return launch_step(e, a, (cudaStream_t)stream);
+}
+
+int qs_step(qs_env_t* e, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out, void* stream) {
+  return qs_step_ex(e, actions, obs_out, reward_out, done_out, nullptr, nullptr, stream);
+}
+
+int qs_host_alloc(void** out, uint64_t bytes) {
+  if (!out) return fail(QS_ERR_INVALID, "qs_host_alloc: null argument");
+  QS_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+  return QS_OK;
+}
+int qs_host_free(void* p) {
+  if (p) QS_CUDA(cudaFreeHost(p));
+  return QS_OK;
+}
+
+int qs_step_host(qs_env_t* e, const void* actions_host, void* obs_host, void* reward_host, uint8_t* done_host) {
+  if (!e || !actions_host || !obs_host || !reward_host || !done_host) return fail(QS_ERR_INVALID, "qs_step_host: null argument");
+  DeviceGuard g(e->cfg.device);
+  const int64_t N = e->cfg.n_envs;
+  const size_t es = e->esize;
+  if (!e->h_act) {
+    for (auto& s : e->hstreams) QS_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    QS_CUDA(cudaMalloc(&e->h_act, (size_t)N * 4 * es));
+    QS_CUDA(cudaMalloc(&e->h_obs, (size_t)N * e->obs_dim * es));
+    QS_CUDA(cudaMalloc(&e->h_rew, (size_t)N * es));
+    QS_CUDA(cudaMalloc((void**)&e->h_done, (size_t)N));
+  }
+  // work enqueued earlier on the legacy default stream (reset, import) must be visible to the non-blocking streams
+  QS_CUDA(cudaStreamSynchronize(0));
+  int k = 0;
+  for (int64_t first = 0; first < N; first += kHostChunk, k++) {
+    const int64_t n = (N - first) < kHostChunk ? (N - first) : kHostChunk;
+    cudaStream_t st = e->hstreams[k % kHostStreams];
+    QS_CUDA(cudaMemcpyAsync((char*)e->h_act + first * 4 * es, (const char*)actions_host + first * 4 * es, (size_t)n * 4 * es, cudaMemcpyHostToDevice, st));
+    StepArgs a = make_args(e, first, n);
+    a.actions = e->h_act; a.obs = e->h_obs; a.reward = e->h_rew; a.done = e->h_done;
+    int rc = launch_step(e, a, st);
+    if (rc != QS_OK) return rc;
+    QS_CUDA(cudaMemcpyAsync((char*)obs_host + first * e->obs_dim * es, (char*)e->h_obs + first * e->obs_dim * es, (size_t)n * e->obs_dim * es, cudaMemcpyDeviceToHost, st));
+    QS_CUDA(cudaMemcpyAsync((char*)reward_host + first * es, (char*)e->h_rew + first * es, (size_t)n * es, cudaMemcpyDeviceToHost, st));
+    QS_CUDA(cudaMemcpyAsync(done_host + first, e->h_done + first, (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
+  for (auto& s : e->hstreams) QS_CUDA(cudaStreamSynchronize(s));
+  return QS_OK;
+}
+
+int qs_export_state(qs_env_t* e, const qs_state_arrays_t* dst, void* stream) {
+  if (!e || !dst) return fail(QS_ERR_INVALID, "qs_export_state: null argument");
+  DeviceGuard g(e->cfg.device);
+  return e->cfg.dtype == QS_F32 ? launch_state_io<float, false>(e, dst, (cudaStream_t)stream) : launch_state_io<double, false>(e, dst, (cudaStream_t)stream);
+}
+int qs_import_state(qs_env_t* e, const qs_state_arrays_t* src, void* stream) {
+  if (!e || !src) return fail(QS_ERR_INVALID, "qs_import_state: null argument");
+  DeviceGuard g(e->cfg.device);
+  return e->cfg.dtype == QS_F32 ? launch_state_io<float, true>(e, src, (cudaStream_t)stream) : launch_state_io<double, true>(e, src, (cudaStream_t)stream);
+}
+
+int qs_get_stats(qs_env_t* e, double stats[5], void* stream) {
+  if (!e || !stats) return fail(QS_ERR_INVALID, "qs_get_stats: null argument");
+  DeviceGuard g(e->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  stats_reduce_kernel<<<1, 1024, 0, st>>>(e->warp_stats, e->n_slots, e->stats_dev);
+  QS_CUDA(cudaGetLastError());
+  QS_CUDA(cudaMemcpyAsync(e->stats_host, e->stats_dev, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  QS_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < 5; k++) stats[k] = e->stats_host[k];
+  return QS_OK;
+}
+
+int qs_fn_apply(int fn, int dtype, int64_t n, const void* in0, const void* in1, const void* in2, void* out0, void* out1, void* stream) {
+  if (n <= 0) return QS_OK;
+  if (fn < QS_FN_QUAT2EULER || fn > QS_FN_PHILOX) return fail(QS_ERR_INVALID, "qs_fn_apply: unknown fn %d", fn);
+  if (!in0 || !out0) return fail(QS_ERR_INVALID, "qs_fn_apply: null in0/out0");
+  const bool two_in = fn == QS_FN_DRONE_STEP || fn == QS_FN_PID || fn == QS_FN_VEL_CTRL || fn == QS_FN_STATE2REL || fn == QS_FN_PHILOX;
+  const bool two_out = fn == QS_FN_DRONE_STEP || fn == QS_FN_PID || fn == QS_FN_VEL_CTRL;
+  if ((two_in && !in1) || (two_out && !out1) || (fn == QS_FN_DRONE_STEP && !in2)) return fail(QS_ERR_INVALID, "qs_fn_apply: missing operand for fn %d", fn);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if (fn == QS_FN_PHILOX) philox_kernel<<<grid, 128, 0, st>>>(n, (const uint32_t*)in0, (const uint32_t*)in1, (uint32_t*)out0);
+  else if (dtype == QS_F32) fn_kernel<float><<<grid, 128, 0, st>>>(fn, n, (const float*)in0, (const float*)in1, (const float*)in2, (float*)out0, (float*)out1);
+  else if (dtype == QS_F64) fn_kernel<double><<<grid, 128, 0, st>>>(fn, n, (const double*)in0, (const double*)in1, (const double*)in2, (double*)out0, (double*)out1);
+  else return fail(QS_ERR_INVALID, "qs_fn_apply: unknown dtype %d", dtype);
+  QS_CUDA(cudaGetLastError());
+  return QS_OK;
+}
+
+}  // extern "C"

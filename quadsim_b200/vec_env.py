@@ -1,0 +1,312 @@
+"""Batched, device-resident drop-in for the reference's gym environments.
+
+Mirrors the stable-baselines VecEnv protocol the reference's trainers drive
+(`rl_baselines/ppo2/ppo2.py:472-498`: ``env.reset()``, ``env.step(actions[n,4]) -> obs[n,12], rews[n], dones[n], infos``)
+for the env ids `gym-docking/gym_docking/__init__.py:3-21` registers.  Observations, rewards and dones stay on
+the GPU as torch tensors; every call goes through the C ABI of libquadsim_b200.so (include/quadsim_b200.h).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+from .spaces import make_box
+
+MASS, GRAVITY, ARM_LENGTH = 0.18, 9.81, 0.086          # dynamics/quadrotor.py:16-21
+MOTOR_LAMBDA = 1.5e-9 / 6.11e-8                         # quadrotor.py:43-45
+ROTOR2CONTROL = np.array([[1, 1, 1, 1], [0, ARM_LENGTH, 0, -ARM_LENGTH], [-ARM_LENGTH, 0, ARM_LENGTH, 0],
+                          [MOTOR_LAMBDA, -MOTOR_LAMBDA, MOTOR_LAMBDA, -MOTOR_LAMBDA]])  # quadrotor.py:56-59
+
+# id -> (kind, default randomize, default half width)
+ENV_IDS = {
+    "hovering-v0": (_capi.HOVER, _capi.RAND_ONCE, 1.0),     # hovering_env.py:23-24: sampled once at construction
+    "docking-v0": (_capi.DOCK_V0, _capi.RAND_NONE, 0.5),    # docking_env.py:34: jitter commented out
+    "docking-v1": (_capi.DOCK_V0, _capi.RAND_ONCE, 0.3),    # imitating_docking_env.py:34: U(-0.3,0.3)^3 once
+    "docking-v2": (_capi.DOCK_V2, _capi.RAND_NONE, 0.5),    # moving_docking_env.py:34
+}
+_RAND = {None: None, False: _capi.RAND_NONE, "none": _capi.RAND_NONE, True: _capi.RAND_EPISODE,
+         "episode": _capi.RAND_EPISODE, "once": _capi.RAND_ONCE}
+
+
+def _space_bounds(kind):
+    if kind == _capi.HOVER:  # hovering_env.py:37-41 with Drone.state_lim_* (quadrotor.py:35-39)
+        lo = np.array([-100, -100, 0, -100, -100, -100, -100, -100, -100, -100] + [-10 * 2 * np.pi] * 3)
+        hi = np.array([100] * 10 + [10 * 2 * np.pi] * 3)
+        return lo, hi, np.zeros(4), np.ones(4)
+    lo = np.array([-np.inf] * 3 + [-100] * 3 + [-np.pi, -np.pi / 2, -np.pi] + [-10 * np.pi] * 3)  # docking_env.py:85-89
+    return lo, -lo, -np.ones(4), np.ones(4)                                                          # :93
+
+
+class VecInfo:
+    """Lazy stand-in for SB's per-env list of info dicts (docking_env.py:226-229): tensors, not N python dicts."""
+
+    def __init__(self, env, bits, terminal_obs):
+        self._env, self.bits, self.terminal_observation = env, bits, terminal_obs
+
+    @property
+    def flag_docking(self):
+        return (self.bits & _capi.INFO_DOCKING) != 0
+
+    @property
+    def done_overlimit(self):
+        return (self.bits & _capi.INFO_OVERLIMIT) != 0
+
+    @property
+    def done_overtime(self):
+        return (self.bits & _capi.INFO_OVERTIME) != 0
+
+    def __len__(self):
+        return self._env.num_envs
+
+    def __getitem__(self, i):
+        b = int(self.bits[i])
+        d = {"flag_docking": bool(b & _capi.INFO_DOCKING), "done_overlimit": bool(b & _capi.INFO_OVERLIMIT)}
+        if self.terminal_observation is not None and (b & _capi.INFO_DONE):
+            d["terminal_observation"] = self.terminal_observation[i]
+        return d
+
+
+class QuadVecEnv:
+    """N independent QuadSim environments stepped by one CUDA kernel launch (one thread per env)."""
+
+    def __init__(self, env_id="docking-v2", num_envs=1, *, dtype=torch.float32, device=None, seed=0, env_id0=None,
+                 randomize=None, half_width=None, auto_reset=True, want_info=True, want_terminal_obs=False,
+                 reuse_buffers=False):
+        env_id = env_id.split(":")[-1]  # accept 'gym_docking:docking-v2'
+        if env_id not in ENV_IDS:
+            raise ValueError("unknown env id %r (have %s)" % (env_id, sorted(ENV_IDS)))
+        if not torch.cuda.is_available():
+            raise _capi.QuadSimError("quadsim_b200 needs a CUDA device: there is no CPU fallback")
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("dtype must be torch.float32 or torch.float64")
+        self.lib = _capi.load()
+        self.env_id, self.num_envs, self.dtype = env_id, int(num_envs), dtype
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        kind, rand_default, hw_default = ENV_IDS[env_id]
+        self.kind = kind
+        rand = _RAND[randomize] if not isinstance(randomize, int) or isinstance(randomize, bool) else randomize
+        self.randomize = rand_default if rand is None else rand
+        self.half_width = float(hw_default if half_width is None else half_width)
+        if env_id0 is None:
+            env_id0 = 0
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                env_id0 = torch.distributed.get_rank() * self.num_envs  # global env ids
+        self.env_id0 = int(env_id0)
+        self.want_info, self.want_terminal_obs, self.reuse_buffers = want_info, want_terminal_obs, reuse_buffers
+        cfg = _capi.Config(kind, _capi.F32 if dtype == torch.float32 else _capi.F64, self.num_envs, int(seed),
+                           self.env_id0, self.randomize, self.device.index, self.half_width, int(bool(auto_reset)), 0)
+        h = C.c_void_p()
+        _capi.check(self.lib.qs_create(C.byref(h), C.byref(cfg)))
+        self._h = h
+        self.obs_dim = self.lib.qs_obs_dim(self._h)
+        lo, hi, alo, ahi = _space_bounds(kind)
+        self.observation_space = make_box(lo, hi, np.float32)
+        self.action_space = make_box(alo, ahi, np.float32)
+        # what the reference's scripts reach into (run_expert_policy.py:61-69, run_trained_moving_docking_ppo2.py:49)
+        scale = MASS * GRAVITY if kind == _capi.HOVER else MASS * GRAVITY / 2.0
+        self.action_mean = np.ones(4) * (0.0 if kind == _capi.HOVER else scale)
+        self.action_std = np.ones(4) * scale
+        self._bufs = None
+        self._pending = None
+        self._host = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _new_bufs(self):
+        n, dev = self.num_envs, self.device
+        obs = torch.empty((n, self.obs_dim), dtype=self.dtype, device=dev)
+        rew = torch.empty((n,), dtype=self.dtype, device=dev)
+        done = torch.empty((n,), dtype=torch.uint8, device=dev)
+        bits = torch.empty((n,), dtype=torch.uint8, device=dev) if self.want_info else None
+        term = torch.empty((n, self.obs_dim), dtype=self.dtype, device=dev) if self.want_terminal_obs else None
+        return obs, rew, done, bits, term
+
+    def _out(self):
+        if not self.reuse_buffers:
+            return self._new_bufs()
+        if self._bufs is None:
+            self._bufs = self._new_bufs()
+        return self._bufs
+
+    @staticmethod
+    def _ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    def _check_open(self):
+        if self._h is None:
+            raise _capi.QuadSimError("environment is closed")
+
+    # ------------------------------------------------------------------ VecEnv protocol
+    def reset(self):
+        """-> obs[N, obs_dim].  Envs that stepped since their last (auto-)reset start a new episode."""
+        self._check_open()
+        obs = torch.empty((self.num_envs, self.obs_dim), dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.qs_reset(self._h, self._ptr(obs), self._stream()))
+        return obs
+
+    def step_async(self, actions):
+        self._check_open()
+        if isinstance(actions, np.ndarray):
+            self._pending = ("host", actions)
+            return
+        a = actions
+        if a.device != self.device or a.dtype != self.dtype:
+            a = a.to(device=self.device, dtype=self.dtype)
+        a = a.contiguous()
+        if a.shape != (self.num_envs, 4):
+            raise ValueError("actions must have shape (%d, 4), got %s" % (self.num_envs, tuple(a.shape)))
+        obs, rew, done, bits, term = self._out()
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.qs_step_ex(self._h, self._ptr(a), self._ptr(obs), self._ptr(rew), self._ptr(done),
+                                            self._ptr(bits), self._ptr(term), self._stream()))
+        self._pending = ("dev", (obs, rew, done, bits, term, a))
+
+    def step_wait(self):
+        kind, payload = self._pending
+        self._pending = None
+        if kind == "host":
+            return self.step_host(payload)
+        obs, rew, done, bits, term, _keepalive = payload
+        return obs, rew, done.view(torch.bool), VecInfo(self, bits, term) if bits is not None else None
+
+    def step(self, actions):
+        """actions[N,4] (torch CUDA tensor, or numpy for the host path) -> obs, rewards, dones, infos."""
+        self.step_async(actions)
+        return self.step_wait()
+
+    def pinned_host_buffers(self, n_action_buffers=1):
+        """Pinned numpy staging buffers for the host path: ([actions...], obs, rewards, dones).  Passing these to
+        step_host avoids every extra host-side copy (the DMA engines read/write them directly)."""
+        npdt = self.dtype
+        mk = lambda *shape, dt=npdt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+        acts = [mk(self.num_envs, 4) for _ in range(n_action_buffers)]
+        return acts, mk(self.num_envs, self.obs_dim), mk(self.num_envs), mk(self.num_envs, dt=torch.uint8)
+
+    def step_host(self, actions, out=None):
+        """numpy in / numpy out through qs_step_host: H2D of the actions, the step kernel and D2H of obs/reward/done are
+        chunked over internal streams so they overlap.  `out=(obs, rew, done)` numpy buffers are written in place (use
+        pinned_host_buffers() for full-speed DMA); without `out`, fresh arrays are returned."""
+        self._check_open()
+        npdt = np.float32 if self.dtype == torch.float32 else np.float64
+        a = np.asarray(actions)
+        if a.shape != (self.num_envs, 4):
+            raise ValueError("actions must have shape (%d, 4), got %s" % (self.num_envs, a.shape))
+        if a.dtype != npdt or not a.flags["C_CONTIGUOUS"]:
+            a = np.ascontiguousarray(a, dtype=npdt)
+        if out is None:
+            if self._host is None:
+                self._host = self.pinned_host_buffers()[1:]
+            ho, hr, hd = self._host
+        else:
+            ho, hr, hd = out
+            if (ho.shape != (self.num_envs, self.obs_dim) or ho.dtype != npdt or hr.shape != (self.num_envs,)
+                    or hr.dtype != npdt or hd.shape != (self.num_envs,) or hd.dtype != np.uint8
+                    or not (ho.flags["C_CONTIGUOUS"] and hr.flags["C_CONTIGUOUS"] and hd.flags["C_CONTIGUOUS"])):
+                raise ValueError("out buffers must be C-contiguous (obs[N,%d], rew[N]) of %s and done[N] uint8" % (self.obs_dim, npdt))
+        vp = lambda x: C.c_void_p(x.ctypes.data)
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.qs_step_host(self._h, vp(a), vp(ho), vp(hr), vp(hd)))
+        if out is None:
+            return ho.copy(), hr.copy(), hd.astype(bool), None
+        return ho, hr, hd.view(np.bool_), None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self.lib.qs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def seed(self, seed=None):
+        """env.seed (docking_env.py:252-254): re-keys the Philox stream used for randomised (re)starts."""
+        self._check_open()
+        _capi.check(self.lib.qs_seed(self._h, int(0 if seed is None else seed)))
+        return [seed] * min(self.num_envs, 1)
+
+    def render(self, mode="human"):
+        return None
+
+    def get_attr(self, name, indices=None):
+        n = self.num_envs if indices is None else len(np.atleast_1d(indices))
+        return [getattr(self, name)] * n
+
+    def set_attr(self, name, value, indices=None):
+        setattr(self, name, value)
+
+    def env_method(self, name, *args, indices=None, **kwargs):
+        raise NotImplementedError("per-env python methods do not exist on the batched CUDA env")
+
+    # ------------------------------------------------------------------ state access / checkpoint
+    _FIELDS = (("chaser", 13), ("target", 13), ("u_chaser", 4), ("u_target", 4), ("des_q", 4), ("last_shaping", 0),
+               ("ep_return", 0), ("t", 0), ("episode", 0))
+    _DOCK_ONLY = ("target", "u_target", "des_q", "last_shaping")
+
+    def _arrays(self, tensors):
+        sa = _capi.StateArrays()
+        for name, _ in self._FIELDS:
+            t = tensors.get(name)
+            setattr(sa, name, t.data_ptr() if t is not None else None)
+        return sa
+
+    def get_state(self):
+        """dict of device tensors (float64 whatever the env dtype; t/episode int32): env.chaser.state, env.target.state,
+        Drone.u x2, target_state_des[6:10], last_shaping, ep_return.  get_state -> set_state is bit-transparent."""
+        self._check_open()
+        out = {}
+        for name, w in self._FIELDS:
+            if self.kind == _capi.HOVER and name in self._DOCK_ONLY:
+                continue
+            dt = torch.int32 if name in ("t", "episode") else torch.float64
+            shape = (self.num_envs, w) if w else (self.num_envs,)
+            out[name] = torch.empty(shape, dtype=dt, device=self.device)
+        sa = self._arrays(out)
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.qs_export_state(self._h, C.byref(sa), self._stream()))
+        return out
+
+    def set_state(self, state):
+        """Inverse of get_state; missing keys are left untouched."""
+        self._check_open()
+        conv = {}
+        for name, w in self._FIELDS:
+            if name not in state or state[name] is None:
+                continue
+            if self.kind == _capi.HOVER and name in self._DOCK_ONLY:
+                raise ValueError("%s does not exist in hovering-v0" % name)
+            dt = torch.int32 if name in ("t", "episode") else torch.float64
+            t = torch.as_tensor(state[name]).to(device=self.device, dtype=dt).contiguous()
+            shape = (self.num_envs, w) if w else (self.num_envs,)
+            if tuple(t.shape) != shape:
+                raise ValueError("%s must have shape %s, got %s" % (name, shape, tuple(t.shape)))
+            conv[name] = t
+        sa = self._arrays(conv)
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.qs_import_state(self._h, C.byref(sa), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()  # conv tensors must outlive the kernel
+
+    STAT_NAMES = ("return_sum", "length_sum", "episodes", "docked_steps", "nonfinite_steps")
+
+    def stats(self, all_reduce=False):
+        """Episode statistics since the last call (device-accumulated); optionally summed over ranks (32+8 bytes)."""
+        self._check_open()
+        buf = (C.c_double * 5)()
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.qs_get_stats(self._h, buf, self._stream()))
+        vals = torch.tensor(list(buf), dtype=torch.float64)
+        if all_reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+            from .distributed import all_reduce_stats
+            vals = all_reduce_stats(vals, self.device)
+        d = dict(zip(self.STAT_NAMES, vals.tolist()))
+        d["mean_return"] = d["return_sum"] / d["episodes"] if d["episodes"] else float("nan")
+        d["mean_length"] = d["length_sum"] / d["episodes"] if d["episodes"] else float("nan")
+        return d

@@ -1,0 +1,79 @@
+"""TEST-ONLY ctypes face of tests/host_harness.cpp: the kernels' arithmetic (qs_core.cuh) compiled for the host."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "libqs_host_harness.so")
+SRC = [os.path.join(HERE, "host_harness.cpp"), os.path.join(HERE, "..", "quadsim_b200", "csrc", "qs_core.cuh")]
+KINDS = {"hovering-v0": 0, "docking-v0": 1, "docking-v2": 2}
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB) or any(os.path.getmtime(LIB) < os.path.getmtime(s) for s in SRC):
+            os.makedirs(os.path.dirname(LIB), exist_ok=True)
+            # -ffp-contract=fast mirrors nvcc's default FMA contraction as far as the host ISA allows
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fno-fast-math",
+                                   "-o", LIB, SRC[0]])
+        L = C.CDLL(LIB)
+        L.hh_create.restype = C.c_void_p
+        L.hh_create.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_int]
+        L.hh_destroy.argtypes = [C.c_int, C.c_void_p]
+        L.hh_reset.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.hh_step.argtypes = [C.c_int, C.c_void_p] + [C.c_void_p] * 6
+        L.hh_io.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class HostVecEnv:
+    def __init__(self, env_id, n, dtype=np.float32, seed=0, env_id0=0, randomize=0, half_width=0.0, auto_reset=True):
+        self.kind, self.n, self.dtype = KINDS[env_id], n, np.dtype(dtype)
+        self.f64 = int(self.dtype == np.float64)
+        self.obs_dim = 13 if self.kind == 0 else 12
+        self._h = lib().hh_create(self.f64, self.kind, n, seed, env_id0, randomize, half_width, int(auto_reset))
+
+    def reset(self):
+        obs = np.zeros((self.n, self.obs_dim), self.dtype)
+        lib().hh_reset(self.f64, self._h, _p(obs))
+        return obs
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=self.dtype)
+        obs = np.zeros((self.n, self.obs_dim), self.dtype)
+        term = np.zeros((self.n, self.obs_dim), self.dtype)
+        rew = np.zeros(self.n, self.dtype)
+        done = np.zeros(self.n, np.uint8)
+        info = np.zeros(self.n, np.uint8)
+        lib().hh_step(self.f64, self._h, _p(a), _p(obs), _p(rew), _p(done), _p(info), _p(term))
+        return obs, rew, done, info, term
+
+    FIELDS = {"chaser": (0, 13), "u_c": (13, 17), "target": (17, 30), "u_t": (30, 34), "des_q": (34, 38),
+              "last_shaping": (38, 39), "ep_return": (39, 40), "t": (40, 41), "episode": (41, 42)}
+
+    def get_state(self):
+        buf = np.zeros((self.n, 42), np.float64)
+        lib().hh_io(self.f64, self._h, _p(buf), 0)
+        return {k: buf[:, a:b].copy() if b - a > 1 else buf[:, a].copy() for k, (a, b) in self.FIELDS.items()}
+
+    def set_state(self, **kw):
+        buf = np.zeros((self.n, 42), np.float64)
+        lib().hh_io(self.f64, self._h, _p(buf), 0)
+        for k, v in kw.items():
+            a, b = self.FIELDS[k]
+            buf[:, a:b] = np.asarray(v, dtype=np.float64).reshape(self.n, b - a)
+        lib().hh_io(self.f64, self._h, _p(buf), 1)
+
+    def close(self):
+        if self._h:
+            lib().hh_destroy(self.f64, self._h)
+            self._h = None

@@ -1,0 +1,98 @@
+"""CPU checks of the kernels' arithmetic: quadsim_b200/csrc/qs_core.cuh compiled for the host (tests/host_harness.cpp,
+test-only) replays the reference's golden tapes in float64 (literal path, bar 1e-9 + exact flags) and float32 (fast path,
+bar 1e-4 * max(1,|ref|)) and is compared with the fp64 oracle at larger N.  The CUDA build of the same header is what
+the `-m gpu` tests exercise through the C ABI."""
+import numpy as np
+import pytest
+
+from host_harness import HostVecEnv
+from oracle import oracle as O
+from qs_testutil import load_golden
+
+
+def rel_err(a, ref):
+    a = np.asarray(a, dtype=np.float64)
+    return float(np.max(np.abs(a - ref) / np.maximum(1.0, np.abs(ref)))) if a.size else 0.0
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 1e-4)])
+@pytest.mark.parametrize("name", ["dock_v0_kat", "dock_v2_kat", "dock_v0_rand", "dock_v2_rand", "dock_v0_docked"])
+def test_reference_tapes(name, dtype, tol):
+    g = load_golden(name)
+    env_id = {0: "docking-v0", 1: "docking-v2"}[int(g["kind"])]
+    K, Tn = g["actions"].shape[:2]
+    seed = int(g["seed"])
+    env = HostVecEnv(env_id, K, dtype, seed=max(seed, 0), env_id0=int(g["env_id0"]), randomize=1 if seed >= 0 else 0,
+                     half_width=float(g["half_width"]))
+    assert rel_err(env.reset(), g["obs0"]) <= (1e-13 if dtype == np.float64 else 1e-6)
+    assert np.array_equal(env.get_state()["chaser"][:, :3], g["ini_pos0"])
+    for t in range(Tn):
+        obs, rew, done, info, term = env.step(g["actions"][:, t])
+        assert np.array_equal(done, g["done"][:, t]), t  # these tapes stay clear of thresholds, even in fp32
+        assert np.array_equal((info & 4) != 0, g["docking"][:, t] != 0), t
+        assert np.array_equal((info & 2) != 0, g["overlimit"][:, t] != 0), t
+        assert max(rel_err(obs, g["obs"][:, t]), rel_err(term, g["term_obs"][:, t]), rel_err(rew, g["reward"][:, t])) <= tol, t
+        st = env.get_state()
+        nd = done == 0
+        assert rel_err(st["des_q"], g["des_q"][:, t]) <= tol
+        if nd.any():
+            assert max(rel_err(st["chaser"][nd], g["chaser"][nd, t]), rel_err(st["target"][nd], g["target"][nd, t]),
+                       rel_err(st["u_c"][nd], g["u_c"][nd, t]), rel_err(st["u_t"][nd], g["u_t"][nd, t])) <= tol, t
+        for k in np.nonzero(done)[0]:
+            assert np.array_equal(st["chaser"][k, :3], g["ini_pos"][k, t])
+    env.close()
+
+
+@pytest.mark.parametrize("v", [0, 2])
+def test_wild_single_step_fp64(v):
+    g = load_golden("dock_v%d_wild" % v)
+    n = g["in_t"].shape[0]
+    env = HostVecEnv("docking-v%d" % v, n, np.float64)
+    env.reset()
+    env.set_state(chaser=g["in_chaser"], target=g["in_target"], u_c=g["in_u_c"], u_t=g["in_u_t"], des_q=g["in_des_q"],
+                  last_shaping=g["in_last_shaping"], t=g["in_t"])
+    obs, rew, done, info, term = env.step(g["in_actions"])
+    assert np.array_equal(done, g["out_done"])
+    assert np.array_equal((info & 4) != 0, g["out_docking"] != 0) and np.array_equal((info & 2) != 0, g["out_overlimit"] != 0)
+    assert rel_err(term, g["out_obs"]) < 1e-10 and rel_err(rew, g["out_reward"]) < 1e-10
+    st = env.get_state()
+    nd = done == 0
+    assert rel_err(st["chaser"][nd], g["out_chaser"][nd]) < 1e-11 and rel_err(st["target"][nd], g["out_target"][nd]) < 1e-11
+    assert rel_err(st["u_t"][nd], g["out_u_t"][nd]) < 1e-10 and rel_err(st["des_q"], g["out_des_q"]) < 1e-13
+
+
+def test_hover_tape():
+    g = load_golden("hover_rand")
+    K, Tn = g["actions"].shape[:2]
+    for dtype, tol in ((np.float64, 1e-9), (np.float32, 1e-4)):
+        env = HostVecEnv("hovering-v0", K, dtype, seed=int(g["seed"]), env_id0=int(g["env_id0"]), randomize=2)
+        assert rel_err(env.reset(), g["obs0"]) <= (1e-15 if dtype == np.float64 else 1e-6)
+        for t in range(Tn):
+            obs, rew, done, info, term = env.step(g["actions"][:, t])
+            assert np.array_equal(done, g["done"][:, t]), t
+            assert max(rel_err(obs, g["obs"][:, t]), rel_err(term, g["state"][:, t]), rel_err(rew, g["reward"][:, t])) <= tol, t
+
+
+@pytest.mark.parametrize("env_id", ["docking-v0", "docking-v2", "hovering-v0"])
+def test_fp32_fast_path_vs_oracle(env_id):
+    """256 envs x 600 steps with Philox auto-resets: the fp32 fast path stays within 1e-4*max(1,|ref|) of the fp64 oracle;
+    done flags may flip only where the oracle sits within fp32 rounding of a threshold (then that env is dropped)."""
+    n, steps, seed = 256, 600, 5
+    hover = env_id.startswith("hover")
+    rand = 2 if hover else 1
+    env = HostVecEnv(env_id, n, np.float32, seed=seed, randomize=rand)
+    ora = O.OracleVecEnv(env_id, n, seed=seed, randomize=rand, nthreads=4)
+    assert rel_err(env.reset(), ora.reset()) < 1e-6
+    rng = np.random.RandomState(0)
+    alive = np.ones(n, bool)
+    worst = 0.0
+    for t in range(steps):
+        a = rng.uniform(0 if hover else -1, 1, (n, 4)).astype(np.float32)
+        obs, rew, done, info, term = env.step(a)
+        o_obs, o_rew, o_done, o_info, o_term = ora.step(a.astype(np.float64), want_term_obs=True)
+        alive &= done == o_done
+        e = max(rel_err(term[alive], o_term[alive]), rel_err(rew[alive], o_rew[alive]), rel_err(obs[alive], o_obs[alive]))
+        worst = max(worst, e)
+        assert e <= 1e-4, (t, e)
+    assert alive.mean() > 0.98, alive.mean()
+    print(env_id, "fp32 worst", worst, "in phase", alive.mean())

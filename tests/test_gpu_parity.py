@@ -1,0 +1,377 @@
+"""GPU parity tests: the CUDA library (through its C ABI / the Python face) against
+  (a) the committed golden fixtures produced by the unmodified reference, and
+  (b) the fp64 CPU oracle (oracle/quadsim_oracle.c, itself pinned to those fixtures) on seeded inputs.
+
+Bars (BASELINE.json north_star): fp64 -- done / reset indices bit-exact, state/obs/reward max abs err <= 1e-9;
+fp32 -- |a-b| <= 1e-4 * max(1, |ref|), flags may differ only within fp32 rounding of a threshold.
+"""
+import numpy as np
+import pytest
+import torch
+
+from qs_testutil import close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import quadsim_b200 as qs
+    from quadsim_b200 import functional as F
+    from oracle import oracle as O
+
+DEV = "cuda"
+RAND = {"none": 0, "episode": 1, "once": 2}
+
+
+def T(x, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype, device=DEV)
+
+
+def N(t):
+    return t.detach().double().cpu().numpy()
+
+
+def rel_err(a, ref):
+    return float(np.max(np.abs(a - ref) / np.maximum(1.0, np.abs(ref)))) if a.size else 0.0
+
+
+# ----------------------------------------------------------------------------------------------- leaf functions
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 5e-13), (torch.float32, 2e-5)])
+def test_leaf_functions_vs_reference_golden(dtype, tol):
+    g = load_golden("functions")
+    q, e = T(g["q"], dtype), T(g["euler"], dtype)
+    assert rel_err(N(F.quat2euler(q)), g["quat2euler"]) < (tol if dtype == torch.float64 else 2e-3)  # atan2 near 0/0 in fp32
+    assert rel_err(N(F.euler2quat(e)), g["euler2quat"]) < tol
+    assert rel_err(N(F.quat2rot(q)), g["quat2rot"]) < tol * 10
+    assert rel_err(N(F.u_limit(T(g["u"], dtype))), g["u_limit"]) < tol
+    ref = g["rot2euler"]
+    got = N(F.rot2euler(T(g["rot"], dtype)))
+    ok = np.isfinite(ref).all(axis=1)
+    if dtype == torch.float64:
+        assert np.array_equal(np.isnan(ref), np.isnan(got))
+        assert rel_err(got[ok], ref[ok]) < tol
+    s, u = F.drone_step(T(g["state"], dtype), T(g["u_limit"], dtype), T(g["ucmd"], dtype))
+    if dtype == torch.float64:
+        assert rel_err(N(s), g["step_state"]) < 1e-11
+        assert rel_err(N(u), g["step_u"]) < 1e-13
+        u1, dq1 = F.pid(T(g["des"], dtype), T(g["state"], dtype))
+        assert rel_err(N(u1), g["pid_u"]) < 5e-13 and rel_err(N(dq1), g["pid_des"][:, 6:10]) < 1e-13
+        u2, dq2 = F.vel_controller(T(g["des"], dtype), T(g["state"], dtype))
+        assert rel_err(N(u2), g["vel_u"]) < 5e-13 and rel_err(N(dq2), g["vel_des"][:, 6:10]) < 1e-13
+        rel = N(F.state2rel(T(g["state"], dtype), T(g["state_b"], dtype)))
+        ok = np.isfinite(g["state2rel"]).all(axis=1)
+        assert rel_err(rel[ok], g["state2rel"][ok]) < 1e-10
+    else:
+        assert rel_err(N(u), g["step_u"]) < 1e-5
+
+
+def test_philox_known_answers():
+    import json
+    import os
+    from qs_testutil import GOLDEN
+    kat = json.load(open(os.path.join(GOLDEN, "philox_kat.json")))["philox"]
+    kat.append([[0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]])  # Random123 published vector
+    c = torch.tensor([k[0] for k in kat], dtype=torch.int64, device=DEV)
+    k = torch.tensor([k[1] for k in kat], dtype=torch.int64, device=DEV)
+    out = F.philox4x32_10(c, k).cpu().tolist()
+    assert out == [k[2] for k in kat]
+
+
+# ----------------------------------------------------------------------------------------------- reference tapes
+def _replay_tape(name, dtype, tol, flags_exact=True):
+    g = load_golden(name)
+    env_id = {0: "docking-v0", 1: "docking-v2"}[int(g["kind"])]
+    K, Tn = g["actions"].shape[:2]
+    seed = int(g["seed"])
+    env = qs.make_vec(env_id, K, dtype=dtype, seed=max(seed, 0), env_id0=int(g["env_id0"]),
+                      randomize="episode" if seed >= 0 else "none", half_width=float(g["half_width"]),
+                      want_info=True, want_terminal_obs=True)
+    obs0 = N(env.reset())
+    assert rel_err(obs0, g["obs0"]) <= tol
+    st = env.get_state()
+    assert np.array_equal(N(st["chaser"])[:, :3], g["ini_pos0"])  # Philox start positions are bit-identical
+    worst, alive = 0.0, np.ones(K, bool)
+    for t in range(Tn):
+        obs, rew, done, info = env.step(T(g["actions"][:, t], dtype))
+        done = done.cpu().numpy()
+        if flags_exact:
+            assert np.array_equal(done, g["done"][:, t] != 0), t
+            assert np.array_equal(info.flag_docking.cpu().numpy(), g["docking"][:, t] != 0), t
+            assert np.array_equal(info.done_overlimit.cpu().numpy(), g["overlimit"][:, t] != 0), t
+        else:
+            alive &= done == (g["done"][:, t] != 0)  # an fp32 flag flip desynchronises that env's episode phase
+            if not alive.any():
+                break
+        a = alive
+        st = env.get_state()
+        e = max(rel_err(N(obs)[a], g["obs"][a, t]), rel_err(N(info.terminal_observation)[a], g["term_obs"][a, t]),
+                rel_err(N(rew)[a], g["reward"][a, t]), rel_err(N(st["des_q"])[a], g["des_q"][a, t]))
+        nd = a & ~done
+        if nd.any():
+            e = max(e, rel_err(N(st["chaser"])[nd], g["chaser"][nd, t]), rel_err(N(st["target"])[nd], g["target"][nd, t]),
+                    rel_err(N(st["u_chaser"])[nd], g["u_c"][nd, t]), rel_err(N(st["u_target"])[nd], g["u_t"][nd, t]))
+        for k in np.nonzero(done & a)[0]:
+            assert np.array_equal(N(st["chaser"])[k, :3], g["ini_pos"][k, t]), (k, t)
+        worst = max(worst, e)
+        assert e <= tol, (name, t, e)
+    env.close()
+    return worst, alive
+
+
+@pytest.mark.parametrize("name", ["dock_v0_kat", "dock_v2_kat", "dock_v0_rand", "dock_v2_rand", "dock_v0_docked"])
+def test_reference_tapes_fp64(name):
+    worst, _ = _replay_tape(name, torch.float64, 1e-9)
+    print(name, "fp64 worst err", worst)
+
+
+@pytest.mark.parametrize("name", ["dock_v0_kat", "dock_v2_kat", "dock_v0_rand", "dock_v2_rand", "dock_v0_docked"])
+def test_reference_tapes_fp32(name):
+    worst, alive = _replay_tape(name, torch.float32, 1e-4, flags_exact=False)
+    print(name, "fp32 worst rel err", worst, "envs still in phase", alive.sum(), "/", alive.size)
+    assert alive.any()
+
+
+@pytest.mark.parametrize("v", [0, 2])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_wild_single_step_vs_reference(v, dtype):
+    g = load_golden("dock_v%d_wild" % v)
+    n = g["in_t"].shape[0]
+    env = qs.make_vec("docking-v%d" % v, n, dtype=dtype, want_info=True, want_terminal_obs=True)
+    env.reset()
+    env.set_state({"chaser": g["in_chaser"], "target": g["in_target"], "u_chaser": g["in_u_c"], "u_target": g["in_u_t"],
+                   "des_q": g["in_des_q"], "last_shaping": g["in_last_shaping"], "t": g["in_t"]})
+    obs, rew, done, info = env.step(T(g["in_actions"], dtype))
+    done = done.cpu().numpy()
+    st = env.get_state()
+    term = N(info.terminal_observation)
+    if dtype == torch.float64:
+        assert np.array_equal(done, g["out_done"] != 0)
+        assert np.array_equal(info.flag_docking.cpu().numpy(), g["out_docking"] != 0)
+        assert np.array_equal(info.done_overlimit.cpu().numpy(), g["out_overlimit"] != 0)
+        assert rel_err(term, g["out_obs"]) < 1e-10
+        assert rel_err(N(rew), g["out_reward"]) < 1e-10
+        nd = ~done
+        assert rel_err(N(st["chaser"])[nd], g["out_chaser"][nd]) < 1e-11
+        assert rel_err(N(st["target"])[nd], g["out_target"][nd]) < 1e-11
+        assert rel_err(N(st["u_target"])[nd], g["out_u_t"][nd]) < 1e-10
+        assert rel_err(N(st["des_q"]), g["out_des_q"]) < 1e-13
+    else:
+        # wild states sit near rot2euler's |R12|>=1 branch and 1/cos(phi) singularities: compare the well-conditioned rows
+        ok = (np.abs(g["out_obs"]).max(axis=1) < 50) & (np.abs(np.abs(g["out_obs"][:, 6]) - np.pi / 2) > 0.05)
+        agree = done == (g["out_done"] != 0)
+        assert agree.mean() > 0.99
+        ok &= agree
+        assert ok.sum() > 200
+        assert rel_err(term[ok][:, :9], g["out_obs"][ok][:, :9]) < 1e-4
+        assert rel_err(term[ok][:, 9:], g["out_obs"][ok][:, 9:]) < 2e-3  # rates amplified by tan/sec(phi) up to ~20x
+        nd = ok & ~done
+        assert rel_err(N(st["chaser"])[nd], g["out_chaser"][nd]) < 1e-4
+        assert rel_err(N(st["target"])[nd], g["out_target"][nd]) < 1e-4
+    env.close()
+
+
+def test_hover_tape_vs_reference():
+    g = load_golden("hover_rand")
+    K, Tn = g["actions"].shape[:2]
+    for dtype, tol in ((torch.float64, 1e-9), (torch.float32, 1e-4)):
+        env = qs.make_vec("hovering-v0", K, dtype=dtype, seed=int(g["seed"]), env_id0=int(g["env_id0"]), randomize="once",
+                          want_terminal_obs=True)
+        assert rel_err(N(env.reset()), g["obs0"]) <= (1e-15 if dtype == torch.float64 else 1e-6)
+        for t in range(Tn):
+            obs, rew, done, info = env.step(T(g["actions"][:, t], dtype))
+            assert np.array_equal(done.cpu().numpy(), g["done"][:, t] != 0), t
+            assert rel_err(N(obs), g["obs"][:, t]) <= tol, t
+            assert rel_err(N(info.terminal_observation), g["state"][:, t]) <= tol, t
+            assert rel_err(N(rew), g["reward"][:, t]) <= tol, t
+        env.close()
+
+
+def test_sim_pid_config1_functional():
+    """BASELINE config 1 (run_sim_PID.py:9-54) driven through the device leaf functions."""
+    g = load_golden("sim_pid")
+    s = T(g["ini"][None])
+    up = torch.zeros((1, 4), dtype=torch.float64, device=DEV)
+    des = torch.zeros((1, 13), dtype=torch.float64, device=DEV)
+    des[0, 0:3] = T(g["pos_des"])
+    des[0, 6] = 1.0
+    for t in range(2000):
+        u, dq = F.pid(des, s)
+        des[:, 6:10] = dq
+        if t % 100 == 0:
+            assert rel_err(N(s)[0], g["states"][t]) < 1e-10 and rel_err(N(u)[0], g["u_all"][t]) < 1e-9
+        s, up = F.drone_step(s, up, u)
+    assert rel_err(N(s)[0], g["final"]) < 1e-10
+
+
+# ----------------------------------------------------------------------------------------------- vs the oracle at scale
+@pytest.mark.parametrize("env_id", ["docking-v0", "docking-v2", "hovering-v0"])
+def test_fp64_vs_oracle_1000_steps(env_id):
+    n, steps, seed = 2048, 1000, 42
+    rand = "once" if env_id.startswith("hover") else "episode"
+    env = qs.make_vec(env_id, n, dtype=torch.float64, seed=seed, env_id0=5, randomize=rand, want_terminal_obs=True)
+    ora = O.OracleVecEnv(env_id, n, seed=seed, env_id0=5, randomize=RAND[rand], nthreads=8)
+    close(N(env.reset()), ora.reset(), 1e-13)
+    gen = torch.Generator(device="cpu").manual_seed(1)
+    lo = 0.0 if env_id.startswith("hover") else -1.0
+    worst, n_done = 0.0, 0
+    for t in range(steps):
+        a = (torch.rand((n, 4), generator=gen) * (1 - lo) + lo).float().double()
+        obs, rew, done, info = env.step(a.to(DEV))
+        o_obs, o_rew, o_done, o_info, o_term = ora.step(a.numpy(), want_term_obs=True)
+        assert np.array_equal(done.cpu().numpy(), o_done != 0), t  # done flags / reset indices bit-exact
+        assert np.array_equal(info.bits.cpu().numpy(), o_info), t
+        e = max(rel_err(N(obs), o_obs), rel_err(N(rew), o_rew), rel_err(N(info.terminal_observation), o_term))
+        worst = max(worst, e)
+        assert e <= 1e-9, (t, e)
+        n_done += int(o_done.sum())
+    st = env.get_state()
+    close(N(st["chaser"]), ora.field("chaser"), 1e-9)
+    assert np.array_equal(st["t"].cpu().numpy(), ora.field("t"))
+    assert np.array_equal(st["episode"].cpu().numpy(), ora.field("episode"))
+    if not env_id.startswith("hover"):
+        close(N(st["target"]), ora.field("target"), 1e-9)
+        close(N(st["des_q"]), ora.field("des_q"), 1e-12)
+    s_gpu, s_cpu = env.stats(), ora.stats()
+    assert s_gpu["episodes"] == s_cpu[2] == n_done and s_gpu["length_sum"] == s_cpu[1]
+    assert abs(s_gpu["return_sum"] - s_cpu[0]) < 1e-6 and s_gpu["docked_steps"] == s_cpu[3] and s_gpu["nonfinite_steps"] == s_cpu[4]
+    assert n_done > n  # every env went through several auto-resets
+    print(env_id, "fp64 vs oracle worst", worst, "episodes", n_done)
+    env.close()
+
+
+@pytest.mark.parametrize("env_id", ["docking-v0", "docking-v2", "hovering-v0"])
+def test_fp32_vs_oracle_1000_steps(env_id):
+    """fp32 path: 1e-4 * max(1,|ref|) after 1000 steps; a done flag may flip only when the fp64 reference is within fp32
+    rounding of the threshold -- such envs are re-synchronised from the oracle and counted."""
+    n, steps, seed = 2048, 1000, 7
+    hover = env_id.startswith("hover")
+    rand = "once" if hover else "episode"
+    env = qs.make_vec(env_id, n, dtype=torch.float32, seed=seed, randomize=rand, want_terminal_obs=True)
+    ora = O.OracleVecEnv(env_id, n, seed=seed, randomize=RAND[rand], nthreads=8)
+    assert rel_err(N(env.reset()), ora.reset()) < 1e-6
+    gen = torch.Generator(device="cpu").manual_seed(2)
+    lo = 0.0 if hover else -1.0
+    worst, flips = 0.0, 0
+    for t in range(steps):
+        a = (torch.rand((n, 4), generator=gen) * (1 - lo) + lo).float()
+        obs, rew, done, info = env.step(a.to(DEV))
+        o_obs, o_rew, o_done, o_info, o_term = ora.step(a.double().numpy(), want_term_obs=True)
+        same = done.cpu().numpy() == (o_done != 0)
+        if not same.all():
+            bad = np.nonzero(~same)[0]
+            flips += len(bad)
+            # the reference must be within fp32 resolution of a threshold for a flip to be legitimate
+            radius = 3.0 if env_id == "docking-v0" else 10.0
+            z_gpu = N(env.get_state()["chaser"])[:, 2]
+            for k in bad:
+                if hover:
+                    margin = min(abs(np.linalg.norm(o_term[k, :3]) - 100), abs(np.linalg.norm(o_term[k, 3:6]) - 100))
+                else:
+                    z = ora.field("chaser")[k, 2] if not o_done[k] else z_gpu[k]  # the side that did not reset
+                    margin = min(abs(np.linalg.norm(o_term[k, :3]) - radius), abs(z - 0.1))
+                assert margin < 1e-3, (t, k, margin)
+            # resync the kernel from the oracle so the comparison can continue
+            st = {"chaser": ora.field("chaser"), "u_chaser": ora.field("u_c"), "t": ora.field("t"),
+                  "episode": ora.field("episode"), "ep_return": ora.field("ep_return")}
+            if not hover:
+                st.update({"target": ora.field("target"), "u_target": ora.field("u_t"), "des_q": ora.field("des_q"),
+                           "last_shaping": ora.field("last_shaping")})
+            env.set_state(st)
+        e = max(rel_err(N(info.terminal_observation)[same], o_term[same]), rel_err(N(rew)[same], o_rew[same]),
+                rel_err(N(obs)[same], o_obs[same]))
+        worst = max(worst, e)
+        assert e <= 1e-4, (t, e)
+    print(env_id, "fp32 vs oracle worst rel err", worst, "flag flips", flips, "of", n * steps)
+    assert flips <= n * steps * 1e-4
+    env.close()
+
+
+# ----------------------------------------------------------------------------------------------- API behaviour
+def test_state_roundtrip_and_reset_semantics():
+    env = qs.make_vec("docking-v2", 300, dtype=torch.float32, seed=3, randomize="episode")
+    o1 = env.reset()
+    o2 = env.reset()
+    assert torch.equal(o1, o2)  # idempotent while no env has stepped
+    s0 = env.get_state()
+    assert int(s0["episode"].max()) == 0 and int(s0["t"].max()) == 0
+    a = torch.rand((300, 4), device=DEV) * 2 - 1
+    env.step(a)
+    s1 = env.get_state()
+    env.set_state(s1)
+    s2 = env.get_state()
+    for k in s1:
+        assert torch.equal(s1[k], s2[k]), k  # bit-exact export -> import -> export
+    o3 = env.reset()
+    s3 = env.get_state()
+    assert int(s3["episode"].min()) == 1 and int(s3["t"].max()) == 0
+    assert not torch.equal(o3, o1)  # new Philox draw for episode 1
+    assert torch.equal(s3["des_q"], s1["des_q"])  # target_state_des survives reset
+    assert float(s3["u_chaser"].abs().max()) == 0.0
+    env.close()
+
+
+def test_host_path_matches_device_path():
+    n = 5000
+    for dtype in (torch.float32, torch.float64):
+        e1 = qs.make_vec("docking-v2", n, dtype=dtype, seed=11, randomize="episode")
+        e2 = qs.make_vec("docking-v2", n, dtype=dtype, seed=11, randomize="episode")
+        e1.reset(); e2.reset()
+        gen = torch.Generator().manual_seed(0)
+        for t in range(100):
+            a = (torch.rand((n, 4), generator=gen) * 2 - 1).to(dtype)
+            o1, r1, d1, _ = e1.step(a.to(DEV))
+            o2, r2, d2, _ = e2.step(a.numpy())
+            assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+            assert np.array_equal(d1.cpu().numpy(), d2)
+        e1.close(); e2.close()
+
+
+def test_sharding_invariance_and_determinism_full_size():
+    """BASELINE size (2^20 envs): the same global env ids give bit-identical trajectories whether they live in one
+    handle or in two half-size handles with env_id0 offsets (what ranks do), and a re-run reproduces the checksum."""
+    n, steps = 1 << 20, 120
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    acts = torch.rand((8, n, 4), generator=gen, device=DEV) * 2 - 1
+
+    def run(parts):
+        envs = [qs.make_vec("docking-v2", hi - lo, seed=9, env_id0=lo, randomize="episode") for lo, hi in parts]
+        for e in envs:
+            e.reset()
+        chk = torch.zeros(3, dtype=torch.float64, device=DEV)
+        for t in range(steps):
+            for e, (lo, hi) in zip(envs, parts):
+                obs, rew, done, _ = e.step(acts[t % 8, lo:hi])
+                chk += torch.stack([obs.double().sum(), rew.double().sum(), done.double().sum()])
+        stats = [e.stats() for e in envs]
+        finals = torch.cat([e.get_state()["chaser"] for e in envs])
+        for e in envs:
+            e.close()
+        return chk.cpu(), finals, stats
+
+    c1, f1, s1 = run([(0, n)])
+    c2, f2, s2 = run([(0, n // 2), (n // 2, n)])
+    assert torch.equal(f1, f2) and torch.equal(c1[2], c2[2])
+    assert abs(float(c1[0] - c2[0])) < 1e-6 * abs(float(c1[0])) + 1e-6
+    assert s1[0]["episodes"] == s2[0]["episodes"] + s2[1]["episodes"] > n  # every env reset at least once on average
+    assert s1[0]["nonfinite_steps"] == 0
+    c3, f3, _ = run([(0, n)])
+    assert torch.equal(c1, c3) and torch.equal(f1, f3)
+
+
+def test_single_env_facade_matches_reference_tape():
+    """The reference-style gym.Env facade (N=1, numpy, info dict, no auto-reset) on the shipped-policy tape: exercises
+    the docked (+1) and overtime (t>=600) branches end to end."""
+    g = load_golden("dock_v0_docked")
+    env = qs.make("docking-v0")
+    obs = env.reset()
+    close(obs, g["obs0"][0], 1e-13)
+    ret = 0.0
+    for t in range(600):
+        obs, r, d, info = env.step(g["actions"][0, t])
+        assert d == bool(g["done"][0, t]) and info["flag_docking"] == bool(g["docking"][0, t])
+        assert rel_err(obs, g["term_obs"][0, t]) < 1e-9 and abs(r - g["reward"][0, t]) < 1e-9
+        assert rel_err(info["chaser"], g["chaser"][0, t]) < 1e-9 and rel_err(info["target"], g["target"][0, t]) < 1e-9
+        ret += r
+    assert d and env.t == 600
+    assert abs(ret - g["reward"][0, :600].sum()) < 1e-8
+    close(env.reset(), g["obs0"][0], 1e-13)
+    env.close()
