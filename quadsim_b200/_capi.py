@@ -45,8 +45,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not _build.up_to_date():
+    path = os.environ.get("QUADSIM_B200_LIB") or _build.LIB_PATH  # override: kernel-variant experiments (tools/kbench.py)
+    if path == _build.LIB_PATH and not _build.up_to_date():
         try:
             path = _build.build()
         except Exception as exc:  # no nvcc on this box: use the shipped .so if there is one

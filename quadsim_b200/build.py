@@ -18,6 +18,11 @@ DEPS = SOURCES + [os.path.join(CSRC, "qs_core.cuh"), os.path.join(ROOT, "include
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+    # fp32 only (fp64 is unaffected): flush denormals, 2-ulp division and sqrt -- measured +13 % on the fp32 step kernel,
+    # identical episode statistics; sinf/cosf/atan2f/asinf stay the accurate library versions (no --use_fast_math)
+    "-ftz=true", "-prec-div=false", "-prec-sqrt=false",
+    # 6 resident CTAs/SM for the fp32 step kernels (<= 80 registers): measured best of {4,5,6,8}
+    "-DQS_MINB32=6",
 ]
 
 
@@ -32,24 +37,25 @@ def up_to_date():
     return os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in DEPS)
 
 
-def build(force=False, verbose=False, extra_flags=()):
+def build(force=False, verbose=False, extra_flags=(), out=None):
     """Compile the CUDA library if it is missing or older than its sources; returns its path."""
-    if not force and up_to_date():
+    if out is None and not force and up_to_date():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
+    target = out or LIB_PATH
     # g++ from the system: the image exports CC/CXX pointing at a toolchain nvcc does not need
-    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(ROOT, "include"), "-o", LIB_PATH] + SOURCES
+    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(ROOT, "include"), "-o", target] + SOURCES
     if os.path.exists("/usr/bin/g++"):
         cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    log = os.path.join(LIB_DIR, "build.log")
+    log = os.path.join(LIB_DIR, "build.log" if out is None else os.path.basename(out) + ".log")
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + res.stdout)
     if verbose or res.returncode != 0:
         print(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed (exit %d); see %s" % (res.returncode, log))
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":

@@ -71,11 +71,34 @@ QS_HD float m_atan2(float y, float x) { return atan2f(y, x); }
 QS_HD double m_atan2(double y, double x) { return atan2(y, x); }
 QS_HD float m_tan(float x) { return tanf(x); }
 QS_HD double m_tan(double x) { return tan(x); }
-QS_HD void m_sincos(float x, float* s, float* c) {
+// fp32 sin & cos together.  Every angle the envs feed in is bounded (half-angles of atan2 results, desired tilt = acc/g),
+// so the common path is a 3-constant Cody-Waite reduction to [-pi/4, pi/4] plus the Cephes single-precision minimax
+// polynomials (~1-2 ulp there): straight-line code, no Payne-Hanek slow path inlined at every call site (that cost ~40 %
+// of the kernel's code size and showed up as instruction-cache stalls).  |x| > 1e4 (only reachable from injected wild
+// states) defers to the library.
+QS_HD void m_sincos_big(float x, float* s, float* c) {
 #if defined(__CUDA_ARCH__)
   sincosf(x, s, c);
 #else
   *s = sinf(x); *c = cosf(x);
+#endif
+}
+QS_HD void m_sincos(float x, float* s, float* c) {
+#ifdef QS_LITERAL32
+  m_sincos_big(x, s, c);
+#else
+  if (!(fabsf(x) <= 1.0e4f)) { m_sincos_big(x, s, c); return; }
+  const float k = rintf(x * 0.636619772367581343f);  // 2/pi
+  float r = fmaf(k, -1.5707962512969971f, x);        // pi/2 = hi + mid + lo
+  r = fmaf(k, -7.5497894158615964e-08f, r);
+  r = fmaf(k, -5.3903029534742384e-15f, r);
+  const float z = r * r;
+  const float sn = fmaf(r * z, fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), r);
+  const float cs = fmaf(z * z, fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f), fmaf(-0.5f, z, 1.0f));
+  const int q = (int)k;
+  const float a = (q & 1) ? cs : sn, b = (q & 1) ? sn : cs;
+  *s = (q & 2) ? -a : a;
+  *c = ((q + 1) & 2) ? -b : b;
 #endif
 }
 QS_HD void m_sincos(double x, double* s, double* c) {
@@ -190,6 +213,37 @@ template <typename T> QS_HD void rotor2control(T f0, T f1, T f2, T f3, T& F, T& 
   Mz = ((lam * f0 - lam * f1) + lam * f2) - lam * f3;
 }
 
+// dynamics/quadrotor.py:146-168  attitude_limit + the overwrite in Drone.step (:135-138).  The reference runs three
+// independent `if`s, each rebuilding the quaternion from the RAW other two angles and overriding the previous one, then
+// cancels everything if all three are within (<=) their limits: the last limit that fires wins (yaw, else pitch, else
+// roll).  Cold path (never taken under the benchmark's action distribution), kept out of line on the device.
+template <typename T> struct ClampResult { T w, x, y, z; bool fired; };
+template <typename T> QS_HD ClampResult<T> attitude_clamp(T q0, T q1, T q2, T q3) {
+  using C = K<T>;
+  ClampResult<T> out = {q0, q1, q2, q3, false};
+  Euler<T> e = quat2euler(q0, q1, q2, q3);
+  const T r = e.phi, p = e.theta, y = e.psi;
+  const bool cr = m_abs(r) >= C::d85, cp = m_abs(p) >= C::d85, cy = m_abs(y) >= C::d175;
+  const bool inside = m_abs(r) <= C::d85 && m_abs(p) <= C::d85 && m_abs(y) <= C::d175;
+  if (!(cr || cp || cy) || inside) return out;
+  T lr = r, lp = p, ly = y;
+  if (cy) ly = m_sign(y) * C::d175;
+  else if (cp) lp = m_sign(p) * C::d85;
+  else lr = m_sign(r) * C::d85;
+  Quat<T> lim = euler2quat(lr, lp, ly);
+  out.w = lim.w; out.x = lim.x; out.y = lim.y; out.z = lim.z; out.fired = true;
+  return out;
+}
+// out-of-line copy for the fp32 fast path, where the clamp is a cold branch behind a transcendental-free pre-test
+// (by-value in/out so the caller's drone state never has to live in local memory)
+template <typename T>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+ClampResult<T> attitude_clamp_cold(T q0, T q1, T q2, T q3) { return attitude_clamp(q0, q1, q2, q3); }
+
 // dynamics/quadrotor.py:126-144  Drone.step(u_cmd): Euler step with frozen RHS df(state, u_prev) (:80-113),
 // attitude_limit (:146-168), then u_prev <- u_limit(u_cmd).  Returns true if the attitude clamp fired.
 template <typename T> QS_HD bool drone_step(Drone<T>& d, T c0, T c1, T c2, T c3) {
@@ -239,17 +293,10 @@ template <typename T> QS_HD bool drone_step(Drone<T>& d, T c0, T c1, T c2, T c3)
     clamp = true;
   }
   if (clamp) {
-    Euler<T> e = quat2euler(d.q0, d.q1, d.q2, d.q3);
-    T r = e.phi, p = e.theta, y = e.psi;
-    bool flag = false;
-    Quat<T> lim = {d.q0, d.q1, d.q2, d.q3};
-    if (m_abs(r) >= C::d85) { lim = euler2quat(m_sign(r) * C::d85, p, y); flag = true; }
-    if (m_abs(p) >= C::d85) { lim = euler2quat(r, m_sign(p) * C::d85, y); flag = true; }
-    if (m_abs(y) >= C::d175) { lim = euler2quat(r, p, m_sign(y) * C::d175); flag = true; }
-    if (m_abs(r) <= C::d85 && m_abs(p) <= C::d85 && m_abs(y) <= C::d175) flag = false;
-    clamp = flag;
-    if (flag) {
-      d.q0 = lim.w; d.q1 = lim.x; d.q2 = lim.y; d.q3 = lim.z;
+    ClampResult<T> cr = kFast<T> ? attitude_clamp_cold(d.q0, d.q1, d.q2, d.q3) : attitude_clamp(d.q0, d.q1, d.q2, d.q3);
+    clamp = cr.fired;
+    if (cr.fired) {
+      d.q0 = cr.w; d.q1 = cr.x; d.q2 = cr.y; d.q3 = cr.z;
       d.wx = T(0); d.wy = T(0); d.wz = T(0);
     }
   }
@@ -438,7 +485,8 @@ template <> struct Origin<float> { static constexpr float x = 10.f, y = -50.f, z
 template <typename T> struct DockEnv {
   Drone<T> c, t;        // chaser (drone A), target (drone B)
   Quat<T> dq;           // target_state_des[6:10] (Q4)
-  T last_shaping, ep_return;
+  T last_shaping;       // also the running episode return: reward_k = shaping_k - shaping_{k-1} and shaping_0 = 0
+                        // (docking_env.py:221-222,243), so sum(reward) telescopes to the latest shaping
   int32_t tt, episode;  // env.t ; Philox counter word 2
 };
 template <typename T> struct HoverEnv {
@@ -467,7 +515,7 @@ template <typename T> QS_HD void dock_env_seat(DockEnv<T>& e, const RngCfg& rng,
   using O = Origin<T>;  // the fp32 subtractions below are exact (result has fewer significant bits than the minuend)
   e.c = drone_at<T>(T(f_add(8.f, j[0])) - O::x, T(f_add(-50.f, j[1])) - O::y, T(f_add(5.f, j[2])) - O::z);
   e.t = drone_at<T>(T(10) - O::x, T(-50) - O::y, T(5) - O::z);
-  e.tt = 0; e.last_shaping = T(0); e.ep_return = T(0);
+  e.tt = 0; e.last_shaping = T(0);
   if (kFast<T>) obs[0] = (e.t.px - e.c.px) + T(-0.2);
   else obs[0] = (e.t.px + T(-0.1)) - (e.c.px + T(0.1));
   obs[1] = e.t.py - e.c.py; obs[2] = e.t.pz - e.c.pz;
@@ -512,7 +560,6 @@ template <typename T, int KIND> QS_HD void dock_env_step(DockEnv<T>& e, const T 
   }
   o.reward = shaping - e.last_shaping;
   e.last_shaping = shaping;
-  e.ep_return += o.reward;
   T fsum = m_abs(o.reward);
 #pragma unroll
   for (int k = 0; k < 12; k++) fsum += m_abs(rel[k]);

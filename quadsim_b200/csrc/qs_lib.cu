@@ -10,6 +10,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -21,6 +22,11 @@ namespace {
 using namespace qs;
 
 constexpr int kBlock = 128;        // threads per CTA (4 warps); grid = ceil(n / 128)
+#ifndef QS_MINB32
+#define QS_MINB32 1
+#endif
+// resident CTAs per SM requested from ptxas for the fp32 step kernels (register cap = 65536 / (128 * minb))
+template <typename T> constexpr int min_blocks() { return is_f32<T>::value ? QS_MINB32 : 1; }
 constexpr int kStatWords = 8;      // doubles per warp statistics slot (5 used), 64-byte stride
 constexpr int64_t kHostChunk = 1 << 17;  // envs per pipelined chunk in qs_step_host
 constexpr int kHostStreams = 4;
@@ -52,18 +58,22 @@ struct DeviceGuard {
 
 // ---------------------------------------------------------------------------------------------------------
 // HBM layout.  A "row" is 16 bytes per env: Row<float>::V = float4 (4 words), Row<double>::V = double2 (2 words).
-// Row r of env i sits at rows[r * stride + i].  Word order (docking, 44 words; fp64 stores the first 42):
+// Rows are stored TILE-MAJOR: the NR rows of one 128-env tile are adjacent, row r of env i sits at
+// rows[((i / 128) * NR + r) * 128 + i % 128].  A warp-level access is one contiguous 512 B span (every sector fully
+// used) and a CTA's whole tile state is ONE contiguous NR x 2 KB block, so a step streams a single read stream and a
+// single write stream through the state instead of NR interleaved ones (DRAM page locality).  Word order (docking, exactly 40 words = 10 fp32 rows / 20 fp64 rows):
 //    0- 3  chaser p.xyz, w.x      4- 7  chaser v.xyz, w.y     8-11  chaser q      12-15  chaser u_prev
 //   16-19  target p.xyz, w.x     20-23  target v.xyz, w.y    24-27  target q      28-31  target u_prev
-//   32-35  des_q                 36-39  chaser w.z, target w.z, last_shaping, ep_return
-//   40-43  t (int), episode (uint), spare, spare
+//   32-35  des_q                 36-39  chaser w.z, target w.z, last_shaping, counters
+// counters = t | episode << 10 in a 32-bit word (fp32: t < 1024 -- episodes end at t = 600 --, episode mod 2^22) or
+// t | episode << 32 in a 64-bit word (fp64).  The episode return is not stored: it equals last_shaping (telescoping).
 // Hover (20 words): 0-15 as the chaser above; 16-19 = w.z, ep_return, t (int), episode (uint).
 // ---------------------------------------------------------------------------------------------------------
 template <typename T> struct Row;
 template <> struct Row<float> { using V = float4; static constexpr int W = 4; };
 template <> struct Row<double> { using V = double2; static constexpr int W = 2; };
 
-template <typename T> constexpr int dock_words() { return is_f32<T>::value ? 44 : 42; }
+template <typename T> constexpr int dock_words() { return 40; }
 constexpr int kHoverWords = 20;
 
 __device__ __forceinline__ void unpack(const float4& v, float* w) { w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
@@ -71,19 +81,19 @@ __device__ __forceinline__ void unpack(const double2& v, double* w) { w[0] = v.x
 __device__ __forceinline__ float4 pack(const float* w) { return make_float4(w[0], w[1], w[2], w[3]); }
 __device__ __forceinline__ double2 pack(const double* w) { return make_double2(w[0], w[1]); }
 
-template <typename T, int NW> __device__ __forceinline__ void load_words(const void* base, int64_t stride, int64_t i, T (&w)[NW]) {
+template <typename T, int NW> __device__ __forceinline__ void load_words(const void* base, int64_t i, T (&w)[NW]) {
   using V = typename Row<T>::V;
-  constexpr int W = Row<T>::W;
-  const V* rows = reinterpret_cast<const V*>(base);
+  constexpr int W = Row<T>::W, NR = NW / W;
+  const V* rows = reinterpret_cast<const V*>(base) + (i / kBlock) * (NR * kBlock) + (i % kBlock);
 #pragma unroll
-  for (int r = 0; r < NW / W; r++) unpack(rows[r * stride + i], &w[r * W]);
+  for (int r = 0; r < NR; r++) unpack(rows[r * kBlock], &w[r * W]);
 }
-template <typename T, int NW> __device__ __forceinline__ void store_words(void* base, int64_t stride, int64_t i, const T (&w)[NW]) {
+template <typename T, int NW> __device__ __forceinline__ void store_words(void* base, int64_t i, const T (&w)[NW]) {
   using V = typename Row<T>::V;
-  constexpr int W = Row<T>::W;
-  V* rows = reinterpret_cast<V*>(base);
+  constexpr int W = Row<T>::W, NR = NW / W;
+  V* rows = reinterpret_cast<V*>(base) + (i / kBlock) * (NR * kBlock) + (i % kBlock);
 #pragma unroll
-  for (int r = 0; r < NW / W; r++) rows[r * stride + i] = pack(&w[r * W]);
+  for (int r = 0; r < NR; r++) rows[r * kBlock] = pack(&w[r * W]);
 }
 
 __device__ __forceinline__ int32_t word_to_int(float x) { return __float_as_int(x); }
@@ -91,6 +101,24 @@ __device__ __forceinline__ int32_t word_to_int(double x) { return (int32_t)__dou
 template <typename T> __device__ __forceinline__ T int_to_word(int32_t v);
 template <> __device__ __forceinline__ float int_to_word<float>(int32_t v) { return __int_as_float(v); }
 template <> __device__ __forceinline__ double int_to_word<double>(int32_t v) { return __longlong_as_double((long long)v); }
+// docking counters word
+__device__ __forceinline__ void unpack_counters(float x, int32_t& t, int32_t& ep) {
+  const uint32_t u = __float_as_uint(x);
+  t = (int32_t)(u & 1023u); ep = (int32_t)(u >> 10);
+}
+__device__ __forceinline__ void unpack_counters(double x, int32_t& t, int32_t& ep) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  t = (int32_t)(u & 0xffffffffull); ep = (int32_t)(u >> 32);
+}
+__device__ __forceinline__ float pack_counters_f(int32_t t, int32_t ep) {
+  return __uint_as_float((uint32_t)(t > 1023 ? 1023 : t) | ((uint32_t)ep << 10));
+}
+__device__ __forceinline__ double pack_counters_d(int32_t t, int32_t ep) {
+  return __longlong_as_double((long long)((unsigned long long)(uint32_t)t | ((unsigned long long)(uint32_t)ep << 32)));
+}
+template <typename T> __device__ __forceinline__ T pack_counters(int32_t t, int32_t ep);
+template <> __device__ __forceinline__ float pack_counters<float>(int32_t t, int32_t ep) { return pack_counters_f(t, ep); }
+template <> __device__ __forceinline__ double pack_counters<double>(int32_t t, int32_t ep) { return pack_counters_d(t, ep); }
 
 // row-major [N, C] outputs written as 16-byte vectors (C*sizeof(T) is a multiple of 16 for C in {4, 12})
 template <typename T, int C> __device__ __forceinline__ void store_row(void* base, int64_t i, const T* v) {
@@ -149,8 +177,8 @@ template <typename T, int NW> __device__ __forceinline__ void words_to_dock(cons
   e.c = Drone<T>{w[0], w[1], w[2], w[4], w[5], w[6], w[8], w[9], w[10], w[11], w[3], w[7], w[36], w[12], w[13], w[14], w[15]};
   e.t = Drone<T>{w[16], w[17], w[18], w[20], w[21], w[22], w[24], w[25], w[26], w[27], w[19], w[23], w[37], w[28], w[29], w[30], w[31]};
   e.dq = Quat<T>{w[32], w[33], w[34], w[35]};
-  e.last_shaping = w[38]; e.ep_return = w[39];
-  e.tt = word_to_int(w[40]); e.episode = word_to_int(w[41]);
+  e.last_shaping = w[38];
+  unpack_counters(w[39], e.tt, e.episode);
 }
 template <typename T, int NW> __device__ __forceinline__ void dock_to_words(const DockEnv<T>& e, T (&w)[NW]) {
   const Drone<T>&c = e.c, &t = e.t;
@@ -159,9 +187,7 @@ template <typename T, int NW> __device__ __forceinline__ void dock_to_words(cons
   w[16] = t.px; w[17] = t.py; w[18] = t.pz; w[19] = t.wx; w[20] = t.vx; w[21] = t.vy; w[22] = t.vz; w[23] = t.wy;
   w[24] = t.q0; w[25] = t.q1; w[26] = t.q2; w[27] = t.q3; w[28] = t.u0; w[29] = t.u1; w[30] = t.u2; w[31] = t.u3;
   w[32] = e.dq.w; w[33] = e.dq.x; w[34] = e.dq.y; w[35] = e.dq.z;
-  w[36] = c.wz; w[37] = t.wz; w[38] = e.last_shaping; w[39] = e.ep_return;
-  w[40] = int_to_word<T>(e.tt); w[41] = int_to_word<T>(e.episode);
-  if (NW > 42) { w[NW - 2] = T(0); w[NW - 1] = T(0); }
+  w[36] = c.wz; w[37] = t.wz; w[38] = e.last_shaping; w[39] = pack_counters<T>(e.tt, e.episode);
 }
 template <typename T> __device__ __forceinline__ void words_to_hover(const T (&w)[kHoverWords], HoverEnv<T>& e) {
   e.d = Drone<T>{w[0], w[1], w[2], w[4], w[5], w[6], w[8], w[9], w[10], w[11], w[3], w[7], w[16], w[12], w[13], w[14], w[15]};
@@ -178,6 +204,20 @@ template <typename T> __device__ __forceinline__ void store_obs13(void* base, in
 #pragma unroll
   for (int k = 0; k < 13; k++) o[k] = v[k];
 }
+// [N,13] rows are 52 (fp32) / 104 (fp64) bytes: per-thread scalar stores would touch 13 sectors per instruction.  The
+// CTA stages its 128 rows in shared memory and writes the tile's contiguous 128*13 words with fully coalesced stores.
+// Must be called by every thread of the CTA (tile0 = first env of the tile, cnt = valid envs in it).
+template <typename T> __device__ __forceinline__ void store_obs13_tile(T* stage, void* base, int64_t tile0, int cnt, const T* v, bool active) {
+  const int tid = threadIdx.x;
+  __syncthreads();  // previous use of the stage is finished
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 13; k++) stage[tid * 13 + k] = v[k];
+  }
+  __syncthreads();
+  T* o = reinterpret_cast<T*>(base) + tile0 * 13;
+  for (int k = tid; k < cnt * 13; k += kBlock) o[k] = stage[k];
+}
 
 // =========================================================================================================
 // Fused docking step: gym_docking/envs/docking_env.py:104-231 (KIND = QS_DOCK_V0) and
@@ -185,7 +225,7 @@ template <typename T> __device__ __forceinline__ void store_obs13(void* base, in
 // The arithmetic is qs::dock_env_step / dock_env_seat (qs_core.cuh); this kernel is load -> step -> store.
 // =========================================================================================================
 template <typename T, int KIND>
-__global__ void __launch_bounds__(kBlock) dock_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_kernel(const StepArgs a) {
   constexpr int NW = dock_words<T>();
   const int64_t i = a.first + (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const bool active = i < a.first + a.n;
@@ -193,7 +233,7 @@ __global__ void __launch_bounds__(kBlock) dock_step_kernel(const StepArgs a) {
   if (!active) return;
 
   T w[NW];
-  load_words<T, NW>(a.state, a.stride, i, w);
+  load_words<T, NW>(a.state, i, w);
   T act[4];
   load_action<T>(a.actions, i, act);
   DockEnv<T> e;
@@ -207,7 +247,7 @@ __global__ void __launch_bounds__(kBlock) dock_step_kernel(const StepArgs a) {
   a.done[i] = o.done ? 1 : 0;
   if (a.info) a.info[i] = (uint8_t)o.info();
   if (a.term_obs) store_row<T, 12>(a.term_obs, i, rel);
-  const double stat_ret = (double)e.ep_return;
+  const double stat_ret = (double)e.last_shaping;  // == sum of the episode's rewards (telescoping)
   const int stat_len = e.tt;
   if (o.done && a.auto_reset) {
     e.episode += 1;
@@ -215,8 +255,125 @@ __global__ void __launch_bounds__(kBlock) dock_step_kernel(const StepArgs a) {
   }
   store_row<T, 12>(a.obs, i, rel);
   dock_to_words<T, NW>(e, w);
-  store_words<T, NW>(a.state, a.stride, i, w);
+  store_words<T, NW>(a.state, i, w);
   warp_stats_update(a.warp_stats, i, mask, o.done, o.docking, o.nonfinite, stat_ret, stat_len);
+}
+
+// =========================================================================================================
+// Persistent, bulk-async (TMA 1-D) pipelined variant of the fp32 docking step.
+//   * grid = SMs x resident CTAs; each CTA walks 128-env tiles handed out by a global atomic counter;
+//   * one elected thread issues two cp.async.bulk (SASS UBLKCP) copies -- the tile's 20 KB state block (contiguous in the
+//     tile-major layout) and its 2 KB of actions -- into shared memory, completion counted on an mbarrier;
+//   * the tile for iteration j+1 is requested as soon as every thread has moved tile j from shared memory to registers,
+//     so its HBM latency is covered by the ~1k-instruction compute phase of tile j: registers are the second buffer and
+//     ONE 22 KB shared stage per CTA suffices (6 CTAs/SM = 132 KB in flight per SM).
+// Results go straight from registers to HBM (coalesced 16-byte stores), as in the direct kernel.
+// =========================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  }
+}
+
+constexpr int kPipeRows = 11;  // 10 state rows + 1 action row (fp32)
+constexpr int kPipeSmemBytes = kPipeRows * kBlock * 16 + 64;
+
+template <int KIND>
+__global__ void __launch_bounds__(kBlock, QS_MINB32) dock_step_pipe_kernel(const StepArgs a, unsigned int* sched) {
+  using T = float;
+  constexpr int NW = 40, NR = 10;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4* buf = reinterpret_cast<float4*>(smem_raw);                        // [kPipeRows][kBlock]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kPipeRows * kBlock * 16);
+  volatile int* s_tile = reinterpret_cast<volatile int*>(full + 1);         // [2]: tile index for iteration parity
+  const int tid = threadIdx.x;
+  const int tiles = (int)((a.n + kBlock - 1) / kBlock);
+  const float4* state = reinterpret_cast<const float4*>(a.state);
+  const float4* actions = reinterpret_cast<const float4*>(a.actions);
+
+  auto request = [&](int tile) {  // elected thread: one mbarrier phase = 12 bulk copies
+    const int64_t env0 = a.first + (int64_t)tile * kBlock;
+    const int64_t left = a.first + a.n - env0;
+    const uint32_t cnt = (uint32_t)(left < kBlock ? left : kBlock);
+    mbar_expect_tx(full, NR * kBlock * 16 + cnt * 16);
+    bulk_g2s(buf, state + env0 * NR, NR * kBlock * 16, full);  // tile-major layout: the tile's state is one 20 KB span
+    bulk_g2s(buf + NR * kBlock, actions + env0, cnt * 16, full);
+  };
+
+  int next = -1;  // thread 0 only: tile whose data is in flight / landed
+  if (tid == 0) {
+    mbar_init(full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int t0 = (int)atomicAdd(sched, 1u);
+    s_tile[0] = t0 < tiles ? t0 : -1;
+    if (t0 < tiles) {
+      request(t0);
+      next = (int)atomicAdd(sched, 1u);
+    }
+  }
+  __syncthreads();
+
+  for (int it = 0;; it++) {
+    const int tile = s_tile[it & 1];
+    if (tile < 0) break;
+    mbar_wait(full, it & 1);
+    const int64_t i = a.first + (int64_t)tile * kBlock + tid;
+    const bool active = i < a.first + a.n;
+    T w[NW];
+#pragma unroll
+    for (int r = 0; r < NR; r++) unpack(buf[r * kBlock + tid], &w[r * 4]);
+    T act[4];
+    unpack(buf[NR * kBlock + tid], act);
+    if (tid == 0) s_tile[(it + 1) & 1] = next < tiles ? next : -1;
+    __syncthreads();  // every thread has drained the stage (and sees the next tile index)
+    if (tid == 0 && next >= 0 && next < tiles) {
+      request(next);
+      next = (int)atomicAdd(sched, 1u);  // latency hidden behind this tile's compute
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, active);
+    if (active) {
+      DockEnv<T> e;
+      words_to_dock<T, NW>(w, e);
+      T rel[12];
+      StepOut<T> o;
+      dock_env_step<T, KIND>(e, act, rel, o);
+      reinterpret_cast<T*>(a.reward)[i] = o.reward;
+      a.done[i] = o.done ? 1 : 0;
+      if (a.info) a.info[i] = (uint8_t)o.info();
+      if (a.term_obs) store_row<T, 12>(a.term_obs, i, rel);
+      const double stat_ret = (double)e.last_shaping;
+      const int stat_len = e.tt;
+      if (o.done && a.auto_reset) {
+        e.episode += 1;
+        dock_env_seat<T>(e, a.rng, i, rel);
+      }
+      store_row<T, 12>(a.obs, i, rel);
+      dock_to_words<T, NW>(e, w);
+      store_words<T, NW>(a.state, i, w);
+      warp_stats_update(a.warp_stats, i, mask, o.done, o.docking, o.nonfinite, stat_ret, stat_len);
+    }
+  }
+  // self-resetting scheduler: the last CTA out clears the counters for the next launch on this stream
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(sched + 1, 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
+  }
 }
 
 // =========================================================================================================
@@ -224,33 +381,43 @@ __global__ void __launch_bounds__(kBlock) dock_step_kernel(const StepArgs a) {
 // =========================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(kBlock) hover_step_kernel(const StepArgs a) {
-  const int64_t i = a.first + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  __shared__ T stage[kBlock * 13];
+  const int64_t tile0 = a.first + (int64_t)blockIdx.x * kBlock;
+  const int64_t i = tile0 + threadIdx.x;
   const bool active = i < a.first + a.n;
+  const int64_t left = a.first + a.n - tile0;
+  const int cnt = (int)(left < kBlock ? left : kBlock);
   const unsigned mask = __ballot_sync(0xffffffffu, active);
-  if (!active) return;
   T w[kHoverWords];
-  load_words<T, kHoverWords>(a.state, a.stride, i, w);
-  T act[4];
-  load_action<T>(a.actions, i, act);
-  HoverEnv<T> e;
-  words_to_hover<T>(w, e);
   T obs[13];
+  HoverEnv<T> e;
   StepOut<T> o;
-  hover_env_step<T>(e, act, obs, o);
-  reinterpret_cast<T*>(a.reward)[i] = o.reward;
-  a.done[i] = o.done ? 1 : 0;
-  if (a.info) a.info[i] = (uint8_t)o.info();
-  if (a.term_obs) store_obs13<T>(a.term_obs, i, obs);
-  const double stat_ret = (double)e.ep_return;
-  const int stat_len = e.tt;
-  if (o.done && a.auto_reset) {
+  o.done = o.docking = o.nonfinite = false;
+  double stat_ret = 0.0;
+  int stat_len = 0;
+  if (active) {
+    load_words<T, kHoverWords>(a.state, i, w);
+    T act[4];
+    load_action<T>(a.actions, i, act);
+    words_to_hover<T>(w, e);
+    hover_env_step<T>(e, act, obs, o);
+    reinterpret_cast<T*>(a.reward)[i] = o.reward;
+    a.done[i] = o.done ? 1 : 0;
+    if (a.info) a.info[i] = (uint8_t)o.info();
+    stat_ret = (double)e.ep_return;
+    stat_len = e.tt;
+  }
+  if (a.term_obs) store_obs13_tile<T>(stage, a.term_obs, tile0, cnt, obs, active);
+  if (active && o.done && a.auto_reset) {
     e.episode += 1;
     hover_env_seat<T>(e, a.rng, i, obs);
   }
-  store_obs13<T>(a.obs, i, obs);
-  hover_to_words<T>(e, w);
-  store_words<T, kHoverWords>(a.state, a.stride, i, w);
-  warp_stats_update(a.warp_stats, i, mask, o.done, o.docking, o.nonfinite, stat_ret, stat_len);
+  store_obs13_tile<T>(stage, a.obs, tile0, cnt, obs, active);
+  if (active) {
+    hover_to_words<T>(e, w);
+    store_words<T, kHoverWords>(a.state, i, w);
+    warp_stats_update(a.warp_stats, i, mask, o.done, o.docking, o.nonfinite, stat_ret, stat_len);
+  }
 }
 
 // =========================================================================================================
@@ -267,14 +434,14 @@ __global__ void __launch_bounds__(kBlock) seat_kernel(const StepArgs a, int mode
     HoverEnv<T> e;
     e.episode = 0;
     if (mode == 1) {
-      load_words<T, kHoverWords>(a.state, a.stride, i, w);
+      load_words<T, kHoverWords>(a.state, i, w);
       words_to_hover<T>(w, e);
       e.episode += e.tt != 0 ? 1 : 0;
     }
     T obs[13];
     hover_env_seat<T>(e, a.rng, i, obs);
     hover_to_words<T>(e, w);
-    store_words<T, kHoverWords>(a.state, a.stride, i, w);
+    store_words<T, kHoverWords>(a.state, i, w);
     if (a.obs) store_obs13<T>(a.obs, i, obs);
   } else {
     constexpr int NW = dock_words<T>();
@@ -283,14 +450,14 @@ __global__ void __launch_bounds__(kBlock) seat_kernel(const StepArgs a, int mode
     e.episode = 0;
     e.dq = Quat<T>{T(1), T(0), T(0), T(0)};
     if (mode == 1) {
-      load_words<T, NW>(a.state, a.stride, i, w);
+      load_words<T, NW>(a.state, i, w);
       words_to_dock<T, NW>(w, e);
       e.episode += e.tt != 0 ? 1 : 0;
     }
     T obs[12];
     dock_env_seat<T>(e, a.rng, i, obs);
     dock_to_words<T, NW>(e, w);
-    store_words<T, NW>(a.state, a.stride, i, w);
+    store_words<T, NW>(a.state, i, w);
     if (a.obs) store_row<T, 12>(a.obs, i, obs);
   }
 }
@@ -306,7 +473,7 @@ __global__ void __launch_bounds__(kBlock) state_io_kernel(void* state, int64_t s
   if (i >= n) return;
   constexpr int NW = HOVER ? kHoverWords : dock_words<T>();
   T w[NW];
-  load_words<T, NW>(state, stride, i, w);
+  load_words<T, NW>(state, i, w);
   // word index of state[k] (k = 0..12) relative to a drone's base word; positions (k < 3) are stored relative to Origin<T>
   const int sidx[13] = {0, 1, 2, 4, 5, 6, 8, 9, 10, 11, 3, 7, -1};
   const double org[3] = {HOVER ? 0.0 : (double)Origin<T>::x, HOVER ? 0.0 : (double)Origin<T>::y, HOVER ? 0.0 : (double)Origin<T>::z};
@@ -317,7 +484,7 @@ __global__ void __launch_bounds__(kBlock) state_io_kernel(void* state, int64_t s
   double* dq = reinterpret_cast<double*>(s.desq);
   double* ls = reinterpret_cast<double*>(s.last_shaping);
   double* er = reinterpret_cast<double*>(s.ep_return);
-  constexpr int WZ_C = HOVER ? 16 : 36, WZ_T = 37, ER = HOVER ? 17 : 39, TT = HOVER ? 18 : 40, EP = HOVER ? 19 : 41;
+  constexpr int WZ_C = HOVER ? 16 : 36, WZ_T = 37;
 #pragma unroll
   for (int k = 0; k < 13; k++) {
     const double o = k < 3 ? org[k] : 0.0;
@@ -335,10 +502,21 @@ __global__ void __launch_bounds__(kBlock) state_io_kernel(void* state, int64_t s
     if (!HOVER && dq) { if (IMPORT) w[32 + k] = (T)dq[i * 4 + k]; else dq[i * 4 + k] = (double)w[32 + k]; }
   }
   if (!HOVER && ls) { if (IMPORT) w[38] = (T)ls[i]; else ls[i] = (double)w[38]; }
-  if (er) { if (IMPORT) w[ER] = (T)er[i]; else er[i] = (double)w[ER]; }
-  if (s.t) { if (IMPORT) w[TT] = int_to_word<T>(s.t[i]); else s.t[i] = word_to_int(w[TT]); }
-  if (s.episode) { if (IMPORT) w[EP] = int_to_word<T>(s.episode[i]); else s.episode[i] = word_to_int(w[EP]); }
-  if (IMPORT) store_words<T, NW>(state, stride, i, w);
+  int32_t tt, ep;
+  if (HOVER) {
+    if (er) { if (IMPORT) w[17] = (T)er[i]; else er[i] = (double)w[17]; }
+    tt = word_to_int(w[18]); ep = word_to_int(w[19]);
+  } else {
+    if (er && !IMPORT) er[i] = (double)w[38];  // docking: the running return IS last_shaping; nothing to import
+    unpack_counters(w[39], tt, ep);
+  }
+  if (s.t) { if (IMPORT) tt = s.t[i]; else s.t[i] = tt; }
+  if (s.episode) { if (IMPORT) ep = s.episode[i]; else s.episode[i] = ep; }
+  if (IMPORT) {
+    if (HOVER) { w[18] = int_to_word<T>(tt); w[19] = int_to_word<T>(ep); }
+    else w[39] = pack_counters<T>(tt, ep);
+  }
+  if (IMPORT) store_words<T, NW>(state, i, w);
 }
 
 // statistics: fixed-order reduction of the per-warp slots, then clear them
@@ -451,6 +629,9 @@ struct qs_env {
   double* stats_dev = nullptr;
   double* stats_host = nullptr;  // pinned
   float jitter_scale;
+  int use_pipe = 0;               // persistent bulk-async kernel for fp32 docking
+  int pipe_grid = 0;
+  unsigned int* sched = nullptr;  // [kHostStreams + 1][2] tile counters (one pair per stream slot)
   // qs_step_host pipeline
   cudaStream_t hstreams[kHostStreams] = {};
   void *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
@@ -479,8 +660,17 @@ template <typename T> int launch_step_t(qs_env* e, const StepArgs& a, cudaStream
   QS_CUDA(cudaGetLastError());
   return QS_OK;
 }
-int launch_step(qs_env* e, const StepArgs& a, cudaStream_t st) {
+int launch_step(qs_env* e, const StepArgs& a, cudaStream_t st, int slot = 0) {
   if (a.n <= 0) return QS_OK;
+  if (e->use_pipe) {
+    const int tiles = (int)((a.n + kBlock - 1) / kBlock);
+    const unsigned grid = (unsigned)(tiles < e->pipe_grid ? tiles : e->pipe_grid);
+    unsigned int* sched = e->sched + 2 * slot;
+    if (e->cfg.env_kind == QS_DOCK_V0) dock_step_pipe_kernel<QS_DOCK_V0><<<grid, kBlock, kPipeSmemBytes, st>>>(a, sched);
+    else dock_step_pipe_kernel<QS_DOCK_V2><<<grid, kBlock, kPipeSmemBytes, st>>>(a, sched);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+  }
   return e->cfg.dtype == QS_F32 ? launch_step_t<float>(e, a, st) : launch_step_t<double>(e, a, st);
 }
 
@@ -537,7 +727,7 @@ int qs_create(qs_env_t** out, const qs_config_t* cfg) {
   e->jitter_scale = (float)(2.0 * e->cfg.half_width);
   e->obs_dim = cfg->env_kind == QS_HOVER ? 13 : 12;
   e->esize = cfg->dtype == QS_F32 ? 4 : 8;
-  const int words = cfg->env_kind == QS_HOVER ? kHoverWords : (cfg->dtype == QS_F32 ? 44 : 42);
+  const int words = cfg->env_kind == QS_HOVER ? kHoverWords : 40;
   e->n_rows = words / (cfg->dtype == QS_F32 ? 4 : 2);
   e->stride = (cfg->n_envs + kBlock - 1) / kBlock * kBlock;
   e->n_slots = e->stride / 32;
@@ -551,6 +741,24 @@ int qs_create(qs_env_t** out, const qs_config_t* cfg) {
     int rc = fail(QS_ERR_ALLOC, "qs_create: device allocation failed: %s", cudaGetErrorString(err));
     qs_destroy(e);
     return rc;
+  }
+  if (const char* k = getenv("QUADSIM_B200_KERNEL")) e->use_pipe = strcmp(k, "pipe") == 0;
+  if (e->cfg.dtype != QS_F32 || e->cfg.env_kind == QS_HOVER) e->use_pipe = 0;
+  if (e->use_pipe) {
+    cudaDeviceProp prop;
+    int per_sm = 0;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess ||
+        cudaFuncSetAttribute(dock_step_pipe_kernel<QS_DOCK_V0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(dock_step_pipe_kernel<QS_DOCK_V2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemBytes) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dock_step_pipe_kernel<QS_DOCK_V2>, kBlock, kPipeSmemBytes) != cudaSuccess ||
+        per_sm < 1 || cudaMalloc(&e->sched, (kHostStreams + 1) * 2 * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(e->sched, 0, (kHostStreams + 1) * 2 * sizeof(unsigned int)) != cudaSuccess) {
+      int rc = fail(QS_ERR_CUDA, "qs_create: pipelined kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+      qs_destroy(e);
+      return rc;
+    }
+    if (const char* g = getenv("QUADSIM_B200_PIPE_CTAS")) per_sm = atoi(g) < per_sm && atoi(g) > 0 ? atoi(g) : per_sm;
+    e->pipe_grid = per_sm * prop.multiProcessorCount;
   }
   int rc = launch_seat(e, nullptr, 0, 0);
   if (rc != QS_OK) { qs_destroy(e); return rc; }
@@ -568,7 +776,7 @@ int qs_destroy(qs_env_t* e) {
   DeviceGuard g(e->cfg.device);
   for (auto& s : e->hstreams) if (s) cudaStreamDestroy(s);
   cudaFree(e->h_act); cudaFree(e->h_obs); cudaFree(e->h_rew); cudaFree(e->h_done);
-  cudaFree(e->state); cudaFree(e->warp_stats); cudaFree(e->stats_dev);
+  cudaFree(e->state); cudaFree(e->warp_stats); cudaFree(e->stats_dev); cudaFree(e->sched);
   if (e->stats_host) cudaFreeHost(e->stats_host);
   delete e;
   return QS_OK;
@@ -633,7 +841,7 @@ int qs_step_host(qs_env_t* e, const void* actions_host, void* obs_host, void* re
     QS_CUDA(cudaMemcpyAsync((char*)e->h_act + first * 4 * es, (const char*)actions_host + first * 4 * es, (size_t)n * 4 * es, cudaMemcpyHostToDevice, st));
     StepArgs a = make_args(e, first, n);
     a.actions = e->h_act; a.obs = e->h_obs; a.reward = e->h_rew; a.done = e->h_done;
-    int rc = launch_step(e, a, st);
+    int rc = launch_step(e, a, st, 1 + k % kHostStreams);
     if (rc != QS_OK) return rc;
     QS_CUDA(cudaMemcpyAsync((char*)obs_host + first * e->obs_dim * es, (char*)e->h_obs + first * e->obs_dim * es, (size_t)n * e->obs_dim * es, cudaMemcpyDeviceToHost, st));
     QS_CUDA(cudaMemcpyAsync((char*)reward_host + first * es, (char*)e->h_rew + first * es, (size_t)n * es, cudaMemcpyDeviceToHost, st));

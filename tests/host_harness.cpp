@@ -84,10 +84,10 @@ template <typename T> void vec_io(void* h, double* buf, int import) {
       auto& e = v->dock[i];
       if (import) {
         get13(e.c, b, b + 13, org); get13(e.t, b + 17, b + 30, org); e.dq = Quat<T>{T(b[34]), T(b[35]), T(b[36]), T(b[37])};
-        e.last_shaping = T(b[38]); e.ep_return = T(b[39]); e.tt = (int)b[40]; e.episode = (int)b[41];
+        e.last_shaping = T(b[38]); e.tt = (int)b[40]; e.episode = (int)b[41];
       } else {
         put13(e.c, b, b + 13, org); put13(e.t, b + 17, b + 30, org); b[34] = e.dq.w; b[35] = e.dq.x; b[36] = e.dq.y; b[37] = e.dq.z;
-        b[38] = e.last_shaping; b[39] = e.ep_return; b[40] = e.tt; b[41] = e.episode;
+        b[38] = e.last_shaping; b[39] = e.last_shaping; b[40] = e.tt; b[41] = e.episode;
       }
     }
   }
