@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALGO_BYTES = {"f32": 405, "f64": 793}  # SURVEY.md section 8d / DESIGN.md "Algorithmic bytes"
+LAYOUT_BYTES = {"f32": 389, "f64": 777}  # what the 40-word layout really moves per env-step (state R+W, actions, obs, reward, done)
 
 
 def parse():
@@ -100,7 +101,7 @@ def run_reference(args):
 def workload_config(args, envs_per_gpu):
     return {"workload": "%s fused step (PID/vel target controller + 2x Drone.step + state2rel + reward/done + Philox auto-reset)" % args.env,
             "env": args.env, "envs_per_gpu": envs_per_gpu, "actions": "synthetic U(-1,1)^4 fp32, 8 pre-generated tensors cycled",
-            "randomize_init": "episode (Philox4x32-10, +-0.5 m)", "l2": "working set (state 185 MB + actions 134 MB + outputs) > 126 MB L2",
+            "randomize_init": "episode (Philox4x32-10, +-0.5 m)", "l2": "working set (state 168 MB + 8 action tensors 134 MB + outputs 56 MB) > 126 MB L2, no flush needed",
             "parallelism": "env-sharded, dp%d, no collective on the step path" % args.gpus}
 
 
@@ -241,7 +242,8 @@ def run_ours(args):
     traffic = ncu_traffic(args.dtype)
     kernel = "dock_step_kernel<%s,%s>" % ("float" if args.dtype == "f32" else "double", args.env)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": kernel, "algorithmic_bytes_per_env_step": algo, "kernel_ms": kernel_ms, "peak_source": peak_src,
+                "kernel": kernel, "algorithmic_bytes_per_env_step": algo, "layout_bytes_per_env_step": LAYOUT_BYTES[args.dtype],
+                "layout_GBps": LAYOUT_BYTES[args.dtype] * n / (kernel_ms * 1e-3) / 1e9, "kernel_ms": kernel_ms, "peak_source": peak_src,
                 "timing": "CUDA events on the launch stream around the %d timed launches / %d" % (args.steps, args.steps)}
     cpu = None
     if not args.no_cpu_baseline:
