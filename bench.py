@@ -75,6 +75,10 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is meant to use all host cores (libgomp reads the
+    # variable when it is first loaded, which happens below)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ.setdefault("OMP_PROC_BIND", "false")
     n = 1 << 15
     # size the sample so K steps stay within ~60 s: calibrate on a few steps
     cal = cpu_port_run(args.env, n, 3, 1, threads=threads)
@@ -95,7 +99,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "unmodified Python reference measured in the build container: ~340 env-steps/s/core (BASELINE.md section 2)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, envs_per_gpu):
@@ -259,11 +263,29 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu,
         "episode_stats": {k: stats[k] for k in ("episodes", "mean_length", "mean_return", "docked_steps", "nonfinite_steps")},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL's version banner, library chatter
+    written straight to fd 1) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -26,7 +26,10 @@ constexpr int kBlock = 128;        // threads per CTA (4 warps); grid = ceil(n /
 #define QS_MINB32 1
 #endif
 // resident CTAs per SM requested from ptxas for the fp32 step kernels (register cap = 65536 / (128 * minb))
-template <typename T> constexpr int min_blocks() { return is_f32<T>::value ? QS_MINB32 : 1; }
+#ifndef QS_MINB64
+#define QS_MINB64 1
+#endif
+template <typename T> constexpr int min_blocks() { return is_f32<T>::value ? QS_MINB32 : QS_MINB64; }
 constexpr int kStatWords = 8;      // doubles per warp statistics slot (5 used), 64-byte stride
 constexpr int64_t kHostChunk = 1 << 17;  // envs per pipelined chunk in qs_step_host
 constexpr int kHostStreams = 4;
