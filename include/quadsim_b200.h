@@ -143,6 +143,18 @@ typedef enum {
 int qs_fn_apply(int fn, int dtype, int64_t n, const void* in0, const void* in1, const void* in2, void* out0,
                 void* out1, void* stream);
 
+/* Generalised advantage estimation over a device-resident rollout, the backward loop of Runner._run
+ * (rl_baselines/ppo2/ppo2.py:511-521): for step = T-1..0
+ *   nextnonterminal = 1 - (step == T-1 ? last_dones : dones[step+1]);  nextvalues = (step == T-1 ? last_values : values[step+1])
+ *   delta = rewards[step] + gamma * nextvalues * nextnonterminal - values[step]
+ *   advs[step] = lastgaelam = delta + gamma * lam * nextnonterminal * lastgaelam ;  returns = advs + values
+ * All arrays are [T, N] time-major float32 device pointers (dones: uint8, dones[t] = the done flag BEFORE step t, as the
+ * reference stores it); last_values/last_dones are [N].  gamma/lam are doubles like the reference's python floats.
+ * One thread per env, coalesced along N; numpy's float32/float64 promotion in that loop is mirrored exactly. */
+int qs_gae(int64_t n_steps, int64_t n_envs, const float* rewards, const float* values, const uint8_t* dones,
+           const float* last_values, const uint8_t* last_dones, double gamma, double lam, float* advs_out,
+           float* returns_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

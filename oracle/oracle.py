@@ -213,3 +213,18 @@ class OracleVecEnv:
             self.close()
         except Exception:
             pass
+
+
+def gae(rewards, values, dones, last_values, last_dones, gamma, lam):
+    """Runner._run's GAE loop (ppo2.py:511-521) on [T,N] float32 arrays -> (advs, returns)."""
+    r = np.ascontiguousarray(rewards, dtype=np.float32)
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    d = np.ascontiguousarray(dones, dtype=np.uint8)
+    lv = np.ascontiguousarray(last_values, dtype=np.float32)
+    ld = np.ascontiguousarray(last_dones, dtype=np.uint8)
+    T, n = r.shape
+    adv, ret = np.zeros_like(r), np.zeros_like(r)
+    L = lib()
+    L.qo_gae.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 5 + [C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    L.qo_gae(T, n, _p(r), _p(v), _p(d), _p(lv), _p(ld), gamma, lam, _p(adv), _p(ret))
+    return adv, ret

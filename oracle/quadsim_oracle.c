@@ -518,3 +518,29 @@ void qo_vec_stats(qo_vec* v, double out[5]) {
   memcpy(out, v->stats, sizeof v->stats);
   memset(v->stats, 0, sizeof v->stats);
 }
+
+/* rl_baselines/ppo2/ppo2.py:511-521.  numpy's promotion rules make the reference evaluate
+ * `mb_rewards[step] + self.gamma * nextvalues * nextnonterminal - mb_values[step]` as: gamma*nextvalues in float32 (python
+ * scalar times float32 array), the rest in float64 because nextnonterminal = 1.0 - <bool array> is float64; last_gae_lam
+ * stays float64 across iterations; mb_advs[step] is stored float32; mb_returns = mb_advs + mb_values in float32.
+ * gamma and lam are python floats (doubles); gamma is rounded to float32 only inside gamma*nextvalues. */
+void qo_gae(int64_t T, int64_t n, const float* rew, const float* val, const uint8_t* dones, const float* last_val,
+            const uint8_t* last_dones, double gamma, double lam, float* adv, float* ret) {
+  const double gl = gamma * lam;
+  const float gf = (float)gamma;
+  for (int64_t i = 0; i < n; i++) {
+    double nextnonterminal = 1.0 - (double)last_dones[i];
+    float nextvalues = last_val[i];
+    double lastgaelam = 0.0;
+    for (int64_t t = T - 1; t >= 0; t--) {
+      volatile float gv = gf * nextvalues;
+      double delta = ((double)rew[t * n + i] + (double)gv * nextnonterminal) - (double)val[t * n + i];
+      lastgaelam = delta + (gl * nextnonterminal) * lastgaelam;
+      adv[t * n + i] = (float)lastgaelam;
+      volatile float r = adv[t * n + i] + val[t * n + i];
+      ret[t * n + i] = r;
+      nextnonterminal = 1.0 - (double)dones[t * n + i];
+      nextvalues = val[t * n + i];
+    }
+  }
+}

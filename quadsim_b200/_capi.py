@@ -19,7 +19,7 @@ ABI_VERSION = 1
 # every symbol include/quadsim_b200.h declares (tests check the built library exports all of them)
 SYMBOLS = ["qs_abi_version", "qs_last_error", "qs_create", "qs_destroy", "qs_obs_dim", "qs_num_envs", "qs_seed",
            "qs_reset", "qs_step", "qs_step_ex", "qs_step_host", "qs_host_alloc", "qs_host_free", "qs_export_state",
-           "qs_import_state", "qs_get_stats", "qs_fn_apply"]
+           "qs_import_state", "qs_get_stats", "qs_fn_apply", "qs_gae"]
 
 
 class Config(C.Structure):
@@ -73,6 +73,7 @@ def load():
     L.qs_import_state.argtypes = [vp, C.POINTER(StateArrays), vp]
     L.qs_get_stats.argtypes = [vp, C.POINTER(C.c_double), vp]
     L.qs_fn_apply.argtypes = [C.c_int, C.c_int, i64, vp, vp, vp, vp, vp, vp]
+    L.qs_gae.argtypes = [i64, i64, vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp]
     if L.qs_abi_version() != ABI_VERSION:
         raise QuadSimError("libquadsim_b200.so ABI %d != expected %d; rebuild" % (L.qs_abi_version(), ABI_VERSION))
     _lib = L

@@ -23,6 +23,8 @@ NVCC_FLAGS = [
     "-ftz=true", "-prec-div=false", "-prec-sqrt=false",
     # 6 resident CTAs/SM for the fp32 step kernels (<= 80 registers): measured best of {4,5,6,8}
     "-DQS_MINB32=6",
+    # fp64 step kernels: 4 CTAs/SM (128 registers, some spills) measured best of {2,3,4,5,6}: 385 -> 293 us/step
+    "-DQS_MINB64=4",
 ]
 
 

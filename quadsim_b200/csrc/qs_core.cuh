@@ -66,9 +66,14 @@ QS_HD double m_rsqrt(double x) { return 1.0 / sqrt(x); }
 QS_HD float m_abs(float x) { return fabsf(x); }
 QS_HD double m_abs(double x) { return fabs(x); }
 QS_HD float m_asin(float x) { return asinf(x); }
-QS_HD double m_asin(double x) { return asin(x); }
+#if defined(__CUDACC__) && defined(QS_F64_OUTLINE)
+#define QS_F64_FN __host__ __device__ __noinline__
+#else
+#define QS_F64_FN QS_HD
+#endif
+QS_F64_FN double m_asin(double x) { return asin(x); }
 QS_HD float m_atan2(float y, float x) { return atan2f(y, x); }
-QS_HD double m_atan2(double y, double x) { return atan2(y, x); }
+QS_F64_FN double m_atan2(double y, double x) { return atan2(y, x); }
 QS_HD float m_tan(float x) { return tanf(x); }
 QS_HD double m_tan(double x) { return tan(x); }
 // fp32 sin & cos together.  Every angle the envs feed in is bounded (half-angles of atan2 results, desired tilt = acc/g),
@@ -101,13 +106,17 @@ QS_HD void m_sincos(float x, float* s, float* c) {
   *c = ((q + 1) & 2) ? -b : b;
 #endif
 }
-QS_HD void m_sincos(double x, double* s, double* c) {
+struct SinCosD { double s, c; };
+QS_F64_FN SinCosD m_sincos_d(double x) {
+  SinCosD r;
 #if defined(__CUDA_ARCH__)
-  sincos(x, s, c);
+  sincos(x, &r.s, &r.c);
 #else
-  *s = sin(x); *c = cos(x);
+  r.s = sin(x); r.c = cos(x);
 #endif
+  return r;
 }
+QS_HD void m_sincos(double x, double* s, double* c) { SinCosD r = m_sincos_d(x); *s = r.s; *c = r.c; }
 QS_HD float m_min(float a, float b) { return fminf(a, b); }
 QS_HD double m_min(double a, double b) { return fmin(a, b); }
 QS_HD float m_max(float a, float b) { return fmaxf(a, b); }
@@ -217,6 +226,15 @@ template <typename T> QS_HD void rotor2control(T f0, T f1, T f2, T f3, T& F, T& 
 // independent `if`s, each rebuilding the quaternion from the RAW other two angles and overriding the previous one, then
 // cancels everything if all three are within (<=) their limits: the last limit that fires wins (yaw, else pitch, else
 // roll).  Cold path (never taken under the benchmark's action distribution), kept out of line on the device.
+// out-of-line euler2quat for cold paths (by value in and out: nothing of the caller's has to live in local memory)
+template <typename T>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+Quat<T> euler2quat_cold(T roll, T pitch, T yaw) { return euler2quat(roll, pitch, yaw); }
+
 template <typename T> struct ClampResult { T w, x, y, z; bool fired; };
 template <typename T> QS_HD ClampResult<T> attitude_clamp(T q0, T q1, T q2, T q3) {
   using C = K<T>;
@@ -230,7 +248,7 @@ template <typename T> QS_HD ClampResult<T> attitude_clamp(T q0, T q1, T q2, T q3
   if (cy) ly = m_sign(y) * C::d175;
   else if (cp) lp = m_sign(p) * C::d85;
   else lr = m_sign(r) * C::d85;
-  Quat<T> lim = euler2quat(lr, lp, ly);
+  Quat<T> lim = euler2quat_cold(lr, lp, ly);
   out.w = lim.w; out.x = lim.x; out.y = lim.y; out.z = lim.z; out.fired = true;
   return out;
 }

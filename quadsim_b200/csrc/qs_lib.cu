@@ -607,6 +607,32 @@ __global__ void fn_kernel(int fn, int64_t n, const T* in0, const T* in1, const T
   }
 }
 
+// Runner._run's GAE loop, rl_baselines/ppo2/ppo2.py:511-521.  numpy's promotion rules make the reference evaluate it as:
+// gamma*nextvalues in float32 (python scalar x float32 array), everything after that in float64 (nextnonterminal =
+// 1.0 - bool array is float64), advs stored as float32, returns = advs + values in float32.  Mirrored exactly.
+__global__ void __launch_bounds__(256) gae_kernel(int64_t T, int64_t n, const float* __restrict__ rew, const float* __restrict__ val,
+                                                  const uint8_t* __restrict__ dones, const float* __restrict__ last_val,
+                                                  const uint8_t* __restrict__ last_done, double gamma, double lam,
+                                                  float* __restrict__ adv, float* __restrict__ ret) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double nextnonterminal = 1.0 - (double)last_done[i];
+  float nextvalues = last_val[i];
+  double lastgaelam = 0.0;
+  const double gl = gamma * lam;
+  const float gf = (float)gamma;
+  for (int64_t t = T - 1; t >= 0; t--) {
+    const float v = val[t * n + i];
+    const double delta = __dadd_rn(__dadd_rn((double)rew[t * n + i], __dmul_rn((double)__fmul_rn(gf, nextvalues), nextnonterminal)), -(double)v);
+    lastgaelam = __dadd_rn(delta, __dmul_rn(__dmul_rn(gl, nextnonterminal), lastgaelam));
+    const float a = (float)lastgaelam;
+    adv[t * n + i] = a;
+    ret[t * n + i] = __fadd_rn(a, v);
+    nextnonterminal = 1.0 - (double)dones[t * n + i];
+    nextvalues = v;
+  }
+}
+
 __global__ void philox_kernel(int64_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -890,6 +916,15 @@ int qs_fn_apply(int fn, int dtype, int64_t n, const void* in0, const void* in1, 
   else if (dtype == QS_F32) fn_kernel<float><<<grid, 128, 0, st>>>(fn, n, (const float*)in0, (const float*)in1, (const float*)in2, (float*)out0, (float*)out1);
   else if (dtype == QS_F64) fn_kernel<double><<<grid, 128, 0, st>>>(fn, n, (const double*)in0, (const double*)in1, (const double*)in2, (double*)out0, (double*)out1);
   else return fail(QS_ERR_INVALID, "qs_fn_apply: unknown dtype %d", dtype);
+  QS_CUDA(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_gae(int64_t T, int64_t n, const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+           const uint8_t* last_dones, double gamma, double lam, float* advs_out, float* returns_out, void* stream) {
+  if (T <= 0 || n <= 0) return fail(QS_ERR_INVALID, "qs_gae: n_steps and n_envs must be positive");
+  if (!rewards || !values || !dones || !last_values || !last_dones || !advs_out || !returns_out) return fail(QS_ERR_INVALID, "qs_gae: null argument");
+  gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, n, rewards, values, dones, last_values, last_dones, gamma, lam, advs_out, returns_out);
   QS_CUDA(cudaGetLastError());
   return QS_OK;
 }

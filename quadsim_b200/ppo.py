@@ -1,0 +1,256 @@
+"""Device-resident PPO2 around the CUDA environments (BASELINE config 5).
+
+The reference trains with stable-baselines' PPO2 (`run_moving_docking_ppo2.py:88-104`; in-tree fork
+`rl_baselines/ppo2/ppo2.py`): a numpy `Runner` that round-trips observations/actions through host memory every step
+(`ppo2.py:471-498`), GAE in a python loop (`:511-521`) and a TF1 graph for the clipped-surrogate loss (`:138-189`).  Here
+observations, actions, rewards, dones, values and advantages never leave the GPU: the env step is the fused CUDA kernel, GAE
+is `qs_gae` (one thread per env), the policy MLP and its update use torch (library GEMMs + autograd: this is the *caller* of
+the hot path, not the hot path).  Hyper-parameter defaults are the reference's.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _capi
+from .sb_zip import load_sb_zip, save_sb_zip
+
+
+def _ortho_(linear, scale):
+    nn.init.orthogonal_(linear.weight, gain=scale)  # SB `linear(..., init_scale)`: orthogonal weights, zero bias
+    nn.init.zeros_(linear.bias)
+
+
+class MlpPolicy(nn.Module):
+    """MlpPolicy with net_arch=[128, dict(pi=[128], vf=[128])], act_fun=relu (run_moving_docking_ppo2.py:90-91), diagonal
+    Gaussian actions with a state-independent log-std.  Parameter names follow the SB archive (sb_zip.py)."""
+
+    def __init__(self, obs_dim=12, act_dim=4, hidden=128):
+        super().__init__()
+        self.shared_fc0 = nn.Linear(obs_dim, hidden)
+        self.pi_fc0 = nn.Linear(hidden, hidden)
+        self.vf_fc0 = nn.Linear(hidden, hidden)
+        self.pi = nn.Linear(hidden, act_dim)
+        self.vf = nn.Linear(hidden, 1)
+        self.q = nn.Linear(hidden, act_dim)  # SB creates it from the vf latent; unused for Gaussian policies, kept for round trips
+        self.logstd = nn.Parameter(torch.zeros(1, act_dim))
+        for lin in (self.shared_fc0, self.pi_fc0, self.vf_fc0):
+            _ortho_(lin, math.sqrt(2))
+        _ortho_(self.pi, 0.01)
+        _ortho_(self.vf, 1.0)
+        _ortho_(self.q, 0.01)
+
+    def forward(self, obs):
+        h = torch.relu(self.shared_fc0(obs))
+        mean = self.pi(torch.relu(self.pi_fc0(h)))
+        value = self.vf(torch.relu(self.vf_fc0(h))).squeeze(-1)
+        return mean, value
+
+    def neglogp(self, mean, actions):
+        # DiagGaussianProbabilityDistribution.neglogp (stable-baselines common/distributions.py)
+        std = torch.exp(self.logstd)
+        return 0.5 * (((actions - mean) / std) ** 2).sum(-1) + 0.5 * math.log(2.0 * math.pi) * actions.shape[-1] + self.logstd.sum()
+
+    def entropy(self):
+        return (self.logstd + 0.5 * math.log(2.0 * math.pi * math.e)).sum()
+
+    @torch.no_grad()
+    def step(self, obs, deterministic=False, generator=None):
+        """model.step: -> actions (unclipped), values, neglogp   (ppo2.py:472)"""
+        mean, value = self.forward(obs)
+        if deterministic:
+            actions = mean
+        else:
+            noise = torch.randn(mean.shape, device=mean.device, dtype=mean.dtype, generator=generator)
+            actions = mean + torch.exp(self.logstd) * noise
+        return actions, value, self.neglogp(mean, actions)
+
+    @torch.no_grad()
+    def predict(self, obs, deterministic=True):
+        """model.predict as the replay scripts use it (run_trained_moving_docking_ppo2.py:46): clipped to the action Box."""
+        return self.step(obs, deterministic=deterministic)[0].clamp(-1.0, 1.0)
+
+    # ---- stable-baselines archive
+    _MAP = (("shared_fc0", "model/shared_fc0"), ("pi_fc0", "model/pi_fc0"), ("vf_fc0", "model/vf_fc0"), ("vf", "model/vf"),
+            ("pi", "model/pi"), ("q", "model/q"))
+
+    def load_sb_params(self, params):
+        with torch.no_grad():
+            for attr, name in self._MAP:
+                lin = getattr(self, attr)
+                if name + "/w:0" in params:
+                    lin.weight.copy_(torch.as_tensor(np.asarray(params[name + "/w:0"])).t())
+                    lin.bias.copy_(torch.as_tensor(np.asarray(params[name + "/b:0"])))
+            if "model/pi/logstd:0" in params:
+                self.logstd.copy_(torch.as_tensor(np.asarray(params["model/pi/logstd:0"])))
+        return self
+
+    def sb_params(self):
+        from collections import OrderedDict
+        out = OrderedDict()
+        for attr, name in self._MAP[:5]:
+            lin = getattr(self, attr)
+            out[name + "/w:0"] = lin.weight.detach().t().cpu().numpy().copy()
+            out[name + "/b:0"] = lin.bias.detach().cpu().numpy().copy()
+        out["model/pi/logstd:0"] = self.logstd.detach().cpu().numpy().copy()
+        out["model/q/w:0"] = self.q.weight.detach().t().cpu().numpy().copy()
+        out["model/q/b:0"] = self.q.bias.detach().cpu().numpy().copy()
+        return out
+
+    @classmethod
+    def from_sb_zip(cls, path, device=None):
+        _, params = load_sb_zip(path)
+        w = params["model/shared_fc0/w:0"]
+        pol = cls(obs_dim=w.shape[0], act_dim=params["model/pi/w:0"].shape[1], hidden=w.shape[1]).load_sb_params(params)
+        return pol.to(device) if device is not None else pol
+
+    def save_sb_zip(self, path, data=None):
+        return save_sb_zip(path, self.sb_params(), data)
+
+
+def gae(rewards, values, dones, last_values, last_dones, gamma, lam):
+    """qs_gae: Runner._run's advantage loop (ppo2.py:511-521) on [T,N] float32 CUDA tensors -> (advs, returns)."""
+    T, n = rewards.shape
+    r, v = rewards.contiguous(), values.contiguous()
+    d = dones.to(torch.uint8).contiguous()
+    lv, ld = last_values.contiguous(), last_dones.to(torch.uint8).contiguous()
+    for t in (r, v, lv):
+        if t.dtype != torch.float32 or not t.is_cuda:
+            raise ValueError("gae needs float32 CUDA tensors")
+    adv, ret = torch.empty_like(r), torch.empty_like(r)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    with torch.cuda.device(r.device):
+        st = C.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)
+        _capi.check(_capi.load().qs_gae(T, n, p(r), p(v), p(d), p(lv), p(ld), float(gamma), float(lam), p(adv), p(ret), st))
+    return adv, ret
+
+
+class DeviceRunner:
+    """Runner (ppo2.py:453-527) with every buffer resident on the GPU, time-major [T, N, ...]."""
+
+    def __init__(self, env, policy, n_steps, gamma=0.99, lam=0.95, reset_each_rollout=False, generator=None):
+        self.env, self.policy, self.n_steps, self.gamma, self.lam = env, policy, int(n_steps), gamma, lam
+        self.reset_each_rollout = reset_each_rollout  # the in-tree fork's `self.obs = self.env.reset()` (ppo2.py:525)
+        self.generator = generator
+        n, dev = env.num_envs, env.device
+        T = self.n_steps
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.mb_obs = torch.empty((T, n, env.obs_dim), **f32)
+        self.mb_actions = torch.empty((T, n, 4), **f32)
+        self.mb_values = torch.empty((T, n), **f32)
+        self.mb_neglogp = torch.empty((T, n), **f32)
+        self.mb_rewards = torch.empty((T, n), **f32)
+        self.mb_dones = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        self.obs = env.reset().float()
+        self.dones = torch.zeros(n, dtype=torch.uint8, device=dev)
+
+    @torch.no_grad()
+    def run(self):
+        env, pol = self.env, self.policy
+        for t in range(self.n_steps):
+            actions, values, neglogp = pol.step(self.obs, generator=self.generator)
+            self.mb_obs[t], self.mb_actions[t], self.mb_values[t], self.mb_neglogp[t] = self.obs, actions, values, neglogp
+            self.mb_dones[t] = self.dones
+            clipped = actions.clamp(-1.0, 1.0).to(env.dtype)  # np.clip to the action Box, ppo2.py:478-481
+            obs, rew, done, _ = env.step(clipped)
+            self.obs = obs.float()
+            self.dones = done.to(torch.uint8)
+            self.mb_rewards[t] = rew.float()
+        last_values = pol.forward(self.obs)[1]
+        advs, returns = gae(self.mb_rewards, self.mb_values, self.mb_dones, last_values, self.dones, self.gamma, self.lam)
+        if self.reset_each_rollout:
+            self.obs = env.reset().float()
+        flat = lambda x: x.reshape((-1,) + tuple(x.shape[2:]))  # time-major flatten; minibatches are shuffled anyway
+        return dict(obs=flat(self.mb_obs), returns=flat(returns), actions=flat(self.mb_actions), values=flat(self.mb_values),
+                    neglogp=flat(self.mb_neglogp), advs=flat(advs), rewards=self.mb_rewards)
+
+
+class PPO2:
+    """PPO2 with the reference's settings (run_moving_docking_ppo2.py:88-104): n_steps=600, nminibatches=10, noptepochs=10,
+    lr=3e-4, gamma=.99, lam=.95, cliprange=.2, ent_coef=0, vf_coef=.5, max_grad_norm=.5, Adam(eps=1e-5).  Loss: ppo2.py:138-189."""
+
+    def __init__(self, env, policy=None, n_steps=600, nminibatches=10, noptepochs=10, learning_rate=3e-4, gamma=0.99, lam=0.95,
+                 cliprange=0.2, cliprange_vf=None, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, seed=0, reset_each_rollout=False):
+        self.env = env
+        self.device = env.device
+        torch.manual_seed(seed)
+        self.policy = (policy if policy is not None else MlpPolicy(env.obs_dim, 4)).to(self.device)
+        self.gen = torch.Generator(device=self.device).manual_seed(seed)
+        self.runner = DeviceRunner(env, self.policy, n_steps, gamma, lam, reset_each_rollout, self.gen)
+        self.nminibatches, self.noptepochs = nminibatches, noptepochs
+        self.cliprange, self.ent_coef, self.vf_coef, self.max_grad_norm = cliprange, ent_coef, vf_coef, max_grad_norm
+        self.cliprange_vf = cliprange if cliprange_vf is None else cliprange_vf  # legacy default: same as the policy's (ppo2.py:152-156)
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5)
+        self.num_timesteps = 0
+        self.dist = torch.distributed.is_available() and torch.distributed.is_initialized()
+        if self.dist:  # every rank starts from rank 0's weights
+            for p in self.policy.parameters():
+                torch.distributed.broadcast(p.data, 0)
+
+    def loss(self, mb):
+        mean, vpred = self.policy.forward(mb["obs"])
+        neglogp = self.policy.neglogp(mean, mb["actions"])
+        advs = mb["returns"] - mb["values"]
+        advs = (advs - advs.mean()) / (advs.std(unbiased=False) + 1e-8)  # ppo2.py:265-266 (numpy population std)
+        old_v, ret = mb["values"], mb["returns"]
+        if self.cliprange_vf is not None and self.cliprange_vf >= 0:
+            vclip = old_v + torch.clamp(vpred - old_v, -self.cliprange_vf, self.cliprange_vf)
+        else:
+            vclip = vpred
+        vf_loss = 0.5 * torch.maximum((vpred - ret) ** 2, (vclip - ret) ** 2).mean()
+        ratio = torch.exp(mb["neglogp"] - neglogp)
+        pg_loss = torch.maximum(-advs * ratio, -advs * torch.clamp(ratio, 1.0 - self.cliprange, 1.0 + self.cliprange)).mean()
+        entropy = self.policy.entropy()
+        total = pg_loss - entropy * self.ent_coef + vf_loss * self.vf_coef
+        with torch.no_grad():
+            approxkl = 0.5 * ((neglogp - mb["neglogp"]) ** 2).mean()
+            clipfrac = ((ratio - 1.0).abs() > self.cliprange).float().mean()
+        return total, dict(pg_loss=pg_loss.detach(), vf_loss=vf_loss.detach(), entropy=entropy.detach(), approxkl=approxkl, clipfrac=clipfrac)
+
+    def update(self, batch):
+        n_batch = batch["obs"].shape[0]
+        mb_size = n_batch // self.nminibatches
+        keys = ("obs", "returns", "actions", "values", "neglogp")
+        logs = []
+        for _ in range(self.noptepochs):
+            perm = torch.randperm(n_batch, device=self.device, generator=self.gen)
+            for start in range(0, mb_size * self.nminibatches, mb_size):
+                idx = perm[start:start + mb_size]
+                mb = {k: batch[k][idx] for k in keys}
+                total, log = self.loss(mb)
+                self.opt.zero_grad(set_to_none=True)
+                total.backward()
+                if self.dist:
+                    world = torch.distributed.get_world_size()
+                    for p in self.policy.parameters():
+                        if p.grad is not None:
+                            torch.distributed.all_reduce(p.grad)
+                            p.grad /= world
+                if self.max_grad_norm is not None:
+                    nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)  # tf.clip_by_global_norm
+                self.opt.step()
+                logs.append(log)
+        return {k: float(torch.stack([l[k] for l in logs]).mean()) for k in logs[0]}
+
+    def learn(self, total_timesteps, log_fn=None):
+        n_batch = self.env.num_envs * self.runner.n_steps
+        n_updates = max(int(total_timesteps) // n_batch, 1)
+        history = []
+        for upd in range(1, n_updates + 1):
+            batch = self.runner.run()
+            log = self.update(batch)
+            self.num_timesteps += n_batch
+            log.update(update=upd, timesteps=self.num_timesteps, mean_step_reward=float(batch["rewards"].mean()))
+            log.update({"ep_" + k: v for k, v in self.env.stats(all_reduce=self.dist).items() if k in ("mean_return", "mean_length", "episodes", "docked_steps")})
+            history.append(log)
+            if log_fn:
+                log_fn(log)
+        return history
+
+    def save(self, path):
+        data = dict(gamma=self.runner.gamma, lam=self.runner.lam, n_steps=self.runner.n_steps, nminibatches=self.nminibatches,
+                    noptepochs=self.noptepochs, cliprange=self.cliprange, ent_coef=self.ent_coef, vf_coef=self.vf_coef,
+                    max_grad_norm=self.max_grad_norm, n_envs=self.env.num_envs)
+        return self.policy.save_sb_zip(path, data)

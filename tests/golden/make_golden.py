@@ -19,6 +19,8 @@ Fixtures
                         branches), recorded as an action tape
   dock_v{0,2}_wild.npz  single steps from injected wild states (clamp branches, non-unit quaternions, t=599)
   hover_rand.npz     hovering-v0, random actions, auto-reset, Philox-sampled per-env init (once per env)
+  policy_v0.npz      weights of the shipped policy best_model_v0.zip + its numpy forward on tape observations
+  gae_numpy.npz      the GAE loop of Runner._run (ppo2.py:511-521) transcribed and run by numpy on float32 buffers
 """
 import io
 import json
@@ -377,6 +379,53 @@ def gen_hover_rand(K=2, T=1000, seed=99, env_id0=3):
     return rec
 
 
+def gen_gae_numpy():
+    """The GAE loop of Runner._run (rl_baselines/ppo2/ppo2.py:503-521) transcribed statement by statement and run by numpy
+    on float32 buffers with python-float gamma/lam, exactly as the reference holds them (stable-baselines/TensorFlow are not
+    installed, so Runner itself cannot run; this loop has no other dependency)."""
+    rng = np.random.RandomState(11)
+    n_steps, n = 64, 96
+    mb_rewards = rng.normal(size=(n_steps, n)).astype(np.float32)
+    mb_values = rng.normal(size=(n_steps, n)).astype(np.float32)
+    mb_dones = rng.rand(n_steps, n) < 0.08
+    last_values = rng.normal(size=n).astype(np.float32)
+    dones = rng.rand(n) < 0.08
+    gamma, lam = 0.99, 0.95  # run_moving_docking_ppo2.py:88-104
+    mb_advs = np.zeros_like(mb_rewards)
+    last_gae_lam = 0
+    for step in reversed(range(n_steps)):
+        if step == n_steps - 1:
+            nextnonterminal = 1.0 - dones
+            nextvalues = last_values
+        else:
+            nextnonterminal = 1.0 - mb_dones[step + 1]
+            nextvalues = mb_values[step + 1]
+        delta = mb_rewards[step] + gamma * nextvalues * nextnonterminal - mb_values[step]
+        mb_advs[step] = last_gae_lam = delta + gamma * lam * nextnonterminal * last_gae_lam
+    mb_returns = mb_advs + mb_values
+    return dict(rew=mb_rewards, val=mb_values, dones=mb_dones, last_val=last_values, last_d=dones, gamma=gamma, lam=lam,
+                adv=mb_advs, ret=mb_returns)
+
+
+def gen_policy_v0():
+    """Weights of the reference's shipped policy trained_model/best_model_v0.zip (a stable-baselines PPO2 archive) and its
+    deterministic actions on the first 64 observations of the docked tape, computed with plain numpy float32."""
+    z = zipfile.ZipFile(os.path.join(ref_shim.REF_ROOT, "trained_model", "best_model_v0.zip"))
+    p = np.load(io.BytesIO(z.read("parameters")))
+    order = json.loads(z.read("parameter_list").decode())
+    rec = {"param_order": np.array(order)}
+    for k in order:
+        rec["param::" + k] = p[k]
+    tape = np.load(os.path.join(HERE, "dock_v0_docked.npz"))
+    obs = np.concatenate([tape["obs0"], tape["obs"][0, :63]]).astype(np.float32)
+    W = {k: p[k].astype(np.float32) for k in p.files}
+    h = np.maximum(obs @ W["model/shared_fc0/w:0"] + W["model/shared_fc0/b:0"], 0)
+    hp = np.maximum(h @ W["model/pi_fc0/w:0"] + W["model/pi_fc0/b:0"], 0)
+    hv = np.maximum(h @ W["model/vf_fc0/w:0"] + W["model/vf_fc0/b:0"], 0)
+    rec["obs"], rec["mean"], rec["value"] = obs, hp @ W["model/pi/w:0"] + W["model/pi/b:0"], (hv @ W["model/vf/w:0"] + W["model/vf/b:0"])[:, 0]
+    return rec
+
+
 def main():
     np.random.seed(0)  # HoveringEnv.__init__ draws from the global RNG (hovering_env.py:23-24); overwritten anyway
     jobs = {
@@ -390,6 +439,8 @@ def main():
         "dock_v0_wild": lambda: gen_dock_wild(0),
         "dock_v2_wild": lambda: gen_dock_wild(1),
         "hover_rand": gen_hover_rand,
+        "gae_numpy": gen_gae_numpy,
+        "policy_v0": gen_policy_v0,
     }
     only = sys.argv[1:]
     for name, fn in jobs.items():

@@ -1,0 +1,100 @@
+"""GPU checks of the device-resident PPO2 pieces around the CUDA env (BASELINE config 5): the GAE kernel
+(bit-exact against the reference loop and the oracle), the shipped policy flying batched docking-v0 into the docked regime,
+rollout bookkeeping, and a short learn() run."""
+import numpy as np
+import pytest
+import torch
+
+from qs_testutil import load_golden
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import quadsim_b200 as qs
+    from quadsim_b200 import ppo
+    from oracle import oracle as O
+
+
+def test_gae_kernel_bit_exact():
+    g = load_golden("gae_numpy")
+    dev = "cuda"
+    adv, ret = ppo.gae(torch.as_tensor(g["rew"], device=dev), torch.as_tensor(g["val"], device=dev),
+                       torch.as_tensor(g["dones"], device=dev), torch.as_tensor(g["last_val"], device=dev),
+                       torch.as_tensor(g["last_d"], device=dev), float(g["gamma"]), float(g["lam"]))
+    assert np.array_equal(adv.cpu().numpy(), g["adv"]) and np.array_equal(ret.cpu().numpy(), g["ret"])
+    # larger, ragged, vs the oracle
+    rng = np.random.RandomState(0)
+    T, n = 96, 10007
+    rew, val = rng.normal(size=(T, n)).astype(np.float32), rng.normal(size=(T, n)).astype(np.float32)
+    dones, lv, ld = rng.rand(T, n) < 0.02, rng.normal(size=n).astype(np.float32), rng.rand(n) < 0.02
+    a_ref, r_ref = O.gae(rew, val, dones, lv, ld, 0.99, 0.95)
+    adv, ret = ppo.gae(*[torch.as_tensor(x, device=dev) for x in (rew, val, dones, lv, ld)], 0.99, 0.95)
+    assert np.array_equal(adv.cpu().numpy(), a_ref) and np.array_equal(ret.cpu().numpy(), r_ref)
+
+
+def _shipped_policy():
+    g = load_golden("policy_v0")
+    return ppo.MlpPolicy().load_sb_params({k: g["param::" + k] for k in g["param_order"]}).cuda()
+
+
+def test_shipped_policy_docks_batched_env():
+    """The reference's trained policy (trained_model/best_model_v0.zip) on the CUDA docking-v0: the reference run docks on
+    183 of 600 steps and ends by overtime with return ~0.71.  GPU matmul rounding differs from numpy's, so
+    the closed loop is compared statistically, and a jittered batch must stay in the same regime."""
+    pol = _shipped_policy()
+    n = 512
+    env = qs.make_vec("docking-v0", n, dtype=torch.float64, seed=4, randomize="episode", half_width=0.05)
+    st = env.get_state()
+    st["chaser"][0, :3] = torch.tensor([8.0, -50.0, 5.0], dtype=torch.float64)  # env 0: the reference's exact start
+    env.set_state(st)
+    obs = env.reset()
+    docked = torch.zeros(n, device="cuda")
+    ret = torch.zeros(n, dtype=torch.float64, device="cuda")
+    for t in range(600):
+        obs, rew, done, info = env.step(pol.predict(obs.float()).double())
+        docked += info.flag_docking
+        ret += rew
+        if t < 599:
+            assert not bool(done.any()), t
+    assert bool(done.all()) and bool(info.done_overtime.all())
+    assert 150 <= float(docked[0]) <= 215 and abs(float(ret[0]) - 0.707) < 0.15, (float(docked[0]), float(ret[0]))
+    assert float((docked > 100).float().mean()) > 0.9
+    s = env.stats()
+    assert s["episodes"] == n and s["mean_length"] == 600 and s["docked_steps"] == float(docked.sum())
+    assert abs(s["mean_return"] - float(ret.mean())) < 1e-9
+    env.close()
+
+
+def test_runner_bookkeeping_and_gae_vs_oracle():
+    n, T = 1024, 48
+    env = qs.make_vec("docking-v2", n, seed=2, randomize="episode")
+    torch.manual_seed(0)
+    pol = ppo.MlpPolicy().cuda()
+    with torch.no_grad():
+        pol.logstd.fill_(0.5)  # noisy actions -> some episodes end inside the rollout
+    runner = ppo.DeviceRunner(env, pol, T)
+    b1 = runner.run()
+    b2 = runner.run()  # continues from where the first rollout stopped (stock SB; the in-tree fork resets instead)
+    assert b2["obs"].shape == (T * n, 12) and b2["actions"].shape == (T * n, 4)
+    assert torch.equal(runner.mb_dones[0], (b1["rewards"][-1] * 0).to(torch.uint8) + runner.mb_dones[0])  # uint8 flags
+    a_ref, r_ref = O.gae(runner.mb_rewards.cpu().numpy(), runner.mb_values.cpu().numpy(), runner.mb_dones.cpu().numpy(),
+                         pol.forward(runner.obs)[1].detach().cpu().numpy(), runner.dones.cpu().numpy(), 0.99, 0.95)
+    assert np.array_equal(b2["advs"].view(T, n).cpu().numpy(), a_ref)
+    assert np.array_equal(b2["returns"].view(T, n).cpu().numpy(), r_ref)
+    assert int(runner.mb_dones.sum()) > 0
+    env.close()
+
+
+def test_ppo2_learn_runs_and_updates():
+    n = 2048
+    env = qs.make_vec("docking-v2", n, seed=3, randomize="episode")
+    algo = ppo.PPO2(env, n_steps=32, nminibatches=4, noptepochs=2, seed=1)
+    before = [p.detach().clone() for p in algo.policy.parameters()]
+    hist = algo.learn(3 * n * 32)
+    assert len(hist) == 3
+    for h in hist:
+        assert all(np.isfinite(v) for k, v in h.items() if k not in ("ep_mean_return", "ep_mean_length")), h
+        assert h["approxkl"] < 0.05 and 0 <= h["clipfrac"] <= 1
+    assert any(not torch.equal(a, b) for a, b in zip(before, algo.policy.parameters()))
+    assert hist[-1]["vf_loss"] < hist[0]["vf_loss"]  # the value head fits the (large, negative) shaped returns
+    env.close()

@@ -166,3 +166,11 @@ def test_hover_tape():
         close(term, g["state"][:, t], 1e-9)
         close(rew, g["reward"][:, t], 1e-9)
     assert g["done"].sum() >= 4
+
+
+def test_gae_matches_reference_loop_bit_exact():
+    """Runner._run's GAE loop (rl_baselines/ppo2/ppo2.py:511-521), including numpy's float32/float64 promotion."""
+    g = load_golden("gae_numpy")
+    adv, ret = O.gae(g["rew"], g["val"], g["dones"], g["last_val"], g["last_d"], float(g["gamma"]), float(g["lam"]))
+    assert np.array_equal(adv, g["adv"]) and np.array_equal(ret, g["ret"])
+    assert adv.dtype == np.float32 and g["ret"].dtype == np.float32

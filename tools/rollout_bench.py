@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""BASELINE config 5 measurement: PPO2 rollout-in-the-loop on device-resident tensors (policy forward + env step + GAE) and
+one optimisation pass, at N envs per GPU.  Prints one JSON line.
+
+    python tools/rollout_bench.py [--n 1048576] [--n-steps 16] [--rollouts 5] [--amp]
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import quadsim_b200 as qs
+from quadsim_b200 import ppo
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=1 << 20)
+ap.add_argument("--n-steps", type=int, default=16)
+ap.add_argument("--rollouts", type=int, default=5)
+ap.add_argument("--tf32", action="store_true")
+args = ap.parse_args()
+torch.backends.cuda.matmul.allow_tf32 = args.tf32
+env = qs.make_vec("docking-v2", args.n, seed=0, randomize="episode", want_info=False, reuse_buffers=True)
+algo = ppo.PPO2(env, n_steps=args.n_steps, nminibatches=10, noptepochs=1)
+algo.runner.run()
+torch.cuda.synchronize()
+e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+e0.record()
+for _ in range(args.rollouts):
+    batch = algo.runner.run()
+e1.record()
+log = algo.update(batch)
+e2.record()
+torch.cuda.synchronize()
+steps = args.n * args.n_steps
+t_roll = e0.elapsed_time(e1) / args.rollouts
+t_upd = e1.elapsed_time(e2)
+print(json.dumps({"config": "PPO2 docking-v2 rollout-in-the-loop", "envs": args.n, "n_steps": args.n_steps, "tf32": args.tf32,
+                  "rollout_ms": t_roll, "rollout_env_steps_per_s": steps / (t_roll * 1e-3),
+                  "ms_per_env_step_launch": t_roll / args.n_steps, "update_ms_1epoch_10minibatches": t_upd,
+                  "update_samples_per_s": steps / (t_upd * 1e-3), "log": log,
+                  "gpu_mem_GB": torch.cuda.max_memory_allocated() / 1e9}))
