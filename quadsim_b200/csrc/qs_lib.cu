@@ -522,11 +522,13 @@ __global__ void __launch_bounds__(kBlock) state_io_kernel(void* state, int64_t s
   if (IMPORT) store_words<T, NW>(state, i, w);
 }
 
-// statistics: fixed-order reduction of the per-warp slots, then clear them
-__global__ void __launch_bounds__(1024) stats_reduce_kernel(double* warp_stats, int64_t n_slots, double* out) {
-  __shared__ double sm[5][1024];
+// statistics: fixed-order two-phase reduction of the per-warp slots (then cleared): kStatBlocks partial sums, then one
+// block adds the partials in index order -- bit-reproducible whatever the launch geometry of the step kernels was
+constexpr int kStatBlocks = 64;
+__global__ void __launch_bounds__(256) stats_partial_kernel(double* warp_stats, int64_t n_slots, double* partial) {
+  __shared__ double sm[5][256];
   double acc[5] = {0, 0, 0, 0, 0};
-  for (int64_t s = threadIdx.x; s < n_slots; s += 1024) {
+  for (int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x; s < n_slots; s += (int64_t)kStatBlocks * 256) {
     double* p = warp_stats + s * kStatWords;
 #pragma unroll
     for (int k = 0; k < 5; k++) { acc[k] += p[k]; p[k] = 0.0; }
@@ -534,14 +536,21 @@ __global__ void __launch_bounds__(1024) stats_reduce_kernel(double* warp_stats, 
 #pragma unroll
   for (int k = 0; k < 5; k++) sm[k][threadIdx.x] = acc[k];
   __syncthreads();
-  for (int off = 512; off > 0; off >>= 1) {
+  for (int off = 128; off > 0; off >>= 1) {
     if ((int)threadIdx.x < off) {
 #pragma unroll
       for (int k = 0; k < 5; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + off];
     }
     __syncthreads();
   }
-  if (threadIdx.x < 5) out[threadIdx.x] = sm[threadIdx.x][0];
+  if (threadIdx.x < 5) partial[blockIdx.x * 8 + threadIdx.x] = sm[threadIdx.x][0];
+}
+__global__ void stats_final_kernel(const double* partial, double* out) {
+  if (threadIdx.x < 5) {
+    double a = 0.0;
+    for (int b = 0; b < kStatBlocks; b++) a += partial[b * 8 + threadIdx.x];
+    out[threadIdx.x] = a;
+  }
 }
 
 // =========================================================================================================
@@ -763,7 +772,7 @@ int qs_create(qs_env_t** out, const qs_config_t* cfg) {
   cudaError_t err;
   if ((err = cudaMalloc(&e->state, (size_t)e->n_rows * e->stride * 16)) != cudaSuccess ||
       (err = cudaMalloc(&e->warp_stats, (size_t)e->n_slots * kStatWords * sizeof(double))) != cudaSuccess ||
-      (err = cudaMalloc(&e->stats_dev, 8 * sizeof(double))) != cudaSuccess ||
+      (err = cudaMalloc(&e->stats_dev, (8 + 8 * kStatBlocks) * sizeof(double))) != cudaSuccess ||
       (err = cudaMallocHost(&e->stats_host, 8 * sizeof(double))) != cudaSuccess ||
       (err = cudaMemset(e->state, 0, (size_t)e->n_rows * e->stride * 16)) != cudaSuccess ||
       (err = cudaMemset(e->warp_stats, 0, (size_t)e->n_slots * kStatWords * sizeof(double))) != cudaSuccess) {
@@ -895,7 +904,8 @@ int qs_get_stats(qs_env_t* e, double stats[5], void* stream) {
   if (!e || !stats) return fail(QS_ERR_INVALID, "qs_get_stats: null argument");
   DeviceGuard g(e->cfg.device);
   cudaStream_t st = (cudaStream_t)stream;
-  stats_reduce_kernel<<<1, 1024, 0, st>>>(e->warp_stats, e->n_slots, e->stats_dev);
+  stats_partial_kernel<<<kStatBlocks, 256, 0, st>>>(e->warp_stats, e->n_slots, e->stats_dev + 8);
+  stats_final_kernel<<<1, 32, 0, st>>>(e->stats_dev + 8, e->stats_dev);
   QS_CUDA(cudaGetLastError());
   QS_CUDA(cudaMemcpyAsync(e->stats_host, e->stats_dev, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
   QS_CUDA(cudaStreamSynchronize(st));

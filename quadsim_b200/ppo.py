@@ -44,8 +44,8 @@ class MlpPolicy(nn.Module):
 
     def forward(self, obs):
         h = torch.relu(self.shared_fc0(obs))
-        mean = self.pi(torch.relu(self.pi_fc0(h)))
-        value = self.vf(torch.relu(self.vf_fc0(h))).squeeze(-1)
+        mean = self.pi(torch.relu(self.pi_fc0(h))).float()  # .float(): no-ops in fp32, widen under bf16 autocast
+        value = self.vf(torch.relu(self.vf_fc0(h))).squeeze(-1).float()
         return mean, value
 
     def neglogp(self, mean, actions):

@@ -19,6 +19,7 @@ ap.add_argument("--n", type=int, default=1 << 20)
 ap.add_argument("--n-steps", type=int, default=16)
 ap.add_argument("--rollouts", type=int, default=5)
 ap.add_argument("--tf32", action="store_true")
+ap.add_argument("--bf16", action="store_true", help="bf16 autocast for the rollout forward (cuBLAS tensor cores)")
 args = ap.parse_args()
 torch.backends.cuda.matmul.allow_tf32 = args.tf32
 env = qs.make_vec("docking-v2", args.n, seed=0, randomize="episode", want_info=False, reuse_buffers=True)
@@ -27,8 +28,9 @@ algo.runner.run()
 torch.cuda.synchronize()
 e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 e0.record()
-for _ in range(args.rollouts):
-    batch = algo.runner.run()
+with torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.bf16):
+    for _ in range(args.rollouts):
+        batch = algo.runner.run()
 e1.record()
 log = algo.update(batch)
 e2.record()
@@ -36,7 +38,7 @@ torch.cuda.synchronize()
 steps = args.n * args.n_steps
 t_roll = e0.elapsed_time(e1) / args.rollouts
 t_upd = e1.elapsed_time(e2)
-print(json.dumps({"config": "PPO2 docking-v2 rollout-in-the-loop", "envs": args.n, "n_steps": args.n_steps, "tf32": args.tf32,
+print(json.dumps({"config": "PPO2 docking-v2 rollout-in-the-loop", "envs": args.n, "n_steps": args.n_steps, "tf32": args.tf32, "bf16_rollout": args.bf16,
                   "rollout_ms": t_roll, "rollout_env_steps_per_s": steps / (t_roll * 1e-3),
                   "ms_per_env_step_launch": t_roll / args.n_steps, "update_ms_1epoch_10minibatches": t_upd,
                   "update_samples_per_s": steps / (t_upd * 1e-3), "log": log,
