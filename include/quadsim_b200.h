@@ -155,6 +155,30 @@ int qs_gae(int64_t n_steps, int64_t n_envs, const float* rewards, const float* v
            const float* last_values, const uint8_t* last_dones, double gamma, double lam, float* advs_out,
            float* returns_out, void* stream);
 
+/* ---- fused policy forward (tcgen05 / TMEM), the caller side of BASELINE config 5 ------------------------------------
+ * model.step(obs) of the reference's PPO2 MlpPolicy (rl_baselines/ppo2/ppo2.py:472; architecture and hyper-parameters
+ * run_moving_docking_ppo2.py:88-91: 12 -> 128 relu -> {128 relu -> 4 Gaussian mean, 128 relu -> 1 value}, state-independent
+ * logstd).  Weights are float32 device pointers in torch.nn.Linear layout [out, in] (== the SB archive's [in, out] transposed). */
+typedef struct qs_policy qs_policy_t;
+typedef struct {
+  const float *shared_w, *shared_b;  /* [128,12], [128]   model/shared_fc0 */
+  const float *pi_fc_w, *pi_fc_b;    /* [128,128], [128]  model/pi_fc0 */
+  const float *vf_fc_w, *vf_fc_b;    /* [128,128], [128]  model/vf_fc0 */
+  const float *pi_w, *pi_b;          /* [4,128], [4]      model/pi */
+  const float *vf_w, *vf_b;          /* [1,128], [1]      model/vf */
+  const float *logstd;               /* [4]               model/pi/logstd */
+} qs_policy_weights_t;
+int qs_policy_create(qs_policy_t** out, int device);
+int qs_policy_destroy(qs_policy_t* p);
+/* Packs the weights into bf16 tensor-core operand images on the device; call again after every optimiser step. */
+int qs_policy_set_weights(qs_policy_t* p, const qs_policy_weights_t* w, void* stream);
+/* actions = mean + exp(logstd) * N(0,1) (noise: Philox4x32-10 keyed by seed, counter (env_id0 + i, step_idx, stream 2),
+ * Box-Muller), values, neglogp for obs[N,12]; clipped_out (nullable) = actions clamped to the action Box [-1,1]
+ * (ppo2.py:478-481).  deterministic != 0 returns the mean (model.predict(deterministic=True)). */
+int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, uint64_t env_id0, uint32_t step_idx,
+                   int deterministic, float* actions_out, float* clipped_out, float* values_out, float* neglogp_out,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

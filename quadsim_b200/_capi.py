@@ -19,7 +19,8 @@ ABI_VERSION = 1
 # every symbol include/quadsim_b200.h declares (tests check the built library exports all of them)
 SYMBOLS = ["qs_abi_version", "qs_last_error", "qs_create", "qs_destroy", "qs_obs_dim", "qs_num_envs", "qs_seed",
            "qs_reset", "qs_step", "qs_step_ex", "qs_step_host", "qs_host_alloc", "qs_host_free", "qs_export_state",
-           "qs_import_state", "qs_get_stats", "qs_fn_apply", "qs_gae"]
+           "qs_import_state", "qs_get_stats", "qs_fn_apply", "qs_gae", "qs_policy_create", "qs_policy_destroy",
+           "qs_policy_set_weights", "qs_policy_step"]
 
 
 class Config(C.Structure):
@@ -31,6 +32,11 @@ class Config(C.Structure):
 class StateArrays(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("chaser", "target", "u_chaser", "u_target", "des_q", "last_shaping",
                                           "ep_return", "t", "episode")]
+
+
+class PolicyWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("shared_w", "shared_b", "pi_fc_w", "pi_fc_b", "vf_fc_w", "vf_fc_b", "pi_w", "pi_b",
+                                          "vf_w", "vf_b", "logstd")]
 
 
 class QuadSimError(RuntimeError):
@@ -73,6 +79,10 @@ def load():
     L.qs_import_state.argtypes = [vp, C.POINTER(StateArrays), vp]
     L.qs_get_stats.argtypes = [vp, C.POINTER(C.c_double), vp]
     L.qs_fn_apply.argtypes = [C.c_int, C.c_int, i64, vp, vp, vp, vp, vp, vp]
+    L.qs_policy_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.qs_policy_destroy.argtypes = [vp]
+    L.qs_policy_set_weights.argtypes = [vp, C.POINTER(PolicyWeights), vp]
+    L.qs_policy_step.argtypes = [vp, i64, vp, u64, u64, C.c_uint32, C.c_int, vp, vp, vp, vp, vp]
     L.qs_gae.argtypes = [i64, i64, vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp]
     if L.qs_abi_version() != ABI_VERSION:
         raise QuadSimError("libquadsim_b200.so ABI %d != expected %d; rebuild" % (L.qs_abi_version(), ABI_VERSION))

@@ -49,6 +49,17 @@ int fail(int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(QS_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+}  // namespace
+// shared with qs_policy.cu: set the thread-local error string and return `code`
+int qs_fail_(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+namespace {
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = true;
