@@ -130,8 +130,9 @@ def gae(rewards, values, dones, last_values, last_dones, gamma, lam):
 class DeviceRunner:
     """Runner (ppo2.py:453-527) with every buffer resident on the GPU, time-major [T, N, ...]."""
 
-    def __init__(self, env, policy, n_steps, gamma=0.99, lam=0.95, reset_each_rollout=False, generator=None):
+    def __init__(self, env, policy, n_steps, gamma=0.99, lam=0.95, reset_each_rollout=False, generator=None, fused=None):
         self.env, self.policy, self.n_steps, self.gamma, self.lam = env, policy, int(n_steps), gamma, lam
+        self.fused = fused  # FusedPolicy (tcgen05 kernel) or None for the torch forward
         self.reset_each_rollout = reset_each_rollout  # the in-tree fork's `self.obs = self.env.reset()` (ppo2.py:525)
         self.generator = generator
         n, dev = env.num_envs, env.device
@@ -150,15 +151,19 @@ class DeviceRunner:
     def run(self):
         env, pol = self.env, self.policy
         for t in range(self.n_steps):
-            actions, values, neglogp = pol.step(self.obs, generator=self.generator)
+            if self.fused is not None:
+                actions, clipped, values, neglogp = self.fused.step(self.obs)
+                clipped = clipped.to(env.dtype)
+            else:
+                actions, values, neglogp = pol.step(self.obs, generator=self.generator)
+                clipped = actions.clamp(-1.0, 1.0).to(env.dtype)  # np.clip to the action Box, ppo2.py:478-481
             self.mb_obs[t], self.mb_actions[t], self.mb_values[t], self.mb_neglogp[t] = self.obs, actions, values, neglogp
             self.mb_dones[t] = self.dones
-            clipped = actions.clamp(-1.0, 1.0).to(env.dtype)  # np.clip to the action Box, ppo2.py:478-481
             obs, rew, done, _ = env.step(clipped)
             self.obs = obs.float()
             self.dones = done.to(torch.uint8)
             self.mb_rewards[t] = rew.float()
-        last_values = pol.forward(self.obs)[1]
+        last_values = self.fused.step(self.obs, deterministic=True, want_clipped=False)[2] if self.fused is not None else pol.forward(self.obs)[1]
         advs, returns = gae(self.mb_rewards, self.mb_values, self.mb_dones, last_values, self.dones, self.gamma, self.lam)
         if self.reset_each_rollout:
             self.obs = env.reset().float()
@@ -172,13 +177,18 @@ class PPO2:
     lr=3e-4, gamma=.99, lam=.95, cliprange=.2, ent_coef=0, vf_coef=.5, max_grad_norm=.5, Adam(eps=1e-5).  Loss: ppo2.py:138-189."""
 
     def __init__(self, env, policy=None, n_steps=600, nminibatches=10, noptepochs=10, learning_rate=3e-4, gamma=0.99, lam=0.95,
-                 cliprange=0.2, cliprange_vf=None, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, seed=0, reset_each_rollout=False):
+                 cliprange=0.2, cliprange_vf=None, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, seed=0, reset_each_rollout=False,
+                 fused_policy=False):
         self.env = env
         self.device = env.device
         torch.manual_seed(seed)
         self.policy = (policy if policy is not None else MlpPolicy(env.obs_dim, 4)).to(self.device)
         self.gen = torch.Generator(device=self.device).manual_seed(seed)
-        self.runner = DeviceRunner(env, self.policy, n_steps, gamma, lam, reset_each_rollout, self.gen)
+        self.fused = None
+        if fused_policy:
+            from .fused_policy import FusedPolicy
+            self.fused = FusedPolicy(self.policy, seed=seed, env_id0=getattr(env, "env_id0", 0))
+        self.runner = DeviceRunner(env, self.policy, n_steps, gamma, lam, reset_each_rollout, self.gen, fused=self.fused)
         self.nminibatches, self.noptepochs = nminibatches, noptepochs
         self.cliprange, self.ent_coef, self.vf_coef, self.max_grad_norm = cliprange, ent_coef, vf_coef, max_grad_norm
         self.cliprange_vf = cliprange if cliprange_vf is None else cliprange_vf  # legacy default: same as the policy's (ppo2.py:152-156)
@@ -232,6 +242,8 @@ class PPO2:
                     nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)  # tf.clip_by_global_norm
                 self.opt.step()
                 logs.append(log)
+        if self.fused is not None:
+            self.fused.sync_weights()  # re-pack the updated parameters into the tensor-core operand images
         return {k: float(torch.stack([l[k] for l in logs]).mean()) for k in logs[0]}
 
     def learn(self, total_timesteps, log_fn=None):
