@@ -95,6 +95,8 @@ int qs_destroy(qs_env_t* env);
 /* observation_space.shape[0]: 12 for docking (docking_env.py:85-95), 13 for hover (hovering_env.py:36-40). */
 int qs_obs_dim(const qs_env_t* env);
 int64_t qs_num_envs(const qs_env_t* env);
+int qs_env_dtype(const qs_env_t* env);       /* qs_dtype of the handle */
+uint64_t qs_env_id0(const qs_env_t* env);    /* global id of env 0 (qs_config_t.env_id0) */
 /* env.seed(seed)  (docking_env.py:252-254; the reference never reads it -- here it re-keys Philox). */
 int qs_seed(qs_env_t* env, uint64_t seed);
 
@@ -110,6 +112,11 @@ int qs_step(qs_env_t* env, const void* actions, void* obs_out, void* reward_out,
  * (the pre-reset observation, SB's info['terminal_observation']).  Either may be NULL. */
 int qs_step_ex(qs_env_t* env, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out,
                uint8_t* info_out, void* terminal_obs_out, void* stream);
+/* qs_step for the env slice [first, first + n) only (first: a multiple of 128).  Pointers are the FULL arrays' bases, as in
+ * qs_step.  Slices of one handle may be stepped concurrently on different streams (they share nothing); used by qs_rollout
+ * to overlap the HBM-bound env kernel of one slice with the tensor-core policy kernel of another. */
+int qs_step_range(qs_env_t* env, int64_t first, int64_t n, const void* actions, void* obs_out, void* reward_out,
+                  uint8_t* done_out, void* stream);
 /* Same step for HOST buffers (what a numpy VecEnv caller holds): copies actions in, steps, copies results out, chunked
  * over internal streams so H2D, kernel and D2H overlap.  Blocking.  Buffers should come from qs_host_alloc (pinned). */
 int qs_step_host(qs_env_t* env, const void* actions_host, void* obs_host, void* reward_host, uint8_t* done_host);
@@ -175,9 +182,32 @@ int qs_policy_set_weights(qs_policy_t* p, const qs_policy_weights_t* w, void* st
 /* actions = mean + exp(logstd) * N(0,1) (noise: Philox4x32-10 keyed by seed, counter (env_id0 + i, step_idx, stream 2),
  * Box-Muller), values, neglogp for obs[N,12]; clipped_out (nullable) = actions clamped to the action Box [-1,1]
  * (ppo2.py:478-481).  deterministic != 0 returns the mean (model.predict(deterministic=True)). */
+/* actions_out, clipped_out and neglogp_out may each be NULL (values only: model.value). */
 int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, uint64_t env_id0, uint32_t step_idx,
                    int deterministic, float* actions_out, float* clipped_out, float* values_out, float* neglogp_out,
                    void* stream);
+
+
+/* ---- device-resident rollout: the step loop of Runner._run (rl_baselines/ppo2/ppo2.py:471-510) ------------------------
+ * for t in 0..T-1:  actions, values, neglogp = model.step(obs[t]);  obs[t+1], rewards[t], dones[t+1] = env.step(clip(actions))
+ * then values[T] = model.value(obs[T]).  Every kernel reads and writes the rollout storage in place (no staging copies,
+ * no host round trip: two launches per step).  The caller seeds obs[0] / dones[0] (env.reset() the first time, the previous
+ * rollout's row T afterwards) and runs qs_gae on the result.  float32 docking environments only. */
+typedef struct {
+  float* obs;       /* [T+1, N, 12]  row 0 in, rows 1..T out */
+  float* actions;   /* [T, N, 4]     unclipped samples (what the PPO loss consumes) */
+  float* values;    /* [T+1, N]      row T = bootstrap value of obs[T] */
+  float* neglogp;   /* [T, N] */
+  float* rewards;   /* [T, N] */
+  uint8_t* dones;   /* [T+1, N]      row 0 in; row t+1 = done flag returned by step t (== "done before step t+1") */
+  float* clipped;   /* [N, 4]        scratch: the clipped actions handed to the env */
+} qs_rollout_t;
+/* Noise for step t uses Philox counter word step_idx0 + t (see qs_policy_step).  n_slices = 1: everything in order on
+ * `stream`.  n_slices = 2: the envs are cut in two halves that run their step loops on two internal streams (forked from
+ * and joined back into `stream`), so one half's env kernel (HBM-bound) overlaps the other half's policy kernel (tensor
+ * cores); results are bit-identical to n_slices = 1. */
+int qs_rollout(qs_env_t* env, qs_policy_t* policy, int64_t n_steps, const qs_rollout_t* buffers, uint64_t seed,
+               uint32_t step_idx0, int n_slices, void* stream);
 
 #ifdef __cplusplus
 }

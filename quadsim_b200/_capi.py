@@ -20,7 +20,8 @@ ABI_VERSION = 1
 SYMBOLS = ["qs_abi_version", "qs_last_error", "qs_create", "qs_destroy", "qs_obs_dim", "qs_num_envs", "qs_seed",
            "qs_reset", "qs_step", "qs_step_ex", "qs_step_host", "qs_host_alloc", "qs_host_free", "qs_export_state",
            "qs_import_state", "qs_get_stats", "qs_fn_apply", "qs_gae", "qs_policy_create", "qs_policy_destroy",
-           "qs_policy_set_weights", "qs_policy_step"]
+           "qs_policy_set_weights", "qs_policy_step", "qs_env_dtype", "qs_env_id0", "qs_rollout",
+           "qs_step_range"]
 
 
 class Config(C.Structure):
@@ -37,6 +38,10 @@ class StateArrays(C.Structure):
 class PolicyWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("shared_w", "shared_b", "pi_fc_w", "pi_fc_b", "vf_fc_w", "vf_fc_b", "pi_w", "pi_b",
                                           "vf_w", "vf_b", "logstd")]
+
+
+class RolloutBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "actions", "values", "neglogp", "rewards", "dones", "clipped")]
 
 
 class QuadSimError(RuntimeError):
@@ -83,6 +88,11 @@ def load():
     L.qs_policy_destroy.argtypes = [vp]
     L.qs_policy_set_weights.argtypes = [vp, C.POINTER(PolicyWeights), vp]
     L.qs_policy_step.argtypes = [vp, i64, vp, u64, u64, C.c_uint32, C.c_int, vp, vp, vp, vp, vp]
+    L.qs_env_dtype.argtypes = [vp]
+    L.qs_env_id0.argtypes = [vp]
+    L.qs_env_id0.restype = u64
+    L.qs_rollout.argtypes = [vp, vp, i64, C.POINTER(RolloutBuffers), u64, C.c_uint32, C.c_int, vp]
+    L.qs_step_range.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp]
     L.qs_gae.argtypes = [i64, i64, vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp]
     if L.qs_abi_version() != ABI_VERSION:
         raise QuadSimError("libquadsim_b200.so ABI %d != expected %d; rebuild" % (L.qs_abi_version(), ABI_VERSION))

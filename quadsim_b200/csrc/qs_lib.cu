@@ -834,6 +834,9 @@ int qs_destroy(qs_env_t* e) {
 int qs_obs_dim(const qs_env_t* e) { return e ? e->obs_dim : fail(QS_ERR_INVALID, "null handle"); }
 int64_t qs_num_envs(const qs_env_t* e) { return e ? e->cfg.n_envs : (int64_t)fail(QS_ERR_INVALID, "null handle"); }
 
+int qs_env_dtype(const qs_env_t* e) { return e ? e->cfg.dtype : fail(QS_ERR_INVALID, "null handle"); }
+uint64_t qs_env_id0(const qs_env_t* e) { return e ? e->cfg.env_id0 : 0; }
+
 int qs_seed(qs_env_t* e, uint64_t seed) {
   if (!e) return fail(QS_ERR_INVALID, "null handle");
   e->cfg.seed = seed;
@@ -852,6 +855,17 @@ int qs_step_ex(qs_env_t* e, const void* actions, void* obs_out, void* reward_out
   DeviceGuard g(e->cfg.device);
   StepArgs a = make_args(e, 0, e->cfg.n_envs);
   a.actions = actions; a.obs = obs_out; a.reward = reward_out; a.done = done_out; a.info = info_out; a.term_obs = terminal_obs_out;
+  return launch_step(e, a, (cudaStream_t)stream);
+}
+
+int qs_step_range(qs_env_t* e, int64_t first, int64_t n, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out,
+                  void* stream) {
+  if (!e || !actions || !obs_out || !reward_out || !done_out) return fail(QS_ERR_INVALID, "qs_step_range: null argument");
+  if (first < 0 || n < 0 || first + n > e->cfg.n_envs || first % kBlock != 0)
+    return fail(QS_ERR_INVALID, "qs_step_range: [first, first+n) must lie inside the handle's envs and start on a multiple of %d", kBlock);
+  DeviceGuard g(e->cfg.device);
+  StepArgs a = make_args(e, first, n);
+  a.actions = actions; a.obs = obs_out; a.reward = reward_out; a.done = done_out;
   return launch_step(e, a, (cudaStream_t)stream);
 }
 

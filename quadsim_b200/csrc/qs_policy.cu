@@ -7,17 +7,27 @@
 //     mean = hp W3p^T + b3p (4) ; value = hv . w3v + b3v    128 -> 4, 1 (pi, vf)
 //     action = mean + exp(logstd) * N(0,1) ; neglogp        (model.step, rl_baselines/ppo2/ppo2.py:472)
 // This is the CALLER of the env hot path: with the env step at ~66 us per 2^20 envs, the unfused torch
-// forward (1.5-4 ms) dominated rollout-in-the-loop by 20-60x.  It is the only dense contraction in the system, so it goes
-// on the tensor cores: one CTA = 128 envs = one M=128 UMMA tile.
-//   layer 1:  D1[128x128] = A1[128x32] . B1[128x32]^T   obs split hi+lo in bf16 (x = hi + lo, |lo| <= 2^-9 |x|) against W1
-//             duplicated along K, so inputs keep ~16 mantissa bits (a plain bf16 cast would quantise a 1.8 m range to 8 mm)
-//   layer 2:  D2[128x256] = A2[128x128] . [Wp;Wv]^T      one N=256 accumulator, 8 tcgen05.mma (K=16 each)
-//   layer 3 + sampling: in registers from the TMEM read-out (tcgen05.ld), 5 dot products per row on the CUDA cores.
-// Operands sit in shared memory in the canonical no-swizzle K-major UMMA layout (8x8 core matrices: 8 rows x 16 bytes
-// contiguous; SBO = next 8 rows, LBO = next 8 k), weights pre-packed once on the device by pack_kernel and bulk-copied
-// (cp.async.bulk) per CTA.  D1 and D2 share TMEM columns (D1 is dead once the layer-1 epilogue has written A2), so a CTA
-// needs 256 of the SM's 512 TMEM columns and 108 KB of shared memory: two CTAs per SM overlap one CTA's MMAs with the
-// other's epilogue.
+// forward (1.5-4 ms) dominated rollout-in-the-loop by 20-60x.  It is the only dense contraction in the system, so all three
+// layers go on the tensor cores; one 128-env tile = one M=128 UMMA tile:
+//   layer 1:  D1[128x128] = A1[128x32]  . B1[128x32]^T    obs split hi+lo in bf16 (x = hi + lo, |lo| <= 2^-9 |x|) against W1
+//             duplicated along K, so inputs keep ~16 mantissa bits (a plain bf16 cast would quantise a 1.8 m range to 8 mm);
+//             two spare K slots carry 1.0 against (b1_hi, b1_lo): the bias add rides the MMA.  A1, B1 in shared memory.
+//   layer 2:  D2[128x256] = A2[128x144] . [Wp;Wv | b_hi b_lo]^T   one N=256 accumulator, 9 tcgen05.mma (K=16 each); A2 in
+//             shared memory (canonical no-swizzle K-major UMMA layout: 8x8 core matrices, 8 rows x 16 bytes contiguous).
+//   layer 3:  D3[128x16]  = A3[128x256] . B3[16x256]^T    rows 0-3 = W3p over the pi half, row 4 = w3v over the vf half.
+//             A3 never touches shared memory: relu(D2) is packed to bf16 and written back INTO TENSOR MEMORY over the
+//             accumulator columns it came from (tcgen05.st), and the MMA takes its A operand from TMEM (the .ts form).
+// The CUDA cores only move accumulators: tcgen05.ld -> cvt.rn.relu.bf16x2 (relu and the bf16 pack are ONE instruction per
+// two elements) -> st.shared / tcgen05.st, then Philox/Box-Muller sampling and the stores.  Shared-memory traffic per tile
+// is 176 KB (operand reads by the tensor cores + the A1/A2 stores); with A3 in shared memory as well (304 KB) the
+// shared-memory pipe was the busiest unit (59 % at 127 us per 2^20 envs, profiles/r1_policy_v2_ncu_full.txt).
+//
+// One persistent 512-thread CTA per SM = two independent 256-thread GROUPS, each with its own 36 KB A-operand buffer, 256
+// TMEM columns (D1, D2, A3, D3 alias: each is dead when the next is written), a named barrier and an mbarrier; the weight
+// images (88 KB, bulk-copied once per CTA with cp.async.bulk) are shared.  While one group waits on its MMAs the other runs
+// its epilogue.  Inside a group two warps serve each 32-lane TMEM quadrant: the "pi side" takes accumulator columns
+// [0,64) of D1 / [0,128) of D2, samples the action and stores actions/neglogp; the "vf side" takes the other halves and
+// stores the value -- twice the warps per scheduler for the latency-bound tcgen05.ld -> cvt -> store chains.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -33,20 +43,36 @@ extern int qs_fail_(int code, const char* fmt, ...);  // qs_lib.cu: sets the thr
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kTileRows = 128;                       // envs per tile == UMMA M == TMEM lanes
+#ifndef QS_POLICY_SIDES
+#define QS_POLICY_SIDES 1  // warps per TMEM lane quadrant in a group: 1 (128-thread groups) or 2 (256: pi side + vf side)
+#endif
+constexpr int kSides = QS_POLICY_SIDES;
+constexpr int kGroupThreads = kTileRows * kSides, kGroups = 2, kThreads = kGroupThreads * kGroups;
 constexpr int kObs = 12, kHid = 128, kAct = 4;
-constexpr int kK1 = 32;  // layer-1 K: [hi(12)+pad(4) | lo(12)+pad(4)]
+constexpr int kK1 = 32;    // layer-1 K: [hi(12) 1 1 0 0 | lo(12) 0 0 0 0]
+constexpr int kK2 = 144;   // layer-2 K: h(128) 1 1 0...
+constexpr int kK3 = 256;   // layer-3 K: [hp(128) | hv(128)]
+constexpr int kN3 = 16;    // layer-3 N (UMMA minimum for M=128): mean(4), value, zero padding
 
-// ---- shared-memory map (bytes) ----
-constexpr int kOffA = 0;                          // A2 [128 x 128] bf16 (32 KB); A1 [128 x 32] aliases its first 8 KB
-constexpr int kOffW1 = 32768;                     // B1 [128 x 32] bf16 (8 KB)
-constexpr int kOffW2 = kOffW1 + 8192;             // B2 [256 x 128] bf16 (64 KB)
-constexpr int kOffF = kOffW2 + 65536;             // fp32 tail
-constexpr int kTailFloats = 128 + 256 + 512 + 128 + 8 + 4;  // b1, b2=[bp;bv], W3p[k][4], w3v[k], b3(4)+b3v+pad(3), logstd(4)
-constexpr int kOffBar = kOffF + kTailFloats * 4;  // 2 mbarriers + weight barrier + tmem ptr
+// ---- shared-memory map (bytes); [W1 | W2 | W3 | tail] is also the packed global image ----
+constexpr int kOffW1 = 0;                                  // B1 [128 x 32] bf16
+constexpr int kOffW2 = kOffW1 + kHid * kK1 * 2;            // B2 [256 x 144] bf16
+constexpr int kOffW3 = kOffW2 + 2 * kHid * kK2 * 2;        // B3 [16 x 256] bf16
+constexpr int kOffTail = kOffW3 + kN3 * kK3 * 2;           // fp32: b3p(4), b3v, pad(3), logstd(4), pad(4)
+constexpr int kTailFloats = 16;
+constexpr int kPackedBytes = kOffTail + kTailFloats * 4;
+constexpr int kOffA = (kPackedBytes + 127) / 128 * 128;    // per group: A2 [128 x 144] bf16 (36 KB); A1 aliases its head
+constexpr int kABytes = kTileRows * kK2 * 2;
+constexpr int kOffBar = kOffA + kGroups * kABytes;         // weight mbarrier, one mbarrier per group, TMEM base slot
 constexpr int kSmemBytes = kOffBar + 64;
-constexpr int kPackedBytes = 8192 + 65536 + kTailFloats * 4;  // global image of [W1 | W2 | tail]
-constexpr uint32_t kTmemCols = 256;
+// ---- tensor-memory map, columns relative to the group's 256-column window ----
+constexpr uint32_t kTmemCols = 512, kTmemColsPerGroup = 256;
+constexpr int kColsPerSide = 2 * kHid / kSides;            // D2 columns one thread reads out (D1: half as many)
+constexpr uint32_t kColD3 = kColsPerSide / 2;              // 16 columns just behind side 0's packed A3 (consumed D2 columns)
+static_assert(kSides == 1 || kSides == 2, "one or two warps per TMEM lane quadrant");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(kPackedBytes % 16 == 0, "bulk copies move 16-byte units");
 
 // canonical K-major, no-swizzle layout: element (row, k) of an operand with R rows
 __host__ __device__ constexpr int canon_off(int row, int k, int rows) {
@@ -65,6 +91,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kGroupThreads) : "memory"); }
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
 // layout_type = SWIZZLE_NONE [61,64)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -72,58 +99,94 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] . B[smem]^T
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T : A is 128 lanes x K/2 columns, column j of lane i = (A[i][2j] : low half, A[i][2j+1] : high half)
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// 32 lanes x 32 consecutive fp32 columns: thread l of the warp gets lane (warp%4)*32 + l
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
+// 32 lanes x 32 consecutive fp32 columns: thread l of the warp gets lane (warp%4)*32 + l.  No wait: pair with tmem_wait_ld().
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
         "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
         "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+      : "r"(taddr)
+      : "memory");
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 16 consecutive 32-bit columns from registers
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+               "r"(r[14]), "r"(r[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// {bf16(max(hi,0)) : bf16(max(lo,0))} from two fp32 accumulator words.  volatile: must stay behind tcgen05.wait::ld.
+__device__ __forceinline__ uint32_t relu_pack_bf16(uint32_t lo_f32_bits, uint32_t hi_f32_bits) {
+  uint32_t d;
+  asm volatile("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi_f32_bits)), "f"(__uint_as_float(lo_f32_bits)));
+  return d;
 }
 
 // ---- one-time weight packing: torch layout [out, in] fp32 -> canonical bf16 operand images + fp32 tail ----
 struct RawWeights { const float *w1, *b1, *wp, *bp, *wv, *bv, *w3p, *b3p, *w3v, *b3v, *logstd; };
 
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
 __global__ void pack_kernel(RawWeights w, unsigned char* packed) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  __nv_bfloat16* W1 = reinterpret_cast<__nv_bfloat16*>(packed);
-  __nv_bfloat16* W2 = reinterpret_cast<__nv_bfloat16*>(packed + 8192);
-  float* tail = reinterpret_cast<float*>(packed + 8192 + 65536);
-  for (int i = tid; i < kHid * kK1; i += nth) {  // B1[n][k] = W1[n][k % 16] for k % 16 < 12 (hi half and lo half see the same weights)
+  __nv_bfloat16* W1 = reinterpret_cast<__nv_bfloat16*>(packed + kOffW1);
+  __nv_bfloat16* W2 = reinterpret_cast<__nv_bfloat16*>(packed + kOffW2);
+  __nv_bfloat16* W3 = reinterpret_cast<__nv_bfloat16*>(packed + kOffW3);
+  float* tail = reinterpret_cast<float*>(packed + kOffTail);
+  for (int i = tid; i < kHid * kK1; i += nth) {  // B1[n][k]: the hi half and the lo half of the input see the same weights
     const int n = i / kK1, k = i % kK1, kk = k & 15;
-    W1[canon_off(n, k, kHid) / 2] = __float2bfloat16(kk < kObs ? w.w1[n * kObs + kk] : 0.f);
+    float v = 0.f;
+    if (kk < kObs) v = w.w1[n * kObs + kk];
+    else if (k == 12) v = w.b1[n];                            // against A1[:,12] = 1
+    else if (k == 13) v = w.b1[n] - bf16_round(w.b1[n]);      // against A1[:,13] = 1: bias keeps ~16 mantissa bits
+    W1[canon_off(n, k, kHid) / 2] = __float2bfloat16(v);
   }
-  for (int i = tid; i < 2 * kHid * kHid; i += nth) {  // B2 = [Wp ; Wv], 256 rows
-    const int n = i / kHid, k = i % kHid;
-    const float v = n < kHid ? w.wp[n * kHid + k] : w.wv[(n - kHid) * kHid + k];
+  for (int i = tid; i < 2 * kHid * kK2; i += nth) {  // B2 = [Wp ; Wv], 256 rows, K = 128 weights + (bias_hi, bias_lo) + zero padding
+    const int n = i / kK2, k = i % kK2;
+    const float b = n < kHid ? w.bp[n] : w.bv[n - kHid];
+    float v = 0.f;
+    if (k < kHid) v = n < kHid ? w.wp[n * kHid + k] : w.wv[(n - kHid) * kHid + k];
+    else if (k == kHid) v = b;
+    else if (k == kHid + 1) v = b - bf16_round(b);
     W2[canon_off(n, k, 2 * kHid) / 2] = __float2bfloat16(v);
+  }
+  for (int i = tid; i < kN3 * kK3; i += nth) {  // B3: rows 0-3 = W3p over k < 128, row 4 = w3v over k >= 128
+    const int n = i / kK3, k = i % kK3;
+    float v = 0.f;
+    if (n < kAct && k < kHid) v = w.w3p[n * kHid + k];
+    else if (n == kAct && k >= kHid) v = w.w3v[k - kHid];
+    W3[canon_off(n, k, kN3) / 2] = __float2bfloat16(v);
   }
   for (int i = tid; i < kTailFloats; i += nth) {
     float v = 0.f;
-    if (i < 128) v = w.b1[i];
-    else if (i < 256) v = w.bp[i - 128];
-    else if (i < 384) v = w.bv[i - 256];
-    else if (i < 896) { const int k = (i - 384) >> 2, a = (i - 384) & 3; v = w.w3p[a * kHid + k]; }  // W3p[k][a]
-    else if (i < 1024) v = w.w3v[i - 896];
-    else if (i < 1028) v = w.b3p[i - 1024];
-    else if (i == 1028) v = w.b3v[0];
-    else if (i >= 1032 && i < 1036) v = w.logstd[i - 1032];
+    if (i < 4) v = w.b3p[i];
+    else if (i == 4) v = w.b3v[0];
+    else if (i >= 8 && i < 12) v = w.logstd[i - 8];
     tail[i] = v;
   }
 }
@@ -135,168 +198,216 @@ struct StepArgs {
   uint64_t seed, env_id0;
   uint32_t step_idx;
   int deterministic;
-  float *actions, *clipped, *values, *neglogp;  // clipped may be null
+  float *actions, *clipped, *values, *neglogp;  // all but values may be null
 };
 
-__global__ void __launch_bounds__(kThreads, 2) policy_step_kernel(const StepArgs a) {
+struct ObsRow { float4 a, b, c; };
+__device__ __forceinline__ ObsRow load_obs(const float* obs, int64_t i, int64_t n) {
+  ObsRow o = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+  if (i < n) {
+    const float4* p = reinterpret_cast<const float4*>(obs + i * kObs);
+    o.a = __ldg(p); o.b = __ldg(p + 1); o.c = __ldg(p + 2);
+  }
+  return o;
+}
+
+#ifndef QS_POLICY_MINB
+#define QS_POLICY_MINB (3 - QS_POLICY_SIDES)  // register cap only (shared memory admits one CTA per SM): <= 128 registers either way
+#endif
+__global__ void __launch_bounds__(kThreads, QS_POLICY_MINB) policy_step_kernel(const StepArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int g = tid / kGroupThreads, tg = tid % kGroupThreads;
+  const int quad = (tg >> 5) & 3, side = tg >> 7;        // TMEM lane quadrant of this warp; side (kSides == 2): 0 = pi, 1 = vf
+  const int row = quad * 32 + (tid & 31);                // accumulator row == TMEM lane == env within the tile
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_w = sbase + kOffBar, bar_mma = sbase + kOffBar + 8;
+  const uint32_t bar_w = sbase + kOffBar, bar_mma = sbase + kOffBar + 8 + 8 * g;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 32);
-  const float* tail = reinterpret_cast<const float*>(smem + kOffF);
-  const int tiles = (int)((a.n + kThreads - 1) / kThreads);
+  const float* tail = reinterpret_cast<const float*>(smem + kOffTail);
+  const int tiles = (int)((a.n + kTileRows - 1) / kTileRows);
+  const int tile0 = blockIdx.x * kGroups + g, tile_stride = gridDim.x * kGroups;
+
+  ObsRow o = load_obs(a.obs, (int64_t)tile0 * kTileRows + row, tile0 < tiles ? a.n : 0);  // in flight during the set-up
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
-    mbar_init(bar_mma, 1);
+    mbar_init(sbase + kOffBar + 8, 1);
+    mbar_init(sbase + kOffBar + 16, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar_w, kPackedBytes);  // weights: W1 | W2 | tail are contiguous in smem and in the packed image
+    mbar_expect_tx(bar_w, kPackedBytes);  // weights: [W1 | W2 | W3 | tail] contiguous in smem and in the packed image
     for (int off = 0; off < kPackedBytes; off += 16384) {
       const int bytes = kPackedBytes - off < 16384 ? kPackedBytes - off : 16384;
       bulk_g2s(sbase + kOffW1 + off, a.packed + off, bytes, bar_w);
     }
   }
-  if (warp == 0) {  // TMEM: 256 columns for this CTA (two CTAs fit an SM's 512)
+  if (warp == 0) {  // all 512 TMEM columns: one CTA per SM, 256 per group
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+  const uint32_t tmem = *tmem_slot + g * kTmemColsPerGroup;          // this group's accumulator columns (lane field 0)
+  const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);        // this warp's 32 TMEM lanes
+  unsigned char* a_row = smem + kOffA + g * kABytes + row * 16;      // canon_off(row, 0, 128) == row * 16
+  const uint32_t a_base = sbase + kOffA + g * kABytes;
   mbar_wait(bar_w, 0);
 
-  constexpr uint32_t idesc1 = umma_idesc(128, 128), idesc2 = umma_idesc(128, 256);
+  constexpr uint32_t idesc1 = umma_idesc(128, kHid), idesc2 = umma_idesc(128, 2 * kHid), idesc3 = umma_idesc(128, kN3);
   uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t i = (int64_t)tile * kThreads + tid;
+  for (int tile = tile0; tile < tiles; tile += tile_stride) {
+    const int64_t i = (int64_t)tile * kTileRows + row;
     const bool active = i < a.n;
-    // ---- A1: this thread's observation row, split hi/lo, into the canonical layout (row = tid, K = 32) ----
+    // ---- A1: the observation row split hi/lo, K = 32 = four 16-byte core-matrix rows (two sides: one stores hi, one lo) ----
     {
-      float o[16];
+      const float x[12] = {o.a.x, o.a.y, o.a.z, o.a.w, o.b.x, o.b.y, o.b.z, o.b.w, o.c.x, o.c.y, o.c.z, o.c.w};
+      uint32_t hi[6], lo[6];
 #pragma unroll
-      for (int k = 0; k < 16; k++) o[k] = 0.f;
-      if (active) {
-        const float4* p = reinterpret_cast<const float4*>(a.obs + i * kObs);
-        const float4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
-        o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v0.w; o[4] = v1.x; o[5] = v1.y; o[6] = v1.z; o[7] = v1.w;
-        o[8] = v2.x; o[9] = v2.y; o[10] = v2.z; o[11] = v2.w;
-      }
-      uint32_t hi[8], lo[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const float h0 = __bfloat162float(__float2bfloat16(o[2 * k])), h1 = __bfloat162float(__float2bfloat16(o[2 * k + 1]));
+      for (int k = 0; k < 6; k++) {
+        const float h0 = bf16_round(x[2 * k]), h1 = bf16_round(x[2 * k + 1]);
         hi[k] = pack_bf16(h0, h1);
-        lo[k] = pack_bf16(o[2 * k] - h0, o[2 * k + 1] - h1);
+        lo[k] = pack_bf16(x[2 * k] - h0, x[2 * k + 1] - h1);
       }
-      unsigned char* A1 = smem + kOffA;
-      *reinterpret_cast<uint4*>(A1 + canon_off(tid, 0, 128)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(A1 + canon_off(tid, 8, 128)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-      *reinterpret_cast<uint4*>(A1 + canon_off(tid, 16, 128)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      *reinterpret_cast<uint4*>(A1 + canon_off(tid, 24, 128)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      if (kSides == 1 || side == 0) {  // k = 12, 13: 1.0 against (b1_hi, b1_lo)
+        *reinterpret_cast<uint4*>(a_row + 0 * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(a_row + 1 * 2048) = make_uint4(hi[4], hi[5], 0x3F803F80u, 0u);
+      }
+      if (kSides == 1 || side == 1) {
+        *reinterpret_cast<uint4*>(a_row + 2 * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(a_row + 3 * 2048) = make_uint4(lo[4], lo[5], 0u, 0u);
+      }
     }
     proxy_fence();       // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     tc_fence_before();   // orders the previous tile's tcgen05.ld before the barrier (TMEM columns are reused)
-    __syncthreads();
-    if (tid == 0) {
+    group_sync(g);
+    if (tg == 0) {
       tc_fence_after();
-      // layer 1: K = 32 -> two K=16 steps; operand rows = 128 -> SBO = 128 B, LBO = 16 row-groups * 128 B = 2048 B
+      // operand rows = 128 -> SBO = 128 B, LBO = 16 row-groups * 128 B = 2048 B; one K=16 step = two k-blocks = 4096 B
 #pragma unroll
-      for (int ks = 0; ks < 2; ks++)
-        umma_bf16(tmem, umma_desc(sbase + kOffA + ks * 4096, 2048, 128), umma_desc(sbase + kOffW1 + ks * 4096, 2048, 128), idesc1, ks);
+      for (int ks = 0; ks < kK1 / 16; ks++)
+        umma_ss(tmem, umma_desc(a_base + ks * 4096, 2048, 128), umma_desc(sbase + kOffW1 + ks * 4096, 2048, 128), idesc1, ks);
       umma_commit(bar_mma);
     }
+    o = load_obs(a.obs, i + (int64_t)tile_stride * kTileRows, a.n);  // next tile's row, in flight under this tile's work
     mbar_wait(bar_mma, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- epilogue 1: h = relu(D1 + b1) -> bf16 -> A2 (row = tid), 32 columns at a time ----
+    // ---- epilogue 1: h = relu(D1) -> A2[:, 0:128] (each side its share of the columns); A2[:, 128:144] = (1, 1, 0, ...)
+    //      carries layer 2's bias ----
 #pragma unroll 1
-    for (int c0 = 0; c0 < kHid; c0 += 32) {
-      float v[32];
-      tmem_ld32(trow + c0, v);
+    for (int c0 = (kHid / kSides) * side; c0 < (kHid / kSides) * (side + 1); c0 += 64) {
+      uint32_t r[64];
+      tmem_ld32(trow + c0, r);
+      tmem_ld32(trow + c0 + 32, r + 32);
+      tmem_wait_ld();
 #pragma unroll
-      for (int g = 0; g < 4; g++) {
-        uint32_t w[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int c = c0 + g * 8 + j * 2;
-          w[j] = pack_bf16(fmaxf(v[g * 8 + j * 2] + tail[c], 0.f), fmaxf(v[g * 8 + j * 2 + 1] + tail[c + 1], 0.f));
-        }
-        *reinterpret_cast<uint4*>(smem + kOffA + canon_off(tid, c0 + g * 8, 128)) = make_uint4(w[0], w[1], w[2], w[3]);
+      for (int j = 0; j < 8; j++) {  // one 8x8 core-matrix row (8 k = 16 bytes) per store; k-blocks are 2048 B apart for 128 rows
+        uint4 w;
+        w.x = relu_pack_bf16(r[8 * j + 0], r[8 * j + 1]);
+        w.y = relu_pack_bf16(r[8 * j + 2], r[8 * j + 3]);
+        w.z = relu_pack_bf16(r[8 * j + 4], r[8 * j + 5]);
+        w.w = relu_pack_bf16(r[8 * j + 6], r[8 * j + 7]);
+        *reinterpret_cast<uint4*>(a_row + ((c0 >> 3) + j) * 2048) = w;
       }
     }
+    if (kSides == 1 || side == 0) *reinterpret_cast<uint4*>(a_row + 16 * 2048) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+    if (kSides == 1 || side == 1) *reinterpret_cast<uint4*>(a_row + 17 * 2048) = make_uint4(0u, 0u, 0u, 0u);
     proxy_fence();
     tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
+    group_sync(g);
+    if (tg == 0) {
       tc_fence_after();
-      // layer 2: D2[128 x 256] = A2[128 x 128] . [Wp;Wv]^T ; B rows = 256 -> LBO = 32 row-groups * 128 B = 4096 B
+      // B rows = 256 -> LBO = 32 row-groups * 128 B = 4096 B, one K step = 8192 B
 #pragma unroll
-      for (int ks = 0; ks < 8; ks++)
-        umma_bf16(tmem, umma_desc(sbase + kOffA + ks * 4096, 2048, 128), umma_desc(sbase + kOffW2 + ks * 8192, 4096, 128), idesc2, ks);
+      for (int ks = 0; ks < kK2 / 16; ks++)
+        umma_ss(tmem, umma_desc(a_base + ks * 4096, 2048, 128), umma_desc(sbase + kOffW2 + ks * 8192, 4096, 128), idesc2, ks);
       umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- epilogue 2: hp/hv = relu(D2 + b2); layer 3 on the CUDA cores: mean[4] and value ----
-    float m0 = tail[1024], m1 = tail[1025], m2 = tail[1026], m3 = tail[1027], val = tail[1028];
+    // ---- epilogue 2: relu(D2) -> bf16 pairs written back over the columns they came from (A3 = the lower half of each
+    //      side's column range).  A side compacts only inside its own range, and chunk c's packed columns land in columns the
+    //      same thread has already loaded, so nothing is overwritten before it is read. ----
+    {
+      const uint32_t half = trow + kColsPerSide * side;
 #pragma unroll 1
-    for (int c0 = 0; c0 < 2 * kHid; c0 += 32) {
-      float v[32];
-      tmem_ld32(trow + c0, v);
-      if (c0 < kHid) {
+      for (int c0 = 0; c0 < kColsPerSide; c0 += 64) {
+        uint32_t r[64], w[32];
+        tmem_ld32(half + c0, r);
+        tmem_ld32(half + c0 + 32, r + 32);
+        tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const float h = fmaxf(v[j] + tail[128 + c0 + j], 0.f);
-          const float4 w3 = *reinterpret_cast<const float4*>(tail + 384 + (c0 + j) * 4);
-          m0 = fmaf(h, w3.x, m0); m1 = fmaf(h, w3.y, m1); m2 = fmaf(h, w3.z, m2); m3 = fmaf(h, w3.w, m3);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; j++) val = fmaf(fmaxf(v[j] + tail[128 + c0 + j], 0.f), tail[896 + c0 - kHid + j], val);
+        for (int j = 0; j < 32; j++) w[j] = relu_pack_bf16(r[2 * j], r[2 * j + 1]);
+        tmem_st16(half + (c0 >> 1), w);
+        tmem_st16(half + (c0 >> 1) + 16, w + 16);
       }
+      tmem_wait_st();
     }
-    // ---- sample, log-prob, store (DiagGaussianProbabilityDistribution: sample / neglogp) ----
+    tc_fence_before();
+    group_sync(g);
+    if (tg == 0) {
+      tc_fence_after();
+      // A from tensor memory: one K=16 step = 8 columns.  B rows = 16 -> LBO = 2 row-groups * 128 B = 256 B, one K step = 512 B
+#pragma unroll
+      for (int ks = 0; ks < kK3 / 16; ks++)
+        umma_ts(tmem + kColD3, tmem + kColsPerSide * (ks / (kColsPerSide / 16)) + 8 * (ks % (kColsPerSide / 16)),
+                umma_desc(sbase + kOffW3 + ks * 512, 256, 128), idesc3, ks);
+      umma_commit(bar_mma);
+    }
+    // ---- Gaussian noise while layer 3 runs (DiagGaussianProbabilityDistribution.sample); pi side only ----
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+    if ((kSides == 1 || side == 0) && !a.deterministic) {
+      qs::U4 c = {(uint32_t)(a.env_id0 + (uint64_t)i), (uint32_t)((a.env_id0 + (uint64_t)i) >> 32), a.step_idx, 2u};
+      qs::U4 x = qs::philox4x32_10(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      const float s = 5.9604644775390625e-08f;  // 2^-24; u in (0,1)
+      const float u0 = ((float)(x.x >> 8) + 0.5f) * s, u1 = ((float)(x.y >> 8) + 0.5f) * s;
+      const float u2 = ((float)(x.z >> 8) + 0.5f) * s, u3 = ((float)(x.w >> 8) + 0.5f) * s;
+      const float r0 = sqrtf(-2.f * __logf(u0)), r1 = sqrtf(-2.f * __logf(u2));
+      float s0, c0_, s1, c1_;
+      __sincosf(6.283185307179586f * u1, &s0, &c0_);
+      __sincosf(6.283185307179586f * u3, &s1, &c1_);
+      n0 = r0 * c0_; n1 = r0 * s0; n2 = r1 * c1_; n3 = r1 * s1;  // Box-Muller
+    }
+    mbar_wait(bar_mma, phase);
+    phase ^= 1;
+    tc_fence_after();
+    uint32_t d3[8];
+    tmem_ld8(trow + kColD3, d3);
+    tmem_wait_ld();
+    // ---- sample, log-prob, store ----
     if (active) {
-      const float ls0 = tail[1032], ls1 = tail[1033], ls2 = tail[1034], ls3 = tail[1035];
-      float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
-      if (!a.deterministic) {
-        qs::U4 c = {(uint32_t)(a.env_id0 + (uint64_t)i), (uint32_t)((a.env_id0 + (uint64_t)i) >> 32), a.step_idx, 2u};
-        qs::U4 x = qs::philox4x32_10(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-        const float s = 5.9604644775390625e-08f;  // 2^-24; u in (0,1)
-        const float u0 = ((float)(x.x >> 8) + 0.5f) * s, u1 = ((float)(x.y >> 8) + 0.5f) * s;
-        const float u2 = ((float)(x.z >> 8) + 0.5f) * s, u3 = ((float)(x.w >> 8) + 0.5f) * s;
-        const float r0 = sqrtf(-2.f * __logf(u0)), r1 = sqrtf(-2.f * __logf(u2));
-        float s0, c0_, s1, c1_;
-        __sincosf(6.283185307179586f * u1, &s0, &c0_);
-        __sincosf(6.283185307179586f * u3, &s1, &c1_);
-        n0 = r0 * c0_; n1 = r0 * s0; n2 = r1 * c1_; n3 = r1 * s1;  // Box-Muller
+      if (kSides == 1 || side == 0) {
+        const float ls0 = tail[8], ls1 = tail[9], ls2 = tail[10], ls3 = tail[11];
+        const float m0 = __uint_as_float(d3[0]) + tail[0], m1 = __uint_as_float(d3[1]) + tail[1];
+        const float m2 = __uint_as_float(d3[2]) + tail[2], m3 = __uint_as_float(d3[3]) + tail[3];
+        const float a0 = fmaf(__expf(ls0), n0, m0), a1 = fmaf(__expf(ls1), n1, m1), a2 = fmaf(__expf(ls2), n2, m2), a3 = fmaf(__expf(ls3), n3, m3);
+        // neglogp = 0.5 * sum(((a - mean)/std)^2) + 0.5*log(2 pi)*4 + sum(logstd); (a - mean)/std == the noise itself
+        const float nlp = 0.5f * (n0 * n0 + n1 * n1 + n2 * n2 + n3 * n3) + 3.6757541328186907f + (ls0 + ls1 + ls2 + ls3);
+        if (a.actions) reinterpret_cast<float4*>(a.actions)[i] = make_float4(a0, a1, a2, a3);
+        if (a.clipped)
+          reinterpret_cast<float4*>(a.clipped)[i] = make_float4(fminf(fmaxf(a0, -1.f), 1.f), fminf(fmaxf(a1, -1.f), 1.f), fminf(fmaxf(a2, -1.f), 1.f), fminf(fmaxf(a3, -1.f), 1.f));
+        if (a.neglogp) a.neglogp[i] = nlp;
       }
-      const float a0 = fmaf(__expf(ls0), n0, m0), a1 = fmaf(__expf(ls1), n1, m1), a2 = fmaf(__expf(ls2), n2, m2), a3 = fmaf(__expf(ls3), n3, m3);
-      // neglogp = 0.5 * sum(((a - mean)/std)^2) + 0.5*log(2 pi)*4 + sum(logstd); (a - mean)/std == the noise itself
-      const float nlp = 0.5f * (n0 * n0 + n1 * n1 + n2 * n2 + n3 * n3) + 3.6757541328186907f + (ls0 + ls1 + ls2 + ls3);
-      reinterpret_cast<float4*>(a.actions)[i] = make_float4(a0, a1, a2, a3);
-      if (a.clipped)
-        reinterpret_cast<float4*>(a.clipped)[i] = make_float4(fminf(fmaxf(a0, -1.f), 1.f), fminf(fmaxf(a1, -1.f), 1.f), fminf(fmaxf(a2, -1.f), 1.f), fminf(fmaxf(a3, -1.f), 1.f));
-      a.values[i] = val;
-      a.neglogp[i] = nlp;
+      if (kSides == 1 || side == 1) a.values[i] = __uint_as_float(d3[4]) + tail[4];
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
 }
 
 }  // namespace
 
+constexpr int kMaxSlices = 2;
 struct qs_policy {
   int device = 0;
   unsigned char* packed = nullptr;
   int grid = 0;
   bool have_weights = false;
+  // qs_rollout with n_slices = 2: one stream per env slice, forked from / joined into the caller's stream
+  cudaStream_t slice_stream[kMaxSlices] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxSlices] = {};
 };
 
 #define QSP_CUDA(call)                                                                                          \
@@ -331,9 +442,14 @@ int qs_policy_create(qs_policy_t** out, int device) {
     cudaSetDevice(prev);
     return rc;
   }
-  if (per_sm > 2) per_sm = 2;  // TMEM: 2 x 256 columns
-  if (per_sm < 1) per_sm = 1;
-  p->grid = per_sm * prop.multiProcessorCount;
+  if (per_sm < 1) {
+    int rc = qs_fail_(QS_ERR_CUDA, "qs_policy_create: the policy kernel does not fit an SM (%d B shared memory)", kSmemBytes);
+    cudaFree(p->packed);
+    delete p;
+    cudaSetDevice(prev);
+    return rc;
+  }
+  p->grid = prop.multiProcessorCount;  // one persistent CTA per SM: it owns all 512 TMEM columns
   cudaSetDevice(prev);
   *out = p;
   return QS_OK;
@@ -345,6 +461,11 @@ int qs_policy_destroy(qs_policy_t* p) {
   cudaGetDevice(&prev);
   cudaSetDevice(p->device);
   cudaFree(p->packed);
+  for (int k = 0; k < kMaxSlices; k++) {
+    if (p->slice_stream[k]) cudaStreamDestroy(p->slice_stream[k]);
+    if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]);
+  }
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   cudaSetDevice(prev);
   delete p;
   return QS_OK;
@@ -369,19 +490,78 @@ int qs_policy_set_weights(qs_policy_t* p, const qs_policy_weights_t* w, void* st
 
 int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, uint64_t env_id0, uint32_t step_idx, int deterministic,
                    float* actions_out, float* clipped_out, float* values_out, float* neglogp_out, void* stream) {
-  if (!p || !obs || !actions_out || !values_out || !neglogp_out) return qs_fail_(QS_ERR_INVALID, "qs_policy_step: null argument");
+  if (!p || !obs || !values_out) return qs_fail_(QS_ERR_INVALID, "qs_policy_step: null argument");
   if (!p->have_weights) return qs_fail_(QS_ERR_INVALID, "qs_policy_step: qs_policy_set_weights has not been called");
   if (n <= 0) return QS_OK;
   int prev = 0;
   QSP_CUDA(cudaGetDevice(&prev));
   QSP_CUDA(cudaSetDevice(p->device));
   StepArgs a = {p->packed, obs, n, seed, env_id0, step_idx, deterministic, actions_out, clipped_out, values_out, neglogp_out};
-  const int tiles = (int)((n + kThreads - 1) / kThreads);
-  policy_step_kernel<<<tiles < p->grid ? tiles : p->grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a);
+  const int ctas = (int)(((n + kTileRows - 1) / kTileRows + kGroups - 1) / kGroups);
+  policy_step_kernel<<<ctas < p->grid ? ctas : p->grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a);
   cudaError_t e = cudaGetLastError();
   cudaSetDevice(prev);
   if (e != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_policy_step: %s", cudaGetErrorString(e));
   return QS_OK;
+}
+
+int qs_rollout(qs_env_t* env, qs_policy_t* pol, int64_t n_steps, const qs_rollout_t* b, uint64_t seed, uint32_t step_idx0, int n_slices,
+               void* stream) {
+  if (!env || !pol || !b || !b->obs || !b->actions || !b->values || !b->neglogp || !b->rewards || !b->dones || !b->clipped)
+    return qs_fail_(QS_ERR_INVALID, "qs_rollout: null argument");
+  if (n_steps < 0 || n_slices < 1 || n_slices > kMaxSlices) return qs_fail_(QS_ERR_INVALID, "qs_rollout: n_steps < 0 or n_slices not in [1, %d]", kMaxSlices);
+  if (qs_env_dtype(env) != QS_F32 || qs_obs_dim(env) != kObs)
+    return qs_fail_(QS_ERR_INVALID, "qs_rollout: needs a float32 docking environment (12 observations, what the policy was built for)");
+  const int64_t n = qs_num_envs(env);
+  const uint64_t id0 = qs_env_id0(env);
+  // slice boundaries on whole 128-env tiles (the state layout's unit)
+  int64_t first[kMaxSlices + 1] = {0, n, n};
+  if (n_slices == 2) first[1] = (n / 2 + kTileRows - 1) / kTileRows * kTileRows;
+  if (first[1] >= n) n_slices = 1, first[1] = n;
+  cudaStream_t st[kMaxSlices] = {(cudaStream_t)stream, (cudaStream_t)stream};
+  if (n_slices == 2) {
+    int prev = 0;
+    QSP_CUDA(cudaGetDevice(&prev));
+    QSP_CUDA(cudaSetDevice(pol->device));
+    cudaError_t e = cudaSuccess;
+    if (!pol->ev_fork) {
+      for (int k = 0; k < kMaxSlices && e == cudaSuccess; k++) {
+        e = cudaStreamCreateWithFlags(&pol->slice_stream[k], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pol->ev_join[k], cudaEventDisableTiming);
+      }
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pol->ev_fork, cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(pol->ev_fork, (cudaStream_t)stream);
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+      st[k] = pol->slice_stream[k];
+      e = cudaStreamWaitEvent(st[k], pol->ev_fork, 0);
+    }
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_rollout: %s", cudaGetErrorString(e));
+  }
+  int rc = QS_OK;
+  for (int64_t t = 0; t <= n_steps && rc == QS_OK; t++) {
+    for (int k = 0; k < n_slices && rc == QS_OK; k++) {
+      const int64_t f = first[k], m = first[k + 1] - first[k];
+      if (t == n_steps) {
+        // last_values = model.value(obs) (ppo2.py:510): deterministic pass, only the value head is stored
+        rc = qs_policy_step(pol, m, b->obs + (t * n + f) * kObs, seed, id0 + f, 0, 1, nullptr, nullptr, b->values + t * n + f, nullptr, st[k]);
+        continue;
+      }
+      // model.step(obs) (ppo2.py:472) writes straight into the rollout's rows; np.clip to the Box (ppo2.py:478-481) -> clipped
+      rc = qs_policy_step(pol, m, b->obs + (t * n + f) * kObs, seed, id0 + f, step_idx0 + (uint32_t)t, 0, b->actions + (t * n + f) * kAct,
+                          b->clipped + f * kAct, b->values + t * n + f, b->neglogp + t * n + f, st[k]);
+      // env.step(clipped_actions) (ppo2.py:482): the next observations / this step's rewards / the next row of dones
+      if (rc == QS_OK)
+        rc = qs_step_range(env, f, m, b->clipped, b->obs + (t + 1) * n * kObs, b->rewards + t * n, b->dones + (t + 1) * n, st[k]);
+    }
+  }
+  if (n_slices == 2) {  // join even after an error so the caller's stream stays ordered behind whatever was enqueued
+    for (int k = 0; k < 2; k++)
+      if (cudaEventRecord(pol->ev_join[k], st[k]) != cudaSuccess || cudaStreamWaitEvent((cudaStream_t)stream, pol->ev_join[k], 0) != cudaSuccess)
+        if (rc == QS_OK) rc = qs_fail_(QS_ERR_CUDA, "qs_rollout: stream join failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  return rc;
 }
 
 }  // extern "C"

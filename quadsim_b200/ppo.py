@@ -110,8 +110,9 @@ class MlpPolicy(nn.Module):
         return save_sb_zip(path, self.sb_params(), data)
 
 
-def gae(rewards, values, dones, last_values, last_dones, gamma, lam):
-    """qs_gae: Runner._run's advantage loop (ppo2.py:511-521) on [T,N] float32 CUDA tensors -> (advs, returns)."""
+def gae(rewards, values, dones, last_values, last_dones, gamma, lam, out=None):
+    """qs_gae: Runner._run's advantage loop (ppo2.py:511-521) on [T,N] float32 CUDA tensors -> (advs, returns).
+    `out=(advs, returns)` reuses preallocated [T,N] buffers (a training loop should not allocate per rollout)."""
     T, n = rewards.shape
     r, v = rewards.contiguous(), values.contiguous()
     d = dones.to(torch.uint8).contiguous()
@@ -119,7 +120,7 @@ def gae(rewards, values, dones, last_values, last_dones, gamma, lam):
     for t in (r, v, lv):
         if t.dtype != torch.float32 or not t.is_cuda:
             raise ValueError("gae needs float32 CUDA tensors")
-    adv, ret = torch.empty_like(r), torch.empty_like(r)
+    adv, ret = (torch.empty_like(r), torch.empty_like(r)) if out is None else out
     p = lambda t: C.c_void_p(t.data_ptr())
     with torch.cuda.device(r.device):
         st = C.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)
@@ -128,43 +129,71 @@ def gae(rewards, values, dones, last_values, last_dones, gamma, lam):
 
 
 class DeviceRunner:
-    """Runner (ppo2.py:453-527) with every buffer resident on the GPU, time-major [T, N, ...]."""
+    """Runner (ppo2.py:453-527) with every buffer resident on the GPU, time-major [T, N, ...].
 
-    def __init__(self, env, policy, n_steps, gamma=0.99, lam=0.95, reset_each_rollout=False, generator=None, fused=None):
+    With a FusedPolicy on a float32 docking env the whole step loop is ONE C-ABI call (qs_rollout): the policy kernel and
+    the env kernel read and write the rollout rows in place (obs/dones/values have T+1 rows), two launches per step, no
+    staging copies.  Otherwise the loop runs here with the torch policy."""
+
+    def __init__(self, env, policy, n_steps, gamma=0.99, lam=0.95, reset_each_rollout=False, generator=None, fused=None, n_slices=2):
         self.env, self.policy, self.n_steps, self.gamma, self.lam = env, policy, int(n_steps), gamma, lam
         self.fused = fused  # FusedPolicy (tcgen05 kernel) or None for the torch forward
+        self.n_slices = int(n_slices)  # qs_rollout: 2 = overlap one half's env kernel with the other half's policy kernel
         self.reset_each_rollout = reset_each_rollout  # the in-tree fork's `self.obs = self.env.reset()` (ppo2.py:525)
         self.generator = generator
         n, dev = env.num_envs, env.device
         T = self.n_steps
         f32 = dict(dtype=torch.float32, device=dev)
-        self.mb_obs = torch.empty((T, n, env.obs_dim), **f32)
+        self.in_place = fused is not None and env.dtype == torch.float32 and env.obs_dim == 12
+        self._obs_all = torch.empty((T + 1, n, env.obs_dim), **f32)
+        self._values_all = torch.empty((T + 1, n), **f32)
+        self._dones_all = torch.zeros((T + 1, n), dtype=torch.uint8, device=dev)
+        self.mb_obs, self.mb_values, self.mb_dones = self._obs_all[:T], self._values_all[:T], self._dones_all[:T]
         self.mb_actions = torch.empty((T, n, 4), **f32)
-        self.mb_values = torch.empty((T, n), **f32)
         self.mb_neglogp = torch.empty((T, n), **f32)
         self.mb_rewards = torch.empty((T, n), **f32)
-        self.mb_dones = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        self._clipped = torch.empty((n, 4), **f32)
+        self._advs, self._returns = torch.empty((T, n), **f32), torch.empty((T, n), **f32)
         self.obs = env.reset().float()
         self.dones = torch.zeros(n, dtype=torch.uint8, device=dev)
+
+    def _run_in_place(self):
+        T, env = self.n_steps, self.env
+        self._obs_all[0].copy_(self.obs)      # one 48 B/env copy per ROLLOUT (row T of the previous one), none per step
+        self._dones_all[0].copy_(self.dones)
+        p = lambda t: t.data_ptr()
+        bufs = _capi.RolloutBuffers(p(self._obs_all), p(self.mb_actions), p(self._values_all), p(self.mb_neglogp), p(self.mb_rewards),
+                                    p(self._dones_all), p(self._clipped))
+        with torch.cuda.device(env.device):
+            st = C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)
+            _capi.check(_capi.load().qs_rollout(env._h, self.fused._h, T, C.byref(bufs), self.fused.seed, self.fused._step & 0xFFFFFFFF,
+                                                self.n_slices, st))
+        self.fused._step += T
+        self.obs, self.dones = self._obs_all[T], self._dones_all[T]
+        return self._values_all[T]
 
     @torch.no_grad()
     def run(self):
         env, pol = self.env, self.policy
-        for t in range(self.n_steps):
-            if self.fused is not None:
-                actions, clipped, values, neglogp = self.fused.step(self.obs)
-                clipped = clipped.to(env.dtype)
-            else:
-                actions, values, neglogp = pol.step(self.obs, generator=self.generator)
-                clipped = actions.clamp(-1.0, 1.0).to(env.dtype)  # np.clip to the action Box, ppo2.py:478-481
-            self.mb_obs[t], self.mb_actions[t], self.mb_values[t], self.mb_neglogp[t] = self.obs, actions, values, neglogp
-            self.mb_dones[t] = self.dones
-            obs, rew, done, _ = env.step(clipped)
-            self.obs = obs.float()
-            self.dones = done.to(torch.uint8)
-            self.mb_rewards[t] = rew.float()
-        last_values = self.fused.step(self.obs, deterministic=True, want_clipped=False)[2] if self.fused is not None else pol.forward(self.obs)[1]
-        advs, returns = gae(self.mb_rewards, self.mb_values, self.mb_dones, last_values, self.dones, self.gamma, self.lam)
+        if self.in_place:
+            last_values = self._run_in_place()
+        else:
+            for t in range(self.n_steps):
+                if self.fused is not None:
+                    actions, clipped, values, neglogp = self.fused.step(self.obs)
+                    clipped = clipped.to(env.dtype)
+                else:
+                    actions, values, neglogp = pol.step(self.obs, generator=self.generator)
+                    clipped = actions.clamp(-1.0, 1.0).to(env.dtype)  # np.clip to the action Box, ppo2.py:478-481
+                self.mb_obs[t], self.mb_actions[t], self.mb_values[t], self.mb_neglogp[t] = self.obs, actions, values, neglogp
+                self.mb_dones[t] = self.dones
+                obs, rew, done, _ = env.step(clipped)
+                self.obs = obs.float()
+                self.dones = done.to(torch.uint8)
+                self.mb_rewards[t] = rew.float()
+            last_values = self.fused.step(self.obs, deterministic=True, want_clipped=False)[2] if self.fused is not None else pol.forward(self.obs)[1]
+        advs, returns = gae(self.mb_rewards, self.mb_values, self.mb_dones, last_values, self.dones, self.gamma, self.lam,
+                            out=(self._advs, self._returns))
         if self.reset_each_rollout:
             self.obs = env.reset().float()
         flat = lambda x: x.reshape((-1,) + tuple(x.shape[2:]))  # time-major flatten; minibatches are shuffled anyway

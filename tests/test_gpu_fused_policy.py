@@ -1,7 +1,9 @@
 """GPU checks of the tcgen05 fused policy forward (csrc/qs_policy.cu) against a plain PyTorch fp32 reference of the same
 MLP, and against a torch emulation of its precision recipe (bf16 weights / hidden activations, fp32 accumulation).
-Tolerances: vs the emulation 2e-3 (accumulation order only); vs pure fp32 5e-2 abs on outputs of magnitude O(1)
-(bf16 weights: 2^-9 relative per weight)."""
+Edge cases: a single env, ragged tile counts, fewer tiles than CTA groups, an odd number of tiles.
+Tolerances: vs the emulation 8e-3 (accumulation order, plus the odd hidden activation that lands on the other side of a
+bf16 rounding boundary: one ulp = 2^-8 of an O(1..4) activation times an O(0.1) head weight ~ 1.5e-3 per flip);
+vs pure fp32 5e-2 abs on outputs of magnitude O(1) (bf16 weights: 2^-9 relative per weight)."""
 import math
 
 import numpy as np
@@ -18,15 +20,16 @@ if torch.cuda.is_available():
 
 
 def _emulate(pol, obs):
+    """The kernel's precision recipe: bf16 weights and bf16 hidden activations on all three layers, fp32 accumulation;
+    inputs and hidden-layer biases are hi+lo bf16 pairs (~16 mantissa bits, fp32 here), head biases fp32."""
     bf = lambda t: t.to(torch.bfloat16).float()
-    h = torch.relu(obs @ bf(pol.shared_fc0.weight).t() + pol.shared_fc0.bias)
-    h = bf(h)
-    hp = torch.relu(h @ bf(pol.pi_fc0.weight).t() + pol.pi_fc0.bias)
-    hv = torch.relu(h @ bf(pol.vf_fc0.weight).t() + pol.vf_fc0.bias)
-    return hp @ pol.pi.weight.t() + pol.pi.bias, (hv @ pol.vf.weight.t() + pol.vf.bias).squeeze(-1)
+    h = bf(torch.relu(obs @ bf(pol.shared_fc0.weight).t() + pol.shared_fc0.bias))
+    hp = bf(torch.relu(h @ bf(pol.pi_fc0.weight).t() + pol.pi_fc0.bias))
+    hv = bf(torch.relu(h @ bf(pol.vf_fc0.weight).t() + pol.vf_fc0.bias))
+    return hp @ bf(pol.pi.weight).t() + pol.pi.bias, (hv @ bf(pol.vf.weight).t() + pol.vf.bias).squeeze(-1)
 
 
-@pytest.mark.parametrize("n", [128, 1000, 70001])
+@pytest.mark.parametrize("n", [1, 128, 129, 1000, 70001, 148 * 256 + 128 * 3 + 5])
 def test_fused_forward_matches_torch_reference(n):
     torch.manual_seed(0)
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -40,7 +43,8 @@ def test_fused_forward_matches_torch_reference(n):
     with torch.no_grad():
         mean_ref, val_ref = pol.forward(obs)
         mean_emu, val_emu = _emulate(pol, obs)
-    assert float((act - mean_emu).abs().max()) < 2e-3 and float((val - val_emu).abs().max()) < 2e-3
+    assert float((act - mean_emu).abs().max()) < 8e-3 and float((val - val_emu).abs().max()) < 8e-3
+    assert float((act - mean_emu).abs().mean()) < 1e-4 and float((val - val_emu).abs().mean()) < 1e-4  # flips are rare
     assert float((act - mean_ref).abs().max()) < 5e-2 and float((val - val_ref).abs().max()) < 5e-2
     assert torch.equal(clip, act.clamp(-1, 1))
     const = 0.5 * math.log(2 * math.pi) * 4 + float(pol.logstd.sum())

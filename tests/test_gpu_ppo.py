@@ -96,3 +96,55 @@ def test_ppo2_learn_runs_and_updates():
     assert any(not torch.equal(a, b) for a, b in zip(before, algo.policy.parameters()))
     assert hist[-1]["vf_loss"] < hist[0]["vf_loss"]  # the value head fits the (large, negative) shaped returns
     env.close()
+
+
+@pytest.mark.parametrize("n_slices", [1, 2])
+def test_in_place_rollout_equals_stepwise_loop(n_slices):
+    """qs_rollout (policy + env kernels writing the rollout rows in place) against the same kernels driven step by step
+    through the public objects on a twin environment: every stored quantity must be bit-identical, over two consecutive
+    rollouts (the second continues from row T of the first)."""
+    from quadsim_b200.fused_policy import FusedPolicy
+    n, T = 3000, 24  # ragged: 23.4 tiles
+    torch.manual_seed(0)
+    pol = ppo.MlpPolicy().cuda()
+    with torch.no_grad():
+        pol.logstd.fill_(0.5)  # noisy actions -> some episodes end (and auto-reset) inside the rollouts
+        pol.pi.weight.mul_(20.0)
+    env_a = qs.make_vec("docking-v2", n, seed=5, randomize="episode", want_info=False)
+    env_b = qs.make_vec("docking-v2", n, seed=5, randomize="episode", want_info=False)
+    fa, fb = FusedPolicy(pol, seed=11), FusedPolicy(pol, seed=11)
+    runner = ppo.DeviceRunner(env_a, pol, T, fused=fa, n_slices=n_slices)
+    assert runner.in_place
+    obs = env_b.reset().float()
+    assert torch.equal(obs, runner.obs)
+    dones = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    n_done = 0
+    for rollout in range(5):
+        batch = runner.run()
+        n_done += int(runner._dones_all[1:].sum())
+        for t in range(T):
+            act, clip, val, nlp = fb.step(obs)
+            assert torch.equal(runner.mb_obs[t], obs) and torch.equal(runner.mb_dones[t], dones), (rollout, t)
+            assert torch.equal(runner.mb_actions[t], act) and torch.equal(runner.mb_values[t], val) and torch.equal(runner.mb_neglogp[t], nlp), (rollout, t)
+            obs, rew, done, _ = env_b.step(clip)
+            dones = done.to(torch.uint8)
+            assert torch.equal(runner.mb_rewards[t], rew), (rollout, t)
+        assert torch.equal(runner.obs, obs) and torch.equal(runner.dones, dones)
+        last_v = fb.step(obs, deterministic=True, step_idx=0)[2]
+        a_ref, r_ref = O.gae(runner.mb_rewards.cpu().numpy(), runner.mb_values.cpu().numpy(), runner.mb_dones.cpu().numpy(),
+                             last_v.cpu().numpy(), dones.cpu().numpy(), 0.99, 0.95)
+        assert np.array_equal(batch["advs"].view(T, n).cpu().numpy(), a_ref) and np.array_equal(batch["returns"].view(T, n).cpu().numpy(), r_ref)
+    assert n_done > 0
+    env_a.close()
+    env_b.close()
+
+
+def test_ppo2_learn_with_fused_policy():
+    n = 4096
+    env = qs.make_vec("docking-v2", n, seed=3, randomize="episode")
+    algo = ppo.PPO2(env, n_steps=32, nminibatches=4, noptepochs=2, seed=1, fused_policy=True)
+    assert algo.runner.in_place
+    hist = algo.learn(3 * n * 32)
+    assert len(hist) == 3 and all(np.isfinite(h["pg_loss"]) and np.isfinite(h["vf_loss"]) for h in hist)
+    assert all(h["approxkl"] < 0.05 for h in hist) and hist[-1]["vf_loss"] < hist[0]["vf_loss"]
+    env.close()

@@ -25,6 +25,9 @@ METRICS = [
     "smsp__thread_inst_executed_per_inst_executed.ratio", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
     "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
     "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "sm__cycles_elapsed.max",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+    "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.sum",
+    "smsp__inst_executed_pipe_uniform.sum", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
 ]
 
 
