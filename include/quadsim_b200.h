@@ -162,6 +162,19 @@ int qs_gae(int64_t n_steps, int64_t n_envs, const float* rewards, const float* v
            const float* last_values, const uint8_t* last_dones, double gamma, double lam, float* advs_out,
            float* returns_out, void* stream);
 
+/* ---- PID expert for the chaser (imitation-learning data) ----------------------------------------------------
+ * The controller loop of run_expert_policy.py:44-69 and run_expert_record.py:40-139 (generate_PID_expert_traj) for every
+ * env of a docking handle:  des_vel = 0.35 * (target_pos + [-0.2,0,0] - chaser_pos);  u = controller.vel_controller(
+ * state_des, chaser_state, .) (PIDController.py:106-141);  action = (inv(rotor2control) @ u - action_mean) / action_std.
+ * expert_mem: [N,8] in the handle's dtype, caller-owned, initialised to (0,0,0,0, 1,0,0,0) per env -- the slice of the
+ * scripts' state_des that persists (des vel [3:6], pad, des quaternion [6:10]).
+ * alias_ini_state != 0 reproduces the scripts literally: state_des IS env.chaser_ini_state, which env.reset() aliases as the
+ * chaser's state (quadrotor.py:75), so every episode after the first starts from the mutated initial state and its first
+ * command is plain hover thrust; on those first steps the chaser rows of the env state are re-seated and, if obs_inout
+ * ([N,12], the observations returned by the last step/reset) is given, the reset observation is rewritten to match.
+ * actions_out [N,4] is what env.step expects (already inside the Box for every state the expert reaches). */
+int qs_expert_action(qs_env_t* env, void* expert_mem, int alias_ini_state, void* actions_out, void* obs_inout, void* stream);
+
 /* ---- fused policy forward (tcgen05 / TMEM), the caller side of BASELINE config 5 ------------------------------------
  * model.step(obs) of the reference's PPO2 MlpPolicy (rl_baselines/ppo2/ppo2.py:472; architecture and hyper-parameters
  * run_moving_docking_ppo2.py:88-91: 12 -> 128 relu -> {128 relu -> 4 Gaussian mean, 128 relu -> 1 value}, state-independent

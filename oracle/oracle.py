@@ -215,6 +215,27 @@ class OracleVecEnv:
             pass
 
 
+class OraclePIDExpert:
+    """The reference's PID expert loop (run_expert_record.py:40-139) driving an OracleVecEnv (docking kinds)."""
+
+    def __init__(self, env, alias_ini_state=True):
+        self.env, self.alias = env, int(bool(alias_ini_state))
+        self.mem = np.zeros((env.n, 8))
+        self.mem[:, 4] = 1.0
+
+    def act(self, obs=None):
+        """-> actions[N,4]; in alias mode rewrites rows of `obs` (the reset observations of re-seated chasers) in place."""
+        L, env = lib(), self.env
+        chaser, target, t = env.field("chaser"), env.field("target"), env.field("t")
+        act = np.zeros((env.n, 4))
+        for i in range(env.n):
+            first = int(t[i] == 0)
+            if L.qo_pid_expert_reseat(_p(chaser[i]), _p(self.mem[i]), first, self.alias) and obs is not None:
+                L.qo_state2rel(_p(chaser[i]), _p(target[i]), _p(obs[i]))
+            L.qo_pid_expert_action(_p(chaser[i]), _p(target[i]), _p(self.mem[i]), first, self.alias, _p(act[i]))
+        return act
+
+
 def gae(rewards, values, dones, last_values, last_dones, gamma, lam):
     """Runner._run's GAE loop (ppo2.py:511-521) on [T,N] float32 arrays -> (advs, returns)."""
     r = np.ascontiguousarray(rewards, dtype=np.float32)

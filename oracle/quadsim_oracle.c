@@ -223,6 +223,46 @@ void qo_vel_controller(double des[13], const double now[13], const double last[1
   attitude_controller(des, now, u + 1);
 }
 
+/* The PID expert of the imitation-learning scripts: run_expert_policy.py:44-69 == run_expert_record.py:40-139.
+ *   des_vel = kp * (env.state_target[0:3] + [-0.2,0,0] - env.state_chaser[0:3]) + kd * (-env.state_chaser[3:6])   (:133-134)
+ *   if idx_per_epi != 0: state_des[3:6] = des_vel                                                               (:135-136)
+ *   u = control.vel_controller(state_des, env.state_chaser, state_last)                                         (:137)
+ *   action = (np.linalg.inv(env.chaser.rotor2control) @ u - env.action_mean) / env.action_std                   (:138)
+ * mem[8] = state_des[3:6], pad, state_des[6:10].  alias != 0: state_des IS env.chaser_ini_state (:41), which env.reset()
+ * hands to Drone.reset as the chaser's state array (quadrotor.py:70,75): on the first step of an episode the chaser is
+ * seated on the mutated ini state and des / now / last are ONE array -- reproduced here by really aliasing them.
+ * Returns 1 when the chaser state was re-seated (the caller recomputes the reset observation BEFORE the controller ran:
+ * use qo_pid_expert_reseat first). */
+int qo_pid_expert_reseat(double chaser[13], const double mem[8], int first, int alias) {
+  if (!(first && alias)) return 0;
+  chaser[3] = mem[0]; chaser[4] = mem[1]; chaser[5] = mem[2];
+  memcpy(chaser + 6, mem + 4, 4 * sizeof(double));
+  return 1;
+}
+void qo_pid_expert_action(double chaser[13], const double target[13], double mem[8], int first, int alias, double act[4]) {
+  const double kp = 0.35, kd = 0;
+  double u[4];
+  if (first && alias) {
+    qo_vel_controller(chaser, chaser, chaser, u); /* des == now == last: writes the levelled quaternion into the chaser itself */
+    mem[0] = chaser[3]; mem[1] = chaser[4]; mem[2] = chaser[5];
+    memcpy(mem + 4, chaser + 6, 4 * sizeof(double));
+  } else {
+    double des[13] = {0};
+    const double off[3] = {-0.2, 0, 0};
+    if (!first)
+      for (int k = 0; k < 3; k++) mem[k] = kp * (target[k] + off[k] - chaser[k]) + kd * (-chaser[3 + k]);
+    memcpy(des + 3, mem, 3 * sizeof(double));
+    memcpy(des + 6, mem + 4, 4 * sizeof(double));
+    qo_vel_controller(des, chaser, chaser, u); /* kd_v* == 0: `last` is never felt (Q5) */
+    memcpy(mem + 4, des + 6, 4 * sizeof(double));
+  }
+  /* inv(rotor2control), quadrotor.py:56-59, in closed form; action_mean = action_std = m g / 2 (docking_env.py:98-99) */
+  const double L = 0.086, lam = 1.5e-9 / 6.11e-8, half = 1.0 * 0.18 * 9.81 / 2.0;
+  const double f[4] = {u[0] / 4 - u[2] / (2 * L) + u[3] / (4 * lam), u[0] / 4 + u[1] / (2 * L) - u[3] / (4 * lam),
+                       u[0] / 4 + u[2] / (2 * L) + u[3] / (4 * lam), u[0] / 4 - u[1] / (2 * L) - u[3] / (4 * lam)};
+  for (int k = 0; k < 4; k++) act[k] = (f[k] - half) / half;
+}
+
 static void mat3mul(const double A[9], const double B[9], double C[9]) {
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];

@@ -584,6 +584,62 @@ template <typename T, int KIND> QS_HD void dock_env_step(DockEnv<T>& e, const T 
   o.nonfinite = !m_finite(fsum);
 }
 
+// =========================================================================================================
+// The PID "expert" that flies the CHASER in the reference's imitation-learning scripts (run_expert_policy.py:44-69,
+// run_expert_record.py:40-139):
+//     des_vel = kp * (target_pos + [-0.2, 0, 0] - chaser_pos) + kd * (-chaser_vel),  kp = 0.35, kd = 0
+//     if not first step of the episode: state_des[3:6] = des_vel          (the first step keeps the stale value)
+//     u = controller.vel_controller(state_des, chaser_state, state_last)  (kd_v* = 0: state_last is never felt)
+//     action = (inv(rotor2control) @ u - action_mean) / action_std
+// ExpertMem = the slice of state_des the controller reads and rewrites: des vel [3:6] and des quaternion [6:10] (Q4).
+// `alias`: the scripts bind state_des = env.chaser_ini_state, and env.reset() -> Drone.reset aliases that same array as
+// the chaser's state (quadrotor.py:75).  So (i) every episode after the first starts from the MUTATED initial state
+// (velocity = last des_vel, attitude = last des quaternion), and (ii) on the first step of an episode des, now and last
+// are one array: the velocity error is exactly 0, the controller levels the chaser's own quaternion (keeping its yaw)
+// and the attitude errors vanish, so u = [m g, 0, 0, 0].  alias = true reproduces that literally (`reseated` tells the
+// caller the chaser state / reset observation changed); alias = false treats state_des as a private copy.
+// =========================================================================================================
+template <typename T> struct ExpertMem { T dvx, dvy, dvz; Quat<T> dq; };
+
+template <typename T> QS_HD bool pid_expert_reseat(Drone<T>& c, const ExpertMem<T>& m, bool first, bool alias) {
+  bool reseated = false;
+  if (first && alias) {
+    // env.reset() seated the chaser on chaser_ini_state == state_des: position untouched, [3:6] = des vel, [6:10] = des q
+    c.vx = m.dvx; c.vy = m.dvy; c.vz = m.dvz;
+    c.q0 = m.dq.w; c.q1 = m.dq.x; c.q2 = m.dq.y; c.q3 = m.dq.z;
+    reseated = true;
+  }
+  return reseated;
+}
+
+// second half of the aliased first step, after the caller has taken the reset observation from the re-seated chaser
+template <typename T> QS_HD void pid_expert_cmd(Drone<T>& c, const Drone<T>& t, ExpertMem<T>& m, bool first, bool alias, T act[4]) {
+  using C = K<T>;
+  T F, M0, M1, M2;
+  if (first && alias) {
+    // vel_controller(des, now, last) on ONE array: e_vel == 0 -> acc_des = 0 -> att_des = (0, 0, psi_des); the write of
+    // state_des[6:10] / [10] / [11] lands in the chaser's own state; attitude_controller then sees des == now.
+    T r10 = T(2) * (m.dq.x * m.dq.y - m.dq.w * m.dq.z), r11 = m.dq.w * m.dq.w - m.dq.x * m.dq.x + m.dq.y * m.dq.y - m.dq.z * m.dq.z;
+    m.dq = euler2quat(T(0), T(0), m_atan2(-r10, r11));
+    c.q0 = m.dq.w; c.q1 = m.dq.x; c.q2 = m.dq.y; c.q3 = m.dq.z;
+    c.wx = T(0); c.wy = T(0);
+    F = C::mass * C::g + C::mass * T(0); M0 = T(0); M1 = T(0); M2 = T(0);
+  } else {
+    if (!first) {
+      const T kp = T(0.35), kd = T(0);
+      m.dvx = kp * ((t.px + T(-0.2)) - c.px) + kd * (-c.vx);
+      m.dvy = kp * ((t.py + T(0)) - c.py) + kd * (-c.vy);
+      m.dvz = kp * ((t.pz + T(0)) - c.pz) + kd * (-c.vz);
+    }
+    vel_controller(m.dvx, m.dvy, m.dvz, m.dq, c, F, M0, M1, M2);
+  }
+  // inv(rotor2control) (quadrotor.py:56-59) in closed form, then the env's action normalisation (docking_env.py:98-99)
+  const T hl = T(0.5 / 0.086), ql = T(0.25 / (1.5e-9 / 6.11e-8)), half = T(1.0 * 0.18 * 9.81 / 2.0);
+  const T f0 = (T(0.25) * F - hl * M1) + ql * M2, f1 = (T(0.25) * F + hl * M0) - ql * M2;
+  const T f2 = (T(0.25) * F + hl * M1) + ql * M2, f3 = (T(0.25) * F - hl * M0) - ql * M2;
+  act[0] = (f0 - half) / half; act[1] = (f1 - half) / half; act[2] = (f2 - half) / half; act[3] = (f3 - half) / half;
+}
+
 template <typename T> QS_HD void drone_to_obs13(const Drone<T>& d, T o[13]) {
   o[0] = d.px; o[1] = d.py; o[2] = d.pz; o[3] = d.vx; o[4] = d.vy; o[5] = d.vz;
   o[6] = d.q0; o[7] = d.q1; o[8] = d.q2; o[9] = d.q3; o[10] = d.wx; o[11] = d.wy; o[12] = d.wz;

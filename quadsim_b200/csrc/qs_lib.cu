@@ -653,6 +653,40 @@ __global__ void __launch_bounds__(256) gae_kernel(int64_t T, int64_t n, const fl
   }
 }
 
+// PID expert for the chaser (qs::pid_expert_*; run_expert_policy.py:44-69, run_expert_record.py:40-139): one thread per env,
+// reads the env state rows, keeps its own [N,8] memory (des vel xyz, pad, des q wxyz).  In alias mode the first step of an
+// episode re-seats the chaser from that memory (the scripts' state_des IS env.chaser_ini_state) and rewrites the reset
+// observation the caller is about to record.
+template <typename T>
+__global__ void __launch_bounds__(kBlock) expert_kernel(void* state, int64_t n, T* __restrict__ mem, int alias, T* __restrict__ actions,
+                                                        void* obs) {
+  constexpr int NW = dock_words<T>();
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  T w[NW];
+  load_words<T, NW>(state, i, w);
+  DockEnv<T> e;
+  words_to_dock<T, NW>(w, e);
+  ExpertMem<T> m = {mem[8 * i], mem[8 * i + 1], mem[8 * i + 2], Quat<T>{mem[8 * i + 4], mem[8 * i + 5], mem[8 * i + 6], mem[8 * i + 7]}};
+  const bool first = e.tt == 0;
+  const bool reseated = pid_expert_reseat(e.c, m, first, alias != 0);
+  if (reseated && obs) {  // env.reset()'s observation of the re-seated chaser (docking_env.py:240-244)
+    T rel[12];
+    state2rel(e.c, e.t, rel);
+    store_row<T, 12>(obs, i, rel);
+  }
+  T act[4];
+  pid_expert_cmd(e.c, e.t, m, first, alias != 0, act);
+  if (reseated) {
+    dock_to_words<T, NW>(e, w);
+    store_words<T, NW>(state, i, w);
+  }
+  mem[8 * i] = m.dvx; mem[8 * i + 1] = m.dvy; mem[8 * i + 2] = m.dvz; mem[8 * i + 3] = T(0);
+  mem[8 * i + 4] = m.dq.w; mem[8 * i + 5] = m.dq.x; mem[8 * i + 6] = m.dq.y; mem[8 * i + 7] = m.dq.z;
+#pragma unroll
+  for (int k = 0; k < 4; k++) actions[4 * i + k] = act[k];
+}
+
 __global__ void philox_kernel(int64_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -960,6 +994,20 @@ int qs_gae(int64_t T, int64_t n, const float* rewards, const float* values, cons
   if (T <= 0 || n <= 0) return fail(QS_ERR_INVALID, "qs_gae: n_steps and n_envs must be positive");
   if (!rewards || !values || !dones || !last_values || !last_dones || !advs_out || !returns_out) return fail(QS_ERR_INVALID, "qs_gae: null argument");
   gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, n, rewards, values, dones, last_values, last_dones, gamma, lam, advs_out, returns_out);
+  QS_CUDA(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_expert_action(qs_env_t* e, void* expert_mem, int alias_ini_state, void* actions_out, void* obs_inout, void* stream) {
+  if (!e || !expert_mem || !actions_out) return fail(QS_ERR_INVALID, "qs_expert_action: null argument");
+  if (e->cfg.env_kind == QS_HOVER) return fail(QS_ERR_INVALID, "qs_expert_action: the PID expert flies the chaser of a docking environment");
+  DeviceGuard g(e->cfg.device);
+  const int64_t n = e->cfg.n_envs;
+  const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+  if (e->cfg.dtype == QS_F32)
+    expert_kernel<float><<<grid, kBlock, 0, (cudaStream_t)stream>>>(e->state, n, (float*)expert_mem, alias_ini_state, (float*)actions_out, obs_inout);
+  else
+    expert_kernel<double><<<grid, kBlock, 0, (cudaStream_t)stream>>>(e->state, n, (double*)expert_mem, alias_ini_state, (double*)actions_out, obs_inout);
   QS_CUDA(cudaGetLastError());
   return QS_OK;
 }

@@ -20,6 +20,8 @@ Fixtures
   dock_v{0,2}_wild.npz  single steps from injected wild states (clamp branches, non-unit quaternions, t=599)
   hover_rand.npz     hovering-v0, random actions, auto-reset, Philox-sampled per-env init (once per env)
   policy_v0.npz      weights of the shipped policy best_model_v0.zip + its numpy forward on tape observations
+  expert_v0.npz      the PID expert loop of run_expert_record.py:103-160 (generate_PID_expert_traj) on docking-v0, two episodes
+                     (crosses a reset, so the scripts' state_des = env.chaser_ini_state aliasing is exercised)
   gae_numpy.npz      the GAE loop of Runner._run (ppo2.py:511-521) transcribed and run by numpy on float32 buffers
 """
 import io
@@ -379,6 +381,70 @@ def gen_hover_rand(K=2, T=1000, seed=99, env_id0=3):
     return rec
 
 
+def gen_expert_v0(n_episodes=2):
+    """run_expert_record.py:40-45 (set-up) and :103-160 (loop), statement for statement, on docking-v0 (docking-v1 is the same
+    env with a once-only np.random position jitter, imitating_docking_env.py:34).
+
+    One deliberate difference, and the literal run kept beside it: the script never clears `info_lst`, so from the second
+    episode on `state_last = info_lst[idx_per_epi - 1]['chaser']` (:128) is the FIRST episode's state at that step index and
+    vel_controller's kd_vz * (vz_now - vz_last) term (PIDController.py:113, kd_vz = 0.1) is fed a difference between
+    episodes.  In the first episode, and in run_expert_policy.py (one episode), state_last is the state the previous step
+    returned == the current state, and the term is 0.  The main tape clears info_lst at every reset (term always 0);
+    `literal_actions` holds the script's own output: identical through the first step of episode 2, different after."""
+    out = _expert_loop(n_episodes, clear_info_lst=True)
+    lit = _expert_loop(n_episodes, clear_info_lst=False)
+    first = len(out["actions"]) // n_episodes
+    assert np.array_equal(out["actions"][:first + 1], lit["actions"][:first + 1]) and not np.array_equal(out["actions"], lit["actions"])
+    out["literal_actions"] = lit["actions"]
+    return out
+
+
+def _expert_loop(n_episodes, clear_info_lst):
+    env = R.DockingEnv()
+    control = R.controller(env.chaser.get_arm_length(), env.chaser.get_mass())
+    state_des = env.chaser_ini_state
+    kp, kd = 0.35, 0
+    rec = dict(actions=[], obs=[], rewards=[], episode_starts=[True], chaser=[], target=[], mem=[], done=[], docking=[])
+    episode_returns = np.zeros(n_episodes)
+    info_lst = []
+    ep_idx, reward_sum, idx_per_epi = 0, 0.0, 0
+    obs = env.reset()
+    while ep_idx < n_episodes:
+        rec["obs"].append(np.array(obs, dtype=np.float64).copy())
+        state_last = info_lst[idx_per_epi - 1]["chaser"] if idx_per_epi != 0 else env.chaser_ini_state
+        des_vel = kp * (env.state_target[0:3] + np.array([-0.2, 0, 0]) - env.state_chaser[0:3]) + kd * (-env.state_chaser[3:6])
+        if idx_per_epi != 0:
+            state_des[3:6] = des_vel
+        u = control.vel_controller(state_des, env.state_chaser, state_last)
+        action = (np.linalg.inv(env.chaser.rotor2control) @ u - env.action_mean) / env.action_std
+        obs, reward, done, info = env.step(action)
+        rec["actions"].append(action.copy())
+        rec["rewards"].append(reward)
+        rec["done"].append(done)
+        rec["docking"].append(info["flag_docking"])
+        rec["chaser"].append(env.chaser.state.copy())
+        rec["target"].append(env.target.state.copy())
+        rec["mem"].append(state_des[3:10].copy())
+        info_lst.append(info)
+        rec["episode_starts"].append(done)
+        reward_sum += reward
+        idx_per_epi += 1
+        if done:
+            obs = env.reset()
+            episode_returns[ep_idx] = reward_sum
+            reward_sum, idx_per_epi = 0.0, 0
+            ep_idx += 1
+            if clear_info_lst:
+                info_lst = []
+    out = {k: np.asarray(v) for k, v in rec.items()}
+    out["episode_starts"] = out["episode_starts"][:-1]
+    out["episode_returns"] = episode_returns
+    out["done"] = out["done"].astype(np.uint8)
+    out["docking"] = out["docking"].astype(np.uint8)
+    assert len(out["obs"]) == len(out["actions"]) and out["docking"].sum() > 100
+    return out
+
+
 def gen_gae_numpy():
     """The GAE loop of Runner._run (rl_baselines/ppo2/ppo2.py:503-521) transcribed statement by statement and run by numpy
     on float32 buffers with python-float gamma/lam, exactly as the reference holds them (stable-baselines/TensorFlow are not
@@ -439,6 +505,7 @@ def main():
         "dock_v0_wild": lambda: gen_dock_wild(0),
         "dock_v2_wild": lambda: gen_dock_wild(1),
         "hover_rand": gen_hover_rand,
+        "expert_v0": gen_expert_v0,
         "gae_numpy": gen_gae_numpy,
         "policy_v0": gen_policy_v0,
     }

@@ -92,6 +92,19 @@ template <typename T> void vec_io(void* h, double* buf, int import) {
     }
   }
 }
+// PID expert (qs::pid_expert_*) over the dock envs; mem [n,8] and obs [n,12] in T, exactly what expert_kernel does
+template <typename T> void vec_expert(void* h, T* mem, int alias, T* act, T* obs) {
+  auto* v = (Vec<T>*)h;
+  for (int64_t i = 0; i < v->n; i++) {
+    auto& e = v->dock[i];
+    ExpertMem<T> m = {mem[8 * i], mem[8 * i + 1], mem[8 * i + 2], Quat<T>{mem[8 * i + 4], mem[8 * i + 5], mem[8 * i + 6], mem[8 * i + 7]}};
+    const bool first = e.tt == 0;
+    if (pid_expert_reseat(e.c, m, first, alias != 0) && obs) state2rel(e.c, e.t, obs + 12 * i);
+    pid_expert_cmd(e.c, e.t, m, first, alias != 0, act + 4 * i);
+    mem[8 * i] = m.dvx; mem[8 * i + 1] = m.dvy; mem[8 * i + 2] = m.dvz; mem[8 * i + 3] = T(0);
+    mem[8 * i + 4] = m.dq.w; mem[8 * i + 5] = m.dq.x; mem[8 * i + 6] = m.dq.y; mem[8 * i + 7] = m.dq.z;
+  }
+}
 template <typename T> void vec_destroy(void* h) { auto* v = (Vec<T>*)h; delete[] v->dock; delete[] v->hover; delete v; }
 }  // namespace
 
@@ -104,6 +117,10 @@ void hh_reset(int f64, void* h, void* obs) { f64 ? vec_reset<double>(h, (double*
 void hh_step(int f64, void* h, const void* act, void* obs, void* rew, uint8_t* done, uint8_t* info, void* term) {
   if (f64) vec_step<double>(h, (const double*)act, (double*)obs, (double*)rew, done, info, (double*)term);
   else vec_step<float>(h, (const float*)act, (float*)obs, (float*)rew, done, info, (float*)term);
+}
+void hh_expert(int f64, void* h, void* mem, int alias, void* act, void* obs) {
+  if (f64) vec_expert<double>(h, (double*)mem, alias, (double*)act, (double*)obs);
+  else vec_expert<float>(h, (float*)mem, alias, (float*)act, (float*)obs);
 }
 void hh_io(int f64, void* h, double* buf, int import) { f64 ? vec_io<double>(h, buf, import) : vec_io<float>(h, buf, import); }
 }

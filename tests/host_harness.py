@@ -27,6 +27,7 @@ def lib():
         L.hh_reset.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.hh_step.argtypes = [C.c_int, C.c_void_p] + [C.c_void_p] * 6
         L.hh_io.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.hh_expert.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -56,6 +57,12 @@ class HostVecEnv:
         info = np.zeros(self.n, np.uint8)
         lib().hh_step(self.f64, self._h, _p(a), _p(obs), _p(rew), _p(done), _p(info), _p(term))
         return obs, rew, done, info, term
+
+    def expert_act(self, mem, alias, obs=None):
+        """qs::pid_expert_* on every env; mem [n,8] (updated in place), obs [n,12] rewritten for re-seated chasers."""
+        act = np.zeros((self.n, 4), self.dtype)
+        lib().hh_expert(self.f64, self._h, _p(mem), int(alias), _p(act), _p(obs) if obs is not None else None)
+        return act
 
     FIELDS = {"chaser": (0, 13), "u_c": (13, 17), "target": (17, 30), "u_t": (30, 34), "des_q": (34, 38),
               "last_shaping": (38, 39), "ep_return": (39, 40), "t": (40, 41), "episode": (41, 42)}
