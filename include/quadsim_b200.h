@@ -127,6 +127,13 @@ int qs_host_free(void* p);
 int qs_export_state(qs_env_t* env, const qs_state_arrays_t* dst, void* stream);
 int qs_import_state(qs_env_t* env, const qs_state_arrays_t* src, void* stream);
 
+/* The states an observer needs from a few envs (the reference streams env.chaser.state / env.target.state to its Unity
+ * client every step: server/pub_server.py:25-36, gym_docking/envs/video_docking_env.py): env_ids[k] (device, int64; ids
+ * outside the handle are skipped) -> chaser_out[k,13], target_out[k,13] (docking; may be NULL) float64 world coordinates,
+ * t_out[k] = env.t (may be NULL).  O(k) work: the batch is not exported. */
+int qs_peek_state(qs_env_t* env, const int64_t* env_ids, int64_t k, double* chaser_out, double* target_out, int32_t* t_out,
+                  void* stream);
+
 /* Episode statistics accumulated on the device since the previous call:
  * [sum of episode returns, sum of episode lengths, episodes finished, docked env-steps, env-steps with a non-finite
  * observation or reward].  Synchronises `stream`.  The reference logs these through SB's Monitor/ep_info

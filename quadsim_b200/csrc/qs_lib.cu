@@ -687,6 +687,32 @@ __global__ void __launch_bounds__(kBlock) expert_kernel(void* state, int64_t n, 
   for (int k = 0; k < 4; k++) actions[4 * i + k] = act[k];
 }
 
+// A few envs' drone states for an observer (the Unity bridge, server/pub_server.py:25-36): gather k env ids into
+// [k,13] float64 world-coordinate rows (chaser / single drone, and target for docking).  t_out: env.t (the sim step).
+template <typename T, bool HOVER>
+__global__ void peek_state_kernel(const void* state, int64_t n, const int64_t* ids, int64_t k, double* chaser, double* target, int32_t* t_out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  const int64_t i = ids[j];
+  if (i < 0 || i >= n) return;
+  constexpr int NW = HOVER ? kHoverWords : dock_words<T>();
+  T w[NW];
+  load_words<T, NW>(state, i, w);
+  const int sidx[13] = {0, 1, 2, 4, 5, 6, 8, 9, 10, 11, 3, 7, -1};
+  const double org[3] = {HOVER ? 0.0 : (double)Origin<T>::x, HOVER ? 0.0 : (double)Origin<T>::y, HOVER ? 0.0 : (double)Origin<T>::z};
+#pragma unroll
+  for (int c = 0; c < 13; c++) {
+    const double o = c < 3 ? org[c] : 0.0;
+    chaser[j * 13 + c] = (double)w[c == 12 ? (HOVER ? 16 : 36) : sidx[c]] + o;
+    if (!HOVER && target) target[j * 13 + c] = (double)w[c == 12 ? 37 : 16 + sidx[c]] + o;
+  }
+  if (t_out) {
+    int32_t tt, ep;
+    if (HOVER) tt = word_to_int(w[18]); else unpack_counters(w[NW - 1], tt, ep);
+    t_out[j] = tt;
+  }
+}
+
 __global__ void philox_kernel(int64_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1008,6 +1034,24 @@ int qs_expert_action(qs_env_t* e, void* expert_mem, int alias_ini_state, void* a
     expert_kernel<float><<<grid, kBlock, 0, (cudaStream_t)stream>>>(e->state, n, (float*)expert_mem, alias_ini_state, (float*)actions_out, obs_inout);
   else
     expert_kernel<double><<<grid, kBlock, 0, (cudaStream_t)stream>>>(e->state, n, (double*)expert_mem, alias_ini_state, (double*)actions_out, obs_inout);
+  QS_CUDA(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_peek_state(qs_env_t* e, const int64_t* env_ids, int64_t k, double* chaser_out, double* target_out, int32_t* t_out, void* stream) {
+  if (!e || !env_ids || !chaser_out) return fail(QS_ERR_INVALID, "qs_peek_state: null argument");
+  if (k <= 0) return QS_OK;
+  DeviceGuard g(e->cfg.device);
+  const unsigned grid = (unsigned)((k + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool hover = e->cfg.env_kind == QS_HOVER;
+  if (e->cfg.dtype == QS_F32) {
+    if (hover) peek_state_kernel<float, true><<<grid, 128, 0, st>>>(e->state, e->cfg.n_envs, env_ids, k, chaser_out, target_out, t_out);
+    else peek_state_kernel<float, false><<<grid, 128, 0, st>>>(e->state, e->cfg.n_envs, env_ids, k, chaser_out, target_out, t_out);
+  } else {
+    if (hover) peek_state_kernel<double, true><<<grid, 128, 0, st>>>(e->state, e->cfg.n_envs, env_ids, k, chaser_out, target_out, t_out);
+    else peek_state_kernel<double, false><<<grid, 128, 0, st>>>(e->state, e->cfg.n_envs, env_ids, k, chaser_out, target_out, t_out);
+  }
   QS_CUDA(cudaGetLastError());
   return QS_OK;
 }
