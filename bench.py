@@ -231,7 +231,9 @@ def run_ours(args):
         el = D.max_over_ranks(el, dev)
         esz = 4 if args.dtype == "f32" else 8
         chunks = (n + (1 << 17) - 1) >> 17
+        numa = D.gpu_numa_node(local_rank)
         e2e = {"value": world * n * args.e2e_steps / el, "unit": "env-steps/s", "h2d_bytes_per_step": n * 4 * esz,
+               "numa": {"gpu_node": numa, "cpus_allowed": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None},
                "d2h_bytes_per_step": n * (henv.obs_dim * esz + esz + 1), "steps": args.e2e_steps,
                "api": "QuadVecEnv.step_host -> qs_step_host (pinned numpy in/out, %d chunks pipelined over 4 streams)" % chunks,
                "checksum_reward": float(h_rew.sum())}
@@ -251,6 +253,7 @@ def run_ours(args):
                 "timing": "CUDA events on the launch stream around the %d timed launches / %d" % (args.steps, args.steps)}
     cpu = None
     if not args.no_cpu_baseline:
+        D.restore_affinity()  # the CPU leg uses every host core, not just the GPU's NUMA node
         threads = os.cpu_count() or 1
         res = cpu_port_run(args.env, 1 << 15, None, 2, seconds=args.cpu_seconds, threads=threads)
         cpu = {"value": res["value"], "unit": "env-steps/s", "cores": threads, "kind": "port",

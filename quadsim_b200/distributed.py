@@ -6,6 +6,64 @@ import torch
 import torch.distributed as dist
 
 
+_orig_affinity = None
+
+
+def restore_affinity():
+    """Undo bind_to_gpu_numa_node (e.g. before a CPU-side job that should use every core)."""
+    if _orig_affinity is not None:
+        os.sched_setaffinity(0, _orig_affinity)
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(device_index, sysfs="/sys"):
+    """NUMA node of a CUDA device from its PCI address (sysfs), or None when the box does not say (single node, VM)."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        addr = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open(os.path.join(sysfs, "bus/pci/devices", addr, "numa_node")) as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(device_index, sysfs="/sys"):
+    """Pin this process to the CPUs of its GPU's NUMA node so that the pinned staging buffers of the host path
+    (QuadVecEnv.step_host) are first-touched on the socket the GPU's PCIe root hangs off.  With one rank per GPU and
+    69 B per env-step crossing PCIe in each rank, un-bound ranks all stage through whichever node they happen to run on
+    and the host path stops scaling at ~2 GPUs (measured: 0.86e9 env-steps/s at 1 GPU, 1.6e9 at 2, 4 and 8).
+    Returns the node bound to, or None (nothing known / QUADSIM_B200_NO_NUMA_BIND=1 / not Linux)."""
+    if os.environ.get("QUADSIM_B200_NO_NUMA_BIND") == "1" or not hasattr(os, "sched_setaffinity"):
+        return None
+    node = gpu_numa_node(device_index, sysfs)
+    if node is None:
+        return None
+    try:
+        with open(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node)) as f:
+            cpus = _parse_cpulist(f.read())
+        global _orig_affinity
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed  # stay inside the cgroup / taskset we were given
+        if not cpus:
+            return None
+        if _orig_affinity is None:
+            _orig_affinity = allowed
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def init_from_env(backend=None):
     """Initialise torch.distributed from torchrun's RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* (no-op for a single process)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -13,6 +71,7 @@ def init_from_env(backend=None):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if torch.cuda.is_available():
         torch.cuda.set_device(local_rank)
+        bind_to_gpu_numa_node(local_rank)
     if world > 1 and not dist.is_initialized():
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"

@@ -48,3 +48,33 @@ def test_stats_allreduce_world2_gloo():
     assert [o[1:3] for o in out] == [(0, 500), (500, 1000)]
     for o in out:
         assert o[3] == [4.5, 30.0, 3.0, 0.0, 1000.0] and abs(o[4] - 0.2) < 1e-12
+
+
+def test_numa_binding_helpers(tmp_path, monkeypatch):
+    """bind_to_gpu_numa_node reads the GPU's node and that node's cpulist from sysfs; exercised on a fake sysfs tree."""
+    import os
+    import types
+
+    import torch
+    from quadsim_b200 import distributed as D
+    assert D._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and D._parse_cpulist("") == set()
+    props = types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1b, pci_device_id=0)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda i: props)
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    node = tmp_path / "devices/system/node/node1"
+    node.mkdir(parents=True)
+    allowed = sorted(os.sched_getaffinity(0))
+    (node / "cpulist").write_text("%d\n" % allowed[0])
+    assert D.gpu_numa_node(0, sysfs=str(tmp_path)) == 1
+    before = os.sched_getaffinity(0)
+    try:
+        assert D.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) == 1 and os.sched_getaffinity(0) == {allowed[0]}
+    finally:
+        os.sched_setaffinity(0, before)
+    (dev / "numa_node").write_text("-1\n")  # VMs report -1: nothing to bind to
+    assert D.gpu_numa_node(0, sysfs=str(tmp_path)) is None and D.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None
+    monkeypatch.setenv("QUADSIM_B200_NO_NUMA_BIND", "1")
+    (dev / "numa_node").write_text("1\n")
+    assert D.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None
