@@ -44,11 +44,7 @@ extern int qs_fail_(int code, const char* fmt, ...);  // qs_lib.cu: sets the thr
 namespace {
 
 constexpr int kTileRows = 128;                       // envs per tile == UMMA M == TMEM lanes
-#ifndef QS_POLICY_SIDES
-#define QS_POLICY_SIDES 1  // warps per TMEM lane quadrant in a group: 1 (128-thread groups) or 2 (256: pi side + vf side)
-#endif
-constexpr int kSides = QS_POLICY_SIDES;
-constexpr int kGroupThreads = kTileRows * kSides, kGroups = 2, kThreads = kGroupThreads * kGroups;
+constexpr int kGroupThreads = kTileRows, kGroups = 2, kThreads = kGroupThreads * kGroups;
 constexpr int kObs = 12, kHid = 128, kAct = 4;
 constexpr int kK1 = 32;    // layer-1 K: [hi(12) 1 1 0 0 | lo(12) 0 0 0 0]
 constexpr int kK2 = 144;   // layer-2 K: h(128) 1 1 0...
@@ -62,15 +58,14 @@ constexpr int kOffW3 = kOffW2 + 2 * kHid * kK2 * 2;        // B3 [16 x 256] bf16
 constexpr int kOffTail = kOffW3 + kN3 * kK3 * 2;           // fp32: b3p(4), b3v, pad(3), logstd(4), pad(4)
 constexpr int kTailFloats = 16;
 constexpr int kPackedBytes = kOffTail + kTailFloats * 4;
-constexpr int kOffA = (kPackedBytes + 127) / 128 * 128;    // per group: A2 [128 x 144] bf16 (36 KB); A1 aliases its head
+constexpr int kOffA = (kPackedBytes + 127) / 128 * 128;    // per group: A2 [128 x 144] bf16 (36 KB); A1 / dOut alias its head
 constexpr int kABytes = kTileRows * kK2 * 2;
 constexpr int kOffBar = kOffA + kGroups * kABytes;         // weight mbarrier, one mbarrier per group, TMEM base slot
 constexpr int kSmemBytes = kOffBar + 64;
 // ---- tensor-memory map, columns relative to the group's 256-column window ----
 constexpr uint32_t kTmemCols = 512, kTmemColsPerGroup = 256;
-constexpr int kColsPerSide = 2 * kHid / kSides;            // D2 columns one thread reads out (D1: half as many)
-constexpr uint32_t kColD3 = kColsPerSide / 2;              // 16 columns just behind side 0's packed A3 (consumed D2 columns)
-static_assert(kSides == 1 || kSides == 2, "one or two warps per TMEM lane quadrant");
+constexpr uint32_t kColD3 = 128;                           // 16 columns just behind the packed A3 (consumed D2 columns)
+constexpr uint32_t kColD5 = 128;                           // backward: dA3 halves, then dA2 [128 x 128], behind the packed bf16 operand
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 static_assert(kPackedBytes % 16 == 0, "bulk copies move 16-byte units");
 
@@ -93,12 +88,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kGroupThreads) : "memory"); }
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
-// layout_type = SWIZZLE_NONE [61,64)
+// layout_type = SWIZZLE_NONE [61,64).  No-swizzle canonical layouts (cute mma_traits_sm100.hpp, T = 8 bf16 = 16 bytes):
+//   K-major : ((8,m),(T,2)) : ((1T,SBO),(1,LBO))      8 rows x 16 B core matrix; SBO = next 8 rows, LBO = next 8 k
+//   MN-major: ((T,1,m),(8,k)) : ((1,T,SBO),(1T,LBO))  the same 128 B core matrix read transposed: 8 MN contiguous x 8 k;
+//                                                     SBO = next 8 MN, LBO = next 8 k
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-// UMMA instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7, 10), A K-major,
+// B K-major or MN-major (bit 16)
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool b_mn_major = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // D[tmem] (+)= A[smem] . B[smem]^T
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
@@ -145,6 +146,20 @@ __device__ __forceinline__ uint32_t relu_pack_bf16(uint32_t lo_f32_bits, uint32_
   uint32_t d;
   asm volatile("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi_f32_bits)), "f"(__uint_as_float(lo_f32_bits)));
   return d;
+}
+// relu backward: {bf16(hi) : bf16(lo)} of two fp32 gradient words, each half zeroed where the forward activation's half
+// (a packed, non-negative bf16x2 word) is zero
+__device__ __forceinline__ uint32_t relu_grad_pack_bf16(uint32_t lo_f32_bits, uint32_t hi_f32_bits, uint32_t act_bf16x2) {
+  uint32_t d;
+  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi_f32_bits)), "f"(__uint_as_float(lo_f32_bits)));
+  return d & __vcmpne2(act_bf16x2, 0u);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                 "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr)
+               : "memory");
 }
 
 // ---- one-time weight packing: torch layout [out, in] fp32 -> canonical bf16 operand images + fp32 tail ----
@@ -193,41 +208,58 @@ __global__ void pack_kernel(RawWeights w, unsigned char* packed) {
 
 struct StepArgs {
   const unsigned char* packed;
-  const float* obs;  // [N,12]
-  int64_t n;
+  const float* obs;  // [N,12] (TRAIN: the whole rollout, rows picked through idx)
+  int64_t n;         // rows this launch covers (TRAIN: the minibatch size)
   uint64_t seed, env_id0;
   uint32_t step_idx;
   int deterministic;
   float *actions, *clipped, *values, *neglogp;  // all but values may be null
 };
+// TRAIN only: PPO2's clipped-surrogate loss and its backward pass through the activations (qs_policy_ppo_grad)
+struct TrainArgs {
+  const float *actions, *returns, *values, *neglogp;  // rollout, flat; rows picked through idx
+  const int64_t* idx;                                  // [n] or null (rows 0..n-1)
+  const float* adv_stats;                              // device [2]: mean and 1/(std + 1e-8) of (returns - values) over the minibatch
+  float cliprange, cliprange_vf, vf_coef, inv_batch;
+  uint4 *a1, *h, *hpv, *dz2, *dz1;                     // bf16 rows: [n,32], [n,128], [n,256], [n,256], [n,128]
+  float4* per_sample;                                  // [n,16] fp32
+};
 
 struct ObsRow { float4 a, b, c; };
-__device__ __forceinline__ ObsRow load_obs(const float* obs, int64_t i, int64_t n) {
+__device__ __forceinline__ ObsRow load_obs(const float* obs, int64_t i, int64_t n, const int64_t* idx) {
   ObsRow o = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
   if (i < n) {
-    const float4* p = reinterpret_cast<const float4*>(obs + i * kObs);
+    const int64_t src = idx ? __ldg(idx + i) : i;
+    const float4* p = reinterpret_cast<const float4*>(obs + src * kObs);
     o.a = __ldg(p); o.b = __ldg(p + 1); o.c = __ldg(p + 2);
   }
   return o;
 }
 
-#ifndef QS_POLICY_MINB
-#define QS_POLICY_MINB (3 - QS_POLICY_SIDES)  // register cap only (shared memory admits one CTA per SM): <= 128 registers either way
-#endif
-__global__ void __launch_bounds__(kThreads, QS_POLICY_MINB) policy_step_kernel(const StepArgs a) {
+// One kernel, two instantiations.  TRAIN = false: model.step (rollout).  TRAIN = true: the same forward pass over a minibatch
+// gathered through idx, then PPO2's loss (rl_baselines/ppo2/ppo2.py:138-189) per sample and the backward pass through the
+// activations, on the tensor cores as well:
+//   dOut[128x16]  = (d loss / d mean(4), d loss / d value, 0...)                       per sample, fp32 math, bf16 operand
+//   dA3 [128x256] = dOut . W3              B operand = the forward W3 image read MN-major (no transposed copy)
+//   dZ2           = dA3 * relu'(hp|hv)     mask bits kept in registers from the forward epilogue; packed in place in TMEM
+//   dA2 [128x128] = dZ2 . [Wp;Wv]          A from TMEM (.ts), B = the forward W2 image read MN-major
+//   dZ1           = dA2 * relu'(h)
+// The operands of the weight-gradient GEMMs (A1, h, hp|hv, dZ2, dZ1 as bf16 rows, plus 16 fp32 per sample: dOut, d logstd
+// and the logged loss terms) go to HBM; those GEMMs reduce over the whole minibatch (K = batch) and are left to the caller.
+template <bool TRAIN>
+__global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const StepArgs a, const TrainArgs t) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int g = tid / kGroupThreads, tg = tid % kGroupThreads;
-  const int quad = (tg >> 5) & 3, side = tg >> 7;        // TMEM lane quadrant of this warp; side (kSides == 2): 0 = pi, 1 = vf
-  const int row = quad * 32 + (tid & 31);                // accumulator row == TMEM lane == env within the tile
+  const int g = tid / kGroupThreads, row = tid % kGroupThreads;  // group; accumulator row == TMEM lane == env within the tile
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_w = sbase + kOffBar, bar_mma = sbase + kOffBar + 8 + 8 * g;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 32);
   const float* tail = reinterpret_cast<const float*>(smem + kOffTail);
   const int tiles = (int)((a.n + kTileRows - 1) / kTileRows);
   const int tile0 = blockIdx.x * kGroups + g, tile_stride = gridDim.x * kGroups;
+  const int64_t* idx = TRAIN ? t.idx : nullptr;
 
-  ObsRow o = load_obs(a.obs, (int64_t)tile0 * kTileRows + row, tile0 < tiles ? a.n : 0);  // in flight during the set-up
+  ObsRow o = load_obs(a.obs, (int64_t)tile0 * kTileRows + row, tile0 < tiles ? a.n : 0, idx);  // in flight during the set-up
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
@@ -248,17 +280,18 @@ __global__ void __launch_bounds__(kThreads, QS_POLICY_MINB) policy_step_kernel(c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot + g * kTmemColsPerGroup;          // this group's accumulator columns (lane field 0)
-  const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);        // this warp's 32 TMEM lanes
+  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 TMEM lanes
   unsigned char* a_row = smem + kOffA + g * kABytes + row * 16;      // canon_off(row, 0, 128) == row * 16
   const uint32_t a_base = sbase + kOffA + g * kABytes;
   mbar_wait(bar_w, 0);
 
   constexpr uint32_t idesc1 = umma_idesc(128, kHid), idesc2 = umma_idesc(128, 2 * kHid), idesc3 = umma_idesc(128, kN3);
+  constexpr uint32_t idesc4 = umma_idesc(128, kHid, true), idesc5 = umma_idesc(128, kHid, true);  // B read MN-major
   uint32_t phase = 0;
   for (int tile = tile0; tile < tiles; tile += tile_stride) {
     const int64_t i = (int64_t)tile * kTileRows + row;
     const bool active = i < a.n;
-    // ---- A1: the observation row split hi/lo, K = 32 = four 16-byte core-matrix rows (two sides: one stores hi, one lo) ----
+    // ---- A1: the observation row split hi/lo, K = 32 = four 16-byte core-matrix rows ----
     {
       const float x[12] = {o.a.x, o.a.y, o.a.z, o.a.w, o.b.x, o.b.y, o.b.z, o.b.w, o.c.x, o.c.y, o.c.z, o.c.w};
       uint32_t hi[6], lo[6];
@@ -268,19 +301,18 @@ __global__ void __launch_bounds__(kThreads, QS_POLICY_MINB) policy_step_kernel(c
         hi[k] = pack_bf16(h0, h1);
         lo[k] = pack_bf16(x[2 * k] - h0, x[2 * k + 1] - h1);
       }
-      if (kSides == 1 || side == 0) {  // k = 12, 13: 1.0 against (b1_hi, b1_lo)
-        *reinterpret_cast<uint4*>(a_row + 0 * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(a_row + 1 * 2048) = make_uint4(hi[4], hi[5], 0x3F803F80u, 0u);
-      }
-      if (kSides == 1 || side == 1) {
-        *reinterpret_cast<uint4*>(a_row + 2 * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(a_row + 3 * 2048) = make_uint4(lo[4], lo[5], 0u, 0u);
-      }
+      const uint4 q0 = make_uint4(hi[0], hi[1], hi[2], hi[3]), q1 = make_uint4(hi[4], hi[5], 0x3F803F80u, 0u);  // k = 12, 13: 1.0 against (b1_hi, b1_lo)
+      const uint4 q2 = make_uint4(lo[0], lo[1], lo[2], lo[3]), q3 = make_uint4(lo[4], lo[5], 0u, 0u);
+      *reinterpret_cast<uint4*>(a_row + 0 * 2048) = q0;
+      *reinterpret_cast<uint4*>(a_row + 1 * 2048) = q1;
+      *reinterpret_cast<uint4*>(a_row + 2 * 2048) = q2;
+      *reinterpret_cast<uint4*>(a_row + 3 * 2048) = q3;
+      if (TRAIN && active) { uint4* dst = t.a1 + i * 4; dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3; }
     }
     proxy_fence();       // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     tc_fence_before();   // orders the previous tile's tcgen05.ld before the barrier (TMEM columns are reused)
     group_sync(g);
-    if (tg == 0) {
+    if (row == 0) {
       tc_fence_after();
       // operand rows = 128 -> SBO = 128 B, LBO = 16 row-groups * 128 B = 2048 B; one K=16 step = two k-blocks = 4096 B
 #pragma unroll
@@ -288,14 +320,21 @@ __global__ void __launch_bounds__(kThreads, QS_POLICY_MINB) policy_step_kernel(c
         umma_ss(tmem, umma_desc(a_base + ks * 4096, 2048, 128), umma_desc(sbase + kOffW1 + ks * 4096, 2048, 128), idesc1, ks);
       umma_commit(bar_mma);
     }
-    o = load_obs(a.obs, i + (int64_t)tile_stride * kTileRows, a.n);  // next tile's row, in flight under this tile's work
+    o = load_obs(a.obs, i + (int64_t)tile_stride * kTileRows, a.n, idx);  // next tile's row, in flight under this tile's work
+    // TRAIN: this sample's rollout record (ppo2.py:244-262 feeds): action, return, old value, old neglogp
+    float4 act4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ret = 0.f, oldv = 0.f, oldnlp = 0.f;
+    if (TRAIN && active) {
+      const int64_t src = idx ? __ldg(idx + i) : i;
+      act4 = __ldg(reinterpret_cast<const float4*>(t.actions) + src);
+      ret = __ldg(t.returns + src); oldv = __ldg(t.values + src); oldnlp = __ldg(t.neglogp + src);
+    }
     mbar_wait(bar_mma, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- epilogue 1: h = relu(D1) -> A2[:, 0:128] (each side its share of the columns); A2[:, 128:144] = (1, 1, 0, ...)
-    //      carries layer 2's bias ----
+    // ---- epilogue 1: h = relu(D1) -> A2[:, 0:128]; A2[:, 128:144] = (1, 1, 0, ...) carries layer 2's bias ----
 #pragma unroll 1
-    for (int c0 = (kHid / kSides) * side; c0 < (kHid / kSides) * (side + 1); c0 += 64) {
+    for (int c0 = 0; c0 < kHid; c0 += 64) {
       uint32_t r[64];
       tmem_ld32(trow + c0, r);
       tmem_ld32(trow + c0 + 32, r + 32);
@@ -308,14 +347,15 @@ __global__ void __launch_bounds__(kThreads, QS_POLICY_MINB) policy_step_kernel(c
         w.z = relu_pack_bf16(r[8 * j + 4], r[8 * j + 5]);
         w.w = relu_pack_bf16(r[8 * j + 6], r[8 * j + 7]);
         *reinterpret_cast<uint4*>(a_row + ((c0 >> 3) + j) * 2048) = w;
+        if (TRAIN && active) t.h[i * 16 + (c0 >> 3) + j] = w;
       }
     }
-    if (kSides == 1 || side == 0) *reinterpret_cast<uint4*>(a_row + 16 * 2048) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
-    if (kSides == 1 || side == 1) *reinterpret_cast<uint4*>(a_row + 17 * 2048) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(a_row + 16 * 2048) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(a_row + 17 * 2048) = make_uint4(0u, 0u, 0u, 0u);
     proxy_fence();
     tc_fence_before();
     group_sync(g);
-    if (tg == 0) {
+    if (row == 0) {
       tc_fence_after();
       // B rows = 256 -> LBO = 32 row-groups * 128 B = 4096 B, one K step = 8192 B
 #pragma unroll
@@ -326,38 +366,36 @@ __global__ void __launch_bounds__(kThreads, QS_POLICY_MINB) policy_step_kernel(c
     mbar_wait(bar_mma, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- epilogue 2: relu(D2) -> bf16 pairs written back over the columns they came from (A3 = the lower half of each
-    //      side's column range).  A side compacts only inside its own range, and chunk c's packed columns land in columns the
-    //      same thread has already loaded, so nothing is overwritten before it is read. ----
-    {
-      const uint32_t half = trow + kColsPerSide * side;
+    // ---- epilogue 2: relu(D2) -> bf16 pairs written back over the columns they came from: A3 = columns [0,128).  Chunk c's
+    //      packed columns land in columns this thread has already loaded, so nothing is overwritten before it is read. ----
 #pragma unroll 1
-      for (int c0 = 0; c0 < kColsPerSide; c0 += 64) {
-        uint32_t r[64], w[32];
-        tmem_ld32(half + c0, r);
-        tmem_ld32(half + c0 + 32, r + 32);
-        tmem_wait_ld();
+    for (int c0 = 0; c0 < 2 * kHid; c0 += 64) {
+      uint32_t r[64], w[32];
+      tmem_ld32(trow + c0, r);
+      tmem_ld32(trow + c0 + 32, r + 32);
+      tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; j++) w[j] = relu_pack_bf16(r[2 * j], r[2 * j + 1]);
-        tmem_st16(half + (c0 >> 1), w);
-        tmem_st16(half + (c0 >> 1) + 16, w + 16);
+      for (int j = 0; j < 32; j++) w[j] = relu_pack_bf16(r[2 * j], r[2 * j + 1]);
+      tmem_st16(trow + (c0 >> 1), w);
+      tmem_st16(trow + (c0 >> 1) + 16, w + 16);
+      if (TRAIN && active) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) t.hpv[i * 32 + (c0 >> 3) + j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
       }
-      tmem_wait_st();
     }
+    tmem_wait_st();
     tc_fence_before();
     group_sync(g);
-    if (tg == 0) {
+    if (row == 0) {
       tc_fence_after();
       // A from tensor memory: one K=16 step = 8 columns.  B rows = 16 -> LBO = 2 row-groups * 128 B = 256 B, one K step = 512 B
 #pragma unroll
-      for (int ks = 0; ks < kK3 / 16; ks++)
-        umma_ts(tmem + kColD3, tmem + kColsPerSide * (ks / (kColsPerSide / 16)) + 8 * (ks % (kColsPerSide / 16)),
-                umma_desc(sbase + kOffW3 + ks * 512, 256, 128), idesc3, ks);
+      for (int ks = 0; ks < kK3 / 16; ks++) umma_ts(tmem + kColD3, tmem + 8 * ks, umma_desc(sbase + kOffW3 + ks * 512, 256, 128), idesc3, ks);
       umma_commit(bar_mma);
     }
-    // ---- Gaussian noise while layer 3 runs (DiagGaussianProbabilityDistribution.sample); pi side only ----
+    // ---- Gaussian noise while layer 3 runs (DiagGaussianProbabilityDistribution.sample) ----
     float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
-    if ((kSides == 1 || side == 0) && !a.deterministic) {
+    if (!TRAIN && !a.deterministic) {
       qs::U4 c = {(uint32_t)(a.env_id0 + (uint64_t)i), (uint32_t)((a.env_id0 + (uint64_t)i) >> 32), a.step_idx, 2u};
       qs::U4 x = qs::philox4x32_10(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
       const float s = 5.9604644775390625e-08f;  // 2^-24; u in (0,1)
@@ -369,27 +407,131 @@ __global__ void __launch_bounds__(kThreads, QS_POLICY_MINB) policy_step_kernel(c
       __sincosf(6.283185307179586f * u3, &s1, &c1_);
       n0 = r0 * c0_; n1 = r0 * s0; n2 = r1 * c1_; n3 = r1 * s1;  // Box-Muller
     }
+    const float ls0 = tail[8], ls1 = tail[9], ls2 = tail[10], ls3 = tail[11];
     mbar_wait(bar_mma, phase);
     phase ^= 1;
     tc_fence_after();
     uint32_t d3[8];
     tmem_ld8(trow + kColD3, d3);
     tmem_wait_ld();
-    // ---- sample, log-prob, store ----
-    if (active) {
-      if (kSides == 1 || side == 0) {
-        const float ls0 = tail[8], ls1 = tail[9], ls2 = tail[10], ls3 = tail[11];
-        const float m0 = __uint_as_float(d3[0]) + tail[0], m1 = __uint_as_float(d3[1]) + tail[1];
-        const float m2 = __uint_as_float(d3[2]) + tail[2], m3 = __uint_as_float(d3[3]) + tail[3];
-        const float a0 = fmaf(__expf(ls0), n0, m0), a1 = fmaf(__expf(ls1), n1, m1), a2 = fmaf(__expf(ls2), n2, m2), a3 = fmaf(__expf(ls3), n3, m3);
+    const float mu0 = __uint_as_float(d3[0]) + tail[0], mu1 = __uint_as_float(d3[1]) + tail[1];
+    const float mu2 = __uint_as_float(d3[2]) + tail[2], mu3 = __uint_as_float(d3[3]) + tail[3];
+    const float val = __uint_as_float(d3[4]) + tail[4];
+    if (!TRAIN) {
+      // ---- sample, log-prob, store ----
+      if (active) {
+        const float a0 = fmaf(__expf(ls0), n0, mu0), a1 = fmaf(__expf(ls1), n1, mu1), a2 = fmaf(__expf(ls2), n2, mu2), a3 = fmaf(__expf(ls3), n3, mu3);
         // neglogp = 0.5 * sum(((a - mean)/std)^2) + 0.5*log(2 pi)*4 + sum(logstd); (a - mean)/std == the noise itself
         const float nlp = 0.5f * (n0 * n0 + n1 * n1 + n2 * n2 + n3 * n3) + 3.6757541328186907f + (ls0 + ls1 + ls2 + ls3);
         if (a.actions) reinterpret_cast<float4*>(a.actions)[i] = make_float4(a0, a1, a2, a3);
         if (a.clipped)
           reinterpret_cast<float4*>(a.clipped)[i] = make_float4(fminf(fmaxf(a0, -1.f), 1.f), fminf(fmaxf(a1, -1.f), 1.f), fminf(fmaxf(a2, -1.f), 1.f), fminf(fmaxf(a3, -1.f), 1.f));
+        a.values[i] = val;
         if (a.neglogp) a.neglogp[i] = nlp;
       }
-      if (kSides == 1 || side == 1) a.values[i] = __uint_as_float(d3[4]) + tail[4];
+    } else {
+      // ---- PPO2 loss of this sample and its gradient w.r.t. the network outputs (ppo2.py:138-189; `train_model.proba
+      //      _distribution.neglogp`, the clipped value loss and the clipped surrogate).  Everything is scaled by 1/batch:
+      //      the losses are means over the minibatch. ----
+      float dm0 = 0.f, dm1 = 0.f, dm2 = 0.f, dm3 = 0.f, dval = 0.f, dl0 = 0.f, dl1 = 0.f, dl2 = 0.f, dl3 = 0.f;
+      float pg = 0.f, vf = 0.f, kl = 0.f, cf = 0.f;
+      if (active) {
+        const float is0 = __expf(-ls0), is1 = __expf(-ls1), is2 = __expf(-ls2), is3 = __expf(-ls3);
+        const float z0 = (act4.x - mu0) * is0, z1 = (act4.y - mu1) * is1, z2 = (act4.z - mu2) * is2, z3 = (act4.w - mu3) * is3;
+        const float nlp = 0.5f * (z0 * z0 + z1 * z1 + z2 * z2 + z3 * z3) + 3.6757541328186907f + (ls0 + ls1 + ls2 + ls3);
+        const float adv = ((ret - oldv) - __ldg(t.adv_stats)) * __ldg(t.adv_stats + 1);  // ppo2.py:265-266
+        const float ratio = __expf(oldnlp - nlp);
+        const float rc = fminf(fmaxf(ratio, 1.f - t.cliprange), 1.f + t.cliprange);
+        const float p1 = -adv * ratio, p2 = -adv * rc;
+        pg = fmaxf(p1, p2);
+        // d max(p1, p2) / d ratio: p1 != p2 only where the clip is active (d p2 = 0); equal values share the same slope
+        const float g_ratio = p1 >= p2 ? -adv : 0.f;
+        const float g_nlp = g_ratio * (-ratio) * t.inv_batch;
+        dm0 = g_nlp * (-z0 * is0); dm1 = g_nlp * (-z1 * is1); dm2 = g_nlp * (-z2 * is2); dm3 = g_nlp * (-z3 * is3);
+        dl0 = g_nlp * (1.f - z0 * z0); dl1 = g_nlp * (1.f - z1 * z1); dl2 = g_nlp * (1.f - z2 * z2); dl3 = g_nlp * (1.f - z3 * z3);
+        float e1 = val - ret, e2 = e1, inside = 1.f;
+        if (t.cliprange_vf >= 0.f) {
+          const float dv = val - oldv;
+          e2 = (oldv + fminf(fmaxf(dv, -t.cliprange_vf), t.cliprange_vf)) - ret;
+          inside = fabsf(dv) <= t.cliprange_vf ? 1.f : 0.f;
+        }
+        const float v1 = e1 * e1, v2 = e2 * e2;
+        vf = 0.5f * fmaxf(v1, v2);
+        dval = t.vf_coef * t.inv_batch * (v1 >= v2 ? e1 : e2 * inside);
+        kl = 0.5f * (nlp - oldnlp) * (nlp - oldnlp);
+        cf = fabsf(ratio - 1.f) > t.cliprange ? 1.f : 0.f;
+        float4* ps = t.per_sample + i * 4;
+        ps[0] = make_float4(dm0, dm1, dm2, dm3); ps[1] = make_float4(dval, 0.f, 0.f, 0.f);
+        ps[2] = make_float4(dl0, dl1, dl2, dl3); ps[3] = make_float4(pg, vf, kl, cf);
+      }
+      // dOut as the A operand of the first backward MMAs: [128 x 16] bf16 in k-blocks 16-17 of the A buffer (the bias block,
+      // rewritten every tile); h stays intact in k-blocks 0-15: its zeros are relu' for the last step
+      *reinterpret_cast<uint4*>(a_row + 16 * 2048) = make_uint4(pack_bf16(dm0, dm1), pack_bf16(dm2, dm3), pack_bf16(dval, 0.f), 0u);
+      *reinterpret_cast<uint4*>(a_row + 17 * 2048) = make_uint4(0u, 0u, 0u, 0u);
+      proxy_fence();
+      // dZ2 = (dOut . W3) * relu'(hp|hv), one 128-feature half at a time: the half's dA3 lands in columns [128,256), its
+      // forward activations (bf16 pairs) are still in TMEM at [64 half, 64 half + 64), and dZ2 is packed over them in place
+#pragma unroll 1
+      for (int half = 0; half < 2; half++) {
+        tc_fence_before();
+        group_sync(g);
+        if (row == 0) {
+          tc_fence_after();
+          // B = the W3 image (16 rows x 256 k, K-major) read MN-major: MN = feature (SBO = next 8 features = 256 B),
+          // K = output index (LBO = next 8 outputs = 128 B); one K=16 step, N = 128 features of this half
+          umma_ss(tmem + kColD5, umma_desc(a_base + 16 * 2048, 2048, 128), umma_desc(sbase + kOffW3 + half * 4096, 128, 256), idesc4, 0);
+          umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, phase);
+        phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < kHid; c0 += 32) {
+          uint32_t r[32], act[16], w[16];
+          tmem_ld32(trow + kColD5 + c0, r);
+          tmem_ld16(trow + 64 * half + (c0 >> 1), act);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; j++) w[j] = relu_grad_pack_bf16(r[2 * j], r[2 * j + 1], act[j]);
+          tmem_st16(trow + 64 * half + (c0 >> 1), w);
+          if (active) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) t.dz2[i * 32 + 16 * half + (c0 >> 3) + j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          }
+        }
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      group_sync(g);
+      if (row == 0) {
+        tc_fence_after();
+        // dA2[128 x 128] = dZ2[128 x 256] . [Wp;Wv]: A from TMEM (8 columns per K=16 step); B = the W2 image (256 rows x 144 k)
+        // read MN-major: MN = input feature k (SBO = next 8 k = 4096 B), K = output row n (LBO = next 8 rows = 128 B;
+        // one K=16 step = 256 B)
+#pragma unroll
+        for (int ks = 0; ks < 2 * kHid / 16; ks++) umma_ts(tmem + kColD5, tmem + 8 * ks, umma_desc(sbase + kOffW2 + ks * 256, 128, 4096), idesc5, ks);
+        umma_commit(bar_mma);
+      }
+      mbar_wait(bar_mma, phase);
+      phase ^= 1;
+      tc_fence_after();
+      // ---- dZ1 = dA2 * relu'(h) -> bf16 rows in HBM; h is read back from this thread's row of the A buffer ----
+#pragma unroll 1
+      for (int c0 = 0; c0 < kHid; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(trow + kColD5 + c0, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint4 hw = *reinterpret_cast<const uint4*>(a_row + ((c0 >> 3) + j) * 2048);
+          uint4 w;
+          w.x = relu_grad_pack_bf16(r[8 * j + 0], r[8 * j + 1], hw.x);
+          w.y = relu_grad_pack_bf16(r[8 * j + 2], r[8 * j + 3], hw.y);
+          w.z = relu_grad_pack_bf16(r[8 * j + 4], r[8 * j + 5], hw.z);
+          w.w = relu_grad_pack_bf16(r[8 * j + 6], r[8 * j + 7], hw.w);
+          if (active) t.dz1[i * 16 + (c0 >> 3) + j] = w;
+        }
+      }
     }
   }
   tc_fence_before();
@@ -434,8 +576,9 @@ int qs_policy_create(qs_policy_t** out, int device) {
   int per_sm = 0;
   cudaError_t err;
   if ((err = cudaGetDeviceProperties(&prop, device)) != cudaSuccess || (err = cudaMalloc(&p->packed, kPackedBytes)) != cudaSuccess ||
-      (err = cudaFuncSetAttribute(policy_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
-      (err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, policy_step_kernel, kThreads, kSmemBytes)) != cudaSuccess) {
+      (err = cudaFuncSetAttribute(policy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
+      (err = cudaFuncSetAttribute(policy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
+      (err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, policy_kernel<true>, kThreads, kSmemBytes)) != cudaSuccess) {
     int rc = qs_fail_(QS_ERR_CUDA, "qs_policy_create: %s", cudaGetErrorString(err));
     cudaFree(p->packed);
     delete p;
@@ -498,10 +641,31 @@ int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, u
   QSP_CUDA(cudaSetDevice(p->device));
   StepArgs a = {p->packed, obs, n, seed, env_id0, step_idx, deterministic, actions_out, clipped_out, values_out, neglogp_out};
   const int ctas = (int)(((n + kTileRows - 1) / kTileRows + kGroups - 1) / kGroups);
-  policy_step_kernel<<<ctas < p->grid ? ctas : p->grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a);
+  policy_kernel<false><<<ctas < p->grid ? ctas : p->grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, TrainArgs{});
   cudaError_t e = cudaGetLastError();
   cudaSetDevice(prev);
   if (e != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_policy_step: %s", cudaGetErrorString(e));
+  return QS_OK;
+}
+
+int qs_policy_ppo_grad(qs_policy_t* p, const qs_ppo_grad_t* g, void* stream) {
+  if (!p || !g) return qs_fail_(QS_ERR_INVALID, "qs_policy_ppo_grad: null argument");
+  if (!p->have_weights) return qs_fail_(QS_ERR_INVALID, "qs_policy_ppo_grad: qs_policy_set_weights has not been called");
+  if (!g->obs || !g->actions || !g->returns || !g->values || !g->neglogp || !g->adv_stats || !g->a1 || !g->h || !g->hpv || !g->dz2 || !g->dz1 ||
+      !g->per_sample)
+    return qs_fail_(QS_ERR_INVALID, "qs_policy_ppo_grad: null buffer");
+  if (g->batch <= 0) return qs_fail_(QS_ERR_INVALID, "qs_policy_ppo_grad: batch must be positive");
+  int prev = 0;
+  QSP_CUDA(cudaGetDevice(&prev));
+  QSP_CUDA(cudaSetDevice(p->device));
+  StepArgs a = {p->packed, g->obs, g->batch, 0, 0, 0, 1, nullptr, nullptr, nullptr, nullptr};
+  TrainArgs t = {g->actions, g->returns, g->values, g->neglogp, g->idx, g->adv_stats, g->cliprange, g->cliprange_vf, g->vf_coef,
+                 (float)(1.0 / (double)g->batch), (uint4*)g->a1, (uint4*)g->h, (uint4*)g->hpv, (uint4*)g->dz2, (uint4*)g->dz1, (float4*)g->per_sample};
+  const int ctas = (int)(((g->batch + kTileRows - 1) / kTileRows + kGroups - 1) / kGroups);
+  policy_kernel<true><<<ctas < p->grid ? ctas : p->grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, t);
+  cudaError_t e = cudaGetLastError();
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_policy_ppo_grad: %s", cudaGetErrorString(e));
   return QS_OK;
 }
 

@@ -29,7 +29,9 @@ class FusedPolicy:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def sync_weights(self):
+    def sync_weights(self, sync=True):
+        """Re-pack the module's parameters into the kernel's operand images.  sync=False skips the stream synchronise and
+        instead keeps the fp32 staging tensors alive until the next call (no host stall inside the update loop)."""
         m = self.module
         ts = [m.shared_fc0.weight, m.shared_fc0.bias, m.pi_fc0.weight, m.pi_fc0.bias, m.vf_fc0.weight, m.vf_fc0.bias,
               m.pi.weight, m.pi.bias, m.vf.weight, m.vf.bias, m.logstd]
@@ -37,7 +39,9 @@ class FusedPolicy:
         w = _capi.PolicyWeights(*[t.data_ptr() for t in keep])
         with torch.cuda.device(self.device):
             _capi.check(self.lib.qs_policy_set_weights(self._h, C.byref(w), self._stream()))
-            torch.cuda.current_stream(self.device).synchronize()  # `keep` may hold temporaries
+            if sync:
+                torch.cuda.current_stream(self.device).synchronize()  # `keep` may hold temporaries
+            self._keep = keep  # same-stream allocator reuse is ordered behind the pack kernel anyway
 
     @torch.no_grad()
     def step(self, obs, deterministic=False, step_idx=None, want_clipped=True):
@@ -60,6 +64,54 @@ class FusedPolicy:
 
     def predict(self, obs, deterministic=True):
         return self.step(obs, deterministic=deterministic)[1]
+
+    # ------------------------------------------------------------------ PPO2 minibatch gradient (qs_policy_ppo_grad)
+    def _workspace(self, batch):
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws["batch"] < batch:
+            bf = dict(dtype=torch.bfloat16, device=self.device)
+            ws = dict(batch=batch, a1=torch.empty((batch, 32), **bf), h=torch.empty((batch, 128), **bf), hpv=torch.empty((batch, 256), **bf),
+                      dz2=torch.empty((batch, 256), **bf), dz1=torch.empty((batch, 128), **bf),
+                      per_sample=torch.empty((batch, 16), dtype=torch.float32, device=self.device))
+            self._ws = ws
+        return ws
+
+    @torch.no_grad()
+    def ppo_grad(self, batch, idx, cliprange=0.2, cliprange_vf=None, vf_coef=0.5, ent_coef=0.0):
+        """Gradient of PPO2's loss (ppo2.py:138-189) over the minibatch rows `idx` of the flat rollout `batch` (the dict
+        DeviceRunner.run returns).  One kernel does forward + per-sample loss + the backward pass through the activations
+        on the tensor cores and leaves bf16 operand rows in a workspace; the weight gradients are then one library GEMM per
+        layer over the whole minibatch (K = batch, fp32 out).  Returns ({param: grad} in the module's layouts, logs)."""
+        m, B = self.module, int(idx.shape[0])
+        ws = self._workspace(B)
+        ret, val = batch["returns"], batch["values"]
+        adv = ret[idx] - val[idx]
+        stats = torch.stack([adv.mean(), 1.0 / (adv.std(unbiased=False) + 1e-8)]).float()  # ppo2.py:265-266 (population std)
+        p = lambda t: t.data_ptr()
+        g = _capi.PPOGrad(p(batch["obs"]), p(batch["actions"]), p(ret), p(val), p(batch["neglogp"]), p(idx), B, p(stats),
+                          float(cliprange), float(-1.0 if cliprange_vf is None or cliprange_vf < 0 else cliprange_vf), float(vf_coef),
+                          p(ws["a1"]), p(ws["h"]), p(ws["hpv"]), p(ws["dz2"]), p(ws["dz1"]), p(ws["per_sample"]))
+        for k in ("obs", "actions", "returns", "values", "neglogp"):
+            t = batch[k]
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+                raise ValueError("rollout tensor %r must be contiguous float32 on %s" % (k, self.device))
+        if idx.dtype != torch.int64 or not idx.is_contiguous():
+            raise ValueError("idx must be a contiguous int64 tensor")
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.qs_policy_ppo_grad(self._h, C.byref(g), self._stream()))
+        a1, h, hpv, dz2, dz1, ps = (ws[k][:B] for k in ("a1", "h", "hpv", "dz2", "dz1", "per_sample"))
+        f32 = torch.float32
+        col = ps.sum(0)                                                       # [16]: dOut / d logstd / logged terms, summed
+        g3 = torch.mm(ps[:, :8].to(torch.bfloat16).t(), hpv, out_dtype=f32)  # [8,256]: rows 0-3 pi over hp, row 4 vf over hv
+        g2 = torch.mm(dz2.t(), h, out_dtype=f32)                             # [256,128]
+        b2 = dz2.sum(0, dtype=f32)
+        g1 = torch.mm(dz1.t(), a1, out_dtype=f32)                            # [128,32]: hi half | 1 1 0 0 | lo half | 0...
+        grads = {m.shared_fc0.weight: g1[:, 0:12] + g1[:, 16:28], m.shared_fc0.bias: g1[:, 12],
+                 m.pi_fc0.weight: g2[:128], m.pi_fc0.bias: b2[:128], m.vf_fc0.weight: g2[128:], m.vf_fc0.bias: b2[128:],
+                 m.pi.weight: g3[0:4, :128], m.pi.bias: col[0:4], m.vf.weight: g3[4:5, 128:], m.vf.bias: col[4:5],
+                 m.logstd: (col[8:12] - ent_coef).view_as(m.logstd)}
+        logs = dict(pg_loss=col[12] / B, vf_loss=col[13] / B, approxkl=col[14] / B, clipfrac=col[15] / B, entropy=m.entropy().detach())
+        return grads, logs
 
     def close(self):
         if getattr(self, "_h", None) is not None:

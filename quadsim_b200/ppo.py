@@ -207,7 +207,7 @@ class PPO2:
 
     def __init__(self, env, policy=None, n_steps=600, nminibatches=10, noptepochs=10, learning_rate=3e-4, gamma=0.99, lam=0.95,
                  cliprange=0.2, cliprange_vf=None, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, seed=0, reset_each_rollout=False,
-                 fused_policy=False):
+                 fused_policy=False, fused_update=None):
         self.env = env
         self.device = env.device
         torch.manual_seed(seed)
@@ -217,6 +217,10 @@ class PPO2:
         if fused_policy:
             from .fused_policy import FusedPolicy
             self.fused = FusedPolicy(self.policy, seed=seed, env_id0=getattr(env, "env_id0", 0))
+        # fused_update: gradients from qs_policy_ppo_grad (tensor-core forward/backward + library GEMMs) instead of autograd
+        self.fused_update = bool(fused_policy) if fused_update is None else bool(fused_update)
+        if self.fused_update and self.fused is None:
+            raise ValueError("fused_update needs fused_policy=True")
         self.runner = DeviceRunner(env, self.policy, n_steps, gamma, lam, reset_each_rollout, self.gen, fused=self.fused)
         self.nminibatches, self.noptepochs = nminibatches, noptepochs
         self.cliprange, self.ent_coef, self.vf_coef, self.max_grad_norm = cliprange, ent_coef, vf_coef, max_grad_norm
@@ -257,10 +261,16 @@ class PPO2:
             perm = torch.randperm(n_batch, device=self.device, generator=self.gen)
             for start in range(0, mb_size * self.nminibatches, mb_size):
                 idx = perm[start:start + mb_size]
-                mb = {k: batch[k][idx] for k in keys}
-                total, log = self.loss(mb)
-                self.opt.zero_grad(set_to_none=True)
-                total.backward()
+                if self.fused_update:
+                    grads, log = self.fused.ppo_grad(batch, idx, self.cliprange, self.cliprange_vf, self.vf_coef, self.ent_coef)
+                    self.opt.zero_grad(set_to_none=True)
+                    for prm, grad in grads.items():
+                        prm.grad = grad.contiguous()
+                else:
+                    mb = {k: batch[k][idx] for k in keys}
+                    total, log = self.loss(mb)
+                    self.opt.zero_grad(set_to_none=True)
+                    total.backward()
                 if self.dist:
                     world = torch.distributed.get_world_size()
                     for p in self.policy.parameters():
@@ -270,6 +280,8 @@ class PPO2:
                 if self.max_grad_norm is not None:
                     nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)  # tf.clip_by_global_norm
                 self.opt.step()
+                if self.fused_update:
+                    self.fused.sync_weights(sync=False)  # the next minibatch's forward uses the updated weights
                 logs.append(log)
         if self.fused is not None:
             self.fused.sync_weights()  # re-pack the updated parameters into the tensor-core operand images

@@ -1,0 +1,131 @@
+"""GPU check of qs_policy_ppo_grad (the PPO2 minibatch gradient on the tensor cores) against torch autograd.
+
+Two references: (1) autograd through a torch emulation of the kernel's precision recipe (bf16 weights and hidden
+activations, fp32 accumulation, straight-through rounding) -- the per-sample quantities (losses, d loss / d outputs) must
+agree tightly and the parameter gradients to bf16-GEMM accuracy; (2) autograd through the plain fp32 module (what
+PPO2.loss does) -- same direction, norm within a few percent.  Then one fused optimisation pass vs the autograd pass."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import quadsim_b200 as qs
+    from quadsim_b200 import ppo
+    from quadsim_b200.fused_policy import FusedPolicy
+
+
+class _STE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _emulated_forward(pol, obs):
+    bf = _STE.apply
+    h = bf(torch.relu(obs @ bf(pol.shared_fc0.weight).t() + pol.shared_fc0.bias))
+    hp = bf(torch.relu(h @ bf(pol.pi_fc0.weight).t() + pol.pi_fc0.bias))
+    hv = bf(torch.relu(h @ bf(pol.vf_fc0.weight).t() + pol.vf_fc0.bias))
+    return hp @ bf(pol.pi.weight).t() + pol.pi.bias, (hv @ bf(pol.vf.weight).t() + pol.vf.bias).squeeze(-1)
+
+
+def _loss(algo, forward, mb):
+    mean, vpred = forward(mb["obs"])
+    neglogp = algo.policy.neglogp(mean, mb["actions"])
+    advs = mb["returns"] - mb["values"]
+    advs = (advs - advs.mean()) / (advs.std(unbiased=False) + 1e-8)
+    vclip = mb["values"] + torch.clamp(vpred - mb["values"], -algo.cliprange_vf, algo.cliprange_vf)
+    vf_i = 0.5 * torch.maximum((vpred - mb["returns"]) ** 2, (vclip - mb["returns"]) ** 2)
+    ratio = torch.exp(mb["neglogp"] - neglogp)
+    pg_i = torch.maximum(-advs * ratio, -advs * torch.clamp(ratio, 1.0 - algo.cliprange, 1.0 + algo.cliprange))
+    total = pg_i.mean() - algo.policy.entropy() * algo.ent_coef + vf_i.mean() * algo.vf_coef
+    return total, pg_i, vf_i, ratio, neglogp
+
+
+def _rollout(n=4096, T=12, seed=0):
+    env = qs.make_vec("docking-v2", n, seed=seed, randomize="episode", want_info=False)
+    algo = ppo.PPO2(env, n_steps=T, nminibatches=4, noptepochs=1, seed=seed, fused_policy=True, ent_coef=0.01)
+    with torch.no_grad():
+        algo.policy.pi.weight.mul_(20.0)  # means of O(1): clip fractions and value clips are exercised
+        algo.policy.logstd.fill_(-0.3)
+    algo.fused.sync_weights()
+    batch = algo.runner.run()
+    with torch.no_grad():  # make the policy differ from the one that acted, as inside an optimisation epoch
+        for p in algo.policy.parameters():
+            p.add_(0.02 * torch.randn_like(p) * p.abs().mean())
+        algo.policy.pi.bias.add_(torch.tensor([0.25, -0.2, 0.1, -0.3], device="cuda"))  # ratios leave [0.8, 1.2]
+        algo.policy.vf.bias.add_(0.5)                                                   # value clip (|dv| > 0.2) fires
+    algo.fused.sync_weights()
+    return env, algo, batch
+
+
+@pytest.mark.parametrize("B", [1000, 4096 * 3])
+def test_ppo_grad_matches_autograd(B):
+    env, algo, batch = _rollout()
+    M = batch["obs"].shape[0]
+    idx = torch.randperm(M, device="cuda")[:B].contiguous()
+    grads, logs = algo.fused.ppo_grad(batch, idx, algo.cliprange, algo.cliprange_vf, algo.vf_coef, algo.ent_coef)
+    ps = algo.fused._ws["per_sample"][:B]
+    mb = {k: batch[k][idx] for k in ("obs", "returns", "actions", "values", "neglogp")}
+    params = list(algo.policy.parameters())
+    # (1) emulated precision
+    mean, vpred = _emulated_forward(algo.policy, mb["obs"])
+    mean.retain_grad(); vpred.retain_grad()
+    algo.policy.zero_grad()
+    total, pg_i, vf_i, ratio, nlp = _loss(algo, lambda o: (mean, vpred), mb)
+    total.backward()
+    assert float((ps[:, 12] - pg_i).abs().max()) < 2e-2 and float((ps[:, 12] - pg_i).abs().mean()) < 2e-4
+    assert float((ps[:, 13] - vf_i).abs().max()) < 2e-2 * max(1.0, float(vf_i.max()))
+    assert float((ps[:, :4] - mean.grad).abs().max()) < 0.05 * float(mean.grad.abs().max())
+    assert float((ps[:, 4] - vpred.grad).abs().max()) < 0.05 * float(vpred.grad.abs().max())
+    assert abs(float(logs["pg_loss"]) - float(pg_i.mean())) < 1e-4 and abs(float(logs["vf_loss"]) - float(vf_i.mean())) < 1e-3 * max(1.0, float(vf_i.mean()))
+    assert abs(float(logs["clipfrac"]) - float(((ratio - 1).abs() > algo.cliprange).float().mean())) < 5e-3
+    assert abs(float(logs["approxkl"]) - float(0.5 * ((nlp - mb["neglogp"]) ** 2).mean())) < 1e-4
+    assert float(logs["clipfrac"]) > 0.01  # the branches are really taken
+    for name, prm in algo.policy.named_parameters():
+        if prm.grad is None:
+            continue  # the unused q head
+        a, b = grads[prm].flatten(), prm.grad.flatten()
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+        rel = float((a - b).norm() / (b.norm() + 1e-30))
+        assert cos > 0.995 and rel < 0.08, (name, cos, rel)
+    # (2) plain fp32 autograd: same direction
+    algo.policy.zero_grad()
+    _loss(algo, algo.policy.forward, mb)[0].backward()
+    for name, prm in algo.policy.named_parameters():
+        if prm.grad is None:
+            continue
+        a, b = grads[prm].flatten(), prm.grad.flatten()
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+        assert cos > 0.98 and 0.85 < float(a.norm() / b.norm()) < 1.15, (name, cos)
+    env.close()
+
+
+def test_fused_update_tracks_autograd_update():
+    env, algo, batch = _rollout(n=2048, T=16, seed=2)
+    state = {k: v.clone() for k, v in algo.policy.state_dict().items()}
+    opt_state = algo.opt.state_dict()
+    gen_state = algo.gen.get_state()
+    log_f = algo.update(batch)
+    after_f = [p.detach().clone() for p in algo.policy.parameters()]
+    algo.policy.load_state_dict(state)
+    algo.opt = torch.optim.Adam(algo.policy.parameters(), lr=3e-4, eps=1e-5)
+    algo.gen.set_state(gen_state)
+    algo.fused_update = False
+    log_a = algo.update(batch)
+    moved = [float((a - s).norm()) for a, s in zip(after_f, state.values())]
+    for (name, p_a), p_f, s0 in zip(algo.policy.named_parameters(), after_f, state.values()):
+        if name.startswith("q."):
+            continue
+        step_a, step_f = p_a.detach() - s0, p_f - s0
+        cos = float(torch.dot(step_a.flatten(), step_f.flatten()) / (step_a.norm() * step_f.norm() + 1e-30))
+        assert cos > 0.9, (name, cos)  # Adam's first steps are sign-like: direction is what can be compared
+    for k in ("pg_loss", "vf_loss", "approxkl", "clipfrac"):
+        assert abs(log_f[k] - log_a[k]) < 0.05 * max(abs(log_a[k]), 0.02), (k, log_f[k], log_a[k])
+    assert sum(moved) > 0
+    env.close()
