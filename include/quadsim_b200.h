@@ -215,7 +215,7 @@ int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, u
  * pushes the gradient back through the two hidden layers on the tensor cores.  It writes the operands of the weight-
  * gradient GEMMs -- which reduce over the whole minibatch and are the caller's (a library GEMM per layer):
  *     d W1  = dz1^T . a1   ([128,32]: columns 0-11 + 16-27 = the two halves of the hi/lo input split; column 12 = d b1)
- *     d [Wp;Wv] = dz2^T . h,  d [bp;bv] = column sums of dz2
+ *     d [Wp;Wv | bp;bv] = dz2^T . h   (h rows are [h(128), 1, 1, 0...]: column 128 of the product = d bias)
  *     d [W3p;w3v] = dOut^T . hpv,  d (b3p, b3v) = column sums of dOut,  d logstd = column sums of per_sample[:, 8:12]
  * per_sample[i] = (dOut: d mean 0-3, d value, 0,0,0 | d logstd 0-3 | pg_loss_i, vf_loss_i, approxkl_i, clipfrac_i); the
  * gradients already carry the 1/batch of the mean and vf_coef; the entropy term (-ent_coef per logstd) is the caller's. */
@@ -225,7 +225,7 @@ typedef struct {
   int64_t batch;
   const float* adv_stats;  /* device [2]: mean and 1/(std + 1e-8) of (returns - values) over the minibatch (ppo2.py:265-266) */
   float cliprange, cliprange_vf, vf_coef; /* cliprange_vf < 0: unclipped value loss */
-  void *a1, *h, *hpv, *dz2, *dz1;         /* bf16 rows out: [batch,32], [batch,128], [batch,256], [batch,256], [batch,128] */
+  void *a1, *h, *hpv, *dz2, *dz1;         /* bf16 rows out: [batch,32], [batch,144], [batch,256], [batch,256], [batch,128] */
   float* per_sample;                      /* [batch,16] out */
 } qs_ppo_grad_t;
 int qs_policy_ppo_grad(qs_policy_t* p, const qs_ppo_grad_t* g, void* stream);

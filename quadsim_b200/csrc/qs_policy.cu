@@ -221,7 +221,7 @@ struct TrainArgs {
   const int64_t* idx;                                  // [n] or null (rows 0..n-1)
   const float* adv_stats;                              // device [2]: mean and 1/(std + 1e-8) of (returns - values) over the minibatch
   float cliprange, cliprange_vf, vf_coef, inv_batch;
-  uint4 *a1, *h, *hpv, *dz2, *dz1;                     // bf16 rows: [n,32], [n,128], [n,256], [n,256], [n,128]
+  uint4 *a1, *h, *hpv, *dz2, *dz1;                     // bf16 rows: [n,32], [n,144], [n,256], [n,256], [n,128]
   float4* per_sample;                                  // [n,16] fp32
 };
 
@@ -347,11 +347,15 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
         w.z = relu_pack_bf16(r[8 * j + 4], r[8 * j + 5]);
         w.w = relu_pack_bf16(r[8 * j + 6], r[8 * j + 7]);
         *reinterpret_cast<uint4*>(a_row + ((c0 >> 3) + j) * 2048) = w;
-        if (TRAIN && active) t.h[i * 16 + (c0 >> 3) + j] = w;
+        if (TRAIN && active) t.h[i * 18 + (c0 >> 3) + j] = w;
       }
     }
     *reinterpret_cast<uint4*>(a_row + 16 * 2048) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(a_row + 17 * 2048) = make_uint4(0u, 0u, 0u, 0u);
+    if (TRAIN && active) {  // the bias block goes out with h: dz2^T . [h | 1 1 0...] carries d bias in column 128
+      t.h[i * 18 + 16] = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+      t.h[i * 18 + 17] = make_uint4(0u, 0u, 0u, 0u);
+    }
     proxy_fence();
     tc_fence_before();
     group_sync(g);

@@ -70,7 +70,7 @@ class FusedPolicy:
         ws = getattr(self, "_ws", None)
         if ws is None or ws["batch"] < batch:
             bf = dict(dtype=torch.bfloat16, device=self.device)
-            ws = dict(batch=batch, a1=torch.empty((batch, 32), **bf), h=torch.empty((batch, 128), **bf), hpv=torch.empty((batch, 256), **bf),
+            ws = dict(batch=batch, a1=torch.empty((batch, 32), **bf), h=torch.empty((batch, 144), **bf), hpv=torch.empty((batch, 256), **bf),
                       dz2=torch.empty((batch, 256), **bf), dz1=torch.empty((batch, 128), **bf),
                       per_sample=torch.empty((batch, 16), dtype=torch.float32, device=self.device))
             self._ws = ws
@@ -103,11 +103,11 @@ class FusedPolicy:
         f32 = torch.float32
         col = ps.sum(0)                                                       # [16]: dOut / d logstd / logged terms, summed
         g3 = torch.mm(ps[:, :8].to(torch.bfloat16).t(), hpv, out_dtype=f32)  # [8,256]: rows 0-3 pi over hp, row 4 vf over hv
-        g2 = torch.mm(dz2.t(), h, out_dtype=f32)                             # [256,128]
-        b2 = dz2.sum(0, dtype=f32)
+        g2 = torch.mm(dz2.t(), h, out_dtype=f32)                             # [256,144]: h rows carry (1, 1, 0...) after the 128 features
+        b2 = g2[:, 128]
         g1 = torch.mm(dz1.t(), a1, out_dtype=f32)                            # [128,32]: hi half | 1 1 0 0 | lo half | 0...
         grads = {m.shared_fc0.weight: g1[:, 0:12] + g1[:, 16:28], m.shared_fc0.bias: g1[:, 12],
-                 m.pi_fc0.weight: g2[:128], m.pi_fc0.bias: b2[:128], m.vf_fc0.weight: g2[128:], m.vf_fc0.bias: b2[128:],
+                 m.pi_fc0.weight: g2[:128, :128], m.pi_fc0.bias: b2[:128], m.vf_fc0.weight: g2[128:, :128], m.vf_fc0.bias: b2[128:],
                  m.pi.weight: g3[0:4, :128], m.pi.bias: col[0:4], m.vf.weight: g3[4:5, 128:], m.vf.bias: col[4:5],
                  m.logstd: (col[8:12] - ent_coef).view_as(m.logstd)}
         logs = dict(pg_loss=col[12] / B, vf_loss=col[13] / B, approxkl=col[14] / B, clipfrac=col[15] / B, entropy=m.entropy().detach())
