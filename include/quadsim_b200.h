@@ -117,6 +117,13 @@ int qs_step_ex(qs_env_t* env, const void* actions, void* obs_out, void* reward_o
  * to overlap the HBM-bound env kernel of one slice with the tensor-core policy kernel of another. */
 int qs_step_range(qs_env_t* env, int64_t first, int64_t n, const void* actions, void* obs_out, void* reward_out,
                   uint8_t* done_out, void* stream);
+/* n_steps consecutive qs_step calls in ONE launch, for open-loop stepping (BASELINE config 2: random actions; replaying an
+ * action tape): actions[T,N,4] in, obs_out[T,N,obs_dim], reward_out[T,N], done_out[T,N] out (time-major, the handle's
+ * dtype).  Each env's state stays in registers across the T steps -- no state traffic and no launch per step -- so small
+ * batches are bound by the dependent-instruction chain of one step instead of launch latency.  Same arithmetic as T qs_step calls, auto-reset
+ * included (a separate compilation of it: results agree to the last bit or two, within the same parity bars). */
+int qs_step_n(qs_env_t* env, int64_t n_steps, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out,
+              void* stream);
 /* Same step for HOST buffers (what a numpy VecEnv caller holds): copies actions in, steps, copies results out, chunked
  * over internal streams so H2D, kernel and D2H overlap.  Blocking.  Buffers should come from qs_host_alloc (pinned). */
 int qs_step_host(qs_env_t* env, const void* actions_host, void* obs_host, void* reward_host, uint8_t* done_host);

@@ -21,7 +21,7 @@ SYMBOLS = ["qs_abi_version", "qs_last_error", "qs_create", "qs_destroy", "qs_obs
            "qs_reset", "qs_step", "qs_step_ex", "qs_step_host", "qs_host_alloc", "qs_host_free", "qs_export_state",
            "qs_import_state", "qs_get_stats", "qs_fn_apply", "qs_gae", "qs_policy_create", "qs_policy_destroy",
            "qs_policy_set_weights", "qs_policy_step", "qs_env_dtype", "qs_env_id0", "qs_rollout",
-           "qs_step_range", "qs_expert_action", "qs_peek_state", "qs_policy_ppo_grad"]
+           "qs_step_range", "qs_expert_action", "qs_peek_state", "qs_policy_ppo_grad", "qs_step_n"]
 
 
 class Config(C.Structure):
@@ -102,6 +102,7 @@ def load():
     L.qs_expert_action.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     L.qs_peek_state.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     L.qs_policy_ppo_grad.argtypes = [vp, C.POINTER(PPOGrad), vp]
+    L.qs_step_n.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.qs_gae.argtypes = [i64, i64, vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp]
     if L.qs_abi_version() != ABI_VERSION:
         raise QuadSimError("libquadsim_b200.so ABI %d != expected %d; rebuild" % (L.qs_abi_version(), ABI_VERSION))

@@ -435,6 +435,65 @@ __global__ void __launch_bounds__(kBlock) hover_step_kernel(const StepArgs a) {
 }
 
 // =========================================================================================================
+// T consecutive steps in ONE launch (qs_step_n): open-loop stepping with pre-generated actions[T,N,4] (BASELINE config 2,
+// random-action rollouts, replaying an action tape).  Each thread loads its env once, keeps the whole state in registers
+// across the T steps (no state traffic between steps, no launch per step) and stores it once; per step it reads 4 action
+// words and writes the step's observation / reward / done.  Same arithmetic (qs_core.cuh) as the single-step kernels.
+// =========================================================================================================
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kBlock, min_blocks<T>()) multi_step_kernel(const StepArgs a, int64_t n_steps) {
+  constexpr bool HOVER = KIND == QS_HOVER;
+  constexpr int NW = HOVER ? kHoverWords : dock_words<T>();
+  constexpr int OD = HOVER ? 13 : 12;
+  __shared__ T stage[HOVER ? kBlock * 13 : 1];
+  const int64_t tile0 = (int64_t)blockIdx.x * kBlock;
+  const int64_t i = tile0 + threadIdx.x;
+  const bool active = i < a.n;
+  const int64_t left = a.n - tile0;
+  const int cnt = (int)(left < kBlock ? left : kBlock);
+  const unsigned mask = __ballot_sync(0xffffffffu, active);
+  T w[NW];
+  DockEnv<T> de;
+  HoverEnv<T> he;
+  if (active) {
+    load_words<T, NW>(a.state, i, w);
+    if constexpr (HOVER) words_to_hover<T>(w, he); else words_to_dock<T, NW>(w, de);
+  }
+  for (int64_t t = 0; t < n_steps; t++) {
+    const int64_t row0 = t * a.n;  // outputs and actions are [T, N, ...]
+    T obs[OD];
+    StepOut<T> o;
+    o.done = o.docking = o.nonfinite = false;
+    double stat_ret = 0.0;
+    int stat_len = 0;
+    if (active) {
+      T act[4];
+      load_action<T>(a.actions, row0 + i, act);
+      if constexpr (HOVER) {
+        hover_env_step<T>(he, act, obs, o);
+        stat_ret = (double)he.ep_return; stat_len = he.tt;
+      } else {
+        dock_env_step<T, KIND>(de, act, obs, o);
+        stat_ret = (double)de.last_shaping; stat_len = de.tt;
+      }
+      reinterpret_cast<T*>(a.reward)[row0 + i] = o.reward;
+      a.done[row0 + i] = o.done ? 1 : 0;
+      if (o.done && a.auto_reset) {
+        if constexpr (HOVER) { he.episode += 1; hover_env_seat<T>(he, a.rng, i, obs); }
+        else { de.episode += 1; dock_env_seat<T>(de, a.rng, i, obs); }
+      }
+    }
+    if constexpr (HOVER) store_obs13_tile<T>(stage, a.obs, row0 + tile0, cnt, obs, active);
+    else if (active) store_row<T, 12>(a.obs, row0 + i, obs);
+    if (active) warp_stats_update(a.warp_stats, i, mask, o.done, o.docking, o.nonfinite, stat_ret, stat_len);
+  }
+  if (active) {
+    if constexpr (HOVER) hover_to_words<T>(he, w); else dock_to_words<T, NW>(de, w);
+    store_words<T, NW>(a.state, i, w);
+  }
+}
+
+// =========================================================================================================
 // construct / reset kernels (VecEnv.reset(): docking_env.py:233-244, hovering_env.py:80-82)
 //   mode 0: construct -- episode 0, des_q = identity (docking_env.py:60-63), u = 0
 //   mode 1: reset()   -- envs with t != 0 start their next episode; des_q survives (Q4)
@@ -927,6 +986,31 @@ int qs_step_range(qs_env_t* e, int64_t first, int64_t n, const void* actions, vo
   StepArgs a = make_args(e, first, n);
   a.actions = actions; a.obs = obs_out; a.reward = reward_out; a.done = done_out;
   return launch_step(e, a, (cudaStream_t)stream);
+}
+
+int qs_step_n(qs_env_t* e, int64_t n_steps, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out, void* stream) {
+  if (!e || !actions || !obs_out || !reward_out || !done_out) return fail(QS_ERR_INVALID, "qs_step_n: null argument");
+  if (n_steps < 0) return fail(QS_ERR_INVALID, "qs_step_n: n_steps < 0");
+  if (n_steps == 0) return QS_OK;
+  DeviceGuard g(e->cfg.device);
+  StepArgs a = make_args(e, 0, e->cfg.n_envs);
+  a.actions = actions; a.obs = obs_out; a.reward = reward_out; a.done = done_out;
+  const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool f32 = e->cfg.dtype == QS_F32;
+  switch (e->cfg.env_kind) {
+    case QS_HOVER:
+      if (f32) multi_step_kernel<float, QS_HOVER><<<grid, kBlock, 0, st>>>(a, n_steps); else multi_step_kernel<double, QS_HOVER><<<grid, kBlock, 0, st>>>(a, n_steps);
+      break;
+    case QS_DOCK_V0:
+      if (f32) multi_step_kernel<float, QS_DOCK_V0><<<grid, kBlock, 0, st>>>(a, n_steps); else multi_step_kernel<double, QS_DOCK_V0><<<grid, kBlock, 0, st>>>(a, n_steps);
+      break;
+    default:
+      if (f32) multi_step_kernel<float, QS_DOCK_V2><<<grid, kBlock, 0, st>>>(a, n_steps); else multi_step_kernel<double, QS_DOCK_V2><<<grid, kBlock, 0, st>>>(a, n_steps);
+      break;
+  }
+  QS_CUDA(cudaGetLastError());
+  return QS_OK;
 }
 
 int qs_step(qs_env_t* e, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out, void* stream) {

@@ -180,6 +180,27 @@ class QuadVecEnv:
         self.step_async(actions)
         return self.step_wait()
 
+    def step_many(self, actions):
+        """T consecutive steps in one kernel launch (qs_step_n): actions[T,N,4] -> obs[T,N,obs_dim], rewards[T,N], dones[T,N]
+        (time-major device tensors).  The arithmetic of T step() calls (same parity bars); the env state never leaves
+        registers in between."""
+        self._check_open()
+        a = actions
+        if a.device != self.device or a.dtype != self.dtype:
+            a = a.to(device=self.device, dtype=self.dtype)
+        a = a.contiguous()
+        if a.dim() != 3 or tuple(a.shape[1:]) != (self.num_envs, 4):
+            raise ValueError("actions must have shape (T, %d, 4), got %s" % (self.num_envs, tuple(a.shape)))
+        T, n, dev = a.shape[0], self.num_envs, self.device
+        obs = torch.empty((T, n, self.obs_dim), dtype=self.dtype, device=dev)
+        rew = torch.empty((T, n), dtype=self.dtype, device=dev)
+        done = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _capi.check(self.lib.qs_step_n(self._h, T, self._ptr(a), self._ptr(obs), self._ptr(rew), self._ptr(done), self._stream()))
+            if a is not actions:
+                torch.cuda.current_stream(dev).synchronize()  # the converted copy must outlive the kernel
+        return obs, rew, done.view(torch.bool)
+
     def pinned_host_buffers(self, n_action_buffers=1):
         """Pinned numpy staging buffers for the host path: ([actions...], obs, rewards, dones).  Passing these to
         step_host avoids every extra host-side copy (the DMA engines read/write them directly)."""

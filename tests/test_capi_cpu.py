@@ -49,6 +49,19 @@ def test_invalid_arguments_return_status_not_crash():
     assert L.qs_get_stats(None, None, None) == -1
     assert L.qs_destroy(None) == 0
     assert L.qs_fn_apply(99, 0, 4, None, None, None, None, None, None) == -1
+    # the callers' entry points refuse bad handles the same way
+    assert L.qs_step_range(None, 0, 0, None, None, None, None, None) == -1
+    assert L.qs_rollout(None, None, 4, None, 0, 0, 1, None) == -1 and b"qs_rollout" in L.qs_last_error()
+    assert L.qs_policy_step(None, 4, None, 0, 0, 0, 0, None, None, None, None, None) == -1
+    assert L.qs_policy_set_weights(None, None, None) == -1
+    assert L.qs_policy_ppo_grad(None, None, None) == -1
+    assert L.qs_policy_destroy(None) == 0
+    assert L.qs_expert_action(None, None, 1, None, None, None) == -1
+    assert L.qs_peek_state(None, None, 1, None, None, None, None) == -1
+    assert L.qs_gae(0, 4, None, None, None, None, None, 0.99, 0.95, None, None, None) == -1
+    assert L.qs_env_dtype(None) == -1 and L.qs_env_id0(None) == 0
+    assert C.sizeof(_capi.RolloutBuffers) == 7 * C.sizeof(C.c_void_p)
+    assert C.sizeof(_capi.PPOGrad) == 6 * 8 + 8 + 8 + 3 * 4 + 4 + 6 * 8  # 12-byte float block padded to the next pointer
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -66,6 +79,12 @@ def test_no_cpu_fallback():
     from quadsim_b200 import functional as F
     with pytest.raises(qs.QuadSimError):
         F.quat2euler(torch.zeros(4, 4))
+    hp = C.c_void_p()
+    assert L.qs_policy_create(C.byref(hp), 0) == -3 and b"no CPU fallback" in L.qs_last_error()
+    from quadsim_b200 import ppo
+    from quadsim_b200.fused_policy import FusedPolicy
+    with pytest.raises(qs.QuadSimError):
+        FusedPolicy(ppo.MlpPolicy())
 
 
 def test_product_never_imports_the_oracle():
