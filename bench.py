@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-callers", action="store_true", help="skip the short PPO2-rollout measurement reported under 'callers'")
     return ap.parse_args()
 
 
@@ -239,6 +240,11 @@ def run_ours(args):
                "checksum_reward": float(h_rew.sum())}
         henv.close()
 
+    # ---- the path's caller (SURVEY 8f-1 / BASELINE config 5), a few seconds: PPO2 rollout with the tcgen05 policy in the loop
+    callers = None
+    if not args.no_callers and args.dtype == "f32" and not args.env.startswith("hover"):
+        callers = measure_callers(args, rank, dev, world, D)
+
     if rank != 0:
         return
     peak, peak_src = measured_peak()
@@ -265,8 +271,42 @@ def run_ours(args):
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, n),
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu,
         "episode_stats": {k: stats[k] for k in ("episodes", "mean_length", "mean_return", "docked_steps", "nonfinite_steps")},
+        "callers": callers,
     }
     emit(line)
+
+
+def measure_callers(args, rank, dev, world, D, n_steps=16, rollouts=5):
+    """Not the headline: the rollout-in-the-loop numbers of the path's caller, measured in the same run.  qs_rollout (policy
+    forward on tcgen05 + env step, in place, 2 launches per step) + qs_gae, then one optimisation epoch of the fused PPO2
+    update (qs_policy_ppo_grad + library GEMMs + Adam).  CUDA-event timed, max over ranks."""
+    import torch
+    import quadsim_b200 as qs
+    from quadsim_b200 import ppo
+    n = args.envs_per_gpu
+    env = qs.make_vec(args.env, n, device=dev, seed=0, env_id0=rank * n, randomize="episode", want_info=False, reuse_buffers=True)
+    algo = ppo.PPO2(env, n_steps=n_steps, nminibatches=10, noptepochs=1, fused_policy=True, seed=0)
+    for _ in range(2):
+        batch = algo.runner.run()
+    algo.update(batch)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        torch.distributed.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    for _ in range(rollouts):
+        batch = algo.runner.run()
+    ev[1].record()
+    algo.update(batch)
+    ev[2].record()
+    torch.cuda.synchronize(dev)
+    roll_ms = D.max_over_ranks(ev[0].elapsed_time(ev[1]) / rollouts, dev)
+    upd_ms = D.max_over_ranks(ev[1].elapsed_time(ev[2]), dev)
+    env.close()
+    return {"what": "PPO2 %s rollout-in-the-loop, %d envs/GPU, %d-step rollouts (BASELINE config 5 shape): tcgen05 policy forward + "
+                    "fused env step written in place (qs_rollout) + qs_gae; then one epoch of the fused update" % (args.env, n, n_steps),
+            "rollout_env_steps_per_s": world * n * n_steps / (roll_ms * 1e-3), "rollout_ms": roll_ms, "gpu_launches_per_rollout": 2 * n_steps + 2,
+            "update_samples_per_s": world * n * n_steps / (upd_ms * 1e-3), "update_epoch_ms": upd_ms}
 
 
 _REAL_STDOUT = None
