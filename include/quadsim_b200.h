@@ -252,9 +252,9 @@ typedef struct {
   float* clipped;   /* [N, 4]        scratch: the clipped actions handed to the env */
 } qs_rollout_t;
 /* Noise for step t uses Philox counter word step_idx0 + t (see qs_policy_step).  n_slices = 1: everything in order on
- * `stream`.  n_slices = 2: the envs are cut in two halves that run their step loops on two internal streams (forked from
- * and joined back into `stream`), so one half's env kernel (HBM-bound) overlaps the other half's policy kernel (tensor
- * cores); results are bit-identical to n_slices = 1. */
+ * `stream`.  n_slices = 2..8: the envs are cut into that many slices (whole 128-env tiles) that run their step loops on
+ * internal streams (forked from and joined back into `stream`), so one slice's env kernel (HBM-bound) overlaps another's
+ * policy kernel (tensor cores); results are bit-identical to n_slices = 1. */
 int qs_rollout(qs_env_t* env, qs_policy_t* policy, int64_t n_steps, const qs_rollout_t* buffers, uint64_t seed,
                uint32_t step_idx0, int n_slices, void* stream);
 

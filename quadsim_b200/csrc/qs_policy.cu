@@ -545,13 +545,13 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
 
 }  // namespace
 
-constexpr int kMaxSlices = 2;
+constexpr int kMaxSlices = 8;
 struct qs_policy {
   int device = 0;
   unsigned char* packed = nullptr;
   int grid = 0;
   bool have_weights = false;
-  // qs_rollout with n_slices = 2: one stream per env slice, forked from / joined into the caller's stream
+  // qs_rollout with n_slices > 1: one stream per env slice, forked from / joined into the caller's stream
   cudaStream_t slice_stream[kMaxSlices] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxSlices] = {};
 };
@@ -683,11 +683,13 @@ int qs_rollout(qs_env_t* env, qs_policy_t* pol, int64_t n_steps, const qs_rollou
   const int64_t n = qs_num_envs(env);
   const uint64_t id0 = qs_env_id0(env);
   // slice boundaries on whole 128-env tiles (the state layout's unit)
-  int64_t first[kMaxSlices + 1] = {0, n, n};
-  if (n_slices == 2) first[1] = (n / 2 + kTileRows - 1) / kTileRows * kTileRows;
-  if (first[1] >= n) n_slices = 1, first[1] = n;
-  cudaStream_t st[kMaxSlices] = {(cudaStream_t)stream, (cudaStream_t)stream};
-  if (n_slices == 2) {
+  int64_t first[kMaxSlices + 1];
+  const int64_t tiles = (n + kTileRows - 1) / kTileRows;
+  if (n_slices > tiles) n_slices = (int)tiles;
+  for (int k = 0; k <= n_slices; k++) first[k] = k == n_slices ? n : (tiles * k / n_slices) * kTileRows;
+  cudaStream_t st[kMaxSlices];
+  for (int k = 0; k < kMaxSlices; k++) st[k] = (cudaStream_t)stream;
+  if (n_slices > 1) {
     int prev = 0;
     QSP_CUDA(cudaGetDevice(&prev));
     QSP_CUDA(cudaSetDevice(pol->device));
@@ -700,7 +702,7 @@ int qs_rollout(qs_env_t* env, qs_policy_t* pol, int64_t n_steps, const qs_rollou
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pol->ev_fork, cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventRecord(pol->ev_fork, (cudaStream_t)stream);
-    for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+    for (int k = 0; k < n_slices && e == cudaSuccess; k++) {
       st[k] = pol->slice_stream[k];
       e = cudaStreamWaitEvent(st[k], pol->ev_fork, 0);
     }
@@ -724,8 +726,8 @@ int qs_rollout(qs_env_t* env, qs_policy_t* pol, int64_t n_steps, const qs_rollou
         rc = qs_step_range(env, f, m, b->clipped, b->obs + (t + 1) * n * kObs, b->rewards + t * n, b->dones + (t + 1) * n, st[k]);
     }
   }
-  if (n_slices == 2) {  // join even after an error so the caller's stream stays ordered behind whatever was enqueued
-    for (int k = 0; k < 2; k++)
+  if (n_slices > 1) {  // join even after an error so the caller's stream stays ordered behind whatever was enqueued
+    for (int k = 0; k < n_slices; k++)
       if (cudaEventRecord(pol->ev_join[k], st[k]) != cudaSuccess || cudaStreamWaitEvent((cudaStream_t)stream, pol->ev_join[k], 0) != cudaSuccess)
         if (rc == QS_OK) rc = qs_fail_(QS_ERR_CUDA, "qs_rollout: stream join failed: %s", cudaGetErrorString(cudaGetLastError()));
   }

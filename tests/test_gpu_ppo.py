@@ -98,7 +98,7 @@ def test_ppo2_learn_runs_and_updates():
     env.close()
 
 
-@pytest.mark.parametrize("n_slices", [1, 2])
+@pytest.mark.parametrize("n_slices", [1, 2, 3, 8])
 def test_in_place_rollout_equals_stepwise_loop(n_slices):
     """qs_rollout (policy + env kernels writing the rollout rows in place) against the same kernels driven step by step
     through the public objects on a twin environment: every stored quantity must be bit-identical, over two consecutive
