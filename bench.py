@@ -232,8 +232,21 @@ def run_ours(args):
         el = D.max_over_ranks(el, dev)
         esz = 4 if args.dtype == "f32" else 8
         chunks = (n + (1 << 17) - 1) >> 17
+        # what bounds this leg: the device->host link.  Plain pinned D2H / H2D copies of the same sizes, same process.
+        d_buf = torch.empty(n * (henv.obs_dim * esz + esz + 1), dtype=torch.uint8, device=dev)
+        h_buf = torch.empty(d_buf.numel(), dtype=torch.uint8, pin_memory=True)
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h_buf.copy_(d_buf, non_blocking=True)
+        pe0.record()
+        for _ in range(10):
+            h_buf.copy_(d_buf, non_blocking=True)
+        pe1.record()
+        torch.cuda.synchronize(dev)
+        d2h_gbs = 10 * d_buf.numel() / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
         numa = D.gpu_numa_node(local_rank)
         e2e = {"value": world * n * args.e2e_steps / el, "unit": "env-steps/s", "h2d_bytes_per_step": n * 4 * esz,
+               "pcie": {"d2h_copy_GBps": d2h_gbs, "d2h_achieved_GBps": n * args.e2e_steps / el * (henv.obs_dim * esz + esz + 1) / 1e9,
+                        "note": "this rank; the leg is bound by the device->host link (53 B out vs 16 B in per env-step)"},
                "numa": {"gpu_node": numa, "cpus_allowed": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None},
                "d2h_bytes_per_step": n * (henv.obs_dim * esz + esz + 1), "steps": args.e2e_steps,
                "api": "QuadVecEnv.step_host -> qs_step_host (pinned numpy in/out, %d chunks pipelined over 4 streams)" % chunks,
