@@ -33,6 +33,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -543,6 +544,226 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
 }
 
+// =========================================================================================================
+// Rollout forward, warp-specialised (the kernel qs_policy_step launches).  Same math, same operand images and the same TMEM
+// tricks as policy_kernel<false>; what changes is WHO waits for WHAT.  With two 128-env tiles in flight per SM the kernel
+// is a dependency chain (MMA -> read-out -> pack -> MMA ...), not a bandwidth problem (tensor pipe 38 % busy, TMEM read-out
+// measured at 907 B/clk/SM vs ~50 used: profiles/r1_tmem_read_bandwidth.json), so the chain is shortened:
+//   * a dedicated MMA-issuer warp per group (warps 8, 9): the 128 epilogue threads never stall behind the issue loop; they
+//     signal "operand ready" with mbarrier arrivals and move on, the tensor pipe signals back with tcgen05.commit;
+//   * layer 2 is issued as two N=128 halves with separate commits: the pi half is read out and packed while the vf half
+//     is still in the tensor pipe, and layer 3's first 8 K-steps (pi) run while the vf half is being packed;
+//   * the NEXT tile's A1 is built and its layer 1 issued before the current tile's layer-3 result is consumed (D1 lives in
+//     the vf half's columns, free by then), so sampling and the output stores overlap the next tile's first MMA.
+// TMEM columns of a group's 256-column window:   D1 [128,256) | D2 pi [0,128) -> A3 pi [0,64), D3 [64,80) | D2 vf [128,256)
+// -> A3 vf [128,192).  Every barrier completes exactly once per tile, so the wait parity is the tile counter's low bit.
+// =========================================================================================================
+constexpr int kWsThreads = kThreads + 32 * kGroups;        // 2 x 128 epilogue threads + one issuer warp per group
+constexpr int kWsBarBytes = 8 + kGroups * 64 + 8;          // weights | per group: full_a1, full_a2, full_a3p, full_a3v, done_1, done_p, done_v, done_3 | TMEM slot
+constexpr int kWsSmemBytes = kOffBar + (kWsBarBytes + 63) / 64 * 64;
+static_assert(kWsSmemBytes <= 227 * 1024, "shared memory budget");
+enum { kFullA1 = 0, kFullA2, kFullA3p, kFullA3v, kDone1, kDoneP, kDoneV, kDone3 };
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+__global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const StepArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool issuer = warp >= 2 * 4;
+  const int g = issuer ? warp - 8 : warp >> 2;  // group
+  const int row = tid & 127;                    // epilogue threads: accumulator row == TMEM lane == env within the tile
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_w = sbase + kOffBar, bars = sbase + kOffBar + 8 + 64 * g;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 + kGroups * 64);
+  const float* tail = reinterpret_cast<const float*>(smem + kOffTail);
+  const int tiles = (int)((a.n + kTileRows - 1) / kTileRows);
+  const int tile0 = blockIdx.x * kGroups + g, tile_stride = gridDim.x * kGroups;
+
+  ObsRow o = {};
+  if (!issuer) o = load_obs(a.obs, (int64_t)tile0 * kTileRows + row, tile0 < tiles ? a.n : 0, nullptr);  // in flight during the set-up
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    for (int gg = 0; gg < kGroups; gg++)
+      for (int j = 0; j < 8; j++) mbar_init(sbase + kOffBar + 8 + 64 * gg + 8 * j, j < kDone1 ? kGroupThreads : 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar_w, kPackedBytes);
+    for (int off = 0; off < kPackedBytes; off += 16384) {
+      const int bytes = kPackedBytes - off < 16384 ? kPackedBytes - off : 16384;
+      bulk_g2s(sbase + kOffW1 + off, a.packed + off, bytes, bar_w);
+    }
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot + g * kTmemColsPerGroup;
+  const uint32_t a_base = sbase + kOffA + g * kABytes;
+  constexpr uint32_t idesc_n128 = umma_idesc(128, kHid), idesc3 = umma_idesc(128, kN3);
+  constexpr uint32_t kColD1 = 128, kColD2v = 128, kColD3ws = 64;
+
+  if (issuer) {
+    // ---------------------------------------------------------------- MMA issuer: one elected lane, the warp waits together
+    mbar_wait(bar_w, 0);
+    uint32_t it = 0;
+    for (int tile = tile0; tile < tiles; tile += tile_stride, it++) {
+      const uint32_t ph = it & 1;
+      mbar_wait(bars + 8 * kFullA1, ph);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int ks = 0; ks < kK1 / 16; ks++)
+          umma_ss(tmem + kColD1, umma_desc(a_base + ks * 4096, 2048, 128), umma_desc(sbase + kOffW1 + ks * 4096, 2048, 128), idesc_n128, ks);
+        umma_commit(bars + 8 * kDone1);
+      }
+      __syncwarp();
+      mbar_wait(bars + 8 * kFullA2, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        // the 256-row W2 image, 128 rows at a time: rows 128.. start 16 row-groups (2048 B) in; LBO stays the image's 4096 B
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+#pragma unroll
+          for (int ks = 0; ks < kK2 / 16; ks++)
+            umma_ss(tmem + half * kColD2v, umma_desc(a_base + ks * 4096, 2048, 128), umma_desc(sbase + kOffW2 + half * 2048 + ks * 8192, 4096, 128), idesc_n128, ks);
+          umma_commit(bars + 8 * (half == 0 ? kDoneP : kDoneV));
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        mbar_wait(bars + 8 * (half == 0 ? kFullA3p : kFullA3v), ph);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int k8 = 0; k8 < 8; k8++) {
+            const int ks = 8 * half + k8;
+            umma_ts(tmem + kColD3ws, tmem + half * kColD2v + 8 * k8, umma_desc(sbase + kOffW3 + ks * 512, 256, 128), idesc3, ks);
+          }
+          if (half == 1) umma_commit(bars + 8 * kDone3);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue threads
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    unsigned char* a_row = smem + kOffA + g * kABytes + row * 16;
+    auto build_a1 = [&](const ObsRow& ob) {
+      const float x[12] = {ob.a.x, ob.a.y, ob.a.z, ob.a.w, ob.b.x, ob.b.y, ob.b.z, ob.b.w, ob.c.x, ob.c.y, ob.c.z, ob.c.w};
+      uint32_t hi[6], lo[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const float h0 = bf16_round(x[2 * k]), h1 = bf16_round(x[2 * k + 1]);
+        hi[k] = pack_bf16(h0, h1);
+        lo[k] = pack_bf16(x[2 * k] - h0, x[2 * k + 1] - h1);
+      }
+      *reinterpret_cast<uint4*>(a_row + 0 * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(a_row + 1 * 2048) = make_uint4(hi[4], hi[5], 0x3F803F80u, 0u);  // k = 12, 13: 1.0 against (b1_hi, b1_lo)
+      *reinterpret_cast<uint4*>(a_row + 2 * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<uint4*>(a_row + 3 * 2048) = make_uint4(lo[4], lo[5], 0u, 0u);
+      proxy_fence();
+      mbar_arrive(bars + 8 * kFullA1);
+    };
+    mbar_wait(bar_w, 0);  // the fp32 tail (biases of the heads, logstd) is read from shared memory below
+    if (tile0 < tiles) build_a1(o);
+    uint32_t it = 0;
+    for (int tile = tile0; tile < tiles; tile += tile_stride, it++) {
+      const uint32_t ph = it & 1;
+      const int64_t i = (int64_t)tile * kTileRows + row;
+      const bool active = i < a.n;
+      const bool more = tile + tile_stride < tiles;
+      o = load_obs(a.obs, i + (int64_t)tile_stride * kTileRows, a.n, nullptr);  // next tile's row, in flight under this tile's work
+      // ---- h = relu(D1) -> A2[:, 0:128]; A2[:, 128:144] = (1, 1, 0, ...) carries layer 2's bias ----
+      mbar_wait(bars + 8 * kDone1, ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < kHid; c0 += 64) {
+        uint32_t r[64];
+        tmem_ld32(trow + kColD1 + c0, r);
+        tmem_ld32(trow + kColD1 + c0 + 32, r + 32);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          uint4 w;
+          w.x = relu_pack_bf16(r[8 * j + 0], r[8 * j + 1]);
+          w.y = relu_pack_bf16(r[8 * j + 2], r[8 * j + 3]);
+          w.z = relu_pack_bf16(r[8 * j + 4], r[8 * j + 5]);
+          w.w = relu_pack_bf16(r[8 * j + 6], r[8 * j + 7]);
+          *reinterpret_cast<uint4*>(a_row + ((c0 >> 3) + j) * 2048) = w;
+        }
+      }
+      *reinterpret_cast<uint4*>(a_row + 16 * 2048) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(a_row + 17 * 2048) = make_uint4(0u, 0u, 0u, 0u);
+      proxy_fence();
+      tc_fence_before();  // D1 is read; the vf half of layer 2 will overwrite its columns
+      mbar_arrive(bars + 8 * kFullA2);
+      // ---- relu(D2 half) -> bf16 pairs packed in place: A3 pi = [0,64), A3 vf = [128,192) ----
+#pragma unroll 1
+      for (int half = 0; half < 2; half++) {
+        mbar_wait(bars + 8 * (half == 0 ? kDoneP : kDoneV), ph);
+        tc_fence_after();
+        const uint32_t base = trow + half * kColD2v;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kHid; c0 += 64) {
+          uint32_t r[64], w[32];
+          tmem_ld32(base + c0, r);
+          tmem_ld32(base + c0 + 32, r + 32);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; j++) w[j] = relu_pack_bf16(r[2 * j], r[2 * j + 1]);
+          tmem_st16(base + (c0 >> 1), w);
+          tmem_st16(base + (c0 >> 1) + 16, w + 16);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bars + 8 * (half == 0 ? kFullA3p : kFullA3v));
+      }
+      // ---- the next tile's A1 (the A buffer is free: both layer-2 halves have completed) and its layer 1, under our tail ----
+      if (more) build_a1(o);
+      // ---- Gaussian noise while layer 3 runs (DiagGaussianProbabilityDistribution.sample) ----
+      float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+      if (!a.deterministic) {
+        qs::U4 c = {(uint32_t)(a.env_id0 + (uint64_t)i), (uint32_t)((a.env_id0 + (uint64_t)i) >> 32), a.step_idx, 2u};
+        qs::U4 x = qs::philox4x32_10(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        const float s = 5.9604644775390625e-08f;  // 2^-24; u in (0,1)
+        const float u0 = ((float)(x.x >> 8) + 0.5f) * s, u1 = ((float)(x.y >> 8) + 0.5f) * s;
+        const float u2 = ((float)(x.z >> 8) + 0.5f) * s, u3 = ((float)(x.w >> 8) + 0.5f) * s;
+        const float r0 = sqrtf(-2.f * __logf(u0)), r1 = sqrtf(-2.f * __logf(u2));
+        float s0, c0_, s1, c1_;
+        __sincosf(6.283185307179586f * u1, &s0, &c0_);
+        __sincosf(6.283185307179586f * u3, &s1, &c1_);
+        n0 = r0 * c0_; n1 = r0 * s0; n2 = r1 * c1_; n3 = r1 * s1;  // Box-Muller
+      }
+      const float ls0 = tail[8], ls1 = tail[9], ls2 = tail[10], ls3 = tail[11];
+      mbar_wait(bars + 8 * kDone3, ph);
+      tc_fence_after();
+      uint32_t d3[8];
+      tmem_ld8(trow + kColD3ws, d3);
+      tmem_wait_ld();
+      tc_fence_before();  // D3 is read before the next tile's pi half (ordered by our full_a2 arrival) overwrites it
+      if (active) {
+        const float mu0 = __uint_as_float(d3[0]) + tail[0], mu1 = __uint_as_float(d3[1]) + tail[1];
+        const float mu2 = __uint_as_float(d3[2]) + tail[2], mu3 = __uint_as_float(d3[3]) + tail[3];
+        const float val = __uint_as_float(d3[4]) + tail[4];
+        const float a0 = fmaf(__expf(ls0), n0, mu0), a1 = fmaf(__expf(ls1), n1, mu1), a2 = fmaf(__expf(ls2), n2, mu2), a3 = fmaf(__expf(ls3), n3, mu3);
+        const float nlp = 0.5f * (n0 * n0 + n1 * n1 + n2 * n2 + n3 * n3) + 3.6757541328186907f + (ls0 + ls1 + ls2 + ls3);
+        if (a.actions) reinterpret_cast<float4*>(a.actions)[i] = make_float4(a0, a1, a2, a3);
+        if (a.clipped)
+          reinterpret_cast<float4*>(a.clipped)[i] = make_float4(fminf(fmaxf(a0, -1.f), 1.f), fminf(fmaxf(a1, -1.f), 1.f), fminf(fmaxf(a2, -1.f), 1.f), fminf(fmaxf(a3, -1.f), 1.f));
+        a.values[i] = val;
+        if (a.neglogp) a.neglogp[i] = nlp;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
+}
+
 }  // namespace
 
 constexpr int kMaxSlices = 8;
@@ -582,6 +803,7 @@ int qs_policy_create(qs_policy_t** out, int device) {
   if ((err = cudaGetDeviceProperties(&prop, device)) != cudaSuccess || (err = cudaMalloc(&p->packed, kPackedBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
+      (err = cudaFuncSetAttribute(policy_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
       (err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, policy_kernel<true>, kThreads, kSmemBytes)) != cudaSuccess) {
     int rc = qs_fail_(QS_ERR_CUDA, "qs_policy_create: %s", cudaGetErrorString(err));
     cudaFree(p->packed);
@@ -645,7 +867,10 @@ int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, u
   QSP_CUDA(cudaSetDevice(p->device));
   StepArgs a = {p->packed, obs, n, seed, env_id0, step_idx, deterministic, actions_out, clipped_out, values_out, neglogp_out};
   const int ctas = (int)(((n + kTileRows - 1) / kTileRows + kGroups - 1) / kGroups);
-  policy_kernel<false><<<ctas < p->grid ? ctas : p->grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, TrainArgs{});
+  // QUADSIM_B200_POLICY=v3 selects the previous (leader-thread-in-group) forward kernel for A/B
+  static const bool use_v3 = [] { const char* v = getenv("QUADSIM_B200_POLICY"); return v && strcmp(v, "v3") == 0; }();
+  if (use_v3) policy_kernel<false><<<ctas < p->grid ? ctas : p->grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, TrainArgs{});
+  else policy_fwd_ws_kernel<<<ctas < p->grid ? ctas : p->grid, kWsThreads, kWsSmemBytes, (cudaStream_t)stream>>>(a);
   cudaError_t e = cudaGetLastError();
   cudaSetDevice(prev);
   if (e != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_policy_step: %s", cudaGetErrorString(e));
