@@ -555,10 +555,23 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
 //     is still in the tensor pipe, and layer 3's first 8 K-steps (pi) run while the vf half is being packed;
 //   * the NEXT tile's A1 is built and its layer 1 issued before the current tile's layer-3 result is consumed (D1 lives in
 //     the vf half's columns, free by then), so sampling and the output stores overlap the next tile's first MMA.
-// TMEM columns of a group's 256-column window:   D1 [128,256) | D2 pi [0,128) -> A3 pi [0,64), D3 [64,80) | D2 vf [128,256)
-// -> A3 vf [128,192).  Every barrier completes exactly once per tile, so the wait parity is the tile counter's low bit.
+//   * optionally (QS_POLICY_WS_SIDES=2) two epilogue warps per TMEM lane quadrant, each reading out / packing half of every
+//     128-column phase, side 0 sampling the action and side 1 storing the value -- measured SLOWER (96 vs 91 us): what is
+//     left of the chain is barrier / commit / fence round trips, not the epilogues' instruction count.
+// TMEM columns of a group's 256-column window (two sides): D1 [128,256) | D2 pi [0,128): side s reads [64s, 64s+64) and
+// packs A3 pi into its own first 32 columns [64s, 64s+32); D3 [32,48) | D2 vf [128,256) likewise -> A3 vf [128+64s, +32).
+// Every barrier completes exactly once per tile, so the wait parity is the tile counter's low bit.
 // =========================================================================================================
-constexpr int kWsThreads = kThreads + 32 * kGroups;        // 2 x 128 epilogue threads + one issuer warp per group
+#ifndef QS_POLICY_WS_SIDES
+#define QS_POLICY_WS_SIDES 1   // epilogue warps per TMEM lane quadrant and group: 1 or 2 (each side takes half the columns);
+                               // measured 90.8 us (1) vs 96.4 us (2) per 2^20 envs: the chain is sync latency, not ALU work
+#endif
+constexpr int kWsSides = QS_POLICY_WS_SIDES;
+constexpr int kWsEpi = kTileRows * kWsSides;               // epilogue threads per group
+constexpr int kWsThreads = kGroups * kWsEpi + 32 * kGroups; // + one issuer warp per group
+constexpr int kWsCols = kHid / kWsSides;                   // accumulator columns one thread reads out per 128-column phase
+constexpr int kWsChunk = kWsSides == 1 ? 64 : 32;          // ... per tcgen05.wait::ld (register budget: 576 threads x <= 112)
+static_assert(kWsSides == 1 || kWsSides == 2, "one or two epilogue warps per quadrant");
 constexpr int kWsBarBytes = 8 + kGroups * 64 + 8;          // weights | per group: full_a1, full_a2, full_a3p, full_a3v, done_1, done_p, done_v, done_3 | TMEM slot
 constexpr int kWsSmemBytes = kOffBar + (kWsBarBytes + 63) / 64 * 64;
 static_assert(kWsSmemBytes <= 227 * 1024, "shared memory budget");
@@ -569,9 +582,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarri
 __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const StepArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool issuer = warp >= 2 * 4;
-  const int g = issuer ? warp - 8 : warp >> 2;  // group
-  const int row = tid & 127;                    // epilogue threads: accumulator row == TMEM lane == env within the tile
+  constexpr int kEpiWarps = kGroups * kWsEpi / 32;
+  const bool issuer = warp >= kEpiWarps;
+  const int g = issuer ? warp - kEpiWarps : tid / kWsEpi;  // group
+  const int side = issuer ? 0 : (tid % kWsEpi) / kTileRows; // which half of the columns this epilogue thread handles
+  const int row = tid & 127;                               // epilogue threads: accumulator row == TMEM lane == env within the tile
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_w = sbase + kOffBar, bars = sbase + kOffBar + 8 + 64 * g;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 + kGroups * 64);
@@ -585,7 +600,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
   if (tid == 0) {
     mbar_init(bar_w, 1);
     for (int gg = 0; gg < kGroups; gg++)
-      for (int j = 0; j < 8; j++) mbar_init(sbase + kOffBar + 8 + 64 * gg + 8 * j, j < kDone1 ? kGroupThreads : 1);
+      for (int j = 0; j < 8; j++) mbar_init(sbase + kOffBar + 8 + 64 * gg + 8 * j, j < kDone1 ? kWsEpi : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(bar_w, kPackedBytes);
     for (int off = 0; off < kPackedBytes; off += 16384) {
@@ -603,7 +618,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
   const uint32_t tmem = *tmem_slot + g * kTmemColsPerGroup;
   const uint32_t a_base = sbase + kOffA + g * kABytes;
   constexpr uint32_t idesc_n128 = umma_idesc(128, kHid), idesc3 = umma_idesc(128, kN3);
-  constexpr uint32_t kColD1 = 128, kColD2v = 128, kColD3ws = 64;
+  constexpr uint32_t kColD1 = 128, kColD2v = 128, kColD3ws = kWsCols / 2;  // D3: 16 columns right behind side 0's packed A3 pi
 
   if (issuer) {
     // ---------------------------------------------------------------- MMA issuer: one elected lane, the warp waits together
@@ -639,9 +654,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
         tc_fence_after();
         if (lane == 0) {
 #pragma unroll
-          for (int k8 = 0; k8 < 8; k8++) {
-            const int ks = 8 * half + k8;
-            umma_ts(tmem + kColD3ws, tmem + half * kColD2v + 8 * k8, umma_desc(sbase + kOffW3 + ks * 512, 256, 128), idesc3, ks);
+          for (int k8 = 0; k8 < 8; k8++) {  // K-step k8 of this half: features 16 k8 .., packed by side (16 k8) / kWsCols
+            const int ks = 8 * half + k8, sd = (16 * k8) / kWsCols, kk = (16 * k8) % kWsCols;
+            umma_ts(tmem + kColD3ws, tmem + half * kColD2v + sd * kWsCols + kk / 2, umma_desc(sbase + kOffW3 + ks * 512, 256, 128), idesc3, ks);
           }
           if (half == 1) umma_commit(bars + 8 * kDone3);
         }
@@ -661,10 +676,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
         hi[k] = pack_bf16(h0, h1);
         lo[k] = pack_bf16(x[2 * k] - h0, x[2 * k + 1] - h1);
       }
-      *reinterpret_cast<uint4*>(a_row + 0 * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(a_row + 1 * 2048) = make_uint4(hi[4], hi[5], 0x3F803F80u, 0u);  // k = 12, 13: 1.0 against (b1_hi, b1_lo)
-      *reinterpret_cast<uint4*>(a_row + 2 * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      *reinterpret_cast<uint4*>(a_row + 3 * 2048) = make_uint4(lo[4], lo[5], 0u, 0u);
+      if (kWsSides == 1 || side == 0) {
+        *reinterpret_cast<uint4*>(a_row + 0 * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(a_row + 1 * 2048) = make_uint4(hi[4], hi[5], 0x3F803F80u, 0u);  // k = 12, 13: 1.0 against (b1_hi, b1_lo)
+      }
+      if (kWsSides == 1 || side == 1) {
+        *reinterpret_cast<uint4*>(a_row + 2 * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(a_row + 3 * 2048) = make_uint4(lo[4], lo[5], 0u, 0u);
+      }
       proxy_fence();
       mbar_arrive(bars + 8 * kFullA1);
     };
@@ -681,13 +700,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
       mbar_wait(bars + 8 * kDone1, ph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < kHid; c0 += 64) {
-        uint32_t r[64];
-        tmem_ld32(trow + kColD1 + c0, r);
-        tmem_ld32(trow + kColD1 + c0 + 32, r + 32);
+      for (int c0 = kWsCols * side; c0 < kWsCols * (side + 1); c0 += kWsChunk) {
+        uint32_t r[kWsChunk];
+#pragma unroll
+        for (int q = 0; q < kWsChunk; q += 32) tmem_ld32(trow + kColD1 + c0 + q, r + q);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < kWsChunk / 8; j++) {
           uint4 w;
           w.x = relu_pack_bf16(r[8 * j + 0], r[8 * j + 1]);
           w.y = relu_pack_bf16(r[8 * j + 2], r[8 * j + 3]);
@@ -696,8 +715,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
           *reinterpret_cast<uint4*>(a_row + ((c0 >> 3) + j) * 2048) = w;
         }
       }
-      *reinterpret_cast<uint4*>(a_row + 16 * 2048) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(a_row + 17 * 2048) = make_uint4(0u, 0u, 0u, 0u);
+      if (kWsSides == 1 || side == 0) *reinterpret_cast<uint4*>(a_row + 16 * 2048) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+      if (kWsSides == 1 || side == 1) *reinterpret_cast<uint4*>(a_row + 17 * 2048) = make_uint4(0u, 0u, 0u, 0u);
       proxy_fence();
       tc_fence_before();  // D1 is read; the vf half of layer 2 will overwrite its columns
       mbar_arrive(bars + 8 * kFullA2);
@@ -706,17 +725,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
       for (int half = 0; half < 2; half++) {
         mbar_wait(bars + 8 * (half == 0 ? kDoneP : kDoneV), ph);
         tc_fence_after();
-        const uint32_t base = trow + half * kColD2v;
+        const uint32_t base = trow + half * kColD2v + kWsCols * side;  // this side's columns; its packed A3 lands at their start
 #pragma unroll 1
-        for (int c0 = 0; c0 < kHid; c0 += 64) {
-          uint32_t r[64], w[32];
-          tmem_ld32(base + c0, r);
-          tmem_ld32(base + c0 + 32, r + 32);
+        for (int c0 = 0; c0 < kWsCols; c0 += kWsChunk) {
+          uint32_t r[kWsChunk], w[kWsChunk / 2];
+#pragma unroll
+          for (int q = 0; q < kWsChunk; q += 32) tmem_ld32(base + c0 + q, r + q);
           tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; j++) w[j] = relu_pack_bf16(r[2 * j], r[2 * j + 1]);
-          tmem_st16(base + (c0 >> 1), w);
-          tmem_st16(base + (c0 >> 1) + 16, w + 16);
+          for (int j = 0; j < kWsChunk / 2; j++) w[j] = relu_pack_bf16(r[2 * j], r[2 * j + 1]);
+#pragma unroll
+          for (int q = 0; q < kWsChunk / 2; q += 16) tmem_st16(base + (c0 >> 1) + q, w + q);
         }
         tmem_wait_st();
         tc_fence_before();
@@ -726,7 +745,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
       if (more) build_a1(o);
       // ---- Gaussian noise while layer 3 runs (DiagGaussianProbabilityDistribution.sample) ----
       float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
-      if (!a.deterministic) {
+      if ((kWsSides == 1 || side == 0) && !a.deterministic) {
         qs::U4 c = {(uint32_t)(a.env_id0 + (uint64_t)i), (uint32_t)((a.env_id0 + (uint64_t)i) >> 32), a.step_idx, 2u};
         qs::U4 x = qs::philox4x32_10(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
         const float s = 5.9604644775390625e-08f;  // 2^-24; u in (0,1)
@@ -749,13 +768,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
         const float mu0 = __uint_as_float(d3[0]) + tail[0], mu1 = __uint_as_float(d3[1]) + tail[1];
         const float mu2 = __uint_as_float(d3[2]) + tail[2], mu3 = __uint_as_float(d3[3]) + tail[3];
         const float val = __uint_as_float(d3[4]) + tail[4];
-        const float a0 = fmaf(__expf(ls0), n0, mu0), a1 = fmaf(__expf(ls1), n1, mu1), a2 = fmaf(__expf(ls2), n2, mu2), a3 = fmaf(__expf(ls3), n3, mu3);
-        const float nlp = 0.5f * (n0 * n0 + n1 * n1 + n2 * n2 + n3 * n3) + 3.6757541328186907f + (ls0 + ls1 + ls2 + ls3);
-        if (a.actions) reinterpret_cast<float4*>(a.actions)[i] = make_float4(a0, a1, a2, a3);
-        if (a.clipped)
-          reinterpret_cast<float4*>(a.clipped)[i] = make_float4(fminf(fmaxf(a0, -1.f), 1.f), fminf(fmaxf(a1, -1.f), 1.f), fminf(fmaxf(a2, -1.f), 1.f), fminf(fmaxf(a3, -1.f), 1.f));
-        a.values[i] = val;
-        if (a.neglogp) a.neglogp[i] = nlp;
+        if (kWsSides == 1 || side == 0) {
+          const float a0 = fmaf(__expf(ls0), n0, mu0), a1 = fmaf(__expf(ls1), n1, mu1), a2 = fmaf(__expf(ls2), n2, mu2), a3 = fmaf(__expf(ls3), n3, mu3);
+          const float nlp = 0.5f * (n0 * n0 + n1 * n1 + n2 * n2 + n3 * n3) + 3.6757541328186907f + (ls0 + ls1 + ls2 + ls3);
+          if (a.actions) reinterpret_cast<float4*>(a.actions)[i] = make_float4(a0, a1, a2, a3);
+          if (a.clipped)
+            reinterpret_cast<float4*>(a.clipped)[i] = make_float4(fminf(fmaxf(a0, -1.f), 1.f), fminf(fmaxf(a1, -1.f), 1.f), fminf(fmaxf(a2, -1.f), 1.f), fminf(fmaxf(a3, -1.f), 1.f));
+          if (a.neglogp) a.neglogp[i] = nlp;
+        }
+        if (kWsSides == 1 || side == 1) a.values[i] = val;
       }
     }
   }
