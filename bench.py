@@ -301,7 +301,7 @@ def measure_callers(args, rank, dev, world, D, n_steps=16, rollouts=5):
     algo = ppo.PPO2(env, n_steps=n_steps, nminibatches=10, noptepochs=1, fused_policy=True, seed=0)
     for _ in range(2):
         batch = algo.runner.run()
-    algo.update(batch)
+        algo.update(batch)  # twice: workspaces, GEMM heuristics and the NCCL communicator are all set up lazily
     torch.cuda.synchronize(dev)
     if world > 1:
         torch.distributed.barrier()

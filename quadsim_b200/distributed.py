@@ -108,6 +108,24 @@ def all_reduce_stats(vals, device=None):
     return t
 
 
+def all_reduce_mean_grads(params):
+    """Average the gradients of `params` over ranks with ONE all-reduce: the words travel as a single flat bucket (the PPO2
+    policy has 11 parameter tensors, ~35 k words; 11 small collectives per minibatch cost more than the gradient kernel).
+    Each p.grad is replaced by a view into the reduced bucket.  No-op without an initialised process group."""
+    if not dist.is_initialized():
+        return
+    with_grad = [p for p in params if p.grad is not None]
+    if not with_grad:
+        return
+    flat = torch.cat([p.grad.reshape(-1) for p in with_grad])
+    dist.all_reduce(flat)
+    flat /= dist.get_world_size()
+    off = 0
+    for p in with_grad:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+
+
 def max_over_ranks(x, device=None):
     """MAX-reduce a python float over ranks (bench timing)."""
     if not dist.is_initialized():

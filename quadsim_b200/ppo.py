@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _capi
+from .distributed import all_reduce_mean_grads
 from .sb_zip import load_sb_zip, save_sb_zip
 
 
@@ -272,11 +273,7 @@ class PPO2:
                     self.opt.zero_grad(set_to_none=True)
                     total.backward()
                 if self.dist:
-                    world = torch.distributed.get_world_size()
-                    for p in self.policy.parameters():
-                        if p.grad is not None:
-                            torch.distributed.all_reduce(p.grad)
-                            p.grad /= world
+                    all_reduce_mean_grads(self.policy.parameters())  # one flat bucket per minibatch
                 if self.max_grad_norm is not None:
                     nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)  # tf.clip_by_global_norm
                 self.opt.step()

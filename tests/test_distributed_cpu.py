@@ -26,6 +26,14 @@ def _worker(rank, world, port, q):
     stats = torch.tensor([1.5 * (r + 1), 10.0 * (r + 1), float(r + 1), 0.0, float(hi - lo)], dtype=torch.float64)
     red = D.all_reduce_stats(stats)
     mx = D.max_over_ranks(0.1 * (r + 1))
+    # gradient averaging of the PPO2 caller: one flat bucket, parameters without a gradient are skipped
+    torch.manual_seed(0)
+    lin, unused = torch.nn.Linear(3, 2), torch.nn.Linear(2, 2)
+    lin.weight.grad = torch.full((2, 3), float(r + 1))
+    lin.bias.grad = torch.tensor([10.0 * (r + 1), -1.0])
+    D.all_reduce_mean_grads(list(lin.parameters()) + list(unused.parameters()))
+    assert unused.weight.grad is None
+    assert torch.equal(lin.weight.grad, torch.full((2, 3), 1.5)) and torch.equal(lin.bias.grad, torch.tensor([15.0, -1.0]))
     q.put((r, lo, hi, red.tolist(), mx))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
