@@ -689,11 +689,40 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
     };
     mbar_wait(bar_w, 0);  // the fp32 tail (biases of the heads, logstd) is read from shared memory below
     if (tile0 < tiles) build_a1(o);
+    // The tail of a tile (layer-3 read-out, sampling, stores) is deferred into the next iteration: D3 is read right before
+    // the next tile's layer-2 operand is handed over (its pi half overwrites D3's columns), and the arithmetic and the
+    // stores then run while that layer 2 is in the tensor pipe.
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;  // this tile's noise, carried to the deferred tail
+    uint32_t d3[8];
+    int64_t i_prev = -1;
+    auto read_d3 = [&](uint32_t ph_prev) {
+      mbar_wait(bars + 8 * kDone3, ph_prev);
+      tc_fence_after();
+      tmem_ld8(trow + kColD3ws, d3);
+      tmem_wait_ld();
+      tc_fence_before();  // D3 is read before the next tile's pi half (ordered by our full_a2 arrival) overwrites it
+    };
+    auto finish = [&](int64_t i, float z0, float z1, float z2, float z3) {
+      if (i >= a.n) return;
+      const float ls0 = tail[8], ls1 = tail[9], ls2 = tail[10], ls3 = tail[11];
+      const float mu0 = __uint_as_float(d3[0]) + tail[0], mu1 = __uint_as_float(d3[1]) + tail[1];
+      const float mu2 = __uint_as_float(d3[2]) + tail[2], mu3 = __uint_as_float(d3[3]) + tail[3];
+      const float val = __uint_as_float(d3[4]) + tail[4];
+      if (kWsSides == 1 || side == 0) {
+        const float a0 = fmaf(__expf(ls0), z0, mu0), a1 = fmaf(__expf(ls1), z1, mu1), a2 = fmaf(__expf(ls2), z2, mu2), a3 = fmaf(__expf(ls3), z3, mu3);
+        // neglogp = 0.5 * sum(((a - mean)/std)^2) + 0.5*log(2 pi)*4 + sum(logstd); (a - mean)/std == the noise itself
+        const float nlp = 0.5f * (z0 * z0 + z1 * z1 + z2 * z2 + z3 * z3) + 3.6757541328186907f + (ls0 + ls1 + ls2 + ls3);
+        if (a.actions) reinterpret_cast<float4*>(a.actions)[i] = make_float4(a0, a1, a2, a3);
+        if (a.clipped)
+          reinterpret_cast<float4*>(a.clipped)[i] = make_float4(fminf(fmaxf(a0, -1.f), 1.f), fminf(fmaxf(a1, -1.f), 1.f), fminf(fmaxf(a2, -1.f), 1.f), fminf(fmaxf(a3, -1.f), 1.f));
+        if (a.neglogp) a.neglogp[i] = nlp;
+      }
+      if (kWsSides == 1 || side == 1) a.values[i] = val;
+    };
     uint32_t it = 0;
     for (int tile = tile0; tile < tiles; tile += tile_stride, it++) {
       const uint32_t ph = it & 1;
       const int64_t i = (int64_t)tile * kTileRows + row;
-      const bool active = i < a.n;
       const bool more = tile + tile_stride < tiles;
       o = load_obs(a.obs, i + (int64_t)tile_stride * kTileRows, a.n, nullptr);  // next tile's row, in flight under this tile's work
       // ---- h = relu(D1) -> A2[:, 0:128]; A2[:, 128:144] = (1, 1, 0, ...) carries layer 2's bias ----
@@ -718,8 +747,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
       if (kWsSides == 1 || side == 0) *reinterpret_cast<uint4*>(a_row + 16 * 2048) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
       if (kWsSides == 1 || side == 1) *reinterpret_cast<uint4*>(a_row + 17 * 2048) = make_uint4(0u, 0u, 0u, 0u);
       proxy_fence();
+      const float p0 = n0, p1 = n1, p2 = n2, p3 = n3;
+      if (i_prev >= 0) read_d3(ph ^ 1);  // the previous tile's layer-3 result, before this tile's pi half lands on it
       tc_fence_before();  // D1 is read; the vf half of layer 2 will overwrite its columns
       mbar_arrive(bars + 8 * kFullA2);
+      if (i_prev >= 0) finish(i_prev, p0, p1, p2, p3);  // under this tile's layer 2
       // ---- relu(D2 half) -> bf16 pairs packed in place: A3 pi = [0,64), A3 vf = [128,192) ----
 #pragma unroll 1
       for (int half = 0; half < 2; half++) {
@@ -743,8 +775,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
       }
       // ---- the next tile's A1 (the A buffer is free: both layer-2 halves have completed) and its layer 1, under our tail ----
       if (more) build_a1(o);
-      // ---- Gaussian noise while layer 3 runs (DiagGaussianProbabilityDistribution.sample) ----
-      float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+      // ---- Gaussian noise for this tile while its layer 3 and the next tile's layer 1 run (DiagGaussianProbability
+      //      Distribution.sample) ----
+      n0 = n1 = n2 = n3 = 0.f;
       if ((kWsSides == 1 || side == 0) && !a.deterministic) {
         qs::U4 c = {(uint32_t)(a.env_id0 + (uint64_t)i), (uint32_t)((a.env_id0 + (uint64_t)i) >> 32), a.step_idx, 2u};
         qs::U4 x = qs::philox4x32_10(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
@@ -757,27 +790,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
         __sincosf(6.283185307179586f * u3, &s1, &c1_);
         n0 = r0 * c0_; n1 = r0 * s0; n2 = r1 * c1_; n3 = r1 * s1;  // Box-Muller
       }
-      const float ls0 = tail[8], ls1 = tail[9], ls2 = tail[10], ls3 = tail[11];
-      mbar_wait(bars + 8 * kDone3, ph);
-      tc_fence_after();
-      uint32_t d3[8];
-      tmem_ld8(trow + kColD3ws, d3);
-      tmem_wait_ld();
-      tc_fence_before();  // D3 is read before the next tile's pi half (ordered by our full_a2 arrival) overwrites it
-      if (active) {
-        const float mu0 = __uint_as_float(d3[0]) + tail[0], mu1 = __uint_as_float(d3[1]) + tail[1];
-        const float mu2 = __uint_as_float(d3[2]) + tail[2], mu3 = __uint_as_float(d3[3]) + tail[3];
-        const float val = __uint_as_float(d3[4]) + tail[4];
-        if (kWsSides == 1 || side == 0) {
-          const float a0 = fmaf(__expf(ls0), n0, mu0), a1 = fmaf(__expf(ls1), n1, mu1), a2 = fmaf(__expf(ls2), n2, mu2), a3 = fmaf(__expf(ls3), n3, mu3);
-          const float nlp = 0.5f * (n0 * n0 + n1 * n1 + n2 * n2 + n3 * n3) + 3.6757541328186907f + (ls0 + ls1 + ls2 + ls3);
-          if (a.actions) reinterpret_cast<float4*>(a.actions)[i] = make_float4(a0, a1, a2, a3);
-          if (a.clipped)
-            reinterpret_cast<float4*>(a.clipped)[i] = make_float4(fminf(fmaxf(a0, -1.f), 1.f), fminf(fmaxf(a1, -1.f), 1.f), fminf(fmaxf(a2, -1.f), 1.f), fminf(fmaxf(a3, -1.f), 1.f));
-          if (a.neglogp) a.neglogp[i] = nlp;
-        }
-        if (kWsSides == 1 || side == 1) a.values[i] = val;
-      }
+      i_prev = i;
+    }
+    if (i_prev >= 0) {  // the last tile's tail
+      read_d3((it - 1) & 1);
+      finish(i_prev, n0, n1, n2, n3);
     }
   }
   tc_fence_before();
