@@ -34,10 +34,18 @@ class SBVecEnv(_Base):
         obs_np, rew_np, done_np = obs.float().cpu().numpy(), rew.float().cpu().numpy(), done.cpu().numpy()
         infos = [{} for _ in range(self.num_envs)]
         if self.info_dicts:
+            # the reference's info dict (docking_env.py:226-229): 'chaser', 'target', 'flag_docking', 'done_overlimit', plus
+            # SB's 'terminal_observation' on done.  For an env that finished this step 'chaser'/'target' are the re-seated
+            # states (the kernel auto-resets in place; the terminal observation is kept, the terminal 13-states are not).
             bits = info.bits.cpu().numpy()
             term = info.terminal_observation.float().cpu().numpy()
+            st = self._vec.get_state()
+            chaser = st["chaser"].cpu().numpy()
+            target = st["target"].cpu().numpy() if "target" in st else None
             for i in range(self.num_envs):
-                infos[i] = {"flag_docking": bool(bits[i] & 4), "done_overlimit": bool(bits[i] & 2)}
+                infos[i] = {"chaser": chaser[i], "flag_docking": bool(bits[i] & 4), "done_overlimit": bool(bits[i] & 2)}
+                if target is not None:
+                    infos[i]["target"] = target[i]
                 if done_np[i]:
                     infos[i]["terminal_observation"] = term[i]
         return obs_np, rew_np, done_np, infos
