@@ -284,10 +284,14 @@ class PPO2:
             self.fused.sync_weights()  # re-pack the updated parameters into the tensor-core operand images
         return {k: float(torch.stack([l[k] for l in logs]).mean()) for k in logs[0]}
 
-    def learn(self, total_timesteps, log_fn=None):
+    def learn(self, total_timesteps, log_fn=None, save_freq=None, save_path=None):
+        """model.learn(total_timesteps, callback=...) (run_moving_docking_ppo2.py:109).  `save_freq` / `save_path` stand in for
+        the reference's CheckpointCallback(save_freq=..., save_path=...) (:79-80): every `save_freq` env steps the policy is
+        written as a stable-baselines archive `<save_path>/rl_model_<timesteps>_steps.zip` (rank 0 only)."""
         n_batch = self.env.num_envs * self.runner.n_steps
         n_updates = max(int(total_timesteps) // n_batch, 1)
         history = []
+        next_save = self.num_timesteps + save_freq if save_freq else None
         for upd in range(1, n_updates + 1):
             batch = self.runner.run()
             log = self.update(batch)
@@ -297,7 +301,31 @@ class PPO2:
             history.append(log)
             if log_fn:
                 log_fn(log)
+            if next_save is not None and self.num_timesteps >= next_save and (not self.dist or torch.distributed.get_rank() == 0):
+                import os
+                os.makedirs(save_path or ".", exist_ok=True)
+                self.save(os.path.join(save_path or ".", "rl_model_%d_steps.zip" % self.num_timesteps))
+            if next_save is not None:
+                while next_save <= self.num_timesteps:
+                    next_save += save_freq
         return history
+
+    @classmethod
+    def load(cls, path, env, **kw):
+        """PPO2.load(path, env=env) (run_trained_moving_docking_ppo2.py:36): the archive's policy weights on a new trainer
+        whose hyper-parameters come from the archive's `data` member where it has them (keyword arguments win)."""
+        data, _ = load_sb_zip(path)
+        for k in ("n_steps", "nminibatches", "noptepochs", "gamma", "lam", "cliprange", "ent_coef", "vf_coef", "max_grad_norm"):
+            if k in data and k not in kw and isinstance(data[k], (int, float)):
+                kw[k] = data[k]
+        algo = cls(env, policy=MlpPolicy.from_sb_zip(path), **kw)
+        if algo.fused is not None:
+            algo.fused.sync_weights()
+        return algo
+
+    def predict(self, obs, deterministic=True):
+        """model.predict(obs, deterministic=True)[0] (run_trained_moving_docking_ppo2.py:46): clipped to the action Box."""
+        return (self.fused or self.policy).predict(obs, deterministic=deterministic)
 
     def save(self, path):
         data = dict(gamma=self.runner.gamma, lam=self.runner.lam, n_steps=self.runner.n_steps, nminibatches=self.nminibatches,

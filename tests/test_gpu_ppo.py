@@ -148,3 +148,26 @@ def test_ppo2_learn_with_fused_policy():
     assert len(hist) == 3 and all(np.isfinite(h["pg_loss"]) and np.isfinite(h["vf_loss"]) for h in hist)
     assert all(h["approxkl"] < 0.05 for h in hist) and hist[-1]["vf_loss"] < hist[0]["vf_loss"]
     env.close()
+
+
+def test_ppo2_checkpoints_and_load(tmp_path):
+    """CheckpointCallback-style saves during learn(), PPO2.load on a fresh env, identical deterministic predictions; the
+    archive is the stable-baselines layout (data / parameters / parameter_list)."""
+    import zipfile
+    n = 2048
+    env = qs.make_vec("docking-v2", n, seed=3, randomize="episode")
+    algo = ppo.PPO2(env, n_steps=16, nminibatches=4, noptepochs=1, seed=1, fused_policy=True)
+    algo.learn(4 * n * 16, save_freq=2 * n * 16, save_path=str(tmp_path))
+    saved = sorted((p.name for p in tmp_path.iterdir()), key=lambda s: int(s.split("_")[2]))
+    assert saved == ["rl_model_%d_steps.zip" % (2 * n * 16), "rl_model_%d_steps.zip" % (4 * n * 16)], saved
+    last = str(tmp_path / saved[-1])
+    assert set(zipfile.ZipFile(last).namelist()) == {"data", "parameters", "parameter_list"}
+    env2 = qs.make_vec("docking-v2", n, seed=3, randomize="episode")
+    again = ppo.PPO2.load(last, env2, fused_policy=True)
+    assert again.runner.n_steps == 16 and again.nminibatches == 4
+    obs = env2.reset().float()
+    assert torch.equal(algo.predict(obs), again.predict(obs))
+    for a, b in zip(algo.policy.parameters(), again.policy.parameters()):
+        assert torch.equal(a, b)
+    env.close()
+    env2.close()
