@@ -218,19 +218,26 @@ template <typename T> __device__ __forceinline__ void store_obs13(void* base, in
 #pragma unroll
   for (int k = 0; k < 13; k++) o[k] = v[k];
 }
-// [N,13] rows are 52 (fp32) / 104 (fp64) bytes: per-thread scalar stores would touch 13 sectors per instruction.  The
-// CTA stages its 128 rows in shared memory and writes the tile's contiguous 128*13 words with fully coalesced stores.
-// Must be called by every thread of the CTA (tile0 = first env of the tile, cnt = valid envs in it).
+// [N,13] rows are 52 (fp32) / 104 (fp64) bytes: per-thread scalar stores would touch 13 sectors per instruction.  Each WARP
+// stages its 32 rows in its own slice of shared memory (row stride 13 words: odd, so conflict-free) and writes the warp's
+// contiguous 32*13 words with 13 fully coalesced stores; only __syncwarp is needed (no CTA-wide barrier on the step path).
+// Must be called by every thread of the warp (tile0 = first env of the CTA's tile, cnt = valid envs in it).
 template <typename T> __device__ __forceinline__ void store_obs13_tile(T* stage, void* base, int64_t tile0, int cnt, const T* v, bool active) {
-  const int tid = threadIdx.x;
-  __syncthreads();  // previous use of the stage is finished
+  const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;  // first row of this warp within the tile
+  T* ws = stage + w0 * 13;
+  __syncwarp();  // the previous use of this warp's slice is finished
   if (active) {
 #pragma unroll
-    for (int k = 0; k < 13; k++) stage[tid * 13 + k] = v[k];
+    for (int k = 0; k < 13; k++) ws[lane * 13 + k] = v[k];
   }
-  __syncthreads();
-  T* o = reinterpret_cast<T*>(base) + tile0 * 13;
-  for (int k = tid; k < cnt * 13; k += kBlock) o[k] = stage[k];
+  __syncwarp();
+  const int rows = cnt - w0 < 32 ? cnt - w0 : 32;  // valid rows of this warp (<= 0: none)
+  T* o = reinterpret_cast<T*>(base) + (tile0 + w0) * 13;
+#pragma unroll
+  for (int k = 0; k < 13; k++) {
+    const int idx = k * 32 + lane;
+    if (idx < rows * 13) o[idx] = ws[idx];
+  }
 }
 
 // =========================================================================================================
