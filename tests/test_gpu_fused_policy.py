@@ -81,3 +81,15 @@ def test_fused_sampling_statistics_and_logprob():
     # sharding: rank offsets reproduce the same noise for the same global env id
     f2 = FusedPolicy(pol, seed=7, env_id0=1000 + 4096)
     assert torch.equal(f2.step(obs[4096:8192], step_idx=3)[0], act[4096:8192])
+
+
+def test_kernels_reproducible_under_concurrent_load():
+    """tools/stress_policy.py for a few seconds: random-size launches of the forward and gradient kernels, bit-for-bit
+    reproducible and within tolerance of torch while env kernels run concurrently on another stream (a missing fence or
+    barrier edge between the issuer and epilogue warps would show up as a rare wrong row)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_policy.py"), "--seconds", "4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "stress ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
