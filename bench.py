@@ -249,7 +249,8 @@ def run_ours(args):
                         "note": "this rank; the leg is bound by the device->host link (53 B out vs 16 B in per env-step)"},
                "numa": {"gpu_node": numa, "cpus_allowed": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None},
                "d2h_bytes_per_step": n * (henv.obs_dim * esz + esz + 1), "steps": args.e2e_steps,
-               "api": "QuadVecEnv.step_host -> qs_step_host (pinned numpy in/out, %d chunks pipelined over 4 streams)" % chunks,
+               "api": "QuadVecEnv.step_host -> qs_step_host (pinned numpy in/out, %d chunks pipelined over 4 streams; obs by DMA, "
+                      "reward/done written by the kernel into the pinned buffers)" % chunks,
                "checksum_reward": float(h_rew.sum())}
         henv.close()
 
@@ -318,7 +319,7 @@ def measure_callers(args, rank, dev, world, D, n_steps=16, rollouts=5):
     env.close()
     return {"what": "PPO2 %s rollout-in-the-loop, %d envs/GPU, %d-step rollouts (BASELINE config 5 shape): tcgen05 policy forward + "
                     "fused env step written in place (qs_rollout) + qs_gae; then one epoch of the fused update" % (args.env, n, n_steps),
-            "rollout_env_steps_per_s": world * n * n_steps / (roll_ms * 1e-3), "rollout_ms": roll_ms, "gpu_launches_per_rollout": 2 * n_steps + 2,
+            "rollout_env_steps_per_s": world * n * n_steps / (roll_ms * 1e-3), "rollout_ms": roll_ms, "gpu_launches_per_rollout": algo.runner.n_slices * (2 * n_steps + 1) + 1, "env_slices": algo.runner.n_slices,
             "update_samples_per_s": world * n * n_steps / (upd_ms * 1e-3), "update_epoch_ms": upd_ms}
 
 
