@@ -186,6 +186,17 @@ __device__ __forceinline__ void warp_stats_update(double* warp_stats, int64_t i,
   }
 }
 
+// Programmatic dependent launch (sm_90+): step k+1 is the same grid over the same state, so consecutive launches are fully
+// dependent -- but the ~3 us between the last CTA of one step retiring and the first CTA of the next doing work (launch
+// latency, CTA ramp) need not be serial.  Every step kernel tells the scheduler at its first instruction that dependents
+// may be staged (they are only launched once ALL of this grid's CTAs have started, so the tail of a step shares the SMs with
+// the head of the next), and waits for the previous grid's completion and memory flush before touching global memory.
+// Both are no-ops for launches without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // word <-> struct mapping of the row layout above
 template <typename T, int NW> __device__ __forceinline__ void words_to_dock(const T (&w)[NW], DockEnv<T>& e) {
   e.c = Drone<T>{w[0], w[1], w[2], w[4], w[5], w[6], w[8], w[9], w[10], w[11], w[3], w[7], w[36], w[12], w[13], w[14], w[15]};
@@ -247,6 +258,7 @@ template <typename T> __device__ __forceinline__ void store_obs13_tile(T* stage,
 // =========================================================================================================
 template <typename T, int KIND>
 __global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_kernel(const StepArgs a) {
+  pdl_prologue();
   constexpr int NW = dock_words<T>();
   const int64_t i = a.first + (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const bool active = i < a.first + a.n;
@@ -402,6 +414,7 @@ __global__ void __launch_bounds__(kBlock, QS_MINB32) dock_step_pipe_kernel(const
 // =========================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(kBlock) hover_step_kernel(const StepArgs a) {
+  pdl_prologue();
   __shared__ T stage[kBlock * 13];
   const int64_t tile0 = a.first + (int64_t)blockIdx.x * kBlock;
   const int64_t i = tile0 + threadIdx.x;
@@ -827,12 +840,19 @@ StepArgs make_args(qs_env* e, int64_t first, int64_t n) {
 
 template <typename T> int launch_step_t(qs_env* e, const StepArgs& a, cudaStream_t st) {
   const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
+  // QUADSIM_B200_PDL=0 launches without programmatic dependent launch (A/B)
+  static const bool pdl = [] { const char* v = getenv("QUADSIM_B200_PDL"); return !(v && v[0] == '0'); }();
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
   switch (e->cfg.env_kind) {
-    case QS_HOVER: hover_step_kernel<T><<<grid, kBlock, 0, st>>>(a); break;
-    case QS_DOCK_V0: dock_step_kernel<T, QS_DOCK_V0><<<grid, kBlock, 0, st>>>(a); break;
-    default: dock_step_kernel<T, QS_DOCK_V2><<<grid, kBlock, 0, st>>>(a); break;
+    case QS_HOVER: QS_CUDA(cudaLaunchKernelEx(&cfg, hover_step_kernel<T>, a)); break;
+    case QS_DOCK_V0: QS_CUDA(cudaLaunchKernelEx(&cfg, dock_step_kernel<T, QS_DOCK_V0>, a)); break;
+    default: QS_CUDA(cudaLaunchKernelEx(&cfg, dock_step_kernel<T, QS_DOCK_V2>, a)); break;
   }
-  QS_CUDA(cudaGetLastError());
   return QS_OK;
 }
 int launch_step(qs_env* e, const StepArgs& a, cudaStream_t st, int slot = 0) {

@@ -577,9 +577,16 @@ constexpr int kWsSmemBytes = kOffBar + (kWsBarBytes + 63) / 64 * 64;
 static_assert(kWsSmemBytes <= 227 * 1024, "shared memory budget");
 enum { kFullA1 = 0, kFullA2, kFullA3p, kFullA3v, kDone1, kDoneP, kDoneV, kDone3 };
 
+// programmatic dependent launch, as in the env step kernels (qs_lib.cu): stage the next kernel early, wait for the previous one
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
 __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const StepArgs a) {
+  pdl_prologue();
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int kEpiWarps = kGroups * kWsEpi / 32;
@@ -908,7 +915,17 @@ int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, u
   // QUADSIM_B200_POLICY=v3 selects the previous (leader-thread-in-group) forward kernel for A/B
   static const bool use_v3 = [] { const char* v = getenv("QUADSIM_B200_POLICY"); return v && strcmp(v, "v3") == 0; }();
   if (use_v3) policy_kernel<false><<<ctas < p->grid ? ctas : p->grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, TrainArgs{});
-  else policy_fwd_ws_kernel<<<ctas < p->grid ? ctas : p->grid, kWsThreads, kWsSmemBytes, (cudaStream_t)stream>>>(a);
+  else {
+    static const bool pdl = [] { const char* v = getenv("QUADSIM_B200_PDL"); return !(v && v[0] == '0'); }();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas < p->grid ? ctas : p->grid); cfg.blockDim = dim3(kWsThreads); cfg.dynamicSmemBytes = kWsSmemBytes;
+    cfg.stream = (cudaStream_t)stream; cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, policy_fwd_ws_kernel, a);
+    if (le != cudaSuccess) { cudaSetDevice(prev); return qs_fail_(QS_ERR_CUDA, "qs_policy_step: %s", cudaGetErrorString(le)); }
+  }
   cudaError_t e = cudaGetLastError();
   cudaSetDevice(prev);
   if (e != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_policy_step: %s", cudaGetErrorString(e));
