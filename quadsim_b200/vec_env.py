@@ -110,6 +110,7 @@ class QuadVecEnv:
         self.action_mean = np.ones(4) * (0.0 if kind == _capi.HOVER else scale)
         self.action_std = np.ones(4) * scale
         self._bufs = None
+        self._fast = None  # (action shape, cached output pointers, return tuple): see step()
         self._pending = None
         self._host = None
 
@@ -131,6 +132,10 @@ class QuadVecEnv:
             return self._new_bufs()
         if self._bufs is None:
             self._bufs = self._new_bufs()
+            obs, rew, done, bits, term = self._bufs
+            p = lambda t: t.data_ptr() if t is not None else None
+            ret = (obs, rew, done.view(torch.bool), VecInfo(self, bits, term) if bits is not None else None)
+            self._fast = ((self.num_envs, 4), p(obs), p(rew), p(done), p(bits), p(term), ret)
         return self._bufs
 
     @staticmethod
@@ -177,6 +182,18 @@ class QuadVecEnv:
 
     def step(self, actions):
         """actions[N,4] (torch CUDA tensor, or numpy for the host path) -> obs, rewards, dones, infos."""
+        # fast path (reuse_buffers=True, a ready-made device tensor): the output pointers are cached and the call goes
+        # straight to the C ABI -- the python side of a step drops from ~35 us to ~10 us, which is what bounds small batches
+        # and the 35 us hover kernel
+        f = self._fast
+        if (f is not None and type(actions) is torch.Tensor and actions.dtype == self.dtype and actions.device == self.device
+                and actions.shape == f[0] and actions.is_contiguous() and self._h is not None):
+            if torch.cuda.current_device() == self.device.index:
+                rc = self.lib.qs_step_ex(self._h, actions.data_ptr(), f[1], f[2], f[3], f[4], f[5],
+                                         torch.cuda.current_stream().cuda_stream)
+                if rc != 0:
+                    _capi.check(rc)
+                return f[6]
         self.step_async(actions)
         return self.step_wait()
 
