@@ -1,4 +1,5 @@
-// qs_policy.cu -- fused forward pass of the reference's PPO2 MlpPolicy on 5th-gen tensor cores (tcgen05 + TMEM).
+// qs_policy.cu -- the reference's PPO2 MlpPolicy on 5th-gen tensor cores (tcgen05 + TMEM): fused forward pass for rollouts,
+// fused forward + loss + backward for the update, and the device-resident rollout loop around them.
 //
 // Policy: net_arch=[128, dict(pi=[128], vf=[128])], relu, diagonal Gaussian (run_moving_docking_ppo2.py:88-91;
 // weights as in the shipped archives, e.g. trained_model/best_model_v0.zip):
@@ -22,12 +23,16 @@
 // is 176 KB (operand reads by the tensor cores + the A1/A2 stores); with A3 in shared memory as well (304 KB) the
 // shared-memory pipe was the busiest unit (59 % at 127 us per 2^20 envs, profiles/r1_policy_v2_ncu_full.txt).
 //
-// One persistent 512-thread CTA per SM = two independent 256-thread GROUPS, each with its own 36 KB A-operand buffer, 256
-// TMEM columns (D1, D2, A3, D3 alias: each is dead when the next is written), a named barrier and an mbarrier; the weight
-// images (88 KB, bulk-copied once per CTA with cp.async.bulk) are shared.  While one group waits on its MMAs the other runs
-// its epilogue.  Inside a group two warps serve each 32-lane TMEM quadrant: the "pi side" takes accumulator columns
-// [0,64) of D1 / [0,128) of D2, samples the action and stores actions/neglogp; the "vf side" takes the other halves and
-// stores the value -- twice the warps per scheduler for the latency-bound tcgen05.ld -> cvt -> store chains.
+// Two kernels share these operand images and helpers:
+//   policy_kernel<TRAIN>   one persistent 256-thread CTA per SM = two independent 128-thread GROUPS, each with its own 36 KB
+//       A-operand buffer, 256 TMEM columns (D1, D2, A3, D3 alias: each is dead when the next is written), a named barrier
+//       and an mbarrier; the weight images (88 KB, bulk-copied once per CTA with cp.async.bulk) are shared.  While one group
+//       waits on its MMAs the other runs its epilogue.  TRAIN = true is the PPO2 minibatch gradient (forward + loss +
+//       backward through the activations, see the kernel); TRAIN = false is the earlier rollout forward, kept for A/B.
+//   policy_fwd_ws_kernel   the rollout forward that qs_policy_step launches: the same two groups plus one MMA-issuer warp per
+//       group and mbarrier hand-offs (see the kernel).
+// file map: operand layout + PTX wrappers | pack_kernel (weights -> operand images) | policy_kernel<TRAIN> |
+//           policy_fwd_ws_kernel | C ABI (qs_policy_*, qs_rollout)
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
