@@ -154,6 +154,8 @@ class DeviceRunner:
         self.mb_neglogp = torch.empty((T, n), **f32)
         self.mb_rewards = torch.empty((T, n), **f32)
         self._clipped = torch.empty((n, 4), **f32)
+        self._act_lo = torch.as_tensor(env.action_space.low, **f32)   # docking: [-1, 1]^4 (docking_env.py:93); hover: [0, 1]^4 (hovering_env.py:42)
+        self._act_hi = torch.as_tensor(env.action_space.high, **f32)
         self._advs, self._returns = torch.empty((T, n), **f32), torch.empty((T, n), **f32)
         self.obs = env.reset().float()
         self.dones = torch.zeros(n, dtype=torch.uint8, device=dev)
@@ -185,7 +187,7 @@ class DeviceRunner:
                     clipped = clipped.to(env.dtype)
                 else:
                     actions, values, neglogp = pol.step(self.obs, generator=self.generator)
-                    clipped = actions.clamp(-1.0, 1.0).to(env.dtype)  # np.clip to the action Box, ppo2.py:478-481
+                    clipped = torch.minimum(torch.maximum(actions, self._act_lo), self._act_hi).to(env.dtype)  # np.clip to the action Box, ppo2.py:478-481
                 self.mb_obs[t], self.mb_actions[t], self.mb_values[t], self.mb_neglogp[t] = self.obs, actions, values, neglogp
                 self.mb_dones[t] = self.dones
                 obs, rew, done, _ = env.step(clipped)

@@ -171,3 +171,23 @@ def test_ppo2_checkpoints_and_load(tmp_path):
         assert torch.equal(a, b)
     env.close()
     env2.close()
+
+
+def test_ppo2_on_hovering_env_clips_to_its_box():
+    """train_drl_hover_ppo2.py's setting: hovering-v0 has 13 observations and actions in [0, 1]^4 (hovering_env.py:36-42); the
+    runner must clip to THAT Box before stepping (ppo2.py:478-481) and the torch policy path is used (the tensor-core kernel
+    is built for the 12-observation docking policy)."""
+    n = 1024
+    env = qs.make_vec("hovering-v0", n, seed=1)
+    algo = ppo.PPO2(env, n_steps=8, nminibatches=2, noptepochs=1, seed=0)
+    assert algo.policy.shared_fc0.in_features == 13 and not algo.runner.in_place
+    seen = []
+    orig = env.step
+    env.step = lambda a: (seen.append(a.clone()), orig(a))[1]
+    hist = algo.learn(2 * n * 8)
+    assert len(hist) == 2 and all(np.isfinite(h["vf_loss"]) for h in hist)
+    lo, hi = min(float(a.min()) for a in seen), max(float(a.max()) for a in seen)
+    assert lo >= 0.0 and hi <= 1.0 and lo == 0.0  # a zero-mean Gaussian policy: about half the raw samples are clipped at 0
+    with pytest.raises(ValueError):
+        ppo.PPO2(env, fused_policy=True)
+    env.close()
