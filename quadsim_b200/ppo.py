@@ -226,14 +226,27 @@ class PPO2:
             raise ValueError("fused_update needs fused_policy=True")
         self.runner = DeviceRunner(env, self.policy, n_steps, gamma, lam, reset_each_rollout, self.gen, fused=self.fused)
         self.nminibatches, self.noptepochs = nminibatches, noptepochs
-        self.cliprange, self.ent_coef, self.vf_coef, self.max_grad_norm = cliprange, ent_coef, vf_coef, max_grad_norm
-        self.cliprange_vf = cliprange if cliprange_vf is None else cliprange_vf  # legacy default: same as the policy's (ppo2.py:152-156)
-        self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5)
+        self.ent_coef, self.vf_coef, self.max_grad_norm = ent_coef, vf_coef, max_grad_norm
+        # learning_rate / cliprange may be callables of the remaining-progress fraction (1 -> 0), as in stable-baselines
+        # (ppo2.py:316-331: `frac = 1.0 - (update - 1.0) / n_updates; lr_now = self.learning_rate(frac)`)
+        self.learning_rate = learning_rate
+        self._cliprange_arg, self._cliprange_vf_arg = cliprange, cliprange_vf
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate(1.0) if callable(learning_rate) else learning_rate, eps=1e-5)
+        self._set_schedules(1.0)
         self.num_timesteps = 0
         self.dist = torch.distributed.is_available() and torch.distributed.is_initialized()
         if self.dist:  # every rank starts from rank 0's weights
             for p in self.policy.parameters():
                 torch.distributed.broadcast(p.data, 0)
+
+    def _set_schedules(self, frac):
+        val = lambda x: float(x(frac)) if callable(x) else x
+        self.cliprange = val(self._cliprange_arg)
+        cv = val(self._cliprange_vf_arg)
+        self.cliprange_vf = self.cliprange if cv is None else cv  # legacy default: same as the policy's (ppo2.py:152-156)
+        if hasattr(self, "opt") and callable(self.learning_rate):
+            for grp in self.opt.param_groups:
+                grp["lr"] = float(self.learning_rate(frac))
 
     def loss(self, mb):
         mean, vpred = self.policy.forward(mb["obs"])
@@ -295,6 +308,7 @@ class PPO2:
         history = []
         next_save = self.num_timesteps + save_freq if save_freq else None
         for upd in range(1, n_updates + 1):
+            self._set_schedules(1.0 - (upd - 1.0) / n_updates)
             batch = self.runner.run()
             log = self.update(batch)
             self.num_timesteps += n_batch

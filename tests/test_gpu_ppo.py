@@ -150,6 +150,22 @@ def test_ppo2_learn_with_fused_policy():
     env.close()
 
 
+def test_ppo2_schedules_are_callables_of_remaining_progress():
+    """learning_rate / cliprange as functions of frac = 1 - (update - 1) / n_updates (stable-baselines, ppo2.py:316-331; the
+    reference keeps `learning_rate=lr_sch.value` / `linear_schedule(3e-4)` commented in run_moving_docking_ppo2.py:98-99)."""
+    n = 1024
+    env = qs.make_vec("docking-v2", n, seed=3, randomize="episode")
+    seen = []
+    algo = ppo.PPO2(env, n_steps=8, nminibatches=2, noptepochs=1, seed=1, fused_policy=True,
+                    learning_rate=lambda f: 3e-4 * f, cliprange=lambda f: 0.2 * f)
+    algo.learn(4 * n * 8, log_fn=lambda log: seen.append((algo.opt.param_groups[0]["lr"], algo.cliprange, algo.cliprange_vf)))
+    fracs = [1.0, 0.75, 0.5, 0.25]
+    assert len(seen) == 4
+    for (lr, cr, cv), f in zip(seen, fracs):
+        assert abs(lr - 3e-4 * f) < 1e-12 and abs(cr - 0.2 * f) < 1e-12 and cv == cr
+    env.close()
+
+
 def test_ppo2_checkpoints_and_load(tmp_path):
     """CheckpointCallback-style saves during learn(), PPO2.load on a fresh env, identical deterministic predictions; the
     archive is the stable-baselines layout (data / parameters / parameter_list)."""
