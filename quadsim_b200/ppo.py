@@ -154,8 +154,9 @@ class DeviceRunner:
         self.mb_neglogp = torch.empty((T, n), **f32)
         self.mb_rewards = torch.empty((T, n), **f32)
         self._clipped = torch.empty((n, 4), **f32)
-        self._act_lo = torch.as_tensor(env.action_space.low, **f32)   # docking: [-1, 1]^4 (docking_env.py:93); hover: [0, 1]^4 (hovering_env.py:42)
-        self._act_hi = torch.as_tensor(env.action_space.high, **f32)
+        space = getattr(env, "action_space", None)  # docking: [-1, 1]^4 (docking_env.py:93); hover: [0, 1]^4 (hovering_env.py:42)
+        self._act_lo = torch.as_tensor(space.low if space is not None else [-1.0] * 4, **f32)
+        self._act_hi = torch.as_tensor(space.high if space is not None else [1.0] * 4, **f32)
         self._advs, self._returns = torch.empty((T, n), **f32), torch.empty((T, n), **f32)
         self.obs = env.reset().float()
         self.dones = torch.zeros(n, dtype=torch.uint8, device=dev)
