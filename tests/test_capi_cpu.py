@@ -96,3 +96,9 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not banned.search(src), os.path.join(dirpath, f)
+
+
+def test_integration_doc_names_every_entry_point():
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [s for s in _capi.SYMBOLS if s not in doc]
+    assert not missing, missing
