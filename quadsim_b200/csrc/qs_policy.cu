@@ -572,13 +572,22 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
                                // measured 90.8 us (1) vs 96.4 us (2) per 2^20 envs: the chain is sync latency, not ALU work
 #endif
 constexpr int kWsSides = QS_POLICY_WS_SIDES;
+#ifndef QS_POLICY_WS_GROUPS
+#define QS_POLICY_WS_GROUPS 2  // tiles in flight per SM.  2: 256 TMEM columns per group, both layer-2 halves in the tensor pipe
+                               // at once.  3: 144 columns per group -- every accumulator of a tile lives in [0,128) (+ D3 in
+                               // [128,144)), so the vf half of layer 2 can only be issued once the pi half has been packed
+#endif
+constexpr int kWsGroups = QS_POLICY_WS_GROUPS;
+static_assert(kWsGroups == 2 || (kWsGroups == 3 && kWsSides == 1), "two groups, or three with one epilogue warp per quadrant");
 constexpr int kWsEpi = kTileRows * kWsSides;               // epilogue threads per group
-constexpr int kWsThreads = kGroups * kWsEpi + 32 * kGroups; // + one issuer warp per group
+constexpr int kWsThreads = kWsGroups * kWsEpi + 32 * kWsGroups; // + one issuer warp per group
+constexpr uint32_t kWsWindow = kWsGroups == 2 ? 256 : 144; // TMEM columns per group
 constexpr int kWsCols = kHid / kWsSides;                   // accumulator columns one thread reads out per 128-column phase
 constexpr int kWsChunk = kWsSides == 1 ? 64 : 32;          // ... per tcgen05.wait::ld (register budget: 576 threads x <= 112)
 static_assert(kWsSides == 1 || kWsSides == 2, "one or two epilogue warps per quadrant");
-constexpr int kWsBarBytes = 8 + kGroups * 64 + 8;          // weights | per group: full_a1, full_a2, full_a3p, full_a3v, done_1, done_p, done_v, done_3 | TMEM slot
-constexpr int kWsSmemBytes = kOffBar + (kWsBarBytes + 63) / 64 * 64;
+constexpr int kWsOffBar = kOffA + kWsGroups * kABytes;
+constexpr int kWsBarBytes = 8 + kWsGroups * 64 + 8;        // weights | per group: full_a1, full_a2, full_a3p, full_a3v, done_1, done_p, done_v, done_3 | TMEM slot
+constexpr int kWsSmemBytes = kWsOffBar + (kWsBarBytes + 63) / 64 * 64;
 static_assert(kWsSmemBytes <= 227 * 1024, "shared memory budget");
 enum { kFullA1 = 0, kFullA2, kFullA3p, kFullA3v, kDone1, kDoneP, kDoneV, kDone3 };
 
@@ -594,25 +603,25 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
   pdl_prologue();
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int kEpiWarps = kGroups * kWsEpi / 32;
+  constexpr int kEpiWarps = kWsGroups * kWsEpi / 32;
   const bool issuer = warp >= kEpiWarps;
   const int g = issuer ? warp - kEpiWarps : tid / kWsEpi;  // group
   const int side = issuer ? 0 : (tid % kWsEpi) / kTileRows; // which half of the columns this epilogue thread handles
   const int row = tid & 127;                               // epilogue threads: accumulator row == TMEM lane == env within the tile
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_w = sbase + kOffBar, bars = sbase + kOffBar + 8 + 64 * g;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 + kGroups * 64);
+  const uint32_t bar_w = sbase + kWsOffBar, bars = sbase + kWsOffBar + 8 + 64 * g;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kWsOffBar + 8 + kWsGroups * 64);
   const float* tail = reinterpret_cast<const float*>(smem + kOffTail);
   const int tiles = (int)((a.n + kTileRows - 1) / kTileRows);
-  const int tile0 = blockIdx.x * kGroups + g, tile_stride = gridDim.x * kGroups;
+  const int tile0 = blockIdx.x * kWsGroups + g, tile_stride = gridDim.x * kWsGroups;
 
   ObsRow o = {};
   if (!issuer) o = load_obs(a.obs, (int64_t)tile0 * kTileRows + row, tile0 < tiles ? a.n : 0, nullptr);  // in flight during the set-up
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
-    for (int gg = 0; gg < kGroups; gg++)
-      for (int j = 0; j < 8; j++) mbar_init(sbase + kOffBar + 8 + 64 * gg + 8 * j, j < kDone1 ? kWsEpi : 1);
+    for (int gg = 0; gg < kWsGroups; gg++)
+      for (int j = 0; j < 8; j++) mbar_init(sbase + kWsOffBar + 8 + 64 * gg + 8 * j, j < kDone1 ? kWsEpi : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(bar_w, kPackedBytes);
     for (int off = 0; off < kPackedBytes; off += 16384) {
@@ -627,10 +636,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot + g * kTmemColsPerGroup;
+  const uint32_t tmem = *tmem_slot + g * kWsWindow;
   const uint32_t a_base = sbase + kOffA + g * kABytes;
   constexpr uint32_t idesc_n128 = umma_idesc(128, kHid), idesc3 = umma_idesc(128, kN3);
-  constexpr uint32_t kColD1 = 128, kColD2v = 128, kColD3ws = kWsCols / 2;  // D3: 16 columns right behind side 0's packed A3 pi
+  // two groups: D1 and the vf half at [128,256), D3 right behind side 0's packed A3 pi; three groups: everything at [0,128)
+  constexpr uint32_t kColD1 = kWsGroups == 2 ? 128 : 0, kColD2v = kWsGroups == 2 ? 128 : 0, kColD3ws = kWsGroups == 2 ? kWsCols / 2 : 128;
 
   if (issuer) {
     // ---------------------------------------------------------------- MMA issuer: one elected lane, the warp waits together
@@ -649,15 +659,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
       __syncwarp();
       mbar_wait(bars + 8 * kFullA2, ph);
       tc_fence_after();
+      // layer 2 as two N=128 halves of the 256-row W2 image (rows 128.. start 16 row-groups = 2048 B in; LBO stays the image's
+      // 4096 B), each with its own commit; layer 3's 8 K-steps of a half follow as soon as that half has been packed
+      auto issue_l2 = [&](int half) {
+#pragma unroll
+        for (int ks = 0; ks < kK2 / 16; ks++)
+          umma_ss(tmem + half * kColD2v, umma_desc(a_base + ks * 4096, 2048, 128), umma_desc(sbase + kOffW2 + half * 2048 + ks * 8192, 4096, 128), idesc_n128, ks);
+        umma_commit(bars + 8 * (half == 0 ? kDoneP : kDoneV));
+      };
       if (lane == 0) {
-        // the 256-row W2 image, 128 rows at a time: rows 128.. start 16 row-groups (2048 B) in; LBO stays the image's 4096 B
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-#pragma unroll
-          for (int ks = 0; ks < kK2 / 16; ks++)
-            umma_ss(tmem + half * kColD2v, umma_desc(a_base + ks * 4096, 2048, 128), umma_desc(sbase + kOffW2 + half * 2048 + ks * 8192, 4096, 128), idesc_n128, ks);
-          umma_commit(bars + 8 * (half == 0 ? kDoneP : kDoneV));
-        }
+        issue_l2(0);
+        if (kWsGroups == 2) issue_l2(1);  // the vf half has its own columns: both halves go into the pipe back to back
       }
       __syncwarp();
 #pragma unroll
@@ -671,6 +683,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
             umma_ts(tmem + kColD3ws, tmem + half * kColD2v + sd * kWsCols + kk / 2, umma_desc(sbase + kOffW3 + ks * 512, 256, 128), idesc3, ks);
           }
           if (half == 1) umma_commit(bars + 8 * kDone3);
+          // three groups: the vf half reuses the pi half's columns -- in order behind the layer-3 steps that read A3 pi
+          if (kWsGroups == 3 && half == 0) issue_l2(1);
         }
         __syncwarp();
       }
@@ -926,7 +940,8 @@ int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, u
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ctas < p->grid ? ctas : p->grid); cfg.blockDim = dim3(kWsThreads); cfg.dynamicSmemBytes = kWsSmemBytes;
+    const int ws_ctas = (int)(((n + kTileRows - 1) / kTileRows + kWsGroups - 1) / kWsGroups);
+    cfg.gridDim = dim3(ws_ctas < p->grid ? ws_ctas : p->grid); cfg.blockDim = dim3(kWsThreads); cfg.dynamicSmemBytes = kWsSmemBytes;
     cfg.stream = (cudaStream_t)stream; cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
     cudaError_t le = cudaLaunchKernelEx(&cfg, policy_fwd_ws_kernel, a);
     if (le != cudaSuccess) { cudaSetDevice(prev); return qs_fail_(QS_ERR_CUDA, "qs_policy_step: %s", cudaGetErrorString(le)); }
