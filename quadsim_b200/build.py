@@ -23,8 +23,9 @@ NVCC_FLAGS = [
     "-ftz=true", "-prec-div=false", "-prec-sqrt=false",
     # 6 resident CTAs/SM for the fp32 step kernels (<= 80 registers): measured best of {4,5,6,8}
     "-DQS_MINB32=6",
-    # fp64 step kernels: 4 CTAs/SM (128 registers, some spills) measured best of {2,3,4,5,6}: 385 -> 293 us/step
-    "-DQS_MINB64=4",
+    # fp64 step kernels: 3 CTAs/SM (168 registers, no spills) measured best of {3,4,5,6} with the default (shortcut) fp64
+    # arithmetic: 187.7 / 196.4 / 228.7 / 254.6 us per step; the literal build (-DQS_LITERAL64) preferred 4: 293 us
+    "-DQS_MINB64=3",
 ]
 
 

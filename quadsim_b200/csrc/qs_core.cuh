@@ -8,12 +8,13 @@
 //   Q4  the controller's desired quaternion persists across steps and episodes          PIDController.py:100-102
 //   Q5  docking-v2's derivative term is identically zero                                moving_docking_env.py:117,126
 //
-// Two arithmetic modes:
-//   T = double : literal -- follows the reference's formulas step by step (parity <= 1e-9, flags bit-exact).
-//   T = float  : "fast"  -- algebraically identical shortcuts that remove transcendentals from the common path
-//                (threshold tests on sines/tangents instead of angles, rsqrt normalisation, sin/cos of an
-//                atan2 taken from its arguments).  Parity bar: 1e-4 * max(1, |ref|).  -DQS_LITERAL32 turns the
-//                shortcuts off for A/B accuracy checks.
+// Two arithmetic modes, selectable per precision at build time (kFast<T>):
+//   "fast" (default for float and double) -- algebraically identical shortcuts that remove transcendentals from the
+//                common path (threshold tests on sines/tangents instead of angles, rsqrt normalisation, sin/cos of an
+//                atan2 taken from its arguments, quat2euler(euler2quat(.)) elided on its identity range).
+//                Parity bars: fp64 1e-9 with exact flags, fp32 1e-4 * max(1, |ref|) -- both tested on the same tapes.
+//   "literal" (-DQS_LITERAL64 / -DQS_LITERAL32) -- follows the reference's formulas step by step, for A/B checks.
+//   Precision-specific extras (the origin shift, 2-ulp division/sqrt, the in-line sincos) apply to fp32 only.
 //
 // The header also compiles as plain C++ (tests/host_harness.cpp) so tolerances can be explored without a
 // GPU; that build is test-only and never loaded by the package.
@@ -46,11 +47,21 @@ template <typename T> struct K {
 
 template <typename T> struct is_f32 { static constexpr bool value = false; };
 template <> struct is_f32<float> { static constexpr bool value = true; };
+// kFast<T>: algebraically identical shortcuts that take transcendentals off the common path (see the functions below).
+// On by default in both precisions -- they pass the same parity bars (fp64: 1e-9 and exact flags against the reference tapes,
+// the wild single-step states and the oracle; fp32: 1e-4) -- and are worth 1.13x (fp32) / 1.49x (fp64) on the step kernel.
+// -DQS_LITERAL32 / -DQS_LITERAL64 build the literal transcription (reference formulas in reference order) for A/B.
 #ifdef QS_LITERAL32
-template <typename T> constexpr bool kFast = false;
+constexpr bool kFast32 = false;
 #else
-template <typename T> constexpr bool kFast = is_f32<T>::value;
+constexpr bool kFast32 = true;
 #endif
+#ifdef QS_LITERAL64
+constexpr bool kFast64 = false;
+#else
+constexpr bool kFast64 = true;
+#endif
+template <typename T> constexpr bool kFast = is_f32<T>::value ? kFast32 : kFast64;
 
 // ---- scalar math wrappers ----
 QS_HD float m_sqrt(float x) { return sqrtf(x); }
