@@ -211,7 +211,7 @@ class PPO2:
 
     def __init__(self, env, policy=None, n_steps=600, nminibatches=10, noptepochs=10, learning_rate=3e-4, gamma=0.99, lam=0.95,
                  cliprange=0.2, cliprange_vf=None, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, seed=0, reset_each_rollout=False,
-                 fused_policy=False, fused_update=None):
+                 fused_policy=False, fused_update=None, graph_update=False):
         self.env = env
         self.device = env.device
         torch.manual_seed(seed)
@@ -225,6 +225,13 @@ class PPO2:
         self.fused_update = bool(fused_policy) if fused_update is None else bool(fused_update)
         if self.fused_update and self.fused is None:
             raise ValueError("fused_update needs fused_policy=True")
+        # graph_update: the whole minibatch step (gradient kernel, weight-gradient GEMMs, clip, Adam, weight re-pack: ~45
+        # launches) is captured ONCE in a CUDA graph and replayed; for <= 2^18 envs the update is launch-bound without it.
+        # Needs the fused update, constant learning rate / clip ranges and a single process (no collective inside).
+        self.graph_update = bool(graph_update)
+        if self.graph_update and (not self.fused_update or callable(learning_rate) or callable(cliprange) or callable(cliprange_vf)):
+            raise ValueError("graph_update needs fused_update=True and constant learning_rate / cliprange")
+        self._graph = None
         self.runner = DeviceRunner(env, self.policy, n_steps, gamma, lam, reset_each_rollout, self.gen, fused=self.fused)
         self.nminibatches, self.noptepochs = nminibatches, noptepochs
         self.ent_coef, self.vf_coef, self.max_grad_norm = ent_coef, vf_coef, max_grad_norm
@@ -232,7 +239,8 @@ class PPO2:
         # (ppo2.py:316-331: `frac = 1.0 - (update - 1.0) / n_updates; lr_now = self.learning_rate(frac)`)
         self.learning_rate = learning_rate
         self._cliprange_arg, self._cliprange_vf_arg = cliprange, cliprange_vf
-        self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate(1.0) if callable(learning_rate) else learning_rate, eps=1e-5)
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate(1.0) if callable(learning_rate) else learning_rate, eps=1e-5,
+                                    capturable=self.graph_update)
         self._set_schedules(1.0)
         self.num_timesteps = 0
         self.dist = torch.distributed.is_available() and torch.distributed.is_initialized()
@@ -269,6 +277,54 @@ class PPO2:
             clipfrac = ((ratio - 1.0).abs() > self.cliprange).float().mean()
         return total, dict(pg_loss=pg_loss.detach(), vf_loss=vf_loss.detach(), entropy=entropy.detach(), approxkl=approxkl, clipfrac=clipfrac)
 
+    @torch.no_grad()
+    def _minibatch_fused(self, batch, idx):
+        grads, log = self.fused.ppo_grad(batch, idx, self.cliprange, self.cliprange_vf, self.vf_coef, self.ent_coef)
+        for prm, grad in grads.items():
+            if prm.grad is None:
+                prm.grad = torch.empty_like(prm)
+            prm.grad.copy_(grad)
+        if self.max_grad_norm is not None:
+            nn.utils.clip_grad_norm_(list(grads.keys()), self.max_grad_norm)
+        self.opt.step()
+        self.fused.sync_weights(sync=False)
+        return log
+
+    def _graph_step(self, batch, idx):
+        """Replay the captured minibatch step on `idx` (copied into the graph's static index buffer)."""
+        key = (batch["obs"].data_ptr(), batch["returns"].data_ptr(), batch["actions"].data_ptr(), batch["values"].data_ptr(),
+               batch["neglogp"].data_ptr(), idx.shape[0])
+        if self._graph is None or self._graph[0] != key:
+            if self.dist:
+                raise _capi.QuadSimError("graph_update is single-process: the gradient all-reduce is not captured")
+            static_idx = idx.clone()
+            params = list(self.policy.parameters())
+            # One eager step first (outside capture: workspaces, GEMM heuristics and Adam's state tensors are created lazily),
+            # then parameters and optimiser state are put back, so the captured step below is the first one that counts.
+            snap_p = [prm.detach().clone() for prm in params]
+            snap_s = {prm: {k: v.clone() for k, v in self.opt.state[prm].items() if torch.is_tensor(v)} for prm in params if prm in self.opt.state}
+            for prm in params:  # the unused q head keeps grad None; everything else gets a static grad tensor
+                prm.grad = None
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side), torch.no_grad():
+                self._minibatch_fused(batch, static_idx)
+                for prm, p0 in zip(params, snap_p):
+                    prm.copy_(p0)
+                    for k, v in self.opt.state.get(prm, {}).items():
+                        if torch.is_tensor(v):
+                            v.copy_(snap_s[prm][k]) if prm in snap_s else v.zero_()
+                self.fused.sync_weights(sync=False)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph), torch.no_grad():
+                log = self._minibatch_fused(batch, static_idx)
+            self._graph = (key, graph, static_idx, log)
+        _, graph, static_idx, log = self._graph
+        static_idx.copy_(idx)
+        graph.replay()
+        return {k: v.clone() for k, v in log.items()}
+
     def update(self, batch):
         n_batch = batch["obs"].shape[0]
         mb_size = n_batch // self.nminibatches
@@ -278,6 +334,9 @@ class PPO2:
             perm = torch.randperm(n_batch, device=self.device, generator=self.gen)
             for start in range(0, mb_size * self.nminibatches, mb_size):
                 idx = perm[start:start + mb_size]
+                if self.graph_update:
+                    logs.append(self._graph_step(batch, idx))
+                    continue
                 if self.fused_update:
                     grads, log = self.fused.ppo_grad(batch, idx, self.cliprange, self.cliprange_vf, self.vf_coef, self.ent_coef)
                     self.opt.zero_grad(set_to_none=True)

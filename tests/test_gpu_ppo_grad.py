@@ -129,3 +129,26 @@ def test_fused_update_tracks_autograd_update():
         assert abs(log_f[k] - log_a[k]) < 0.05 * max(abs(log_a[k]), 0.02), (k, log_f[k], log_a[k])
     assert sum(moved) > 0
     env.close()
+
+
+def test_graph_captured_update_equals_eager_fused_update():
+    """PPO2(graph_update=True): the minibatch step replayed from a CUDA graph must leave the same parameters as the eager
+    fused step (same kernels, same order; the capture's warm-up step is undone before the first replay)."""
+    results = []
+    for graph in (False, True):
+        env = qs.make_vec("docking-v2", 2048, seed=5, randomize="episode", want_info=False)
+        algo = ppo.PPO2(env, n_steps=16, nminibatches=4, noptepochs=2, seed=3, fused_policy=True, graph_update=graph)
+        logs = []
+        for _ in range(2):
+            batch = algo.runner.run()
+            logs.append(algo.update(batch))
+        results.append(([p.detach().clone() for p in algo.policy.parameters()], logs))
+        env.close()
+    (p_eager, l_eager), (p_graph, l_graph) = results
+    for a, b in zip(p_eager, p_graph):  # 16 Adam steps of 3e-4 each; the library GEMMs may pick another split-K under capture
+        assert torch.allclose(a, b, rtol=1e-4, atol=3e-5), float((a - b).abs().max())
+    for le, lg in zip(l_eager, l_graph):
+        for k in ("pg_loss", "vf_loss", "approxkl", "clipfrac"):
+            assert abs(le[k] - lg[k]) <= 1e-3 * max(1.0, abs(le[k])), (k, le[k], lg[k])
+    with pytest.raises(ValueError):
+        ppo.PPO2(qs.make_vec("docking-v2", 256), fused_policy=True, graph_update=True, learning_rate=lambda f: 1e-4 * f)
