@@ -13,7 +13,7 @@ F32, F64 = 0, 1
 RAND_NONE, RAND_EPISODE, RAND_ONCE = 0, 1, 2
 INFO_DONE, INFO_OVERLIMIT, INFO_DOCKING, INFO_OVERTIME = 1, 2, 4, 8
 (FN_QUAT2EULER, FN_EULER2QUAT, FN_QUAT2ROT, FN_ROT2EULER, FN_U_LIMIT, FN_DRONE_STEP, FN_PID, FN_VEL_CTRL,
- FN_STATE2REL, FN_PHILOX) = range(10)
+ FN_STATE2REL, FN_PHILOX, FN_MATH) = range(11)
 ABI_VERSION = 1
 
 # every symbol include/quadsim_b200.h declares (tests check the built library exports all of them)

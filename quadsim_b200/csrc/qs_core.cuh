@@ -63,9 +63,153 @@ constexpr bool kFast64 = true;
 #endif
 template <typename T> constexpr bool kFast = is_f32<T>::value ? kFast32 : kFast64;
 
+// ---- fp64 elementary functions of the fast fp64 path (qs::f64m) ----
+// The library's fp64 atan2 / sincos / 1/sqrt cost ~115 / ~68 / ~43 SASS instructions per call inside the step kernel, a
+// third of them UMOV/IMAD.MOV pairs that materialise 64-bit polynomial coefficients (profiles/r1_dock_step_f64_fast_*).
+// These versions keep the coefficients in constant memory (operands of the DFMA itself), split each polynomial into two
+// interleaved Horner chains, and use the MUFU.RCP64H / MUFU.RSQ64H seeds with branch-free Newton steps.  Measured on
+// 4e6 random arguments against the host libm (tests/test_core_arith_host.py): <= 2 ulp.  Coefficients:
+// tools/gen_f64_math_coefs.py (Chebyshev fits at 60 digits).  Arguments outside the plain range (zero, subnormal, huge,
+// non-finite) defer to the library, so the IEEE special cases are the library's.
+#define QS_F64M_ATAN {-0x1.5555555555555p-2, 0x1.999999999934ap-3, -0x1.24924924360cbp-3, 0x1.c71c7185314cbp-4, -0x1.745d0b26b83e7p-4, 0x1.3b1262d95579ep-4, -0x1.10fa75382537fp-4, 0x1.dfe61e80903d2p-5, -0x1.a098bb6ba4941p-5, 0x1.41603647c7a7cp-5, -0x1.3a2b7a07caea9p-6}
+#define QS_F64M_SIN {-0x1.5555555555555p-3, 0x1.1111111110babp-7, -0x1.a01a019e820aep-13, 0x1.71de37946ed6dp-19, -0x1.ae6008d114485p-26, 0x1.5e0a4fc16be59p-33}
+#define QS_F64M_COS {0x1.5555555555555p-5, -0x1.6c16c16c16963p-10, 0x1.a01a019f4ddfdp-16, -0x1.27e4fa16cc2d1p-22, 0x1.1eeb67d026ec6p-29, -0x1.907cd8ff5ede7p-37}
+namespace f64m {
+#if defined(__CUDACC__)
+static __constant__ double c_atan[11] = QS_F64M_ATAN;
+static __constant__ double c_sin[6] = QS_F64M_SIN;
+static __constant__ double c_cos[6] = QS_F64M_COS;
+#endif
+static constexpr double h_atan[11] = QS_F64M_ATAN;
+static constexpr double h_sin[6] = QS_F64M_SIN;
+static constexpr double h_cos[6] = QS_F64M_COS;
+#if defined(__CUDA_ARCH__)
+#define QS_F64M_C(name, i) c_##name[i]
+#else
+#define QS_F64M_C(name, i) h_##name[i]
+#endif
+
+// library fallbacks, one out-of-line copy each (cold: zero / subnormal / huge / non-finite arguments only)
+#if defined(__CUDACC__)
+#define QS_F64M_COLD static __host__ __device__ __noinline__
+#else
+#define QS_F64M_COLD inline
+#endif
+struct SC { double s, c; };
+QS_F64M_COLD double atan2_cold(double y, double x) { return ::atan2(y, x); }
+QS_F64M_COLD double sqrt_cold(double x) { return ::sqrt(x); }
+QS_F64M_COLD SC sincos_cold(double x) {
+  SC r;
+#if defined(__CUDA_ARCH__)
+  ::sincos(x, &r.s, &r.c);
+#else
+  r.s = ::sin(x); r.c = ::cos(x);
+#endif
+  return r;
+}
+
+// 1/d for d in [1e-280, 1e280]: 20-bit seed + two Newton steps (relative error ~2^-52)
+QS_HD double rcp(double d) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+#else
+  return 1.0 / d;
+#endif
+}
+// n/d, d in [1e-280, 1e280], |n| <= |d|: one residual correction on top of n * rcp(d) (<= 1 ulp)
+QS_HD double div(double n, double d) {
+#if defined(__CUDA_ARCH__)
+  const double r = rcp(d);
+  const double q = n * r;
+  return fma(fma(-d, q, n), r, q);
+#else
+  return n / d;
+#endif
+}
+// 1/sqrt(x), x in [1e-300, 1e300]
+QS_HD double rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  // y (1 + e/2 + 3e^2/8), e = 1 - x y^2, twice: 2^-20 -> 2^-57
+  double e = fma(-x * y, y, 1.0);
+  y = fma(y * e, fma(0.375, e, 0.5), y);
+  e = fma(-x * y, y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
+#else
+  return 1.0 / ::sqrt(x);
+#endif
+}
+QS_HD double sqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  const double y = rsqrt(x);
+  const double g = x * y;
+  return fma(fma(-g, g, x), 0.5 * y, g);
+#else
+  return ::sqrt(x);
+#endif
+}
+
+QS_HD double atan2(double y, double x) {
+  const double ax = fabs(x), ay = fabs(y);
+  const bool sw = ay > ax;
+  const double a = sw ? ax : ay, b = sw ? ay : ax;  // a = min, b = max (a NaN lands in b or in the quotient)
+  if (!(b >= 1e-280 && b <= 1e280)) return atan2_cold(y, x);
+  // |a/b| <= 1 ; above tan(pi/8) use atan(a/b) = pi/4 + atan((a-b)/(a+b)): still one division, |u| <= tan(pi/8)
+  const bool hi = a > 0x1.a827999fcef32p-2 * b;
+  const double u = div(hi ? a - b : a, hi ? a + b : b);
+  const double z = u * u, z2 = z * z;
+  double pe = fma(z2, QS_F64M_C(atan, 10), QS_F64M_C(atan, 8));
+  double po = fma(z2, QS_F64M_C(atan, 9), QS_F64M_C(atan, 7));
+  pe = fma(z2, pe, QS_F64M_C(atan, 6)); po = fma(z2, po, QS_F64M_C(atan, 5));
+  pe = fma(z2, pe, QS_F64M_C(atan, 4)); po = fma(z2, po, QS_F64M_C(atan, 3));
+  pe = fma(z2, pe, QS_F64M_C(atan, 2)); po = fma(z2, po, QS_F64M_C(atan, 1));
+  pe = fma(z2, pe, QS_F64M_C(atan, 0));
+  double r = fma(u * z, fma(z, po, pe), u);
+  if (hi) r = 0x1.921fb54442d18p-1 + (0x1.1a62633145c07p-55 + r);
+  if (sw) r = 0x1.921fb54442d18p+0 - (r - 0x1.1a62633145c07p-54);
+  if (x < 0.0) r = 0x1.921fb54442d18p+1 - (r - 0x1.1a62633145c07p-53);
+  return copysign(r, y);
+}
+
+QS_HD void sincos(double x, double* s, double* c) {
+  if (!(fabs(x) <= 1.0e5)) { const SC r = sincos_cold(x); *s = r.s; *c = r.c; return; }
+  // k = nearest integer to x * 2/pi via the 1.5 * 2^52 shift (its low word is k mod 2^32)
+  const double t = fma(x, 0x1.45f306dc9c883p-1, 6755399441055744.0);
+  const double k = t - 6755399441055744.0;
+#if defined(__CUDA_ARCH__)
+  const int q = __double2loint(t);
+#else
+  const int q = (int)k;
+#endif
+  double r = fma(k, -0x1.921fb54400000p+0, x);
+  r = fma(k, -0x1.0b4611a600000p-34, r);
+  r = fma(k, -0x1.3198a2e037073p-69, r);
+  const double z = r * r;
+  double ps = fma(z, QS_F64M_C(sin, 5), QS_F64M_C(sin, 4)), pc = fma(z, QS_F64M_C(cos, 5), QS_F64M_C(cos, 4));
+  ps = fma(z, ps, QS_F64M_C(sin, 3)); pc = fma(z, pc, QS_F64M_C(cos, 3));
+  ps = fma(z, ps, QS_F64M_C(sin, 2)); pc = fma(z, pc, QS_F64M_C(cos, 2));
+  ps = fma(z, ps, QS_F64M_C(sin, 1)); pc = fma(z, pc, QS_F64M_C(cos, 1));
+  ps = fma(z, ps, QS_F64M_C(sin, 0)); pc = fma(z, pc, QS_F64M_C(cos, 0));
+  const double sn = fma(r * z, ps, r);
+  const double cs = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const double a = (q & 1) ? cs : sn, b = (q & 1) ? sn : cs;
+  *s = (q & 2) ? -a : a;
+  *c = ((q + 1) & 2) ? -b : b;
+}
+}  // namespace f64m
+
 // ---- scalar math wrappers ----
 QS_HD float m_sqrt(float x) { return sqrtf(x); }
-QS_HD double m_sqrt(double x) { return sqrt(x); }
+QS_HD double m_sqrt(double x) {
+  if (kFast64) return (x >= 1e-300 && x <= 1e300) ? f64m::sqrt(x) : f64m::sqrt_cold(x);
+  return sqrt(x);
+}
 QS_HD float m_rsqrt(float x) {
 #if defined(__CUDA_ARCH__)
   return rsqrtf(x);
@@ -73,7 +217,10 @@ QS_HD float m_rsqrt(float x) {
   return 1.0f / sqrtf(x);
 #endif
 }
-QS_HD double m_rsqrt(double x) { return 1.0 / sqrt(x); }
+QS_HD double m_rsqrt(double x) {
+  if (kFast64) return (x >= 1e-300 && x <= 1e300) ? f64m::rsqrt(x) : 1.0 / f64m::sqrt_cold(x);
+  return 1.0 / sqrt(x);
+}
 QS_HD float m_abs(float x) { return fabsf(x); }
 QS_HD double m_abs(double x) { return fabs(x); }
 QS_HD float m_asin(float x) { return asinf(x); }
@@ -84,7 +231,7 @@ QS_HD float m_asin(float x) { return asinf(x); }
 #endif
 QS_F64_FN double m_asin(double x) { return asin(x); }
 QS_HD float m_atan2(float y, float x) { return atan2f(y, x); }
-QS_F64_FN double m_atan2(double y, double x) { return atan2(y, x); }
+QS_F64_FN double m_atan2(double y, double x) { return kFast64 ? f64m::atan2(y, x) : atan2(y, x); }
 QS_HD float m_tan(float x) { return tanf(x); }
 QS_HD double m_tan(double x) { return tan(x); }
 // fp32 sin & cos together.  Every angle the envs feed in is bounded (half-angles of atan2 results, desired tilt = acc/g),
@@ -120,6 +267,7 @@ QS_HD void m_sincos(float x, float* s, float* c) {
 struct SinCosD { double s, c; };
 QS_F64_FN SinCosD m_sincos_d(double x) {
   SinCosD r;
+  if (kFast64) { f64m::sincos(x, &r.s, &r.c); return r; }
 #if defined(__CUDA_ARCH__)
   sincos(x, &r.s, &r.c);
 #else
@@ -339,17 +487,27 @@ template <typename T> QS_HD bool drone_step(Drone<T>& d, T c0, T c1, T c2, T c3)
 template <typename T> QS_HD void acc2cmd(T ax, T ay, T az, Quat<T>& dq, const Drone<T>& now, T& F, T& M0, T& M1, T& M2) {
   using C = K<T>;
   F = C::mass * C::g + C::mass * az;
-  T phi_d, theta_d, psi_d;
+  T phi_d, theta_d, psi_d, sp, cp;
   {
     // psi_des = quat2euler(des_q)[2]
     T w = dq.w, x = dq.x, y = dq.y, z = dq.z;
     T r10 = T(2) * (x * y - w * z), r11 = w * w - x * x + y * y - z * z;
     psi_d = m_atan2(-r10, r11);
+    T h2 = r10 * r10 + r11 * r11;
+    if (kFast<T> && !is_f32<T>::value && h2 > T(1e-100) && h2 < T(1e100)) {
+      T inv = m_rsqrt(h2);  // sin/cos of atan2(-r10, r11) from its arguments
+      sp = -r10 * inv; cp = r11 * inv;
+    } else {
+      m_sincos(psi_d, &sp, &cp);
+    }
   }
-  T sp, cp;
-  m_sincos(psi_d, &sp, &cp);
-  phi_d = (ax * sp - ay * cp) / C::g;
-  theta_d = (ax * cp + ay * sp) / C::g;
+  if (kFast<T> && !is_f32<T>::value) {
+    phi_d = (ax * sp - ay * cp) * (T(1) / C::g);
+    theta_d = (ax * cp + ay * sp) * (T(1) / C::g);
+  } else {
+    phi_d = (ax * sp - ay * cp) / C::g;
+    theta_d = (ax * cp + ay * sp) / C::g;
+  }
   dq = euler2quat(phi_d, theta_d, psi_d);
   // attitude_controller re-extracts the desired angles from the quaternion it was just given
   Euler<T> ed;

@@ -702,6 +702,13 @@ __global__ void fn_kernel(int fn, int64_t n, const T* in0, const T* in1, const T
 #pragma unroll
       for (int k = 0; k < 12; k++) out0[12 * i + k] = rel[k];
     } break;
+    case QS_FN_MATH: {
+      const T y = in0[2 * i], x = in0[2 * i + 1];
+      T sn, cs;
+      m_sincos(y, &sn, &cs);
+      T* o = out0 + 5 * i;
+      o[0] = m_atan2(y, x); o[1] = sn; o[2] = cs; o[3] = m_rsqrt(m_abs(x)); o[4] = m_sqrt(m_abs(x));
+    } break;
     default: break;
   }
 }
@@ -1135,7 +1142,7 @@ int qs_get_stats(qs_env_t* e, double stats[5], void* stream) {
 
 int qs_fn_apply(int fn, int dtype, int64_t n, const void* in0, const void* in1, const void* in2, void* out0, void* out1, void* stream) {
   if (n <= 0) return QS_OK;
-  if (fn < QS_FN_QUAT2EULER || fn > QS_FN_PHILOX) return fail(QS_ERR_INVALID, "qs_fn_apply: unknown fn %d", fn);
+  if (fn < QS_FN_QUAT2EULER || fn > QS_FN_MATH) return fail(QS_ERR_INVALID, "qs_fn_apply: unknown fn %d", fn);
   if (!in0 || !out0) return fail(QS_ERR_INVALID, "qs_fn_apply: null in0/out0");
   const bool two_in = fn == QS_FN_DRONE_STEP || fn == QS_FN_PID || fn == QS_FN_VEL_CTRL || fn == QS_FN_STATE2REL || fn == QS_FN_PHILOX;
   const bool two_out = fn == QS_FN_DRONE_STEP || fn == QS_FN_PID || fn == QS_FN_VEL_CTRL;

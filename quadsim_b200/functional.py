@@ -77,6 +77,12 @@ def state2rel(state_chaser, state_target):
     return _apply(_capi.FN_STATE2REL, [state_chaser, state_target], [12])[0]
 
 
+def scalar_math(y, x):
+    """The kernels' own elementary functions (what stands in for numpy's arctan2/sin/cos/sqrt of the reference) on [n]
+    tensors: returns [n,5] = atan2(y,x), sin(y), cos(y), 1/sqrt(|x|), sqrt(|x|).  For accuracy tests."""
+    return _apply(_capi.FN_MATH, [torch.stack([y, x], dim=1)], [5])[0]
+
+
 def philox4x32_10(ctr, key):
     """ctr int64/uint32-valued [n,4], key [n,2] -> [n,4] (as int64 holding uint32 values)."""
     c = ctr.to(torch.int64).contiguous()

@@ -28,8 +28,18 @@ def lib():
         L.hh_step.argtypes = [C.c_int, C.c_void_p] + [C.c_void_p] * 6
         L.hh_io.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.hh_expert.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.hh_math.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
+
+
+def scalar_math(y, x):
+    """qs::m_atan2 / m_sincos / m_rsqrt / m_sqrt (double) -> [n,5]"""
+    y = np.ascontiguousarray(y, np.float64)
+    x = np.ascontiguousarray(x, np.float64)
+    out = np.zeros((y.size, 5), np.float64)
+    lib().hh_math(y.size, y.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 def _p(a):

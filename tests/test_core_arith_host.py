@@ -43,6 +43,32 @@ def test_reference_tapes(name, dtype, tol):
     env.close()
 
 
+def test_f64_scalar_math_polynomials():
+    """qs::f64m atan2 / sincos (the polynomial and argument-reduction code shared by host and device; the device-only
+    MUFU-seeded reciprocal / rsqrt are covered by tests/test_gpu_parity.py::test_scalar_math_accuracy) vs numpy: <= 3 ulp,
+    and the IEEE special cases are the library's."""
+    from host_harness import scalar_math
+    rng = np.random.RandomState(3)
+    n = 1 << 20
+    scale = 10.0 ** rng.uniform(-6, 6, n)
+    y = rng.uniform(-1, 1, n) * scale
+    x = rng.uniform(-1, 1, n) * np.where(rng.rand(n) < 0.5, scale, 1.0)
+    y[: n // 4] = rng.uniform(-8, 8, n // 4)
+    out = scalar_math(y, x)
+    eps = np.finfo(np.float64).eps
+    at = np.arctan2(y, x)
+    assert (np.abs(out[:, 0] - at) <= 3 * eps * np.abs(at)).all()
+    ang = np.abs(y) < 1e4
+    for k, ref in ((1, np.sin(y)), (2, np.cos(y))):
+        assert (np.abs(out[ang, k] - ref[ang]) <= 3 * eps * np.maximum(np.abs(ref[ang]), 2.0 ** -10)).all()
+        assert (np.abs(out[~ang, k] - ref[~ang]) <= 3 * eps).all()
+    sy = np.array([0.0, 0.0, -0.0, -0.0, 1.0, -1.0, 0.0, 0.0, np.inf, 1.0, np.inf, -np.inf, 1e-300, 1e300, 5e-324, 1e-320])
+    sx = np.array([0.0, -0.0, 0.0, -0.0, 0.0, 0.0, 1.0, -1.0, 1.0, np.inf, np.inf, -np.inf, 1e-300, -1e300, 5e-324, 1.0])
+    got, ref = scalar_math(sy, sx)[:, 0], np.arctan2(sy, sx)
+    assert np.array_equal(got, ref) and np.array_equal(np.signbit(got), np.signbit(ref))
+    assert np.isnan(scalar_math(np.array([np.nan, 1.0]), np.array([1.0, np.nan]))[:, 0]).all()
+
+
 @pytest.mark.parametrize("v", [0, 2])
 def test_wild_single_step_fp64(v):
     g = load_golden("dock_v%d_wild" % v)

@@ -64,6 +64,41 @@ def test_leaf_functions_vs_reference_golden(dtype, tol):
         assert rel_err(N(u), g["step_u"]) < 1e-5
 
 
+@pytest.mark.gpu
+def test_scalar_math_accuracy():
+    """qs::f64m (constant-memory polynomials, MUFU-seeded Newton reciprocal / rsqrt) against numpy on 2e6 arguments:
+    <= 4 ulp in fp64 (the host libm and the reference's numpy are themselves <= 1 ulp), 1e-6 relative in fp32."""
+    import quadsim_b200.functional as F
+    rng = np.random.RandomState(3)
+    n = 1 << 21
+    scale = 10.0 ** rng.uniform(-6, 6, n)
+    y = rng.uniform(-1, 1, n) * scale
+    x = rng.uniform(-1, 1, n) * np.where(rng.rand(n) < 0.5, scale, 1.0)
+    y[: n // 4] = rng.uniform(-8, 8, n // 4)  # angle-sized arguments for sin/cos
+    y[:8] = [0.0, -0.0, 1.0, -1.0, 0.0, 1e-300, 1e300, 3.0]
+    x[:8] = [0.0, 0.0, 0.0, 0.0, -1.0, 1e-300, -1e300, 1e-310]
+    ang = np.abs(y) < 1e4
+    for dtype, tol_ulp in ((torch.float64, 4.0), (torch.float32, 8.0)):
+        npd = np.float64 if dtype == torch.float64 else np.float32
+        yy, xx = y.astype(npd), x.astype(npd)
+        out = F.scalar_math(torch.as_tensor(yy).cuda(), torch.as_tensor(xx).cuda()).cpu().numpy().astype(np.float64)
+        y6, x6 = yy.astype(np.float64), xx.astype(np.float64)
+        ref = np.stack([np.arctan2(y6, x6), np.sin(y6), np.cos(y6), 1.0 / np.sqrt(np.abs(x6)), np.sqrt(np.abs(x6))], 1)
+        eps = np.finfo(npd).eps
+        with np.errstate(divide="ignore", invalid="ignore"):
+            err = np.abs(out - ref) / (eps * np.maximum(np.abs(ref), np.finfo(npd).tiny))
+        err[~np.isfinite(ref)] = np.where(out[~np.isfinite(ref)] == ref[~np.isfinite(ref)], 0.0, np.inf)
+        err[out == ref] = 0.0
+        # sin/cos: relative accuracy near their zeros is bounded by the argument reduction, so use absolute ulps of 1 there
+        for k in (1, 2):
+            err[:, k] = np.where(ang, np.abs(out[:, k] - ref[:, k]) / (eps * np.maximum(np.abs(ref[:, k]), 0.5 ** 10)), 0.0)
+        worst = err.max(axis=0)
+        print(dtype, "worst ulp [atan2, sin, cos, rsqrt, sqrt]:", worst)
+        assert (worst <= tol_ulp).all(), worst
+        assert out[0, 0] == 0.0 and out[4, 0] == np.float64(npd(np.pi))  # atan2(0,0), atan2(0,-1)
+
+
+@pytest.mark.gpu
 def test_philox_known_answers():
     import json
     import os
