@@ -161,7 +161,7 @@ typedef enum {
   QS_FN_STATE2REL = 8,  /* docking_env.py:257-295       in0 chaser[n,13] in1 target[n,13] -> out0 rel[n,12] */
   QS_FN_PHILOX = 9,     /* in0 uint32 ctr[n,4], in1 uint32 key[n,2] -> out0 uint32[n,4] (dtype ignored) */
   QS_FN_MATH = 10       /* the kernels' scalar math (numpy's arctan2/sin/cos/sqrt in the reference): in0 (y,x)[n,2] ->
-                           out0 [n,5] = atan2(y,x), sin(y), cos(y), 1/sqrt(|x|), sqrt(|x|) */
+                           out0 [n,6] = atan2(y,x), sin(y), cos(y), 1/sqrt(|x|), sqrt(|x|), asin(y) */
 } qs_fn;
 int qs_fn_apply(int fn, int dtype, int64_t n, const void* in0, const void* in1, const void* in2, void* out0,
                 void* out1, void* stream);

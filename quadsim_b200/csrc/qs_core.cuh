@@ -74,12 +74,15 @@ template <typename T> constexpr bool kFast = is_f32<T>::value ? kFast32 : kFast6
 #define QS_F64M_ATAN {-0x1.5555555555555p-2, 0x1.999999999934ap-3, -0x1.24924924360cbp-3, 0x1.c71c7185314cbp-4, -0x1.745d0b26b83e7p-4, 0x1.3b1262d95579ep-4, -0x1.10fa75382537fp-4, 0x1.dfe61e80903d2p-5, -0x1.a098bb6ba4941p-5, 0x1.41603647c7a7cp-5, -0x1.3a2b7a07caea9p-6}
 #define QS_F64M_SIN {-0x1.5555555555555p-3, 0x1.1111111110babp-7, -0x1.a01a019e820aep-13, 0x1.71de37946ed6dp-19, -0x1.ae6008d114485p-26, 0x1.5e0a4fc16be59p-33}
 #define QS_F64M_COS {0x1.5555555555555p-5, -0x1.6c16c16c16963p-10, 0x1.a01a019f4ddfdp-16, -0x1.27e4fa16cc2d1p-22, 0x1.1eeb67d026ec6p-29, -0x1.907cd8ff5ede7p-37}
+#define QS_F64M_ASIN {0x1.5555555555556p-3, 0x1.3333333332ec4p-4, 0x1.6db6db6e3292ep-5, 0x1.f1c71c1d4aa0dp-6, 0x1.6e8bb1d89492bp-6, 0x1.1c4d343fa57f6p-6, 0x1.c9cf3759fd8ffp-7, 0x1.78246f32d075cp-7, 0x1.524ea8b3aad31p-7, 0x1.653a8f8cfd43cp-8, 0x1.1d661531b222ep-6, -0x1.e7a24f548c99fp-7, 0x1.d78189767524ep-6}
 namespace f64m {
 #if defined(__CUDACC__)
+static __constant__ double c_asin[13] = QS_F64M_ASIN;
 static __constant__ double c_atan[11] = QS_F64M_ATAN;
 static __constant__ double c_sin[6] = QS_F64M_SIN;
 static __constant__ double c_cos[6] = QS_F64M_COS;
 #endif
+static constexpr double h_asin[13] = QS_F64M_ASIN;
 static constexpr double h_atan[11] = QS_F64M_ATAN;
 static constexpr double h_sin[6] = QS_F64M_SIN;
 static constexpr double h_cos[6] = QS_F64M_COS;
@@ -177,6 +180,27 @@ QS_HD double atan2(double y, double x) {
   return copysign(r, y);
 }
 
+// asin(x) = u + u z R(z) with (u, z) = (x, x^2) for |x| <= 1/2, else pi/2 - 2 asin(sqrt((1 - |x|) / 2)); |x| > 1 -> NaN
+QS_HD double asin(double x) {
+  const double ax = fabs(x);
+  const bool big = ax > 0.5;
+  const double w = fma(-0.5, ax, 0.5);
+  const double z = big ? w : x * x;
+  double u = ax;
+  if (big) u = (w >= 1e-300) ? sqrt(w) : sqrt_cold(w);  // w = 0 at |x| = 1, negative (NaN) beyond
+  const double z2 = z * z;
+  double pe = fma(z2, QS_F64M_C(asin, 12), QS_F64M_C(asin, 10));
+  double po = fma(z2, QS_F64M_C(asin, 11), QS_F64M_C(asin, 9));
+  pe = fma(z2, pe, QS_F64M_C(asin, 8)); po = fma(z2, po, QS_F64M_C(asin, 7));
+  pe = fma(z2, pe, QS_F64M_C(asin, 6)); po = fma(z2, po, QS_F64M_C(asin, 5));
+  pe = fma(z2, pe, QS_F64M_C(asin, 4)); po = fma(z2, po, QS_F64M_C(asin, 3));
+  pe = fma(z2, pe, QS_F64M_C(asin, 2)); po = fma(z2, po, QS_F64M_C(asin, 1));
+  pe = fma(z2, pe, QS_F64M_C(asin, 0));
+  double r = fma(u * z, fma(z, po, pe), u);
+  if (big) r = 0x1.921fb54442d18p+0 - (2.0 * r - 0x1.1a62633145c07p-54);
+  return copysign(r, x);
+}
+
 QS_HD void sincos(double x, double* s, double* c) {
   if (!(fabs(x) <= 1.0e5)) { const SC r = sincos_cold(x); *s = r.s; *c = r.c; return; }
   // k = nearest integer to x * 2/pi via the 1.5 * 2^52 shift (its low word is k mod 2^32)
@@ -229,7 +253,7 @@ QS_HD float m_asin(float x) { return asinf(x); }
 #else
 #define QS_F64_FN QS_HD
 #endif
-QS_F64_FN double m_asin(double x) { return asin(x); }
+QS_F64_FN double m_asin(double x) { return kFast64 ? f64m::asin(x) : asin(x); }
 QS_HD float m_atan2(float y, float x) { return atan2f(y, x); }
 QS_F64_FN double m_atan2(double y, double x) { return kFast64 ? f64m::atan2(y, x) : atan2(y, x); }
 QS_HD float m_tan(float x) { return tanf(x); }

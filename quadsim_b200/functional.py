@@ -79,8 +79,8 @@ def state2rel(state_chaser, state_target):
 
 def scalar_math(y, x):
     """The kernels' own elementary functions (what stands in for numpy's arctan2/sin/cos/sqrt of the reference) on [n]
-    tensors: returns [n,5] = atan2(y,x), sin(y), cos(y), 1/sqrt(|x|), sqrt(|x|).  For accuracy tests."""
-    return _apply(_capi.FN_MATH, [torch.stack([y, x], dim=1)], [5])[0]
+    tensors: returns [n,6] = atan2(y,x), sin(y), cos(y), 1/sqrt(|x|), sqrt(|x|), asin(y).  For accuracy tests."""
+    return _apply(_capi.FN_MATH, [torch.stack([y, x], dim=1)], [6])[0]
 
 
 def philox4x32_10(ctr, key):

@@ -123,13 +123,13 @@ void hh_expert(int f64, void* h, void* mem, int alias, void* act, void* obs) {
   else vec_expert<float>(h, (float*)mem, alias, (float*)act, (float*)obs);
 }
 void hh_io(int f64, void* h, double* buf, int import) { f64 ? vec_io<double>(h, buf, import) : vec_io<float>(h, buf, import); }
-// the fp64 scalar math wrappers (qs::f64m polynomials on the host): out[n,5] = atan2(y,x), sin(y), cos(y), rsqrt|x|, sqrt|x|
+// the fp64 scalar math wrappers (qs::f64m polynomials on the host): out[n,6] = atan2(y,x), sin(y), cos(y), rsqrt|x|, sqrt|x|, asin(y)
 void hh_math(int64_t n, const double* y, const double* x, double* out) {
   for (int64_t i = 0; i < n; i++) {
     double s, c;
     qs::m_sincos(y[i], &s, &c);
-    double* o = out + 5 * i;
-    o[0] = qs::m_atan2(y[i], x[i]); o[1] = s; o[2] = c; o[3] = qs::m_rsqrt(fabs(x[i])); o[4] = qs::m_sqrt(fabs(x[i]));
+    double* o = out + 6 * i;
+    o[0] = qs::m_atan2(y[i], x[i]); o[1] = s; o[2] = c; o[3] = qs::m_rsqrt(fabs(x[i])); o[4] = qs::m_sqrt(fabs(x[i])); o[5] = qs::m_asin(y[i]);
   }
 }
 }

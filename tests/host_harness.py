@@ -34,10 +34,10 @@ def lib():
 
 
 def scalar_math(y, x):
-    """qs::m_atan2 / m_sincos / m_rsqrt / m_sqrt (double) -> [n,5]"""
+    """qs::m_atan2 / m_sincos / m_rsqrt / m_sqrt (double) -> [n,6]"""
     y = np.ascontiguousarray(y, np.float64)
     x = np.ascontiguousarray(x, np.float64)
-    out = np.zeros((y.size, 5), np.float64)
+    out = np.zeros((y.size, 6), np.float64)
     lib().hh_math(y.size, y.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     return out
 

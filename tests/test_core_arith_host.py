@@ -67,6 +67,12 @@ def test_f64_scalar_math_polynomials():
     got, ref = scalar_math(sy, sx)[:, 0], np.arctan2(sy, sx)
     assert np.array_equal(got, ref) and np.array_equal(np.signbit(got), np.signbit(ref))
     assert np.isnan(scalar_math(np.array([np.nan, 1.0]), np.array([1.0, np.nan]))[:, 0]).all()
+    ya = np.concatenate([rng.uniform(-1, 1, n // 2), np.sign(rng.uniform(-1, 1, 4096)) * (1 - 10.0 ** rng.uniform(-16, -1, 4096)),
+                         [0.0, 0.5, -0.5, 1.0, -1.0, 1e-300, 0.5000000000000001]])
+    got, ref = scalar_math(ya, np.ones_like(ya))[:, 5], np.arcsin(ya)
+    assert (np.abs(got - ref) <= 3 * eps * np.abs(ref)).all()
+    with np.errstate(invalid="ignore"):
+        assert np.isnan(scalar_math(np.array([1.0000001, -2.0, np.nan]), np.ones(3))[:, 5]).all()
 
 
 @pytest.mark.parametrize("v", [0, 2])

@@ -75,6 +75,7 @@ def test_scalar_math_accuracy():
     y = rng.uniform(-1, 1, n) * scale
     x = rng.uniform(-1, 1, n) * np.where(rng.rand(n) < 0.5, scale, 1.0)
     y[: n // 4] = rng.uniform(-8, 8, n // 4)  # angle-sized arguments for sin/cos
+    y[n // 4: n // 2] = rng.uniform(-1, 1, n // 4)  # asin's domain
     y[:8] = [0.0, -0.0, 1.0, -1.0, 0.0, 1e-300, 1e300, 3.0]
     x[:8] = [0.0, 0.0, 0.0, 0.0, -1.0, 1e-300, -1e300, 1e-310]
     ang = np.abs(y) < 1e4
@@ -83,17 +84,19 @@ def test_scalar_math_accuracy():
         yy, xx = y.astype(npd), x.astype(npd)
         out = F.scalar_math(torch.as_tensor(yy).cuda(), torch.as_tensor(xx).cuda()).cpu().numpy().astype(np.float64)
         y6, x6 = yy.astype(np.float64), xx.astype(np.float64)
-        ref = np.stack([np.arctan2(y6, x6), np.sin(y6), np.cos(y6), 1.0 / np.sqrt(np.abs(x6)), np.sqrt(np.abs(x6))], 1)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            ref = np.stack([np.arctan2(y6, x6), np.sin(y6), np.cos(y6), 1.0 / np.sqrt(np.abs(x6)), np.sqrt(np.abs(x6)), np.arcsin(y6)], 1)
         eps = np.finfo(npd).eps
         with np.errstate(divide="ignore", invalid="ignore"):
             err = np.abs(out - ref) / (eps * np.maximum(np.abs(ref), np.finfo(npd).tiny))
-        err[~np.isfinite(ref)] = np.where(out[~np.isfinite(ref)] == ref[~np.isfinite(ref)], 0.0, np.inf)
+        bad = ~np.isfinite(ref)
+        err[bad] = np.where((out[bad] == ref[bad]) | (np.isnan(out[bad]) & np.isnan(ref[bad])), 0.0, np.inf)
         err[out == ref] = 0.0
         # sin/cos: relative accuracy near their zeros is bounded by the argument reduction, so use absolute ulps of 1 there
         for k in (1, 2):
             err[:, k] = np.where(ang, np.abs(out[:, k] - ref[:, k]) / (eps * np.maximum(np.abs(ref[:, k]), 0.5 ** 10)), 0.0)
         worst = err.max(axis=0)
-        print(dtype, "worst ulp [atan2, sin, cos, rsqrt, sqrt]:", worst)
+        print(dtype, "worst ulp [atan2, sin, cos, rsqrt, sqrt, asin]:", worst)
         assert (worst <= tol_ulp).all(), worst
         assert out[0, 0] == 0.0 and out[4, 0] == np.float64(npd(np.pi))  # atan2(0,0), atan2(0,-1)
 

@@ -7,6 +7,7 @@
 atan(u) = u + u*z*Q(z),  z = u^2 in [0, tan^2(pi/8)]        (11 coefficients, |rel err| < 1e-17)
 sin(r)  = r + r*z*S(z),  z = r^2 in [0, (pi/4)^2]           ( 6 coefficients)
 cos(r)  = 1 - z/2 + z^2*C(z)                                ( 6 coefficients)
+asin(u) = u + u*z*R(z),  z = u^2 in [0, 1/4]                (13 coefficients); |x| > 1/2: pi/2 - 2 asin(sqrt((1-|x|)/2))
 pi/2    = P1 + P2 + P3 with P1, P2 carrying 33 significant bits (Cody-Waite: k*P1, k*P2 exact for |k| < 2^20)
 """
 import mpmath as mp
@@ -40,6 +41,13 @@ def c_cos(z):
     return (mp.cos(r) - 1 + z / 2) / z ** 2
 
 
+def r_asin(z):
+    if z == 0:
+        return mp.mpf(1) / 6
+    u = mp.sqrt(z)
+    return (mp.asin(u) - u) / u ** 3
+
+
 def split33(x):
     """leading 33 significant bits of x as a double"""
     m, e = mp.frexp(x)
@@ -62,6 +70,9 @@ if __name__ == "__main__":
     c, err = fit(c_cos, 0, zs, 6)
     show("QS_F64M_COS", c)
     print("// cos: |C err| %s" % mp.nstr(err, 3))
+    c, err = fit(r_asin, 0, mp.mpf("0.2501"), 13)
+    show("QS_F64M_ASIN", c)
+    print("// asin: |R err| %s" % mp.nstr(err, 3))
     p = mp.pi / 2
     p1 = split33(p)
     p2 = split33(p - p1)
