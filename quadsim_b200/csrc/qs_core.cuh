@@ -61,7 +61,7 @@ constexpr bool kFast64 = false;
 #else
 constexpr bool kFast64 = true;
 #endif
-template <typename T> constexpr bool kFast = is_f32<T>::value ? kFast32 : kFast64;
+template <typename T> constexpr bool kFast = is_f32<T>::value ? kFast32 : kFast64;  // sdouble (below): kFast64
 
 // ---- fp64 elementary functions of the fast fp64 path (qs::f64m) ----
 // The library's fp64 atan2 / sincos / 1/sqrt cost ~115 / ~68 / ~43 SASS instructions per call inside the step kernel, a
@@ -92,6 +92,24 @@ static constexpr double h_cos[6] = QS_F64M_COS;
 #define QS_F64M_C(name, i) h_##name[i]
 #endif
 
+QS_HD double qnan() {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(0x7ff8000000000000LL);
+#else
+  return NAN;
+#endif
+}
+// ok ? v : NaN as an opaque select: written as a plain conditional, the compiler sinks the whole evaluation of v into
+// a branch on ok -- exactly the basic-block split the speculative path exists to avoid
+QS_HD double keep(bool ok, double v) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("{ .reg .pred p; setp.ne.s32 p, %2, 0; selp.f64 %0, %1, %3, p; }" : "=d"(r) : "d"(v), "r"((int)ok), "d"(qnan()));
+  return r;
+#else
+  return ok ? v : qnan();
+#endif
+}
 // library fallbacks, one out-of-line copy each (cold: zero / subnormal / huge / non-finite arguments only)
 #if defined(__CUDACC__)
 #define QS_F64M_COLD static __host__ __device__ __noinline__
@@ -158,11 +176,23 @@ QS_HD double sqrt(double x) {
 #endif
 }
 
-QS_HD double atan2(double y, double x) {
+// atan2 for max(|x|,|y|) in [1e-280, 1e280] (anything else: garbage, the callers below guard or poison)
+// sqrt for x == 0 or x in [1e-300, 1e300], branch-free (the seed is taken of max(x, 1e-300): 0 * finite = 0);
+// negative / NaN x -> NaN
+QS_HD double sqrt0(double x) {
+#if defined(__CUDA_ARCH__)
+  const double y = rsqrt(fmax(x, 1e-300));
+  const double g = x * y;
+  const double r = fma(fma(-g, g, x), 0.5 * y, g);
+  return keep(!(x < 0.0), r);
+#else
+  return ::sqrt(x);
+#endif
+}
+QS_HD double atan2_fast(double y, double x) {
   const double ax = fabs(x), ay = fabs(y);
   const bool sw = ay > ax;
   const double a = sw ? ax : ay, b = sw ? ay : ax;  // a = min, b = max (a NaN lands in b or in the quotient)
-  if (!(b >= 1e-280 && b <= 1e280)) return atan2_cold(y, x);
   // |a/b| <= 1 ; above tan(pi/8) use atan(a/b) = pi/4 + atan((a-b)/(a+b)): still one division, |u| <= tan(pi/8)
   const bool hi = a > 0x1.a827999fcef32p-2 * b;
   const double u = div(hi ? a - b : a, hi ? a + b : b);
@@ -179,15 +209,24 @@ QS_HD double atan2(double y, double x) {
   if (x < 0.0) r = 0x1.921fb54442d18p+1 - (r - 0x1.1a62633145c07p-53);
   return copysign(r, y);
 }
+QS_HD bool atan2_in_range(double y, double x) {
+  const double b = fmax(fabs(x), fabs(y));  // fmax drops a NaN operand: a NaN argument still reaches the quotient
+  return b >= 1e-280 && b <= 1e280;
+}
+QS_HD double atan2(double y, double x) {
+  if (!atan2_in_range(y, x)) return atan2_cold(y, x);
+  return atan2_fast(y, x);
+}
 
 // asin(x) = u + u z R(z) with (u, z) = (x, x^2) for |x| <= 1/2, else pi/2 - 2 asin(sqrt((1 - |x|) / 2)); |x| > 1 -> NaN
-QS_HD double asin(double x) {
+template <bool GUARDED> QS_HD double asin_t(double x) {
   const double ax = fabs(x);
   const bool big = ax > 0.5;
   const double w = fma(-0.5, ax, 0.5);
   const double z = big ? w : x * x;
   double u = ax;
-  if (big) u = (w >= 1e-300) ? sqrt(w) : sqrt_cold(w);  // w = 0 at |x| = 1, negative (NaN) beyond
+  if (GUARDED) { if (big) u = (w >= 1e-300) ? sqrt(w) : sqrt_cold(w); }  // w = 0 at |x| = 1, negative (NaN) beyond
+  else u = big ? sqrt0(w) : ax;                                        // branch-free; |x| > 1 -> NaN as well
   const double z2 = z * z;
   double pe = fma(z2, QS_F64M_C(asin, 12), QS_F64M_C(asin, 10));
   double po = fma(z2, QS_F64M_C(asin, 11), QS_F64M_C(asin, 9));
@@ -200,9 +239,10 @@ QS_HD double asin(double x) {
   if (big) r = 0x1.921fb54442d18p+0 - (2.0 * r - 0x1.1a62633145c07p-54);
   return copysign(r, x);
 }
+QS_HD double asin(double x) { return asin_t<true>(x); }
 
-QS_HD void sincos(double x, double* s, double* c) {
-  if (!(fabs(x) <= 1.0e5)) { const SC r = sincos_cold(x); *s = r.s; *c = r.c; return; }
+// sin and cos for |x| <= 1e5
+QS_HD void sincos_fast(double x, double* s, double* c) {
   // k = nearest integer to x * 2/pi via the 1.5 * 2^52 shift (its low word is k mod 2^32)
   const double t = fma(x, 0x1.45f306dc9c883p-1, 6755399441055744.0);
   const double k = t - 6755399441055744.0;
@@ -225,6 +265,10 @@ QS_HD void sincos(double x, double* s, double* c) {
   const double a = (q & 1) ? cs : sn, b = (q & 1) ? sn : cs;
   *s = (q & 2) ? -a : a;
   *c = ((q + 1) & 2) ? -b : b;
+}
+QS_HD void sincos(double x, double* s, double* c) {
+  if (!(fabs(x) <= 1.0e5)) { const SC r = sincos_cold(x); *s = r.s; *c = r.c; return; }
+  sincos_fast(x, s, c);
 }
 }  // namespace f64m
 
@@ -308,6 +352,66 @@ template <typename T> QS_HD T m_sign(T x) { return T((x > T(0)) - (x < T(0))); }
 template <typename T> QS_HD bool m_finite(T x) { return (x - x) == T(0); }
 template <typename T> QS_HD T norm3(T x, T y, T z) { return m_sqrt(x * x + y * y + z * z); }
 
+// ---- sdouble: the SPECULATIVE fp64 arithmetic type ----
+// The guarded fp64 functions above each carry a range test with an out-of-line library call behind it.  Those branches
+// are never taken on sane states, but they cut the step into ~70 basic blocks that ptxas cannot schedule across; on a
+// kernel that runs 3 warps per scheduler that costs 3.5 % (profiles/r1_fp64_f64m_spec_ab.log).  sdouble is a double whose
+// elementary functions are the same fast cores WITHOUT the branch: an argument outside a core's range yields NaN instead
+// ("poison").  dock_env_step<sdouble> is therefore a handful of long straight-line blocks (only the attitude-clamp tests
+// remain); dock_env_step_spec() below runs it, checks that nothing non-finite reached the observation, the reward or the
+// parts of the state the observation does not see, and otherwise tells the caller to redo the step from the ORIGINAL
+// state with the guarded double arithmetic (a cold, out-of-line replay).  In-range arguments take identical code either
+// way, so the results are bit-identical to the guarded path (tests/test_core_arith_host.py checks that on 1.6e6 wild
+// env-steps); legitimately non-finite states simply always take the replay.  Rules that keep poison from getting lost:
+// NaN-preserving min/max (u_limit), an explicit test before the comparisons of the attitude clamp, and f64m::keep() --
+// an opaque select -- wherever a precondition is recorded.
+struct sdouble {
+  double v;
+  sdouble() = default;
+  constexpr sdouble(double x) : v(x) {}
+  constexpr explicit operator double() const { return v; }
+};
+template <typename T> struct is_spec { static constexpr bool value = false; };
+template <> struct is_spec<sdouble> { static constexpr bool value = true; };
+template <typename T> constexpr bool kSpec = is_spec<T>::value;
+QS_HD sdouble operator+(sdouble a, sdouble b) { return sdouble(a.v + b.v); }
+QS_HD sdouble operator-(sdouble a, sdouble b) { return sdouble(a.v - b.v); }
+QS_HD sdouble operator*(sdouble a, sdouble b) { return sdouble(a.v * b.v); }
+QS_HD sdouble operator/(sdouble a, sdouble b) { return sdouble(a.v / b.v); }
+QS_HD sdouble operator-(sdouble a) { return sdouble(-a.v); }
+QS_HD sdouble& operator+=(sdouble& a, sdouble b) { a.v += b.v; return a; }
+QS_HD sdouble& operator-=(sdouble& a, sdouble b) { a.v -= b.v; return a; }
+QS_HD sdouble& operator*=(sdouble& a, sdouble b) { a.v *= b.v; return a; }
+QS_HD bool operator<(sdouble a, sdouble b) { return a.v < b.v; }
+QS_HD bool operator>(sdouble a, sdouble b) { return a.v > b.v; }
+QS_HD bool operator<=(sdouble a, sdouble b) { return a.v <= b.v; }
+QS_HD bool operator>=(sdouble a, sdouble b) { return a.v >= b.v; }
+QS_HD bool operator==(sdouble a, sdouble b) { return a.v == b.v; }
+QS_HD bool operator!=(sdouble a, sdouble b) { return a.v != b.v; }
+// ok ? v : NaN -- how a model-level precondition of a shortcut is recorded in speculative mode
+QS_HD sdouble spec_keep(sdouble v, bool ok) { return sdouble(f64m::keep(ok, v.v)); }
+QS_HD float spec_keep(float v, bool) { return v; }
+QS_HD double spec_keep(double v, bool) { return v; }
+QS_HD sdouble m_abs(sdouble x) { return sdouble(fabs(x.v)); }
+// NaN-preserving min / max (fmin / fmax would swallow the poison on its way through u_limit)
+QS_HD sdouble m_min(sdouble a, sdouble b) { return sdouble((a.v < b.v || a.v != a.v) ? a.v : b.v); }
+QS_HD sdouble m_max(sdouble a, sdouble b) { return sdouble((a.v > b.v || a.v != a.v) ? a.v : b.v); }
+QS_HD sdouble m_sqrt(sdouble x) {  // 0 is a legitimate argument (norms of zero vectors on the first step of an episode)
+  return sdouble(f64m::keep(x.v == 0.0 || (x.v >= 1e-300 && x.v <= 1e300), f64m::sqrt0(x.v)));
+}
+QS_HD sdouble m_rsqrt(sdouble x) { return sdouble(f64m::keep(x.v >= 1e-300 && x.v <= 1e300, f64m::rsqrt(x.v))); }
+QS_HD sdouble m_asin(sdouble x) { return sdouble(f64m::asin_t<false>(x.v)); }
+QS_HD sdouble m_atan2(sdouble y, sdouble x) {
+  return sdouble(f64m::keep(f64m::atan2_in_range(y.v, x.v), f64m::atan2_fast(y.v, x.v)));
+}
+QS_HD void m_sincos(sdouble x, sdouble* s, sdouble* c) {
+  double sn, cs;
+  f64m::sincos_fast(x.v, &sn, &cs);
+  const bool ok = fabs(x.v) <= 1.0e5;
+  *s = sdouble(f64m::keep(ok, sn)); *c = sdouble(f64m::keep(ok, cs));
+}
+QS_HD sdouble m_tan(sdouble) { return sdouble(f64m::qnan()); }  // only reached from branches the speculative path replaces
+
 template <typename T> struct Euler { T phi, theta, psi; };
 template <typename T> struct Quat { T w, x, y, z; };
 
@@ -329,6 +433,11 @@ template <typename T> QS_HD Euler<T> quat2euler(T w, T x, T y, T z) {
   T r22 = w * w - x * x - y * y + z * z;
   Euler<T> e;
   e.psi = m_atan2(-r10, r11);
+  if (kSpec<T>) {  // straight line; the +-90 degree branches are left to the guarded replay
+    e.phi = spec_keep(m_asin(r12), r12 < T(1) && !(r12 < T(-1)));
+    e.theta = m_atan2(-r02, r22);
+    return e;
+  }
   if (r12 < T(1)) {
     if (r12 < T(-1)) { e.phi = -K<T>::pi / T(2); e.theta = T(0); }
     else { e.phi = m_asin(r12); e.theta = m_atan2(-r02, r22); }
@@ -372,6 +481,11 @@ template <typename T> QS_HD Rot<T> quat2rot(T q0, T q1, T q2, T q3) {
 template <typename T> QS_HD Euler<T> rot2euler(T r12, T r10, T r11, T r02, T r22) {
   Euler<T> e;
   e.psi = m_atan2(-r10, r11);
+  if (kSpec<T>) {  // straight line; the +-90 degree branches are left to the guarded replay
+    e.phi = spec_keep(m_asin(r12), r12 < T(1) && !(r12 < T(-1)));
+    e.theta = m_atan2(-r02, r22);
+    return e;
+  }
   if (r12 < T(1)) {
     if (r12 < T(-1)) { e.phi = -K<T>::pi / T(2); e.theta = T(0); }
     else { e.phi = m_asin(r12); e.theta = m_atan2(-r02, r22); }
@@ -424,6 +538,10 @@ template <typename T> QS_HD ClampResult<T> attitude_clamp(T q0, T q1, T q2, T q3
   ClampResult<T> out = {q0, q1, q2, q3, false};
   Euler<T> e = quat2euler(q0, q1, q2, q3);
   const T r = e.phi, p = e.theta, y = e.psi;
+  if (kSpec<T> && !m_finite((r + p) + y)) {  // poisoned angles must not be swallowed by the comparisons below
+    out.w = out.x = out.y = out.z = r + p + y; out.fired = true;
+    return out;
+  }
   const bool cr = m_abs(r) >= C::d85, cp = m_abs(p) >= C::d85, cy = m_abs(y) >= C::d175;
   const bool inside = m_abs(r) <= C::d85 && m_abs(p) <= C::d85 && m_abs(y) <= C::d175;
   if (!(cr || cp || cy) || inside) return out;
@@ -518,7 +636,10 @@ template <typename T> QS_HD void acc2cmd(T ax, T ay, T az, Quat<T>& dq, const Dr
     T r10 = T(2) * (x * y - w * z), r11 = w * w - x * x + y * y - z * z;
     psi_d = m_atan2(-r10, r11);
     T h2 = r10 * r10 + r11 * r11;
-    if (kFast<T> && !is_f32<T>::value && h2 > T(1e-100) && h2 < T(1e100)) {
+    if (kSpec<T>) {
+      T inv = spec_keep(m_rsqrt(h2), h2 > T(1e-100) && h2 < T(1e100));
+      sp = -r10 * inv; cp = r11 * inv;
+    } else if (kFast<T> && !is_f32<T>::value && h2 > T(1e-100) && h2 < T(1e100)) {
       T inv = m_rsqrt(h2);  // sin/cos of atan2(-r10, r11) from its arguments
       sp = -r10 * inv; cp = r11 * inv;
     } else {
@@ -535,7 +656,9 @@ template <typename T> QS_HD void acc2cmd(T ax, T ay, T az, Quat<T>& dq, const Dr
   dq = euler2quat(phi_d, theta_d, psi_d);
   // attitude_controller re-extracts the desired angles from the quaternion it was just given
   Euler<T> ed;
-  if (kFast<T> && m_abs(phi_d) < T(1.5) && m_abs(theta_d) < T(3.1)) {
+  if (kSpec<T>) {
+    ed.phi = spec_keep(phi_d, m_abs(phi_d) < T(1.5) && m_abs(theta_d) < T(3.1)); ed.theta = theta_d; ed.psi = psi_d;
+  } else if (kFast<T> && m_abs(phi_d) < T(1.5) && m_abs(theta_d) < T(3.1)) {
     ed.phi = phi_d; ed.theta = theta_d; ed.psi = psi_d;  // quat2euler(euler2quat(.)) == identity on this range
   } else {
     ed = quat2euler(dq.w, dq.x, dq.y, dq.z);
@@ -613,7 +736,12 @@ template <typename T> QS_HD void state2rel(const Drone<T>& c, const Drone<T>& t,
   T q = b1 - (ab10 * a0 + ab11 * a1 + ab12 * a2);
   T r = b2 - (ab20 * a0 + ab21 * a1 + ab22 * a2);
   T st, ct, tphi, icphi, cphi = T(1);
-  if (kFast<T> && ab12 < T(1) && ab12 > T(-1)) {
+  if (kSpec<T>) {
+    T h = m_rsqrt(ab02 * ab02 + ab22 * ab22);
+    st = -ab02 * h; ct = ab22 * h;
+    icphi = spec_keep(m_rsqrt((T(1) - ab12) * (T(1) + ab12)), ab12 < T(1) && ab12 > T(-1));
+    tphi = ab12 * icphi;
+  } else if (kFast<T> && ab12 < T(1) && ab12 > T(-1)) {
     // theta = atan2(-ab02, ab22), phi = asin(ab12): their sin/cos/tan follow from the arguments
     T h = m_rsqrt(ab02 * ab02 + ab22 * ab22);
     st = -ab02 * h; ct = ab22 * h;
@@ -630,7 +758,8 @@ template <typename T> QS_HD void state2rel(const Drone<T>& c, const Drone<T>& t,
   T rc_ps = r * ct - p * st;
   rel[9] = p * ct + r * st;
   rel[10] = q - tphi * rc_ps;
-  rel[11] = (icphi != T(0)) ? rc_ps * icphi : rc_ps / cphi;
+  if (kSpec<T>) rel[11] = rc_ps * icphi;
+  else rel[11] = (icphi != T(0)) ? rc_ps * icphi : rc_ps / cphi;
 }
 
 // ---- Philox4x32-10 (Salmon et al., SC'11).  Not in the reference: the north star's counter-based per-env RNG
@@ -775,6 +904,41 @@ template <typename T, int KIND> QS_HD void dock_env_step(DockEnv<T>& e, const T 
 #pragma unroll
   for (int k = 0; k < 12; k++) fsum += m_abs(rel[k]);
   o.nonfinite = !m_finite(fsum);
+}
+
+// Speculative fp64 step (see sdouble): returns false if the step has to be redone from the ORIGINAL state with the
+// guarded arithmetic -- e, rel and o are then meaningless.  Poison can only be born in the elementary functions and the
+// shortcut preconditions; from there it reaches either the observation / reward (covered by o.nonfinite) or, through the
+// target's controller, the target's stored command and desired quaternion, which this step's observation does not see
+// (one step of command latency, Q2) and which are therefore checked explicitly.
+template <typename T> QS_HD Drone<sdouble> to_spec(const Drone<T>& d) {
+  return Drone<sdouble>{sdouble(d.px), sdouble(d.py), sdouble(d.pz), sdouble(d.vx), sdouble(d.vy), sdouble(d.vz), sdouble(d.q0),
+                        sdouble(d.q1), sdouble(d.q2), sdouble(d.q3), sdouble(d.wx), sdouble(d.wy), sdouble(d.wz), sdouble(d.u0),
+                        sdouble(d.u1), sdouble(d.u2), sdouble(d.u3)};
+}
+QS_HD Drone<double> from_spec(const Drone<sdouble>& d) {
+  return Drone<double>{d.px.v, d.py.v, d.pz.v, d.vx.v, d.vy.v, d.vz.v, d.q0.v, d.q1.v, d.q2.v, d.q3.v, d.wx.v, d.wy.v, d.wz.v,
+                       d.u0.v, d.u1.v, d.u2.v, d.u3.v};
+}
+template <int KIND> QS_HD bool dock_env_step_spec(DockEnv<double>& e, const double act[4], double rel[12], StepOut<double>& o) {
+  DockEnv<sdouble> s;
+  s.c = to_spec(e.c); s.t = to_spec(e.t);
+  s.dq = Quat<sdouble>{sdouble(e.dq.w), sdouble(e.dq.x), sdouble(e.dq.y), sdouble(e.dq.z)};
+  s.last_shaping = sdouble(e.last_shaping); s.tt = e.tt; s.episode = e.episode;
+  const sdouble a[4] = {sdouble(act[0]), sdouble(act[1]), sdouble(act[2]), sdouble(act[3])};
+  sdouble r[12];
+  StepOut<sdouble> so;
+  dock_env_step<sdouble, KIND>(s, a, r, so);
+  const double hidden = ((s.t.u0.v + s.t.u1.v) + (s.t.u2.v + s.t.u3.v)) + ((s.dq.w.v + s.dq.x.v) + (s.dq.y.v + s.dq.z.v));
+  const bool ok = !so.nonfinite && (hidden - hidden == 0.0);
+  e.c = from_spec(s.c); e.t = from_spec(s.t);
+  e.dq = Quat<double>{s.dq.w.v, s.dq.x.v, s.dq.y.v, s.dq.z.v};
+  e.last_shaping = s.last_shaping.v; e.tt = s.tt;
+#pragma unroll
+  for (int k = 0; k < 12; k++) rel[k] = r[k].v;
+  o.reward = so.reward.v; o.done = so.done; o.docking = so.docking; o.overlimit = so.overlimit; o.overtime = so.overtime;
+  o.nonfinite = so.nonfinite;
+  return ok;
 }
 
 // =========================================================================================================

@@ -259,15 +259,13 @@ template <typename T> __device__ __forceinline__ void store_obs13_tile(T* stage,
 // moving_docking_env.py:111-192 (KIND = QS_DOCK_V2) + the stable-baselines worker's auto-reset.
 // The arithmetic is qs::dock_env_step / dock_env_seat (qs_core.cuh); this kernel is load -> step -> store.
 // =========================================================================================================
-template <typename T, int KIND>
-__global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_kernel(const StepArgs a) {
-  pdl_prologue();
-  constexpr int NW = dock_words<T>();
-  const int64_t i = a.first + (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  const bool active = i < a.first + a.n;
-  const unsigned mask = __ballot_sync(0xffffffffu, active);
-  if (!active) return;
+// What a thread contributes to the per-warp statistics after its step.
+struct StepTail { double ret; int len; bool done, docking, nonfinite; };
 
+// load -> step -> outputs -> auto-reset -> store for one env, guarded arithmetic.  The whole body of the fp32 kernel; for
+// fp64 the out-of-line replay of an env whose speculative step (qs::sdouble) met an argument outside a fast core's range.
+template <typename T, int KIND> __device__ __forceinline__ StepTail dock_step_one(const StepArgs& a, int64_t i) {
+  constexpr int NW = dock_words<T>();
   T w[NW];
   load_words<T, NW>(a.state, i, w);
   T act[4];
@@ -283,8 +281,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_kernel(cons
   a.done[i] = o.done ? 1 : 0;
   if (a.info) a.info[i] = (uint8_t)o.info();
   if (a.term_obs) store_row<T, 12>(a.term_obs, i, rel);
-  const double stat_ret = (double)e.last_shaping;  // == sum of the episode's rewards (telescoping)
-  const int stat_len = e.tt;
+  const StepTail tail = {(double)e.last_shaping, e.tt, o.done, o.docking, o.nonfinite};  // ret == sum of the episode's rewards (telescoping)
   if (o.done && a.auto_reset) {
     e.episode += 1;
     dock_env_seat<T>(e, a.rng, i, rel);
@@ -292,7 +289,57 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_kernel(cons
   store_row<T, 12>(a.obs, i, rel);
   dock_to_words<T, NW>(e, w);
   store_words<T, NW>(a.state, i, w);
-  warp_stats_update(a.warp_stats, i, mask, o.done, o.docking, o.nonfinite, stat_ret, stat_len);
+  return tail;
+}
+template <int KIND> __device__ __noinline__ StepTail dock_step_replay(const StepArgs& a, int64_t i) {
+  return dock_step_one<double, KIND>(a, i);
+}
+
+#ifdef QS_NO_SPEC64
+constexpr bool kSpec64 = false;
+#else
+constexpr bool kSpec64 = kFast64;  // -DQS_NO_SPEC64: the guarded fp64 arithmetic on the main path (A/B)
+#endif
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_kernel(const __grid_constant__ StepArgs a) {
+  pdl_prologue();
+  const int64_t i = a.first + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const bool active = i < a.first + a.n;
+  const unsigned mask = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  StepTail tail;
+  if constexpr (!is_f32<T>::value && kSpec64) {
+    // fp64: speculative straight-line step; an env that fails the check is replayed from its (still untouched) state in HBM
+    constexpr int NW = dock_words<double>();
+    double w[NW];
+    load_words<double, NW>(a.state, i, w);
+    double act[4];
+    load_action<double>(a.actions, i, act);
+    DockEnv<double> e;
+    words_to_dock<double, NW>(w, e);
+    double rel[12];
+    StepOut<double> o;
+    if (dock_env_step_spec<KIND>(e, act, rel, o)) {
+      reinterpret_cast<double*>(a.reward)[i] = o.reward;
+      a.done[i] = o.done ? 1 : 0;
+      if (a.info) a.info[i] = (uint8_t)o.info();
+      if (a.term_obs) store_row<double, 12>(a.term_obs, i, rel);
+      tail = StepTail{e.last_shaping, e.tt, o.done, o.docking, o.nonfinite};
+      if (o.done && a.auto_reset) {
+        e.episode += 1;
+        dock_env_seat<double>(e, a.rng, i, rel);
+      }
+      store_row<double, 12>(a.obs, i, rel);
+      dock_to_words<double, NW>(e, w);
+      store_words<double, NW>(a.state, i, w);
+    } else {
+      tail = dock_step_replay<KIND>(a, i);
+    }
+  } else {
+    tail = dock_step_one<T, KIND>(a, i);
+  }
+  warp_stats_update(a.warp_stats, i, mask, tail.done, tail.docking, tail.nonfinite, tail.ret, tail.len);
 }
 
 // =========================================================================================================

@@ -13,6 +13,8 @@ namespace {
 template <typename T> struct Vec {
   int kind; int64_t n; RngCfg rng; int auto_reset;
   DockEnv<T>* dock; HoverEnv<T>* hover;
+  int spec = 1;         // fp64 docking: 0 = guarded arithmetic only (what the replay runs), for A/B
+  int64_t replays = 0;  // fp64 docking: steps whose speculative evaluation was redone with the guarded arithmetic
 };
 
 template <typename T> void* vec_create(int kind, int64_t n, uint64_t seed, uint64_t env_id0, int randomize, double half_width, int auto_reset) {
@@ -36,6 +38,23 @@ template <typename T> void vec_reset(void* h, T* obs) {
     else { auto& e = v->dock[i]; e.episode += e.tt != 0; dock_env_seat<T>(e, v->rng, i, obs + 12 * i); }
   }
 }
+// What dock_step_kernel does per env (qs_lib.cu): fp32 -> the guarded step; fp64 -> the speculative straight-line step
+// (qs::sdouble) and, when its check fails, a replay of the guarded step from the original state.
+inline void dock_step_like_kernel(int kind, DockEnv<float>& e, const float* act, float* rel, StepOut<float>& o, int64_t&, int) {
+  if (kind == kDockV0) dock_env_step<float, kDockV0>(e, act, rel, o);
+  else dock_env_step<float, kDockV2>(e, act, rel, o);
+}
+inline void dock_step_like_kernel(int kind, DockEnv<double>& e, const double* act, double* rel, StepOut<double>& o, int64_t& replays, int spec) {
+  if (kFast64 && spec) {
+    const DockEnv<double> e0 = e;
+    const bool ok = kind == kDockV0 ? dock_env_step_spec<kDockV0>(e, act, rel, o) : dock_env_step_spec<kDockV2>(e, act, rel, o);
+    if (ok) return;
+    e = e0;
+    replays++;
+  }
+  if (kind == kDockV0) dock_env_step<double, kDockV0>(e, act, rel, o);
+  else dock_env_step<double, kDockV2>(e, act, rel, o);
+}
 template <typename T> void vec_step(void* h, const T* act, T* obs, T* rew, uint8_t* done, uint8_t* info, T* term) {
   auto* v = (Vec<T>*)h;
   for (int64_t i = 0; i < v->n; i++) {
@@ -50,8 +69,7 @@ template <typename T> void vec_step(void* h, const T* act, T* obs, T* rew, uint8
     } else {
       auto& e = v->dock[i];
       T rel[12];
-      if (v->kind == kDockV0) dock_env_step<T, kDockV0>(e, act + 4 * i, rel, o);
-      else dock_env_step<T, kDockV2>(e, act + 4 * i, rel, o);
+      dock_step_like_kernel(v->kind, e, act + 4 * i, rel, o, v->replays, v->spec);
       if (term) memcpy(term + 12 * i, rel, sizeof rel);
       if (o.done && v->auto_reset) { e.episode += 1; dock_env_seat<T>(e, v->rng, i, rel); }
       memcpy(obs + 12 * i, rel, sizeof rel);
@@ -122,6 +140,8 @@ void hh_expert(int f64, void* h, void* mem, int alias, void* act, void* obs) {
   if (f64) vec_expert<double>(h, (double*)mem, alias, (double*)act, (double*)obs);
   else vec_expert<float>(h, (float*)mem, alias, (float*)act, (float*)obs);
 }
+void hh_set_spec(int f64, void* h, int on) { if (f64) ((Vec<double>*)h)->spec = on; else ((Vec<float>*)h)->spec = on; }
+int64_t hh_replays(int f64, void* h) { return f64 ? ((Vec<double>*)h)->replays : ((Vec<float>*)h)->replays; }
 void hh_io(int f64, void* h, double* buf, int import) { f64 ? vec_io<double>(h, buf, import) : vec_io<float>(h, buf, import); }
 // the fp64 scalar math wrappers (qs::f64m polynomials on the host): out[n,6] = atan2(y,x), sin(y), cos(y), rsqrt|x|, sqrt|x|, asin(y)
 void hh_math(int64_t n, const double* y, const double* x, double* out) {

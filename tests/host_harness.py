@@ -28,6 +28,9 @@ def lib():
         L.hh_step.argtypes = [C.c_int, C.c_void_p] + [C.c_void_p] * 6
         L.hh_io.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.hh_expert.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.hh_set_spec.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.hh_replays.restype = C.c_int64
+        L.hh_replays.argtypes = [C.c_int, C.c_void_p]
         L.hh_math.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -67,6 +70,14 @@ class HostVecEnv:
         info = np.zeros(self.n, np.uint8)
         lib().hh_step(self.f64, self._h, _p(a), _p(obs), _p(rew), _p(done), _p(info), _p(term))
         return obs, rew, done, info, term
+
+    def set_speculative(self, on):
+        """fp64 docking: False = the guarded arithmetic only (what a replay runs)"""
+        lib().hh_set_spec(self.f64, self._h, int(bool(on)))
+
+    def replays(self):
+        """fp64 docking: env-steps whose speculative (qs::sdouble) evaluation was redone with the guarded arithmetic"""
+        return int(lib().hh_replays(self.f64, self._h))
 
     def expert_act(self, mem, alias, obs=None):
         """qs::pid_expert_* on every env; mem [n,8] (updated in place), obs [n,12] rewritten for re-seated chasers."""

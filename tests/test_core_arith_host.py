@@ -93,6 +93,58 @@ def test_wild_single_step_fp64(v):
     assert rel_err(st["u_t"][nd], g["out_u_t"][nd]) < 1e-10 and rel_err(st["des_q"], g["out_des_q"]) < 1e-13
 
 
+@pytest.mark.parametrize("env_id", ["docking-v0", "docking-v2"])
+def test_fp64_speculative_step_equals_guarded_step(env_id):
+    """The fp64 kernel's speculative straight-line step (qs::sdouble: range tests replaced by NaN poison, then a replay of
+    the guarded step when anything non-finite reached the outputs or the hidden state) must be BIT-identical to the
+    guarded step alone -- on flying states (no replays at all) and on wild ones (un-normalised / degenerate quaternions,
+    huge rates, zero vectors, gimbal lock, non-finite entries), where the replay has to catch every out-of-range argument."""
+    rng = np.random.RandomState(11)
+    n = 20000
+    def wild_state():
+        s = np.zeros((n, 13))
+        s[:, :3] = [10, -50, 5] + rng.normal(0, 3, (n, 3))
+        s[:, 3:6] = rng.normal(0, 2, (n, 3)) * 10.0 ** rng.uniform(-3, 2, (n, 1))
+        q = rng.normal(0, 1, (n, 4)) * 10.0 ** rng.uniform(-1, 0.5, (n, 1))
+        s[:, 6:10] = q
+        s[:, 10:13] = rng.normal(0, 1, (n, 3)) * 10.0 ** rng.uniform(-2, 3, (n, 1))
+        k = n // 20
+        s[:k, 6:10] = np.eye(4)[rng.randint(0, 4, k)] * rng.choice([-1, 1, 0.5], (k, 1))  # axis-aligned: exact zeros in the matrices
+        s[k:2 * k, 6:10] = 0.5                                                              # w = x = y = z: atan2(0, 0), r12 = 1
+        s[2 * k:3 * k, 6:10] = [0.5 ** 0.5, 0.5 ** 0.5, 0, 0]                               # phi = 90 degrees
+        s[3 * k:3 * k + 50, rng.randint(0, 13, 50)] = np.nan
+        s[3 * k + 50:3 * k + 100, rng.randint(0, 13, 50)] = np.inf
+        s[3 * k + 100:4 * k, 6:10] *= 1e-160                                                # squares underflow
+        s[4 * k:5 * k, 3:6] = 0.0
+        s[4 * k:5 * k, 10:13] = 0.0
+        return s
+    envs = [HostVecEnv(env_id, n, np.float64, seed=3, randomize=1) for _ in range(2)]
+    envs[1].set_speculative(False)
+    chaser, target = wild_state(), wild_state()
+    des_q = rng.normal(0, 1, (n, 4))
+    des_q[: n // 10] = 0.5
+    des_q[n // 10: n // 5] = [1, 0, 0, 0]
+    u_c, t0 = rng.uniform(0, 1.7, (n, 4)), rng.randint(0, 599, n)
+    for e in envs:
+        e.reset()
+        e.set_state(chaser=chaser, target=target, u_c=u_c, u_t=np.full((n, 4), 0.3), des_q=des_q, t=t0)
+    tame = HostVecEnv(env_id, n, np.float64, seed=3, randomize=1)
+    tame.reset()
+    for t in range(40):
+        a = rng.uniform(-1, 1, (n, 4))
+        with np.errstate(all="ignore"):
+            outs = [e.step(a) for e in envs]
+            for x, y in zip(outs[0], outs[1]):
+                assert np.array_equal(x, y, equal_nan=True), t
+            sa, sb = envs[0].get_state(), envs[1].get_state()
+            for k in sa:
+                assert np.array_equal(sa[k], sb[k], equal_nan=True), (t, k)
+        tame.step(a)
+    assert envs[1].replays() == 0 and envs[0].replays() > n // 20  # the wild states do exercise the replay ...
+    assert tame.replays() == 0                                       # ... and envs that simply fly (and crash, and reset) never do
+    print(env_id, "replayed env-steps:", envs[0].replays(), "of", 40 * n)
+
+
 def test_hover_tape():
     g = load_golden("hover_rand")
     K, Tn = g["actions"].shape[:2]
