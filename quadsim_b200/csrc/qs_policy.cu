@@ -883,6 +883,8 @@ int qs_policy_create(qs_policy_t** out, int device) {
     return rc;
   }
   p->grid = prop.multiProcessorCount;  // one persistent CTA per SM: it owns all 512 TMEM columns
+  // QUADSIM_B200_POLICY_CTAS=<n> runs the forward kernel on fewer SMs (A/B: a sliced rollout leaves the rest to the env kernel)
+  if (const char* v = getenv("QUADSIM_B200_POLICY_CTAS")) { const int c = atoi(v); if (c > 0 && c < p->grid) p->grid = c; }
   cudaSetDevice(prev);
   *out = p;
   return QS_OK;
