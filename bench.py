@@ -266,7 +266,8 @@ def run_ours(args):
     kernel_ms = ms_local / args.steps
     achieved = algo * n / (kernel_ms * 1e-3) / 1e9
     traffic = ncu_traffic(args.dtype)
-    kernel = "dock_step_kernel<%s,%s>" % ("float" if args.dtype == "f32" else "double", args.env)
+    pipe = os.environ.get("QUADSIM_B200_KERNEL", "pipe" if args.dtype == "f64" else "direct") == "pipe" and not args.env.startswith("hover")
+    kernel = "%s<%s,%s>" % ("dock_step_pipe_kernel" if pipe else "dock_step_kernel", "float" if args.dtype == "f32" else "double", args.env)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": kernel, "algorithmic_bytes_per_env_step": algo, "layout_bytes_per_env_step": LAYOUT_BYTES[args.dtype],
                 "layout_GBps": LAYOUT_BYTES[args.dtype] * n / (kernel_ms * 1e-3) / 1e9, "kernel_ms": kernel_ms, "peak_source": peak_src,

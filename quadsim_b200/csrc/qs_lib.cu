@@ -262,21 +262,29 @@ template <typename T> __device__ __forceinline__ void store_obs13_tile(T* stage,
 // What a thread contributes to the per-warp statistics after its step.
 struct StepTail { double ret; int len; bool done, docking, nonfinite; };
 
-// load -> step -> outputs -> auto-reset -> store for one env, guarded arithmetic.  The whole body of the fp32 kernel; for
-// fp64 the out-of-line replay of an env whose speculative step (qs::sdouble) met an argument outside a fast core's range.
-template <typename T, int KIND> __device__ __forceinline__ StepTail dock_step_one(const StepArgs& a, int64_t i) {
+#ifdef QS_NO_SPEC64
+constexpr bool kSpec64 = false;
+#else
+constexpr bool kSpec64 = kFast64;  // -DQS_NO_SPEC64: the guarded fp64 arithmetic on the main path (A/B)
+#endif
+
+template <int KIND> __device__ __noinline__ StepTail dock_step_replay(const StepArgs& a, int64_t i);
+
+// step -> outputs -> auto-reset -> store for one env whose state words and action are in registers.  SPEC (fp64 only):
+// the speculative straight-line step (qs::sdouble); an env that fails its check is replayed out of line from its state
+// in HBM, which nothing has overwritten yet.
+template <typename T, int KIND, bool SPEC>
+__device__ __forceinline__ StepTail dock_step_loaded(const StepArgs& a, int64_t i, T (&w)[dock_words<T>()], const T (&act)[4]) {
   constexpr int NW = dock_words<T>();
-  T w[NW];
-  load_words<T, NW>(a.state, i, w);
-  T act[4];
-  load_action<T>(a.actions, i, act);
   DockEnv<T> e;
   words_to_dock<T, NW>(w, e);
-
   T rel[12];
   StepOut<T> o;
-  dock_env_step<T, KIND>(e, act, rel, o);
-
+  if constexpr (SPEC) {
+    if (!dock_env_step_spec<KIND>(e, act, rel, o)) return dock_step_replay<KIND>(a, i);
+  } else {
+    dock_env_step<T, KIND>(e, act, rel, o);
+  }
   reinterpret_cast<T*>(a.reward)[i] = o.reward;
   a.done[i] = o.done ? 1 : 0;
   if (a.info) a.info[i] = (uint8_t)o.info();
@@ -292,64 +300,37 @@ template <typename T, int KIND> __device__ __forceinline__ StepTail dock_step_on
   return tail;
 }
 template <int KIND> __device__ __noinline__ StepTail dock_step_replay(const StepArgs& a, int64_t i) {
-  return dock_step_one<double, KIND>(a, i);
+  constexpr int NW = dock_words<double>();
+  double w[NW], act[4];
+  load_words<double, NW>(a.state, i, w);
+  load_action<double>(a.actions, i, act);
+  return dock_step_loaded<double, KIND, false>(a, i, w, act);
 }
-
-#ifdef QS_NO_SPEC64
-constexpr bool kSpec64 = false;
-#else
-constexpr bool kSpec64 = kFast64;  // -DQS_NO_SPEC64: the guarded fp64 arithmetic on the main path (A/B)
-#endif
+template <typename T> constexpr bool dock_spec() { return !is_f32<T>::value && kSpec64; }
 
 template <typename T, int KIND>
 __global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_kernel(const __grid_constant__ StepArgs a) {
   pdl_prologue();
+  constexpr int NW = dock_words<T>();
   const int64_t i = a.first + (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const bool active = i < a.first + a.n;
   const unsigned mask = __ballot_sync(0xffffffffu, active);
   if (!active) return;
-  StepTail tail;
-  if constexpr (!is_f32<T>::value && kSpec64) {
-    // fp64: speculative straight-line step; an env that fails the check is replayed from its (still untouched) state in HBM
-    constexpr int NW = dock_words<double>();
-    double w[NW];
-    load_words<double, NW>(a.state, i, w);
-    double act[4];
-    load_action<double>(a.actions, i, act);
-    DockEnv<double> e;
-    words_to_dock<double, NW>(w, e);
-    double rel[12];
-    StepOut<double> o;
-    if (dock_env_step_spec<KIND>(e, act, rel, o)) {
-      reinterpret_cast<double*>(a.reward)[i] = o.reward;
-      a.done[i] = o.done ? 1 : 0;
-      if (a.info) a.info[i] = (uint8_t)o.info();
-      if (a.term_obs) store_row<double, 12>(a.term_obs, i, rel);
-      tail = StepTail{e.last_shaping, e.tt, o.done, o.docking, o.nonfinite};
-      if (o.done && a.auto_reset) {
-        e.episode += 1;
-        dock_env_seat<double>(e, a.rng, i, rel);
-      }
-      store_row<double, 12>(a.obs, i, rel);
-      dock_to_words<double, NW>(e, w);
-      store_words<double, NW>(a.state, i, w);
-    } else {
-      tail = dock_step_replay<KIND>(a, i);
-    }
-  } else {
-    tail = dock_step_one<T, KIND>(a, i);
-  }
+  T w[NW], act[4];
+  load_words<T, NW>(a.state, i, w);
+  load_action<T>(a.actions, i, act);
+  const StepTail tail = dock_step_loaded<T, KIND, dock_spec<T>()>(a, i, w, act);
   warp_stats_update(a.warp_stats, i, mask, tail.done, tail.docking, tail.nonfinite, tail.ret, tail.len);
 }
 
 // =========================================================================================================
-// Persistent, bulk-async (TMA 1-D) pipelined variant of the fp32 docking step.
+// Persistent, bulk-async (TMA 1-D) pipelined variant of the docking step: the default for fp64, an A/B option for fp32.
 //   * grid = SMs x resident CTAs; each CTA walks 128-env tiles handed out by a global atomic counter;
 //   * one elected thread issues two cp.async.bulk (SASS UBLKCP) copies -- the tile's 20 KB state block (contiguous in the
 //     tile-major layout) and its 2 KB of actions -- into shared memory, completion counted on an mbarrier;
 //   * the tile for iteration j+1 is requested as soon as every thread has moved tile j from shared memory to registers,
 //     so its HBM latency is covered by the ~1k-instruction compute phase of tile j: registers are the second buffer and
-//     ONE 22 KB shared stage per CTA suffices (6 CTAs/SM = 132 KB in flight per SM).
+//     ONE shared stage per CTA suffices (fp32: 22 KB x 6 CTAs/SM; fp64: 44 KB x 3 CTAs/SM = 132 KB in flight per SM).
 // Results go straight from registers to HBM (coalesced 16-byte stores), as in the direct kernel.
 // =========================================================================================================
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -374,29 +355,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-constexpr int kPipeRows = 11;  // 10 state rows + 1 action row (fp32)
-constexpr int kPipeSmemBytes = kPipeRows * kBlock * 16 + 64;
+template <typename T> constexpr int pipe_rows() { return (dock_words<T>() + 4) / Row<T>::W; }  // state rows + action rows (16 B each)
+template <typename T> constexpr int pipe_smem_bytes() { return pipe_rows<T>() * kBlock * 16 + 64; }
 
-template <int KIND>
-__global__ void __launch_bounds__(kBlock, QS_MINB32) dock_step_pipe_kernel(const StepArgs a, unsigned int* sched) {
-  using T = float;
-  constexpr int NW = 40, NR = 10;
+// (A warp-granular version -- every warp its own stage, mbarrier and work counter, no CTA barrier, a unit = 20 copies of
+// 512 B -- was measured slower: 158 vs 134 us fp64, 83 vs 73 us fp32.  One 40 KB copy per tile is what the copy engine likes.)
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_pipe_kernel(const __grid_constant__ StepArgs a, unsigned int* sched) {
+  using V = typename Row<T>::V;
+  constexpr int NW = dock_words<T>(), W = Row<T>::W, NR = NW / W, AR = 4 / W;  // AR: 16-byte rows per action
+  pdl_prologue();
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4* buf = reinterpret_cast<float4*>(smem_raw);                        // [kPipeRows][kBlock]
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kPipeRows * kBlock * 16);
+  V* buf = reinterpret_cast<V*>(smem_raw);                                   // [NR + AR][kBlock]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (NR + AR) * kBlock * 16);
   volatile int* s_tile = reinterpret_cast<volatile int*>(full + 1);         // [2]: tile index for iteration parity
   const int tid = threadIdx.x;
   const int tiles = (int)((a.n + kBlock - 1) / kBlock);
-  const float4* state = reinterpret_cast<const float4*>(a.state);
-  const float4* actions = reinterpret_cast<const float4*>(a.actions);
+  const V* state = reinterpret_cast<const V*>(a.state);
+  const V* actions = reinterpret_cast<const V*>(a.actions);
 
-  auto request = [&](int tile) {  // elected thread: one mbarrier phase = 12 bulk copies
+  auto request = [&](int tile) {  // elected thread: one mbarrier phase = two bulk copies
     const int64_t env0 = a.first + (int64_t)tile * kBlock;
     const int64_t left = a.first + a.n - env0;
     const uint32_t cnt = (uint32_t)(left < kBlock ? left : kBlock);
-    mbar_expect_tx(full, NR * kBlock * 16 + cnt * 16);
-    bulk_g2s(buf, state + env0 * NR, NR * kBlock * 16, full);  // tile-major layout: the tile's state is one 20 KB span
-    bulk_g2s(buf + NR * kBlock, actions + env0, cnt * 16, full);
+    mbar_expect_tx(full, NR * kBlock * 16 + cnt * AR * 16);
+    bulk_g2s(buf, state + env0 * NR, NR * kBlock * 16, full);  // tile-major layout: the tile's state is one contiguous span
+    bulk_g2s(buf + NR * kBlock, actions + env0 * AR, cnt * AR * 16, full);
   };
 
   int next = -1;  // thread 0 only: tile whose data is in flight / landed
@@ -420,9 +404,10 @@ __global__ void __launch_bounds__(kBlock, QS_MINB32) dock_step_pipe_kernel(const
     const bool active = i < a.first + a.n;
     T w[NW];
 #pragma unroll
-    for (int r = 0; r < NR; r++) unpack(buf[r * kBlock + tid], &w[r * 4]);
+    for (int r = 0; r < NR; r++) unpack(buf[r * kBlock + tid], &w[r * W]);
     T act[4];
-    unpack(buf[NR * kBlock + tid], act);
+#pragma unroll
+    for (int r = 0; r < AR; r++) unpack(buf[NR * kBlock + tid * AR + r], &act[r * W]);
     if (tid == 0) s_tile[(it + 1) & 1] = next < tiles ? next : -1;
     __syncthreads();  // every thread has drained the stage (and sees the next tile index)
     if (tid == 0 && next >= 0 && next < tiles) {
@@ -431,25 +416,8 @@ __global__ void __launch_bounds__(kBlock, QS_MINB32) dock_step_pipe_kernel(const
     }
     const unsigned mask = __ballot_sync(0xffffffffu, active);
     if (active) {
-      DockEnv<T> e;
-      words_to_dock<T, NW>(w, e);
-      T rel[12];
-      StepOut<T> o;
-      dock_env_step<T, KIND>(e, act, rel, o);
-      reinterpret_cast<T*>(a.reward)[i] = o.reward;
-      a.done[i] = o.done ? 1 : 0;
-      if (a.info) a.info[i] = (uint8_t)o.info();
-      if (a.term_obs) store_row<T, 12>(a.term_obs, i, rel);
-      const double stat_ret = (double)e.last_shaping;
-      const int stat_len = e.tt;
-      if (o.done && a.auto_reset) {
-        e.episode += 1;
-        dock_env_seat<T>(e, a.rng, i, rel);
-      }
-      store_row<T, 12>(a.obs, i, rel);
-      dock_to_words<T, NW>(e, w);
-      store_words<T, NW>(a.state, i, w);
-      warp_stats_update(a.warp_stats, i, mask, o.done, o.docking, o.nonfinite, stat_ret, stat_len);
+      const StepTail tail = dock_step_loaded<T, KIND, dock_spec<T>()>(a, i, w, act);
+      warp_stats_update(a.warp_stats, i, mask, tail.done, tail.docking, tail.nonfinite, tail.ret, tail.len);
     }
   }
   // self-resetting scheduler: the last CTA out clears the counters for the next launch on this stream
@@ -874,7 +842,7 @@ struct qs_env {
   double* stats_dev = nullptr;
   double* stats_host = nullptr;  // pinned
   float jitter_scale;
-  int use_pipe = 0;               // persistent bulk-async kernel for fp32 docking
+  int use_pipe = 0;               // persistent bulk-async docking kernel (default for fp64)
   int pipe_grid = 0;
   unsigned int* sched = nullptr;  // [kHostStreams + 1][2] tile counters (one pair per stream slot)
   // qs_step_host pipeline
@@ -912,15 +880,30 @@ template <typename T> int launch_step_t(qs_env* e, const StepArgs& a, cudaStream
   }
   return QS_OK;
 }
+// slot >= 0: the scheduler-counter pair of the persistent pipelined kernel to use (launches that may run concurrently need
+// different slots); slot < 0: always the direct kernel (qs_step_range: callers may step slices on any number of streams).
 int launch_step(qs_env* e, const StepArgs& a, cudaStream_t st, int slot = 0) {
   if (a.n <= 0) return QS_OK;
-  if (e->use_pipe) {
+  if (e->use_pipe && slot >= 0) {
     const int tiles = (int)((a.n + kBlock - 1) / kBlock);
-    const unsigned grid = (unsigned)(tiles < e->pipe_grid ? tiles : e->pipe_grid);
     unsigned int* sched = e->sched + 2 * slot;
-    if (e->cfg.env_kind == QS_DOCK_V0) dock_step_pipe_kernel<QS_DOCK_V0><<<grid, kBlock, kPipeSmemBytes, st>>>(a, sched);
-    else dock_step_pipe_kernel<QS_DOCK_V2><<<grid, kBlock, kPipeSmemBytes, st>>>(a, sched);
-    QS_CUDA(cudaGetLastError());
+    static const bool pdl = [] { const char* v = getenv("QUADSIM_B200_PDL"); return !(v && v[0] == '0'); }();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(tiles < e->pipe_grid ? tiles : e->pipe_grid)); cfg.blockDim = dim3(kBlock); cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    const bool v0 = e->cfg.env_kind == QS_DOCK_V0;
+    if (e->cfg.dtype == QS_F32) {
+      cfg.dynamicSmemBytes = pipe_smem_bytes<float>();
+      if (v0) QS_CUDA(cudaLaunchKernelEx(&cfg, dock_step_pipe_kernel<float, QS_DOCK_V0>, a, sched));
+      else QS_CUDA(cudaLaunchKernelEx(&cfg, dock_step_pipe_kernel<float, QS_DOCK_V2>, a, sched));
+    } else {
+      cfg.dynamicSmemBytes = pipe_smem_bytes<double>();
+      if (v0) QS_CUDA(cudaLaunchKernelEx(&cfg, dock_step_pipe_kernel<double, QS_DOCK_V0>, a, sched));
+      else QS_CUDA(cudaLaunchKernelEx(&cfg, dock_step_pipe_kernel<double, QS_DOCK_V2>, a, sched));
+    }
     return QS_OK;
   }
   return e->cfg.dtype == QS_F32 ? launch_step_t<float>(e, a, st) : launch_step_t<double>(e, a, st);
@@ -994,15 +977,23 @@ int qs_create(qs_env_t** out, const qs_config_t* cfg) {
     qs_destroy(e);
     return rc;
   }
-  if (const char* k = getenv("QUADSIM_B200_KERNEL")) e->use_pipe = strcmp(k, "pipe") == 0;
-  if (e->cfg.dtype != QS_F32 || e->cfg.env_kind == QS_HOVER) e->use_pipe = 0;
+  // fp64 docking runs 12 warps per SM (168 registers): too few to hide HBM latency with plain loads, so the persistent
+  // bulk-async kernel is its default (138.8 vs 152.1 us per 2^20-env step); fp32 (24 warps per SM) is faster direct (63 vs 73).
+  // QUADSIM_B200_KERNEL=pipe|direct overrides.
+  e->use_pipe = e->cfg.dtype == QS_F64;
+  if (const char* k = getenv("QUADSIM_B200_KERNEL")) e->use_pipe = strcmp(k, "pipe") == 0 ? 1 : (strcmp(k, "direct") == 0 ? 0 : e->use_pipe);
+  if (e->cfg.env_kind == QS_HOVER) e->use_pipe = 0;
   if (e->use_pipe) {
     cudaDeviceProp prop;
     int per_sm = 0;
+    const bool f32 = e->cfg.dtype == QS_F32;
+    const int smem = f32 ? pipe_smem_bytes<float>() : pipe_smem_bytes<double>();
+    const void* k0 = f32 ? (const void*)dock_step_pipe_kernel<float, QS_DOCK_V0> : (const void*)dock_step_pipe_kernel<double, QS_DOCK_V0>;
+    const void* k2 = f32 ? (const void*)dock_step_pipe_kernel<float, QS_DOCK_V2> : (const void*)dock_step_pipe_kernel<double, QS_DOCK_V2>;
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess ||
-        cudaFuncSetAttribute(dock_step_pipe_kernel<QS_DOCK_V0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(dock_step_pipe_kernel<QS_DOCK_V2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemBytes) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dock_step_pipe_kernel<QS_DOCK_V2>, kBlock, kPipeSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, kBlock, smem) != cudaSuccess ||
         per_sm < 1 || cudaMalloc(&e->sched, (kHostStreams + 1) * 2 * sizeof(unsigned int)) != cudaSuccess ||
         cudaMemset(e->sched, 0, (kHostStreams + 1) * 2 * sizeof(unsigned int)) != cudaSuccess) {
       int rc = fail(QS_ERR_CUDA, "qs_create: pipelined kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1069,7 +1060,7 @@ int qs_step_range(qs_env_t* e, int64_t first, int64_t n, const void* actions, vo
   DeviceGuard g(e->cfg.device);
   StepArgs a = make_args(e, first, n);
   a.actions = actions; a.obs = obs_out; a.reward = reward_out; a.done = done_out;
-  return launch_step(e, a, (cudaStream_t)stream);
+  return launch_step(e, a, (cudaStream_t)stream, -1);
 }
 
 int qs_step_n(qs_env_t* e, int64_t n_steps, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out, void* stream) {

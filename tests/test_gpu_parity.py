@@ -65,6 +65,40 @@ def test_leaf_functions_vs_reference_golden(dtype, tol):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("env_id", ["docking-v0", "docking-v2"])
+def test_pipelined_kernel_equals_direct_kernel(env_id, dtype, monkeypatch):
+    """The persistent bulk-async (TMA) step kernel -- the fp64 default -- and the direct one-CTA-per-tile kernel run the same
+    per-env code.  fp64: bit-identical outputs, state and statistics over 120 steps with auto-resets, on a ragged env count.
+    fp32 (where the pipelined kernel is only an A/B option): the two are separate compilations whose FMA contraction differs
+    in the last bit, so 4 steps within 1e-5 * max(1, |x|)."""
+    import quadsim_b200 as qs
+    n = 128 * 700 + 37
+    exact = dtype == torch.float64
+    envs = []
+    for kind in ("direct", "pipe"):
+        monkeypatch.setenv("QUADSIM_B200_KERNEL", kind)
+        envs.append(qs.make_vec(env_id, n, dtype=dtype, seed=5, randomize="episode", want_info=True, want_terminal_obs=True))
+    monkeypatch.delenv("QUADSIM_B200_KERNEL")
+    same = (lambda x, y: torch.equal(x, y)) if exact else (lambda x, y: bool(((x - y).abs() <= 1e-5 * x.abs().clamp(min=1)).all()))
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    o = [e.reset() for e in envs]
+    assert torch.equal(o[0], o[1])
+    n_done = 0
+    for t in range(120 if exact else 4):
+        a = (torch.rand((n, 4), generator=gen, device="cuda") * 2 - 1).to(dtype)
+        r = [e.step(a) for e in envs]
+        assert same(r[0][0], r[1][0]) and same(r[0][1], r[1][1]) and torch.equal(r[0][2], r[1][2]), t
+        assert torch.equal(r[0][3].bits, r[1][3].bits) and same(r[0][3].terminal_observation, r[1][3].terminal_observation)
+        n_done += int(r[0][2].sum())
+    sa, sb = envs[0].get_state(), envs[1].get_state()
+    for k in sa:
+        assert same(sa[k].double(), sb[k].double()), k
+    if exact:
+        assert n_done > n // 2 and envs[0].stats() == envs[1].stats()
+
+
+@pytest.mark.gpu
 def test_scalar_math_accuracy():
     """qs::f64m (constant-memory polynomials, MUFU-seeded Newton reciprocal / rsqrt) against numpy on 2e6 arguments:
     <= 4 ulp in fp64 (the host libm and the reference's numpy are themselves <= 1 ulp), 1e-6 relative in fp32."""
