@@ -16,14 +16,22 @@ except Exception:  # pragma: no cover - not installed in this image
 
 
 class SBVecEnv(_Base):
-    def __init__(self, env_id="docking-v2", num_envs=10, dtype=torch.float64, info_dicts=True, **kw):
+    def __init__(self, env_id="docking-v2", num_envs=10, dtype=torch.float64, info_dicts=True, monitor=False, **kw):
+        """monitor=True adds stable-baselines' Monitor key to the info dict of an env that finished an episode:
+        info['episode'] = {'r': return, 'l': length} -- the one key the reference's trainer reads from infos
+        (rl_baselines/ppo2/ppo2.py:494-497).  The reference's scripts do not wrap their envs in Monitor, hence off by default."""
         self._vec = QuadVecEnv(env_id, num_envs, dtype=dtype, want_info=True, want_terminal_obs=True, **kw)
         self.num_envs = self._vec.num_envs
         self.observation_space, self.action_space = self._vec.observation_space, self._vec.action_space
         self.info_dicts = info_dicts
+        self.monitor = monitor
+        self._ep_ret = np.zeros(self.num_envs, np.float64)
+        self._ep_len = np.zeros(self.num_envs, np.int64)
         self._actions = None
 
     def reset(self):
+        self._ep_ret[:] = 0.0
+        self._ep_len[:] = 0
         return self._vec.reset().float().cpu().numpy()
 
     def step_async(self, actions):
@@ -48,6 +56,13 @@ class SBVecEnv(_Base):
                     infos[i]["target"] = target[i]
                 if done_np[i]:
                     infos[i]["terminal_observation"] = term[i]
+        if self.monitor:
+            self._ep_ret += rew.double().cpu().numpy()
+            self._ep_len += 1
+            for i in np.nonzero(done_np)[0]:
+                infos[i]["episode"] = {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i])}
+                self._ep_ret[i] = 0.0
+                self._ep_len[i] = 0
         return obs_np, rew_np, done_np, infos
 
     def step(self, actions):

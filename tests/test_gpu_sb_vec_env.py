@@ -40,3 +40,25 @@ def test_sb_vec_env_replays_reference_tape(name, env_id):
                 assert np.max(np.abs(info["chaser"] - g["chaser"][k, t])) < 1e-9 and np.max(np.abs(info["target"] - g["target"][k, t])) < 1e-9
     assert n_done >= 4
     env.close()
+
+
+def test_sb_vec_env_monitor_episode_info():
+    """monitor=True: info['episode'] = {'r', 'l'} on done (SB's Monitor; the key rl_baselines/ppo2/ppo2.py:494-497 reads) equals the
+    reference tape's per-episode reward sum and length."""
+    g = load_golden("dock_v2_rand")
+    K = g["actions"].shape[0]
+    env = SBVecEnv("docking-v2", K, seed=int(g["seed"]), env_id0=int(g["env_id0"]), randomize="episode", half_width=float(g["half_width"]),
+                   monitor=True)
+    env.reset()
+    ret, length, seen = np.zeros(K), np.zeros(K, int), 0
+    for t in range(300):
+        _, rew, done, infos = env.step(g["actions"][:, t])
+        ret += g["reward"][:, t]
+        length += 1
+        for k in range(K):
+            assert ("episode" in infos[k]) == bool(done[k])
+            if done[k]:
+                assert infos[k]["episode"]["l"] == length[k] and abs(infos[k]["episode"]["r"] - ret[k]) < 1e-6
+                ret[k], length[k], seen = 0.0, 0, seen + 1
+    assert seen >= 4
+    env.close()
