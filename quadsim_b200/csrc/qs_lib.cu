@@ -1139,8 +1139,15 @@ int qs_step_host(qs_env_t* e, const void* actions_host, void* obs_host, void* re
     const int64_t c = v ? atoll(v) : 0;
     return c >= kBlock && c % kBlock == 0 ? c : kHostChunk;
   }();
-  for (int64_t first = 0; first < N; first += chunk, k++) {
-    const int64_t n = (N - first) < chunk ? (N - first) : chunk;
+  // Default schedule: graduated chunks (32 Ki, 64 Ki, 128 Ki, then 256 Ki envs each) -- the first result copy can start after
+  // a 32 Ki-env upload + kernel instead of a 128 Ki one, and the long tail runs on few large copies (fewer gaps between DMA
+  // descriptors).  A fixed size (QUADSIM_B200_HOST_CHUNK) keeps the old uniform schedule for A/B.
+  static const bool fixed = getenv("QUADSIM_B200_HOST_CHUNK") != nullptr;
+  static const int64_t c0 = [] { const char* v = getenv("QUADSIM_B200_HOST_CHUNK0"); const int64_t c = v ? atoll(v) : 0; return c >= kBlock && c % kBlock == 0 ? c : (int64_t)32768; }();
+  static const int64_t cap = [] { const char* v = getenv("QUADSIM_B200_HOST_CHUNK_CAP"); const int64_t c = v ? atoll(v) : 0; return c >= kBlock && c % kBlock == 0 ? c : (int64_t)262144; }();
+  int64_t cur = fixed ? chunk : c0;
+  for (int64_t first = 0; first < N; k++) {
+    const int64_t n = (N - first) < cur ? (N - first) : cur;
     cudaStream_t st = e->hstreams[k % kHostStreams];
     QS_CUDA(cudaMemcpyAsync((char*)e->h_act + first * 4 * es, (const char*)actions_host + first * 4 * es, (size_t)n * 4 * es, cudaMemcpyHostToDevice, st));
     StepArgs a = make_args(e, first, n);
@@ -1152,6 +1159,8 @@ int qs_step_host(qs_env_t* e, const void* actions_host, void* obs_host, void* re
       QS_CUDA(cudaMemcpyAsync((char*)reward_host + first * es, (char*)e->h_rew + first * es, (size_t)n * es, cudaMemcpyDeviceToHost, st));
       QS_CUDA(cudaMemcpyAsync(done_host + first, e->h_done + first, (size_t)n, cudaMemcpyDeviceToHost, st));
     }
+    first += n;
+    if (!fixed && cur < cap) cur *= 2;
   }
   for (auto& s : e->hstreams) QS_CUDA(cudaStreamSynchronize(s));
   return QS_OK;
