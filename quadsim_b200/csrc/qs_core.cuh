@@ -176,7 +176,6 @@ QS_HD double sqrt(double x) {
 #endif
 }
 
-// atan2 for max(|x|,|y|) in [1e-280, 1e280] (anything else: garbage, the callers below guard or poison)
 // sqrt for x == 0 or x in [1e-300, 1e300], branch-free (the seed is taken of max(x, 1e-300): 0 * finite = 0);
 // negative / NaN x -> NaN
 QS_HD double sqrt0(double x) {
@@ -189,6 +188,7 @@ QS_HD double sqrt0(double x) {
   return ::sqrt(x);
 #endif
 }
+// atan2 for max(|x|,|y|) in [1e-280, 1e280] (anything else: garbage, the callers below guard or poison)
 QS_HD double atan2_fast(double y, double x) {
   const double ax = fabs(x), ay = fabs(y);
   const bool sw = ay > ax;
@@ -275,7 +275,7 @@ QS_HD void sincos(double x, double* s, double* c) {
 // ---- scalar math wrappers ----
 QS_HD float m_sqrt(float x) { return sqrtf(x); }
 QS_HD double m_sqrt(double x) {
-  if (kFast64) return (x >= 1e-300 && x <= 1e300) ? f64m::sqrt(x) : f64m::sqrt_cold(x);
+  if (kFast64) return (x == 0.0 || (x >= 1e-300 && x <= 1e300)) ? f64m::sqrt0(x) : f64m::sqrt_cold(x);  // 0: norms on an episode's first step
   return sqrt(x);
 }
 QS_HD float m_rsqrt(float x) {

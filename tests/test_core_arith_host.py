@@ -75,6 +75,28 @@ def test_f64_scalar_math_polynomials():
         assert np.isnan(scalar_math(np.array([1.0000001, -2.0, np.nan]), np.ones(3))[:, 5]).all()
 
 
+def test_f64_math_coefficients_are_the_generators():
+    """The coefficient tables in qs_core.cuh are exactly what tools/gen_f64_math_coefs.py derives (mpmath Chebyshev fits)."""
+    mp = pytest.importorskip("mpmath")
+    import importlib.util
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_f64_math_coefs", os.path.join(root, "tools", "gen_f64_math_coefs.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    src = open(os.path.join(root, "quadsim_b200", "csrc", "qs_core.cuh")).read()
+    def table(name):
+        body = re.search(r"#define %s \{([^}]*)\}" % name, src).group(1)
+        return [float.fromhex(x.strip()) for x in body.split(",")]
+    zmax = mp.tan(mp.pi / 8) ** 2 * mp.mpf("1.0001")
+    zs = (mp.pi / 4) ** 2 * mp.mpf("1.001")
+    assert table("QS_F64M_ATAN") == gen.fit(gen.q_atan, 0, zmax, 11)[0]
+    assert table("QS_F64M_SIN") == gen.fit(gen.s_sin, 0, zs, 6)[0]
+    assert table("QS_F64M_COS") == gen.fit(gen.c_cos, 0, zs, 6)[0]
+    assert table("QS_F64M_ASIN") == gen.fit(gen.r_asin, 0, mp.mpf("0.2501"), 13)[0]
+
+
 @pytest.mark.parametrize("v", [0, 2])
 def test_wild_single_step_fp64(v):
     g = load_golden("dock_v%d_wild" % v)
