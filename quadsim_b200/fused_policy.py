@@ -85,7 +85,8 @@ class FusedPolicy:
         m, B = self.module, int(idx.shape[0])
         ws = self._workspace(B)
         ret, val = batch["returns"], batch["values"]
-        adv = ret[idx] - val[idx]
+        # PPO2.update leaves returns - values of the whole rollout in batch["adv_raw"]: one gather per minibatch instead of two
+        adv = batch["adv_raw"][idx] if "adv_raw" in batch else ret[idx] - val[idx]
         stats = torch.stack([adv.mean(), 1.0 / (adv.std(unbiased=False) + 1e-8)]).float()  # ppo2.py:265-266 (population std)
         p = lambda t: t.data_ptr()
         g = _capi.PPOGrad(p(batch["obs"]), p(batch["actions"]), p(ret), p(val), p(batch["neglogp"]), p(idx), B, p(stats),
