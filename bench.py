@@ -272,6 +272,14 @@ def run_ours(args):
                 "kernel": kernel, "algorithmic_bytes_per_env_step": algo, "layout_bytes_per_env_step": LAYOUT_BYTES[args.dtype],
                 "layout_GBps": LAYOUT_BYTES[args.dtype] * n / (kernel_ms * 1e-3) / 1e9, "kernel_ms": kernel_ms, "peak_source": peak_src,
                 "timing": "CUDA events on the launch stream around the %d timed launches / %d" % (args.steps, args.steps)}
+    try:  # informational: the no-arithmetic kernel with the step's exact loads/stores (tools/microbench/step_pattern_bw.cu)
+        pc = json.load(open(os.path.join(ROOT, "profiles", "r1_step_pattern_ceiling.json")))["results"]
+        hit = [r for r in pc if r["pdl"] and r["envs"] == n and r["pattern"] == "docking " + args.dtype.replace("f", "fp")]
+        if hit and args.env.startswith("docking"):
+            roofline["pattern_ceiling"] = {"us_per_launch": hit[0]["us_per_launch"], "frac": hit[0]["us_per_launch"] / (kernel_ms * 1e3),
+                                           "source": "profiles/r1_step_pattern_ceiling.json (measured once, not in this run)"}
+    except Exception:
+        pass
     cpu = None
     if not args.no_cpu_baseline:
         D.restore_affinity()  # the CPU leg uses every host core, not just the GPU's NUMA node
