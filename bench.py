@@ -231,7 +231,9 @@ def run_ours(args):
         el = time.perf_counter() - t0
         el = D.max_over_ranks(el, dev)
         esz = 4 if args.dtype == "f32" else 8
-        chunks = (n + (1 << 17) - 1) >> 17
+        chunks, left, cur = 0, n, 1 << 15  # qs_step_host's graduated schedule: 32 Ki, 64 Ki, 128 Ki, then 256 Ki envs per chunk
+        while left > 0:
+            chunks, left, cur = chunks + 1, left - min(left, cur), min(cur * 2, 1 << 18)
         # what bounds this leg: the device->host link.  Plain pinned D2H / H2D copies of the same sizes, same process.
         d_buf = torch.empty(n * (henv.obs_dim * esz + esz + 1), dtype=torch.uint8, device=dev)
         h_buf = torch.empty(d_buf.numel(), dtype=torch.uint8, pin_memory=True)
@@ -249,7 +251,7 @@ def run_ours(args):
                         "note": "this rank; the leg is bound by the device->host link (53 B out vs 16 B in per env-step)"},
                "numa": {"gpu_node": numa, "cpus_allowed": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None},
                "d2h_bytes_per_step": n * (henv.obs_dim * esz + esz + 1), "steps": args.e2e_steps,
-               "api": "QuadVecEnv.step_host -> qs_step_host (pinned numpy in/out, %d chunks pipelined over 4 streams; obs by DMA, "
+               "api": "QuadVecEnv.step_host -> qs_step_host (pinned numpy in/out, %d graduated chunks pipelined over 4 streams; obs by DMA, "
                       "reward/done written by the kernel into the pinned buffers)" % chunks,
                "checksum_reward": float(h_rew.sum())}
         henv.close()
