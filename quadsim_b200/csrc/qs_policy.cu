@@ -938,13 +938,33 @@ int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, u
   if (use_v3) policy_kernel<false><<<ctas < p->grid ? ctas : p->grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, TrainArgs{});
   else {
     static const bool pdl = [] { const char* v = getenv("QUADSIM_B200_PDL"); return !(v && v[0] == '0'); }();
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    // Launch priority: in a sliced rollout the policy kernel of one slice and the env kernel of the other become runnable at
+    // the same moment.  The env kernel's thousands of small CTAs would otherwise take the registers an SM frees before the one
+    // big policy CTA (164 KB of shared memory, all of TMEM) can be placed, and the two kernels end up running one after the
+    // other; with the policy kernel at the highest priority its CTA goes first and the env CTAs fill what is left.
+    // QUADSIM_B200_POLICY_PRIO=0 launches at the default priority (A/B).
+    static const int prio = [] {
+      const char* v = getenv("QUADSIM_B200_POLICY_PRIO");
+      int least = 0, greatest = 0;
+      if ((v && v[0] == '0') || cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return 0;
+      return greatest;
+    }();
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      na++;
+    }
+    if (prio != 0) {
+      attr[na].id = cudaLaunchAttributePriority;
+      attr[na].val.priority = prio;
+      na++;
+    }
     cudaLaunchConfig_t cfg = {};
     const int ws_ctas = (int)(((n + kTileRows - 1) / kTileRows + kWsGroups - 1) / kWsGroups);
     cfg.gridDim = dim3(ws_ctas < p->grid ? ws_ctas : p->grid); cfg.blockDim = dim3(kWsThreads); cfg.dynamicSmemBytes = kWsSmemBytes;
-    cfg.stream = (cudaStream_t)stream; cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cfg.stream = (cudaStream_t)stream; cfg.attrs = attr; cfg.numAttrs = na;
     cudaError_t le = cudaLaunchKernelEx(&cfg, policy_fwd_ws_kernel, a);
     if (le != cudaSuccess) { cudaSetDevice(prev); return qs_fail_(QS_ERR_CUDA, "qs_policy_step: %s", cudaGetErrorString(le)); }
   }
