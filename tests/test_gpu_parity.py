@@ -397,6 +397,29 @@ def test_host_path_matches_device_path():
         e1.close(); e2.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_host_path_graduated_chunks_ragged(dtype):
+    """qs_step_host on an env count that spans several chunks of its graduated schedule (32 Ki, 64 Ki, 128 Ki, 256 Ki, rest)
+    and ends mid-tile: bit-identical to the device path, pinned buffers (reward / done written by the kernel across PCIe)."""
+    n = 32768 + 65536 + 131072 + 262144 + 4000 + 37
+    e1 = qs.make_vec("docking-v2", n, dtype=dtype, seed=4, randomize="episode")
+    e2 = qs.make_vec("docking-v2", n, dtype=dtype, seed=4, randomize="episode")
+    e1.reset(); e2.reset()
+    h_acts, h_obs, h_rew, h_done = e2.pinned_host_buffers(n_action_buffers=1)
+    gen = torch.Generator().manual_seed(1)
+    for t in range(12):
+        a = (torch.rand((n, 4), generator=gen) * 2 - 1).to(dtype)
+        o1, r1, d1, _ = e1.step(a.to(DEV))
+        h_acts[0][...] = a.numpy()
+        e2.step_host(h_acts[0], out=(h_obs, h_rew, h_done))
+        assert np.array_equal(o1.cpu().numpy(), h_obs) and np.array_equal(r1.cpu().numpy(), h_rew)
+        assert np.array_equal(d1.cpu().numpy().astype(bool), np.asarray(h_done).astype(bool))
+    s1, s2 = e1.stats(), e2.stats()
+    assert all(s1[k] == s2[k] for k in ("return_sum", "length_sum", "episodes", "docked_steps", "nonfinite_steps")), (s1, s2)
+    e1.close(); e2.close()
+
+
 def test_sharding_invariance_and_determinism_full_size():
     """BASELINE size (2^20 envs): the same global env ids give bit-identical trajectories whether they live in one
     handle or in two half-size handles with env_id0 offsets (what ranks do), and a re-run reproduces the checksum."""
