@@ -167,6 +167,21 @@ def test_fp64_speculative_step_equals_guarded_step(env_id):
     print(env_id, "replayed env-steps:", envs[0].replays(), "of", 40 * n)
 
 
+@pytest.mark.parametrize("env_id", ["docking-v0", "docking-v2"])
+def test_fp64_speculative_step_never_replays_in_flight(env_id):
+    """2048 envs x 300 steps of random actions with auto-resets (tumbling, clamping, crashing, re-seating -- everything the
+    benchmark workload does): the speculative fp64 step never needs its guarded replay, i.e. the replay is a correctness
+    net for exotic states, not a cost of normal operation."""
+    rng = np.random.RandomState(2)
+    n = 2048
+    env = HostVecEnv(env_id, n, np.float64, seed=9, randomize=1)
+    env.reset()
+    done_total = 0
+    for t in range(300):
+        done_total += int(env.step(rng.uniform(-1, 1, (n, 4)))[2].sum())
+    assert done_total > n and env.replays() == 0
+
+
 def test_hover_tape():
     g = load_golden("hover_rand")
     K, Tn = g["actions"].shape[:2]
