@@ -1,0 +1,46 @@
+"""The bench lines committed under profiles/ (produced by bench.py on a B200) carry every key the bench contract names;
+a CPU-only guard against the JSON line drifting away from the contract."""
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(name):
+    return json.load(open(os.path.join(ROOT, "profiles", name)))
+
+
+def test_headline_line_has_the_contract_keys():
+    d = _load("r1_bench_e.json")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f32"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] == 16 * (1 << 20) and d["e2e"]["d2h_bytes_per_step"] == 53 * (1 << 20)
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm" and r["unit"] == "GB/s"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    # achieved = algorithmic bytes per env-step x envs per launch / kernel time
+    assert abs(r["achieved"] - 405 * (1 << 20) / (r["kernel_ms"] * 1e-3) / 1e9) < 1e-3 * r["achieved"]
+    assert d["gpu_launches"] == d["steps"] and d["gpu_launches"] > 0
+    c = d["cpu_baseline"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("port", "reference")
+    assert abs(d["value"] - (1 << 20) / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+
+
+def test_reference_arm_line():
+    d = _load("r1_bench_reference_arm.json")
+    assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["gpu_launches"] == 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_multi_gpu_lines_are_whole_job_aggregates():
+    one = _load("r1_bench_e.json")["value"]
+    for name, n in (("r1_bench_2gpu_final.json", 2), ("r1_bench_8gpu_pdl.json", 8)):
+        d = _load(name)
+        assert d["n_gpus"] == n and d["scaling"] == "weak"
+        assert 0.9 * n * one < d["value"] < 1.1 * n * one  # no collective on the step path: linear within run-to-run noise
