@@ -9,7 +9,8 @@
  *   - every call returns QS_OK (0) or a negative qs_status and never throws; qs_last_error() (thread-local)
  *     gives the message;
  *   - "device pointer" arguments are caller-owned, contiguous, in the handle's dtype (float for QS_F32, double
- *     for QS_F64); all work is enqueued on the caller's stream, with no hidden synchronisation on the step path;
+ *     for QS_F64); all work is enqueued on the caller's stream, with no hidden synchronisation on the step path
+ *     (qs_step_host is the documented exception: it is a blocking call on host buffers, see there);
  *   - a handle is bound to one CUDA device, owns all persistent per-env state, and is not thread-safe.
  */
 #ifndef QUADSIM_B200_H
@@ -20,7 +21,7 @@
 extern "C" {
 #endif
 
-#define QS_ABI_VERSION 1
+#define QS_ABI_VERSION 2   /* v2: qs_env_params_t in qs_config_t, qs_step_extras_t, qs_step_host takes a stream */
 
 typedef enum {
   QS_OK = 0,
@@ -54,6 +55,31 @@ enum { QS_INFO_DONE = 1, QS_INFO_OVERLIMIT = 2, QS_INFO_DOCKING = 4, QS_INFO_OVE
 
 typedef struct qs_env qs_env_t;
 
+/* Model parameters.  The reference has no configuration system: every constant is a literal in its sources
+ * (dynamics/quadrotor.py:10-63, controller/PIDController.py:10-44, the envs' __init__).  qs_default_params() fills this
+ * block with exactly those literals; a handle created with use_params = 0 runs the kernels that have them compiled in as
+ * immediates, a handle with use_params = 1 runs the same kernels reading this block from the constant bank (it travels
+ * as a __grid_constant__ kernel parameter: per handle, no global state). */
+typedef struct {
+  double dt, gravity, mass, arm_length;   /* quadrotor.py:12-21   0.02, 9.81, 0.18, 0.086 */
+  double inertia[3];                      /* quadrotor.py:23      diag(2.5e-4, 2.32e-4, 3.738e-4) */
+  double motor_lambda;                    /* quadrotor.py:43-45   km / kf = 1.5e-9 / 6.11e-8 */
+  double att_limit_deg[3];                /* quadrotor.py:35-39, :146-168   roll, pitch, yaw clamp: 85, 85, 175 */
+  double kp_att[3], kd_att[3];            /* PIDController.py:10-21   (-10,-10,-9.5), (5.1,5.1,4) */
+  double kp_pos[3], kd_pos[3];            /* PIDController.py:23-33   (-1,-1,50), (-1.65,-1.65,8) */
+  double kp_vel[3];                       /* PIDController.py:35-44   (-0.7,-0.7,1); the kd_v* terms are identically 0 */
+  double chaser_ini_pos[3];               /* docking_env.py:34    (8,-50,5);  hover: hovering_env.py:23 (0,0,5) */
+  double target_ini_pos[3];               /* docking_env.py:47    (10,-50,5) */
+  double target_des_pos[3];               /* docking_env.py:59    (10,-50,5)  docking-v0 set-point */
+  double target_des_vel[3];               /* moving_docking_env.py:62-66  (0.2,0,0)  docking-v2 */
+  double dock_port;                       /* docking_env.py:38,51  chaser port +0.1 m, target port -0.1 m along body x */
+  double dock_pos_tol, dock_vel_tol, dock_angle_deg; /* docking_env.py:130-134  0.1 m, 0.1 m/s, 10 deg */
+  double range_limit;                     /* docking_env.py:141 (3) / moving_docking_env.py:148 (10); hover: hovering_env.py:68 (100) */
+  double min_altitude;                    /* docking_env.py:142   0.1 */
+  int32_t max_steps;                      /* docking_env.py:152   600 */
+  int32_t reserved;
+} qs_env_params_t;
+
 typedef struct {
   int32_t env_kind;   /* qs_env_kind */
   int32_t dtype;      /* qs_dtype */
@@ -65,7 +91,8 @@ typedef struct {
   double half_width;  /* jitter half-width; <= 0 selects the default (0.5 docking, 1.0 hover position) */
   int32_t auto_reset; /* 1: stable-baselines VecEnv semantics (done envs re-seat inside the step);
                          0: plain gym.Env semantics (state stays terminal until qs_reset) */
-  int32_t reserved;
+  int32_t use_params; /* 0: the reference's literals (compiled in); 1: `params` below */
+  qs_env_params_t params;
 } qs_config_t;
 
 /* Device pointers to array-of-struct views of the per-env state: ALWAYS float64 (t/episode: int32), whatever the handle's
@@ -88,6 +115,8 @@ typedef struct {
 
 int qs_abi_version(void);
 const char* qs_last_error(void);
+/* The reference's literals for `env_kind` (see qs_env_params_t). */
+int qs_default_params(int env_kind, qs_env_params_t* out);
 
 /* gym.make(id) / SubprocVecEnv([...]*n)  (run_moving_docking_ppo2.py:65-67): build n_envs environments. */
 int qs_create(qs_env_t** out, const qs_config_t* cfg);
@@ -96,6 +125,7 @@ int qs_destroy(qs_env_t* env);
 int qs_obs_dim(const qs_env_t* env);
 int64_t qs_num_envs(const qs_env_t* env);
 int qs_env_dtype(const qs_env_t* env);       /* qs_dtype of the handle */
+int qs_env_device(const qs_env_t* env);      /* CUDA device ordinal the handle is bound to */
 uint64_t qs_env_id0(const qs_env_t* env);    /* global id of env 0 (qs_config_t.env_id0) */
 /* env.seed(seed)  (docking_env.py:252-254; the reference never reads it -- here it re-keys Philox). */
 int qs_seed(qs_env_t* env, uint64_t seed);
@@ -108,10 +138,19 @@ int qs_reset(qs_env_t* env, void* obs_out, void* stream);
  * docking_env.py:104-231, moving_docking_env.py:111-192, hovering_env.py:47-78) with the stable-baselines worker's
  * auto-reset: for done envs obs is the reset observation while reward/done are the terminal step's. */
 int qs_step(qs_env_t* env, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out, void* stream);
-/* As qs_step, plus the per-step info the reference returns: info_out[N] bitmask (QS_INFO_*), terminal_obs[N,obs_dim]
- * (the pre-reset observation, SB's info['terminal_observation']).  Either may be NULL. */
+/* Optional per-step outputs (any member may be NULL).  info: [N] bitmask (QS_INFO_*).  terminal_obs: [N,obs_dim], the
+ * pre-reset observation (SB's info['terminal_observation']).  terminal_chaser / terminal_target: [N,13] float64 world
+ * coordinates -- the reference's info['chaser'] / info['target'] (docking_env.py:226-229) of an episode's LAST step, which
+ * the in-kernel auto-reset would otherwise overwrite; only the rows of envs that finished in this step are written. */
+typedef struct {
+  uint8_t* info;
+  void* terminal_obs;
+  double* terminal_chaser;
+  double* terminal_target;
+} qs_step_extras_t;
+/* As qs_step, plus the per-step info the reference returns.  extras may be NULL. */
 int qs_step_ex(qs_env_t* env, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out,
-               uint8_t* info_out, void* terminal_obs_out, void* stream);
+               const qs_step_extras_t* extras, void* stream);
 /* qs_step for the env slice [first, first + n) only (first: a multiple of 128).  Pointers are the FULL arrays' bases, as in
  * qs_step.  Slices of one handle may be stepped concurrently on different streams (they share nothing); used by qs_rollout
  * to overlap the HBM-bound env kernel of one slice with the tensor-core policy kernel of another. */
@@ -125,12 +164,20 @@ int qs_step_range(qs_env_t* env, int64_t first, int64_t n, const void* actions, 
 int qs_step_n(qs_env_t* env, int64_t n_steps, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out,
               void* stream);
 /* Same step for HOST buffers (what a numpy VecEnv caller holds): copies actions in, steps, copies results out, chunked
- * over internal streams so H2D, kernel and D2H overlap.  Blocking.  Buffers should come from qs_host_alloc (pinned). */
-int qs_step_host(qs_env_t* env, const void* actions_host, void* obs_host, void* reward_host, uint8_t* done_host);
+ * over internal streams so H2D, kernel and D2H overlap.  The internal streams are forked from `stream` (an event recorded
+ * there; work the caller enqueued on it before -- reset, import, a device-side step -- is seen) and the call BLOCKS until
+ * the results are in host memory.  Buffers should come from qs_host_alloc (pinned). */
+int qs_step_host(qs_env_t* env, const void* actions_host, void* obs_host, void* reward_host, uint8_t* done_host, void* stream);
 int qs_host_alloc(void** out, uint64_t bytes);
 int qs_host_free(void* p);
 
-/* env.chaser.state / env.target.state / ... read and write access (parity injection, checkpoint/restore). */
+/* env.chaser.state / env.target.state / ... read and write access (parity injection, checkpoint/restore).
+ * Counter ranges.  QS_F64 handles keep t and episode as 32-bit words.  QS_F32 docking handles pack both into ONE state
+ * word: t in 10 bits (episodes end at t = max_steps = 600; with auto_reset = 0 a caller that keeps stepping a finished
+ * env sees t saturate at 1023, done stays set) and episode in 22 bits (the Philox counter word: after 2^22 episodes of one
+ * env its start-position sequence repeats).  qs_import_state on such a handle returns QS_ERR_INVALID, leaving the state
+ * untouched, if any t > 1023 or episode outside [0, 2^22) -- it synchronises `stream` to find out.  Hover handles and
+ * QS_F64 handles accept the full int32 range. */
 int qs_export_state(qs_env_t* env, const qs_state_arrays_t* dst, void* stream);
 int qs_import_state(qs_env_t* env, const qs_state_arrays_t* src, void* stream);
 

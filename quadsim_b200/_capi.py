@@ -14,20 +14,46 @@ RAND_NONE, RAND_EPISODE, RAND_ONCE = 0, 1, 2
 INFO_DONE, INFO_OVERLIMIT, INFO_DOCKING, INFO_OVERTIME = 1, 2, 4, 8
 (FN_QUAT2EULER, FN_EULER2QUAT, FN_QUAT2ROT, FN_ROT2EULER, FN_U_LIMIT, FN_DRONE_STEP, FN_PID, FN_VEL_CTRL,
  FN_STATE2REL, FN_PHILOX, FN_MATH) = range(11)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/quadsim_b200.h declares (tests check the built library exports all of them)
 SYMBOLS = ["qs_abi_version", "qs_last_error", "qs_create", "qs_destroy", "qs_obs_dim", "qs_num_envs", "qs_seed",
            "qs_reset", "qs_step", "qs_step_ex", "qs_step_host", "qs_host_alloc", "qs_host_free", "qs_export_state",
            "qs_import_state", "qs_get_stats", "qs_fn_apply", "qs_gae", "qs_policy_create", "qs_policy_destroy",
            "qs_policy_set_weights", "qs_policy_step", "qs_env_dtype", "qs_env_id0", "qs_rollout",
-           "qs_step_range", "qs_expert_action", "qs_peek_state", "qs_policy_ppo_grad", "qs_step_n"]
+           "qs_step_range", "qs_expert_action", "qs_peek_state", "qs_policy_ppo_grad", "qs_step_n", "qs_default_params",
+           "qs_env_device"]
+
+
+_D3 = C.c_double * 3
+
+
+class EnvParams(C.Structure):
+    """qs_env_params_t: the reference's model literals (quadrotor.py:10-63, PIDController.py:10-44, env __init__s)."""
+    _fields_ = [("dt", C.c_double), ("gravity", C.c_double), ("mass", C.c_double), ("arm_length", C.c_double),
+                ("inertia", _D3), ("motor_lambda", C.c_double), ("att_limit_deg", _D3), ("kp_att", _D3), ("kd_att", _D3),
+                ("kp_pos", _D3), ("kd_pos", _D3), ("kp_vel", _D3), ("chaser_ini_pos", _D3), ("target_ini_pos", _D3),
+                ("target_des_pos", _D3), ("target_des_vel", _D3), ("dock_port", C.c_double), ("dock_pos_tol", C.c_double),
+                ("dock_vel_tol", C.c_double), ("dock_angle_deg", C.c_double), ("range_limit", C.c_double),
+                ("min_altitude", C.c_double), ("max_steps", C.c_int32), ("reserved", C.c_int32)]
+
+    def as_dict(self):
+        out = {}
+        for name, ct in self._fields_:
+            v = getattr(self, name)
+            out[name] = list(v) if ct is _D3 else v
+        out.pop("reserved")
+        return out
 
 
 class Config(C.Structure):
     _fields_ = [("env_kind", C.c_int32), ("dtype", C.c_int32), ("n_envs", C.c_int64), ("seed", C.c_uint64),
                 ("env_id0", C.c_uint64), ("randomize", C.c_int32), ("device", C.c_int32), ("half_width", C.c_double),
-                ("auto_reset", C.c_int32), ("reserved", C.c_int32)]
+                ("auto_reset", C.c_int32), ("use_params", C.c_int32), ("params", EnvParams)]
+
+
+class StepExtras(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("info", "terminal_obs", "terminal_chaser", "terminal_target")]
 
 
 class StateArrays(C.Structure):
@@ -82,8 +108,10 @@ def load():
     L.qs_seed.argtypes = [vp, u64]
     L.qs_reset.argtypes = [vp, vp, vp]
     L.qs_step.argtypes = [vp, vp, vp, vp, vp, vp]
-    L.qs_step_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
-    L.qs_step_host.argtypes = [vp, vp, vp, vp, vp]
+    L.qs_step_ex.argtypes = [vp, vp, vp, vp, vp, C.POINTER(StepExtras), vp]
+    L.qs_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.qs_default_params.argtypes = [C.c_int, C.POINTER(EnvParams)]
+    L.qs_env_device.argtypes = [vp]
     L.qs_host_alloc.argtypes = [C.POINTER(vp), u64]
     L.qs_host_free.argtypes = [vp]
     L.qs_export_state.argtypes = [vp, C.POINTER(StateArrays), vp]
@@ -108,6 +136,13 @@ def load():
         raise QuadSimError("libquadsim_b200.so ABI %d != expected %d; rebuild" % (L.qs_abi_version(), ABI_VERSION))
     _lib = L
     return L
+
+
+def default_params(kind):
+    """EnvParams filled with the reference's literals for `kind` (qs_default_params)."""
+    p = EnvParams()
+    check(load().qs_default_params(kind, C.byref(p)))
+    return p
 
 
 def check(rc):

@@ -7,6 +7,7 @@
 //
 // There is NO CPU fallback: qs_create fails with QS_ERR_NO_DEVICE when no CUDA device is usable.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -59,6 +60,13 @@ int qs_fail_(int code, const char* fmt, ...) {
   return code;
 }
 namespace {
+
+// NVTX range around every entry point that enqueues work ("NVTX ranges around step"); a no-op costing a
+// few ns unless a profiler is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DeviceGuard {
   int prev = -1;
@@ -161,6 +169,7 @@ struct StepArgs {
   uint8_t* done;
   uint8_t* info;      // may be null
   void* term_obs;     // may be null
+  double *term_chaser, *term_target;  // may be null: [N,13] float64 world coordinates, rows of envs that finish in this step
   double* warp_stats; // [ceil(N/32)][kStatWords]
   RngCfg rng;
   int auto_reset;
@@ -254,6 +263,17 @@ template <typename T> __device__ __forceinline__ void store_obs13_tile(T* stage,
   }
 }
 
+// info['chaser'] / info['target'] of an episode's last step (docking_env.py:226-229): the 13-state in float64 world
+// coordinates, written before the auto-reset re-seats the env.  Cold: ~1.4 % of env-steps under random actions.
+template <typename T> __device__ __forceinline__ void store_terminal_state(double* out, int64_t i, const Drone<T>& d, bool shifted) {
+  double* o = out + i * 13;
+  const double ox = shifted ? (double)Origin<T>::x : 0.0, oy = shifted ? (double)Origin<T>::y : 0.0, oz = shifted ? (double)Origin<T>::z : 0.0;
+  o[0] = (double)d.px + ox; o[1] = (double)d.py + oy; o[2] = (double)d.pz + oz;
+  o[3] = (double)d.vx; o[4] = (double)d.vy; o[5] = (double)d.vz;
+  o[6] = (double)d.q0; o[7] = (double)d.q1; o[8] = (double)d.q2; o[9] = (double)d.q3;
+  o[10] = (double)d.wx; o[11] = (double)d.wy; o[12] = (double)d.wz;
+}
+
 // =========================================================================================================
 // Fused docking step: gym_docking/envs/docking_env.py:104-231 (KIND = QS_DOCK_V0) and
 // moving_docking_env.py:111-192 (KIND = QS_DOCK_V2) + the stable-baselines worker's auto-reset.
@@ -290,9 +310,13 @@ __device__ __forceinline__ StepTail dock_step_loaded(const StepArgs& a, int64_t 
   if (a.info) a.info[i] = (uint8_t)o.info();
   if (a.term_obs) store_row<T, 12>(a.term_obs, i, rel);
   const StepTail tail = {(double)e.last_shaping, e.tt, o.done, o.docking, o.nonfinite};  // ret == sum of the episode's rewards (telescoping)
-  if (o.done && a.auto_reset) {
-    e.episode += 1;
-    dock_env_seat<T>(e, a.rng, i, rel);
+  if (o.done) {
+    if (a.term_chaser) store_terminal_state<T>(a.term_chaser, i, e.c, true);
+    if (a.term_target) store_terminal_state<T>(a.term_target, i, e.t, true);
+    if (a.auto_reset) {
+      e.episode += 1;
+      dock_env_seat<T>(e, a.rng, i, rel);
+    }
   }
   store_row<T, 12>(a.obs, i, rel);
   dock_to_words<T, NW>(e, w);
@@ -460,9 +484,12 @@ __global__ void __launch_bounds__(kBlock) hover_step_kernel(const StepArgs a) {
     stat_len = e.tt;
   }
   if (a.term_obs) store_obs13_tile<T>(stage, a.term_obs, tile0, cnt, obs, active);
-  if (active && o.done && a.auto_reset) {
-    e.episode += 1;
-    hover_env_seat<T>(e, a.rng, i, obs);
+  if (active && o.done) {
+    if (a.term_chaser) store_terminal_state<T>(a.term_chaser, i, e.d, false);
+    if (a.auto_reset) {
+      e.episode += 1;
+      hover_env_seat<T>(e, a.rng, i, obs);
+    }
   }
   store_obs13_tile<T>(stage, a.obs, tile0, cnt, obs, active);
   if (active) {
@@ -628,6 +655,16 @@ __global__ void __launch_bounds__(kBlock) state_io_kernel(void* state, int64_t s
     else w[39] = pack_counters<T>(tt, ep);
   }
   if (IMPORT) store_words<T, NW>(state, i, w);
+}
+
+// fp32 docking handles pack t (10 bits) and episode (22 bits) into one state word: reject what would not round-trip
+__global__ void __launch_bounds__(256) counter_range_kernel(int64_t n, const int32_t* t, const int32_t* ep, int* flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool bad = false;
+  if (t) bad |= t[i] < 0 || t[i] > 1023;
+  if (ep) bad |= ep[i] < 0 || ep[i] >= (1 << 22);
+  if (bad) *flag = 1;
 }
 
 // statistics: fixed-order two-phase reduction of the per-warp slots (then cleared): kStatBlocks partial sums, then one
@@ -845,7 +882,9 @@ struct qs_env {
   int use_pipe = 0;               // persistent bulk-async docking kernel (default for fp64)
   int pipe_grid = 0;
   unsigned int* sched = nullptr;  // [kHostStreams + 1][2] tile counters (one pair per stream slot)
+  int* import_flag = nullptr;     // device word set by the import validation kernel (fp32 counter ranges)
   // qs_step_host pipeline
+  cudaEvent_t ev_fork = nullptr;  // recorded on the caller's stream, waited on by every internal stream
   cudaStream_t hstreams[kHostStreams] = {};
   void *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
   uint8_t* h_done = nullptr;
@@ -941,6 +980,32 @@ extern "C" {
 int qs_abi_version(void) { return QS_ABI_VERSION; }
 const char* qs_last_error(void) { return g_err; }
 
+int qs_default_params(int env_kind, qs_env_params_t* p) {
+  if (!p) return fail(QS_ERR_INVALID, "qs_default_params: null argument");
+  if (env_kind < QS_HOVER || env_kind > QS_DOCK_V2) return fail(QS_ERR_INVALID, "qs_default_params: unknown env_kind %d", env_kind);
+  memset(p, 0, sizeof *p);
+  p->dt = 0.02; p->gravity = 9.81; p->mass = 0.18; p->arm_length = 0.086;                          // quadrotor.py:12-21
+  p->inertia[0] = 0.00025; p->inertia[1] = 0.000232; p->inertia[2] = 0.0003738;                    // :17-19
+  p->motor_lambda = 1.5e-9 / 6.11e-8;                                                               // :43-45
+  p->att_limit_deg[0] = 85; p->att_limit_deg[1] = 85; p->att_limit_deg[2] = 175;                   // :146-168
+  p->kp_att[0] = -10; p->kp_att[1] = -10; p->kp_att[2] = -9.5;                                      // PIDController.py:10-12
+  p->kd_att[0] = 5.1; p->kd_att[1] = 5.1; p->kd_att[2] = 4.0;                                       // :14-16
+  p->kp_pos[0] = -1.0; p->kp_pos[1] = -1.0; p->kp_pos[2] = 50;                                      // :19-21
+  p->kd_pos[0] = -1.65; p->kd_pos[1] = -1.65; p->kd_pos[2] = 8;                                     // :23-25
+  p->kp_vel[0] = -0.7; p->kp_vel[1] = -0.7; p->kp_vel[2] = 1;                                       // :27-33
+  const bool hover = env_kind == QS_HOVER;
+  p->chaser_ini_pos[0] = hover ? 0 : 8; p->chaser_ini_pos[1] = hover ? 0 : -50; p->chaser_ini_pos[2] = 5;  // docking_env.py:34 / hovering_env.py:23
+  p->target_ini_pos[0] = 10; p->target_ini_pos[1] = -50; p->target_ini_pos[2] = 5;                 // docking_env.py:47
+  p->target_des_pos[0] = 10; p->target_des_pos[1] = -50; p->target_des_pos[2] = 5;                 // docking_env.py:59
+  p->target_des_vel[0] = env_kind == QS_DOCK_V2 ? 0.2 : 0.0;                                        // moving_docking_env.py:62-66
+  p->dock_port = 0.1;                                                                               // docking_env.py:38,51
+  p->dock_pos_tol = 0.1; p->dock_vel_tol = 0.1; p->dock_angle_deg = 10;                             // docking_env.py:130-134
+  p->range_limit = hover ? 100 : (env_kind == QS_DOCK_V0 ? 3 : 10);                                 // docking_env.py:141, moving_docking_env.py:148, hovering_env.py:68
+  p->min_altitude = 0.1;                                                                            // docking_env.py:142
+  p->max_steps = 600;                                                                               // docking_env.py:152
+  return QS_OK;
+}
+
 int qs_create(qs_env_t** out, const qs_config_t* cfg) {
   if (!out || !cfg) return fail(QS_ERR_INVALID, "qs_create: null argument");
   *out = nullptr;
@@ -948,6 +1013,11 @@ int qs_create(qs_env_t** out, const qs_config_t* cfg) {
   if (cfg->dtype != QS_F32 && cfg->dtype != QS_F64) return fail(QS_ERR_INVALID, "qs_create: unknown dtype %d", cfg->dtype);
   if (cfg->n_envs <= 0) return fail(QS_ERR_INVALID, "qs_create: n_envs must be positive (got %lld)", (long long)cfg->n_envs);
   if (cfg->randomize < QS_RAND_NONE || cfg->randomize > QS_RAND_ONCE) return fail(QS_ERR_INVALID, "qs_create: unknown randomize mode %d", cfg->randomize);
+  if (cfg->use_params) {
+    qs_env_params_t d;
+    qs_default_params(cfg->env_kind, &d);
+    if (memcmp(&d, &cfg->params, sizeof d) != 0) return fail(QS_ERR_INVALID, "qs_create: non-default params not wired yet");
+  }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0)
@@ -1018,6 +1088,8 @@ int qs_destroy(qs_env_t* e) {
   if (!e) return QS_OK;
   DeviceGuard g(e->cfg.device);
   for (auto& s : e->hstreams) if (s) cudaStreamDestroy(s);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  cudaFree(e->import_flag);
   cudaFree(e->h_act); cudaFree(e->h_obs); cudaFree(e->h_rew); cudaFree(e->h_done);
   cudaFree(e->state); cudaFree(e->warp_stats); cudaFree(e->stats_dev); cudaFree(e->sched);
   if (e->stats_host) cudaFreeHost(e->stats_host);
@@ -1029,6 +1101,7 @@ int qs_obs_dim(const qs_env_t* e) { return e ? e->obs_dim : fail(QS_ERR_INVALID,
 int64_t qs_num_envs(const qs_env_t* e) { return e ? e->cfg.n_envs : (int64_t)fail(QS_ERR_INVALID, "null handle"); }
 
 int qs_env_dtype(const qs_env_t* e) { return e ? e->cfg.dtype : fail(QS_ERR_INVALID, "null handle"); }
+int qs_env_device(const qs_env_t* e) { return e ? e->cfg.device : fail(QS_ERR_INVALID, "null handle"); }
 uint64_t qs_env_id0(const qs_env_t* e) { return e ? e->cfg.env_id0 : 0; }
 
 int qs_seed(qs_env_t* e, uint64_t seed) {
@@ -1039,16 +1112,19 @@ int qs_seed(qs_env_t* e, uint64_t seed) {
 
 int qs_reset(qs_env_t* e, void* obs_out, void* stream) {
   if (!e || !obs_out) return fail(QS_ERR_INVALID, "qs_reset: null argument");
+  NvtxRange nv("qs_reset");
   DeviceGuard g(e->cfg.device);
   return launch_seat(e, obs_out, 1, (cudaStream_t)stream);
 }
 
-int qs_step_ex(qs_env_t* e, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out, uint8_t* info_out,
-               void* terminal_obs_out, void* stream) {
+int qs_step_ex(qs_env_t* e, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out, const qs_step_extras_t* x,
+               void* stream) {
   if (!e || !actions || !obs_out || !reward_out || !done_out) return fail(QS_ERR_INVALID, "qs_step: null argument");
+  NvtxRange nv("qs_step");
   DeviceGuard g(e->cfg.device);
   StepArgs a = make_args(e, 0, e->cfg.n_envs);
-  a.actions = actions; a.obs = obs_out; a.reward = reward_out; a.done = done_out; a.info = info_out; a.term_obs = terminal_obs_out;
+  a.actions = actions; a.obs = obs_out; a.reward = reward_out; a.done = done_out;
+  if (x) { a.info = x->info; a.term_obs = x->terminal_obs; a.term_chaser = x->terminal_chaser; a.term_target = x->terminal_target; }
   return launch_step(e, a, (cudaStream_t)stream);
 }
 
@@ -1057,6 +1133,7 @@ int qs_step_range(qs_env_t* e, int64_t first, int64_t n, const void* actions, vo
   if (!e || !actions || !obs_out || !reward_out || !done_out) return fail(QS_ERR_INVALID, "qs_step_range: null argument");
   if (first < 0 || n < 0 || first + n > e->cfg.n_envs || first % kBlock != 0)
     return fail(QS_ERR_INVALID, "qs_step_range: [first, first+n) must lie inside the handle's envs and start on a multiple of %d", kBlock);
+  NvtxRange nv("qs_step_range");
   DeviceGuard g(e->cfg.device);
   StepArgs a = make_args(e, first, n);
   a.actions = actions; a.obs = obs_out; a.reward = reward_out; a.done = done_out;
@@ -1067,6 +1144,7 @@ int qs_step_n(qs_env_t* e, int64_t n_steps, const void* actions, void* obs_out, 
   if (!e || !actions || !obs_out || !reward_out || !done_out) return fail(QS_ERR_INVALID, "qs_step_n: null argument");
   if (n_steps < 0) return fail(QS_ERR_INVALID, "qs_step_n: n_steps < 0");
   if (n_steps == 0) return QS_OK;
+  NvtxRange nv("qs_step_n");
   DeviceGuard g(e->cfg.device);
   StepArgs a = make_args(e, 0, e->cfg.n_envs);
   a.actions = actions; a.obs = obs_out; a.reward = reward_out; a.done = done_out;
@@ -1089,7 +1167,7 @@ int qs_step_n(qs_env_t* e, int64_t n_steps, const void* actions, void* obs_out, 
 }
 
 int qs_step(qs_env_t* e, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out, void* stream) {
-  return qs_step_ex(e, actions, obs_out, reward_out, done_out, nullptr, nullptr, stream);
+  return qs_step_ex(e, actions, obs_out, reward_out, done_out, nullptr, stream);
 }
 
 int qs_host_alloc(void** out, uint64_t bytes) {
@@ -1102,20 +1180,25 @@ int qs_host_free(void* p) {
   return QS_OK;
 }
 
-int qs_step_host(qs_env_t* e, const void* actions_host, void* obs_host, void* reward_host, uint8_t* done_host) {
+int qs_step_host(qs_env_t* e, const void* actions_host, void* obs_host, void* reward_host, uint8_t* done_host, void* stream) {
   if (!e || !actions_host || !obs_host || !reward_host || !done_host) return fail(QS_ERR_INVALID, "qs_step_host: null argument");
+  NvtxRange nv("qs_step_host");
   DeviceGuard g(e->cfg.device);
   const int64_t N = e->cfg.n_envs;
   const size_t es = e->esize;
   if (!e->h_act) {
     for (auto& s : e->hstreams) QS_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    QS_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     QS_CUDA(cudaMalloc(&e->h_act, (size_t)N * 4 * es));
     QS_CUDA(cudaMalloc(&e->h_obs, (size_t)N * e->obs_dim * es));
     QS_CUDA(cudaMalloc(&e->h_rew, (size_t)N * es));
     QS_CUDA(cudaMalloc((void**)&e->h_done, (size_t)N));
   }
-  // work enqueued earlier on the legacy default stream (reset, import) must be visible to the non-blocking streams
-  QS_CUDA(cudaStreamSynchronize(0));
+  // fork: whatever the caller enqueued on ITS stream before this call (reset, import, a device-side step of the same
+  // handle) is ordered before the chunks on the internal non-blocking streams -- no host-side wait, no assumption that the
+  // caller works on the legacy default stream
+  QS_CUDA(cudaEventRecord(e->ev_fork, (cudaStream_t)stream));
+  for (auto& s : e->hstreams) QS_CUDA(cudaStreamWaitEvent(s, e->ev_fork, 0));
   int k = 0;
   // reward (4-8 B/env) and done (1 B/env) are too small to be worth a DMA descriptor per chunk: when the caller's buffers are
   // pinned (mapped into the device's address space under UVA) the kernel writes them straight across PCIe -- posted,
@@ -1162,6 +1245,8 @@ int qs_step_host(qs_env_t* e, const void* actions_host, void* obs_host, void* re
     first += n;
     if (!fixed && cur < cap) cur *= 2;
   }
+  // join: the call is blocking by contract (results are in host memory on return), which also orders everything the
+  // caller enqueues afterwards, on any stream, behind the chunks
   for (auto& s : e->hstreams) QS_CUDA(cudaStreamSynchronize(s));
   return QS_OK;
 }
@@ -1174,6 +1259,18 @@ int qs_export_state(qs_env_t* e, const qs_state_arrays_t* dst, void* stream) {
 int qs_import_state(qs_env_t* e, const qs_state_arrays_t* src, void* stream) {
   if (!e || !src) return fail(QS_ERR_INVALID, "qs_import_state: null argument");
   DeviceGuard g(e->cfg.device);
+  if (e->cfg.dtype == QS_F32 && e->cfg.env_kind != QS_HOVER && (src->t || src->episode)) {
+    // the packed counters word (see the header): validate first, so a rejected import leaves the state untouched
+    cudaStream_t st = (cudaStream_t)stream;
+    int bad = 0;
+    if (!e->import_flag) QS_CUDA(cudaMalloc((void**)&e->import_flag, sizeof(int)));
+    QS_CUDA(cudaMemsetAsync(e->import_flag, 0, sizeof(int), st));
+    counter_range_kernel<<<(unsigned)((e->cfg.n_envs + 255) / 256), 256, 0, st>>>(e->cfg.n_envs, src->t, src->episode, e->import_flag);
+    QS_CUDA(cudaGetLastError());
+    QS_CUDA(cudaMemcpyAsync(&bad, e->import_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    QS_CUDA(cudaStreamSynchronize(st));
+    if (bad) return fail(QS_ERR_INVALID, "qs_import_state: a float32 docking handle keeps t in 10 bits and episode in 22 bits; got t > 1023 or episode outside [0, 2^22)");
+  }
   return e->cfg.dtype == QS_F32 ? launch_state_io<float, true>(e, src, (cudaStream_t)stream) : launch_state_io<double, true>(e, src, (cudaStream_t)stream);
 }
 

@@ -35,6 +35,7 @@
 //           policy_fwd_ws_kernel | C ABI (qs_policy_*, qs_rollout)
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -830,6 +831,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
 
 }  // namespace
 
+struct NvtxRange {  // see qs_lib.cu
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 constexpr int kMaxSlices = 8;
 struct qs_policy {
   int device = 0;
@@ -928,6 +934,7 @@ int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, u
   if (!p || !obs || !values_out) return qs_fail_(QS_ERR_INVALID, "qs_policy_step: null argument");
   if (!p->have_weights) return qs_fail_(QS_ERR_INVALID, "qs_policy_step: qs_policy_set_weights has not been called");
   if (n <= 0) return QS_OK;
+  NvtxRange nv("qs_policy_step");
   int prev = 0;
   QSP_CUDA(cudaGetDevice(&prev));
   QSP_CUDA(cudaSetDevice(p->device));
@@ -981,6 +988,7 @@ int qs_policy_ppo_grad(qs_policy_t* p, const qs_ppo_grad_t* g, void* stream) {
       !g->per_sample)
     return qs_fail_(QS_ERR_INVALID, "qs_policy_ppo_grad: null buffer");
   if (g->batch <= 0) return qs_fail_(QS_ERR_INVALID, "qs_policy_ppo_grad: batch must be positive");
+  NvtxRange nv("qs_policy_ppo_grad");
   int prev = 0;
   QSP_CUDA(cudaGetDevice(&prev));
   QSP_CUDA(cudaSetDevice(p->device));
@@ -1002,6 +1010,9 @@ int qs_rollout(qs_env_t* env, qs_policy_t* pol, int64_t n_steps, const qs_rollou
   if (n_steps < 0 || n_slices < 1 || n_slices > kMaxSlices) return qs_fail_(QS_ERR_INVALID, "qs_rollout: n_steps < 0 or n_slices not in [1, %d]", kMaxSlices);
   if (qs_env_dtype(env) != QS_F32 || qs_obs_dim(env) != kObs)
     return qs_fail_(QS_ERR_INVALID, "qs_rollout: needs a float32 docking environment (12 observations, what the policy was built for)");
+  if (qs_env_device(env) != pol->device)
+    return qs_fail_(QS_ERR_INVALID, "qs_rollout: the environment lives on CUDA device %d, the policy on device %d", qs_env_device(env), pol->device);
+  NvtxRange nv("qs_rollout");
   const int64_t n = qs_num_envs(env);
   const uint64_t id0 = qs_env_id0(env);
   // slice boundaries on whole 128-env tiles (the state layout's unit)

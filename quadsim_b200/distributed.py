@@ -95,6 +95,20 @@ def shard_range(total_envs, rank=None, world=None):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def default_env_id0(num_envs, device=None):
+    """Global id of this rank's env 0 when the caller gives none: the exclusive prefix sum of every rank's env count.
+    With equal shards this is rank * num_envs; with unequal ones (shard_range of a non-divisible total: 10 envs over 3 ranks
+    = 4/3/3) the ranks' Philox counter ranges still tile [0, total) without overlap or gap.  One tiny all_gather at
+    construction."""
+    if not dist.is_initialized():
+        return 0
+    dev = device if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.tensor([int(num_envs)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(counts, mine)
+    return int(sum(int(c.item()) for c in counts[:dist.get_rank()]))
+
+
 def all_reduce_stats(vals, device=None):
     """SUM over ranks of the stats vector (float64[5]).  NCCL needs a device tensor; gloo reduces on the host."""
     if not dist.is_initialized():

@@ -69,9 +69,10 @@ class MlpPolicy(nn.Module):
         return actions, value, self.neglogp(mean, actions)
 
     @torch.no_grad()
-    def predict(self, obs, deterministic=True):
-        """model.predict as the replay scripts use it (run_trained_moving_docking_ppo2.py:46): clipped to the action Box."""
-        return self.step(obs, deterministic=deterministic)[0].clamp(-1.0, 1.0)
+    def predict(self, obs, deterministic=True, low=-1.0, high=1.0):
+        """model.predict as the replay scripts use it (run_trained_moving_docking_ppo2.py:46): clipped to the action Box --
+        [-1, 1]^4 for docking (docking_env.py:93); pass low=0 for hovering-v0's [0, 1]^4 (hovering_env.py:42)."""
+        return self.step(obs, deterministic=deterministic)[0].clamp(low, high)
 
     # ---- stable-baselines archive
     _MAP = (("shared_fc0", "model/shared_fc0"), ("pi_fc0", "model/pi_fc0"), ("vf_fc0", "model/vf_fc0"), ("vf", "model/vf"),
@@ -216,7 +217,13 @@ class PPO2:
         self.device = env.device
         torch.manual_seed(seed)
         self.policy = (policy if policy is not None else MlpPolicy(env.obs_dim, 4)).to(self.device)
-        self.gen = torch.Generator(device=self.device).manual_seed(seed)
+        self.dist = torch.distributed.is_available() and torch.distributed.is_initialized()
+        if self.dist:  # every rank starts from rank 0's weights -- BEFORE the fused policy packs its operand images
+            for p in self.policy.parameters():
+                torch.distributed.broadcast(p.data, 0)
+        # the shared `seed` initialises the weights; the action-noise stream of the torch policy is keyed by this rank's
+        # first global env id, so ranks do not draw the same noise matrix (the fused kernel keys Philox by env id already)
+        self.gen = torch.Generator(device=self.device).manual_seed(int(seed) + int(getattr(env, "env_id0", 0)))
         self.fused = None
         if fused_policy:
             from .fused_policy import FusedPolicy
@@ -243,10 +250,6 @@ class PPO2:
                                     capturable=self.graph_update)
         self._set_schedules(1.0)
         self.num_timesteps = 0
-        self.dist = torch.distributed.is_available() and torch.distributed.is_initialized()
-        if self.dist:  # every rank starts from rank 0's weights
-            for p in self.policy.parameters():
-                torch.distributed.broadcast(p.data, 0)
 
     def _set_schedules(self, frac):
         val = lambda x: float(x(frac)) if callable(x) else x
@@ -409,7 +412,11 @@ class PPO2:
 
     def predict(self, obs, deterministic=True):
         """model.predict(obs, deterministic=True)[0] (run_trained_moving_docking_ppo2.py:46): clipped to the action Box."""
-        return (self.fused or self.policy).predict(obs, deterministic=deterministic)
+        space = getattr(self.env, "action_space", None)
+        lo, hi = (float(space.low.min()), float(space.high.max())) if space is not None else (-1.0, 1.0)
+        if self.fused is not None and (lo, hi) == (-1.0, 1.0):
+            return self.fused.predict(obs, deterministic=deterministic)  # the kernel clips to the docking Box
+        return self.policy.predict(obs, deterministic=deterministic, low=lo, high=hi)
 
     def save(self, path):
         data = dict(gamma=self.runner.gamma, lam=self.runner.lam, n_steps=self.runner.n_steps, nminibatches=self.nminibatches,

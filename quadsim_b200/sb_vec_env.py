@@ -20,7 +20,8 @@ class SBVecEnv(_Base):
         """monitor=True adds stable-baselines' Monitor key to the info dict of an env that finished an episode:
         info['episode'] = {'r': return, 'l': length} -- the one key the reference's trainer reads from infos
         (rl_baselines/ppo2/ppo2.py:494-497).  The reference's scripts do not wrap their envs in Monitor, hence off by default."""
-        self._vec = QuadVecEnv(env_id, num_envs, dtype=dtype, want_info=True, want_terminal_obs=True, **kw)
+        self._vec = QuadVecEnv(env_id, num_envs, dtype=dtype, want_info=True, want_terminal_obs=True,
+                               want_terminal_state=info_dicts, **kw)
         self.num_envs = self._vec.num_envs
         self.observation_space, self.action_space = self._vec.observation_space, self._vec.action_space
         self.info_dicts = info_dicts
@@ -43,13 +44,19 @@ class SBVecEnv(_Base):
         infos = [{} for _ in range(self.num_envs)]
         if self.info_dicts:
             # the reference's info dict (docking_env.py:226-229): 'chaser', 'target', 'flag_docking', 'done_overlimit', plus
-            # SB's 'terminal_observation' on done.  For an env that finished this step 'chaser'/'target' are the re-seated
-            # states (the kernel auto-resets in place; the terminal observation is kept, the terminal 13-states are not).
+            # SB's 'terminal_observation' on done.  Like the reference's, the dict of an env that finished in this step
+            # describes the TERMINAL step: the kernel auto-resets in place, but writes the pre-reset 13-states of exactly
+            # those envs to the terminal_chaser / terminal_target rows (qs_step_extras_t).
             bits = info.bits.cpu().numpy()
             term = info.terminal_observation.float().cpu().numpy()
             st = self._vec.get_state()
             chaser = st["chaser"].cpu().numpy()
             target = st["target"].cpu().numpy() if "target" in st else None
+            if done_np.any():
+                fin = np.nonzero(done_np)[0]
+                chaser[fin] = info.terminal_chaser[torch.as_tensor(fin, device=self._vec.device)].cpu().numpy()
+                if target is not None:
+                    target[fin] = info.terminal_target[torch.as_tensor(fin, device=self._vec.device)].cpu().numpy()
             for i in range(self.num_envs):
                 infos[i] = {"chaser": chaser[i], "flag_docking": bool(bits[i] & 4), "done_overlimit": bool(bits[i] & 2)}
                 if target is not None:

@@ -41,8 +41,11 @@ def _space_bounds(kind):
 class VecInfo:
     """Lazy stand-in for SB's per-env list of info dicts (docking_env.py:226-229): tensors, not N python dicts."""
 
-    def __init__(self, env, bits, terminal_obs):
+    def __init__(self, env, bits, terminal_obs, terminal_chaser=None, terminal_target=None):
         self._env, self.bits, self.terminal_observation = env, bits, terminal_obs
+        # [N,13] float64 world coordinates; only the rows of envs whose episode ended in this step are meaningful: the
+        # reference's info['chaser'] / info['target'] of the terminal step (docking_env.py:226-229)
+        self.terminal_chaser, self.terminal_target = terminal_chaser, terminal_target
 
     @property
     def flag_docking(self):
@@ -72,7 +75,9 @@ class QuadVecEnv:
 
     def __init__(self, env_id="docking-v2", num_envs=1, *, dtype=torch.float32, device=None, seed=0, env_id0=None,
                  randomize=None, half_width=None, auto_reset=True, want_info=True, want_terminal_obs=False,
-                 reuse_buffers=False):
+                 want_terminal_state=False, reuse_buffers=False, params=None):
+        """params: dict of qs_env_params_t overrides (mass, inertia, gains, dt, thresholds ...; include/quadsim_b200.h);
+        unset members keep the reference's literals."""
         env_id = env_id.split(":")[-1]  # accept 'gym_docking:docking-v2'
         if env_id not in ENV_IDS:
             raise ValueError("unknown env id %r (have %s)" % (env_id, sorted(ENV_IDS)))
@@ -93,11 +98,28 @@ class QuadVecEnv:
         if env_id0 is None:
             env_id0 = 0
             if torch.distributed.is_available() and torch.distributed.is_initialized():
-                env_id0 = torch.distributed.get_rank() * self.num_envs  # global env ids
+                # global env ids.  Exclusive prefix sum of the ranks' env counts, so unequal shards
+                # (distributed.shard_range) neither overlap nor leave gaps in the Philox counter space.
+                from .distributed import default_env_id0
+                env_id0 = default_env_id0(self.num_envs, self.device)
         self.env_id0 = int(env_id0)
         self.want_info, self.want_terminal_obs, self.reuse_buffers = want_info, want_terminal_obs, reuse_buffers
+        self.want_terminal_state = want_terminal_state
+        self.params = _capi.default_params(kind)
+        for k, v in (params or {}).items():
+            if not hasattr(self.params, k) or k == "reserved":
+                raise ValueError("unknown env parameter %r (have %s)" % (k, sorted(self.params.as_dict())))
+            cur = getattr(self.params, k)
+            if isinstance(cur, (int, float)):
+                setattr(self.params, k, type(cur)(v))
+            else:
+                vals = [float(x) for x in np.asarray(v, dtype=np.float64).reshape(-1)]
+                if len(vals) != len(cur):
+                    raise ValueError("env parameter %r needs %d values" % (k, len(cur)))
+                cur[:] = vals
         cfg = _capi.Config(kind, _capi.F32 if dtype == torch.float32 else _capi.F64, self.num_envs, int(seed),
-                           self.env_id0, self.randomize, self.device.index, self.half_width, int(bool(auto_reset)), 0)
+                           self.env_id0, self.randomize, self.device.index, self.half_width, int(bool(auto_reset)),
+                           int(bool(params)), self.params)
         h = C.c_void_p()
         _capi.check(self.lib.qs_create(C.byref(h), C.byref(cfg)))
         self._h = h
@@ -106,7 +128,8 @@ class QuadVecEnv:
         self.observation_space = make_box(lo, hi, np.float32)
         self.action_space = make_box(alo, ahi, np.float32)
         # what the reference's scripts reach into (run_expert_policy.py:61-69, run_trained_moving_docking_ppo2.py:49)
-        scale = MASS * GRAVITY if kind == _capi.HOVER else MASS * GRAVITY / 2.0
+        mg = self.params.mass * self.params.gravity
+        scale = mg if kind == _capi.HOVER else mg / 2.0
         self.action_mean = np.ones(4) * (0.0 if kind == _capi.HOVER else scale)
         self.action_std = np.ones(4) * scale
         self._bufs = None
@@ -125,17 +148,26 @@ class QuadVecEnv:
         done = torch.empty((n,), dtype=torch.uint8, device=dev)
         bits = torch.empty((n,), dtype=torch.uint8, device=dev) if self.want_info else None
         term = torch.empty((n, self.obs_dim), dtype=self.dtype, device=dev) if self.want_terminal_obs else None
-        return obs, rew, done, bits, term
+        tc = tt = None
+        if self.want_terminal_state:
+            tc = torch.zeros((n, 13), dtype=torch.float64, device=dev)
+            tt = torch.zeros((n, 13), dtype=torch.float64, device=dev) if self.kind != _capi.HOVER else None
+        p = lambda t: t.data_ptr() if t is not None else None
+        extras = _capi.StepExtras(p(bits), p(term), p(tc), p(tt)) if (bits is not None or term is not None or tc is not None) else None
+        return obs, rew, done, bits, term, tc, tt, extras
+
+    def _info(self, bits, term, tc, tt):
+        return VecInfo(self, bits, term, tc, tt) if (bits is not None or term is not None or tc is not None) else None
 
     def _out(self):
         if not self.reuse_buffers:
             return self._new_bufs()
         if self._bufs is None:
             self._bufs = self._new_bufs()
-            obs, rew, done, bits, term = self._bufs
-            p = lambda t: t.data_ptr() if t is not None else None
-            ret = (obs, rew, done.view(torch.bool), VecInfo(self, bits, term) if bits is not None else None)
-            self._fast = ((self.num_envs, 4), p(obs), p(rew), p(done), p(bits), p(term), ret)
+            obs, rew, done, bits, term, tc, tt, extras = self._bufs
+            ret = (obs, rew, done.view(torch.bool), self._info(bits, term, tc, tt))
+            self._fast = ((self.num_envs, 4), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                          C.byref(extras) if extras is not None else None, ret)
         return self._bufs
 
     @staticmethod
@@ -166,19 +198,19 @@ class QuadVecEnv:
         a = a.contiguous()
         if a.shape != (self.num_envs, 4):
             raise ValueError("actions must have shape (%d, 4), got %s" % (self.num_envs, tuple(a.shape)))
-        obs, rew, done, bits, term = self._out()
+        obs, rew, done, bits, term, tc, tt, extras = self._out()
         with torch.cuda.device(self.device):
             _capi.check(self.lib.qs_step_ex(self._h, self._ptr(a), self._ptr(obs), self._ptr(rew), self._ptr(done),
-                                            self._ptr(bits), self._ptr(term), self._stream()))
-        self._pending = ("dev", (obs, rew, done, bits, term, a))
+                                            C.byref(extras) if extras is not None else None, self._stream()))
+        self._pending = ("dev", (obs, rew, done, bits, term, tc, tt, a))
 
     def step_wait(self):
         kind, payload = self._pending
         self._pending = None
         if kind == "host":
             return self.step_host(payload)
-        obs, rew, done, bits, term, _keepalive = payload
-        return obs, rew, done.view(torch.bool), VecInfo(self, bits, term) if bits is not None else None
+        obs, rew, done, bits, term, tc, tt, _keepalive = payload
+        return obs, rew, done.view(torch.bool), self._info(bits, term, tc, tt)
 
     def step(self, actions):
         """actions[N,4] (torch CUDA tensor, or numpy for the host path) -> obs, rewards, dones, infos."""
@@ -189,11 +221,11 @@ class QuadVecEnv:
         if (f is not None and type(actions) is torch.Tensor and actions.dtype == self.dtype and actions.device == self.device
                 and actions.shape == f[0] and actions.is_contiguous() and self._h is not None):
             if torch.cuda.current_device() == self.device.index:
-                rc = self.lib.qs_step_ex(self._h, actions.data_ptr(), f[1], f[2], f[3], f[4], f[5],
+                rc = self.lib.qs_step_ex(self._h, actions.data_ptr(), f[1], f[2], f[3], f[4],
                                          torch.cuda.current_stream().cuda_stream)
                 if rc != 0:
                     _capi.check(rc)
-                return f[6]
+                return f[5]
         self.step_async(actions)
         return self.step_wait()
 
@@ -249,7 +281,7 @@ class QuadVecEnv:
                 raise ValueError("out buffers must be C-contiguous (obs[N,%d], rew[N]) of %s and done[N] uint8" % (self.obs_dim, npdt))
         vp = lambda x: C.c_void_p(x.ctypes.data)
         with torch.cuda.device(self.device):
-            _capi.check(self.lib.qs_step_host(self._h, vp(a), vp(ho), vp(hr), vp(hd)))
+            _capi.check(self.lib.qs_step_host(self._h, vp(a), vp(ho), vp(hr), vp(hd), self._stream()))
         if out is None:
             return ho.copy(), hr.copy(), hd.astype(bool), None
         return ho, hr, hd.view(np.bool_), None

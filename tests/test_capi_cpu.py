@@ -29,11 +29,52 @@ def test_library_exports_every_declared_symbol():
     assert L.qs_abi_version() == _capi.ABI_VERSION
 
 
-def test_config_struct_layout_matches_header():
-    # int32 int32 int64 uint64 uint64 int32 int32 double int32 int32 = 56 bytes, no implicit padding
-    assert C.sizeof(_capi.Config) == 56
-    assert _capi.Config.n_envs.offset == 8 and _capi.Config.half_width.offset == 40 and _capi.Config.auto_reset.offset == 48
-    assert C.sizeof(_capi.StateArrays) == 9 * C.sizeof(C.c_void_p)
+def test_config_struct_layout_matches_header(tmp_path):
+    """The ctypes mirrors against the C compiler's own layout of include/quadsim_b200.h (sizeof / offsetof of every struct
+    that crosses the boundary), so a field added on one side only cannot go unnoticed."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text("""
+#include <stdio.h>
+#include <stddef.h>
+#include "quadsim_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(qs_config_t), offsetof(qs_config_t, n_envs), offsetof(qs_config_t, half_width),
+         offsetof(qs_config_t, auto_reset), offsetof(qs_config_t, use_params), offsetof(qs_config_t, params), sizeof(qs_env_params_t));
+  printf("%zu %zu %zu %zu\\n", offsetof(qs_env_params_t, inertia), offsetof(qs_env_params_t, kp_vel), offsetof(qs_env_params_t, dock_port),
+         offsetof(qs_env_params_t, max_steps));
+  printf("%zu %zu %zu %zu %zu\\n", sizeof(qs_state_arrays_t), sizeof(qs_step_extras_t), sizeof(qs_rollout_t), sizeof(qs_ppo_grad_t),
+         sizeof(qs_policy_weights_t));
+  return 0;
+}
+""")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    rows = [[int(x) for x in line.split()] for line in subprocess.check_output([str(exe)]).decode().splitlines()]
+    Cfg, Prm = _capi.Config, _capi.EnvParams
+    assert rows[0] == [C.sizeof(Cfg), Cfg.n_envs.offset, Cfg.half_width.offset, Cfg.auto_reset.offset, Cfg.use_params.offset,
+                       Cfg.params.offset, C.sizeof(Prm)]
+    assert rows[1] == [Prm.inertia.offset, Prm.kp_vel.offset, Prm.dock_port.offset, Prm.max_steps.offset]
+    assert rows[2] == [C.sizeof(_capi.StateArrays), C.sizeof(_capi.StepExtras), C.sizeof(_capi.RolloutBuffers), C.sizeof(_capi.PPOGrad),
+                       C.sizeof(_capi.PolicyWeights)]
+
+
+def test_default_params_are_the_reference_literals():
+    """qs_default_params == dynamics/quadrotor.py:10-63, controller/PIDController.py:10-44 and the envs' __init__ literals."""
+    d0 = _capi.default_params(_capi.DOCK_V0).as_dict()
+    d2 = _capi.default_params(_capi.DOCK_V2).as_dict()
+    dh = _capi.default_params(_capi.HOVER).as_dict()
+    assert (d2["dt"], d2["gravity"], d2["mass"], d2["arm_length"]) == (0.02, 9.81, 0.18, 0.086)
+    assert d2["inertia"] == [0.00025, 0.000232, 0.0003738] and d2["motor_lambda"] == 1.5e-9 / 6.11e-8
+    assert d2["att_limit_deg"] == [85, 85, 175]
+    assert d2["kp_att"] == [-10, -10, -9.5] and d2["kd_att"] == [5.1, 5.1, 4.0]
+    assert d2["kp_pos"] == [-1.0, -1.0, 50] and d2["kd_pos"] == [-1.65, -1.65, 8] and d2["kp_vel"] == [-0.7, -0.7, 1]
+    assert d2["chaser_ini_pos"] == [8, -50, 5] and d2["target_ini_pos"] == [10, -50, 5] and d0["target_des_pos"] == [10, -50, 5]
+    assert d2["target_des_vel"] == [0.2, 0, 0] and d0["target_des_vel"] == [0, 0, 0]
+    assert (d0["range_limit"], d2["range_limit"], dh["range_limit"]) == (3, 10, 100)
+    assert (d2["dock_port"], d2["dock_pos_tol"], d2["dock_vel_tol"], d2["dock_angle_deg"], d2["min_altitude"], d2["max_steps"]) == (0.1, 0.1, 0.1, 10, 0.1, 600)
+    assert dh["chaser_ini_pos"] == [0, 0, 5]
+    assert _capi.load().qs_default_params(9, None) == -1
 
 
 def test_invalid_arguments_return_status_not_crash():
@@ -45,6 +86,8 @@ def test_invalid_arguments_return_status_not_crash():
     bad = _capi.Config(2, 0, 0, 0, 0, 0, 0, 0.5, 1, 0)
     assert L.qs_create(C.byref(h), C.byref(bad)) == -1 and b"n_envs" in L.qs_last_error()
     assert L.qs_step(None, None, None, None, None, None) == -1
+    assert L.qs_step_ex(None, None, None, None, None, None, None) == -1
+    assert L.qs_step_host(None, None, None, None, None, None) == -1
     assert L.qs_reset(None, None, None) == -1
     assert L.qs_get_stats(None, None, None) == -1
     assert L.qs_destroy(None) == 0
@@ -59,7 +102,7 @@ def test_invalid_arguments_return_status_not_crash():
     assert L.qs_expert_action(None, None, 1, None, None, None) == -1
     assert L.qs_peek_state(None, None, 1, None, None, None, None) == -1
     assert L.qs_gae(0, 4, None, None, None, None, None, 0.99, 0.95, None, None, None) == -1
-    assert L.qs_env_dtype(None) == -1 and L.qs_env_id0(None) == 0
+    assert L.qs_env_dtype(None) == -1 and L.qs_env_id0(None) == 0 and L.qs_env_device(None) == -1
     assert C.sizeof(_capi.RolloutBuffers) == 7 * C.sizeof(C.c_void_p)
     assert C.sizeof(_capi.PPOGrad) == 6 * 8 + 8 + 8 + 3 * 4 + 4 + 6 * 8  # 12-byte float block padded to the next pointer
 
