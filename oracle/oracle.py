@@ -27,9 +27,43 @@ def build(force=False):
     return LIB_PATH
 
 
+_D3 = C.c_double * 3
+
+
+class Params(C.Structure):
+    """qo_params == the CUDA library's qs_env_params_t, field for field."""
+    _fields_ = [("dt", C.c_double), ("gravity", C.c_double), ("mass", C.c_double), ("arm_length", C.c_double),
+                ("inertia", _D3), ("motor_lambda", C.c_double), ("att_limit_deg", _D3), ("kp_att", _D3), ("kd_att", _D3),
+                ("kp_pos", _D3), ("kd_pos", _D3), ("kp_vel", _D3), ("chaser_ini_pos", _D3), ("target_ini_pos", _D3),
+                ("target_des_pos", _D3), ("target_des_vel", _D3), ("dock_port", C.c_double), ("dock_pos_tol", C.c_double),
+                ("dock_vel_tol", C.c_double), ("dock_angle_deg", C.c_double), ("range_limit", C.c_double),
+                ("min_altitude", C.c_double), ("max_steps", C.c_int32), ("reserved", C.c_int32)]
+
+
 class _Config(C.Structure):
     _fields_ = [("kind", C.c_int), ("n_envs", C.c_int64), ("seed", C.c_uint64), ("env_id0", C.c_uint64),
-                ("randomize", C.c_int), ("half_width", C.c_double), ("auto_reset", C.c_int)]
+                ("randomize", C.c_int), ("half_width", C.c_double), ("auto_reset", C.c_int), ("id_stride", C.c_int64),
+                ("params", C.POINTER(Params))]
+
+
+def default_params(kind):
+    if isinstance(kind, str):
+        kind = KINDS[kind]
+    p = Params()
+    lib().qo_default_params(kind, C.byref(p))
+    return p
+
+
+def make_params(kind, overrides):
+    """Params with the reference's literals for `kind`, then `overrides` (dict: scalars or 3-sequences) applied."""
+    p = default_params(kind)
+    for k, v in (overrides or {}).items():
+        cur = getattr(p, k)
+        if isinstance(cur, (int, float)):
+            setattr(p, k, type(cur)(v))
+        else:
+            cur[:] = [float(x) for x in v]
+    return p
 
 
 _lib = None
@@ -50,6 +84,7 @@ def lib():
         L.qo_vec_reset.argtypes = [C.c_void_p, C.c_void_p]
         L.qo_vec_step.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int]
         L.qo_vec_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.qo_default_params.argtypes = [C.c_int, C.POINTER(Params)]
         L.qo_philox_jitter3.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p]
         _lib = L
     return _lib
@@ -165,11 +200,16 @@ _FIELDS = {"chaser": (0, 13, np.float64), "target": (1, 13, np.float64), "u_c": 
 class OracleVecEnv:
     """Batched fp64 CPU environment with stable-baselines auto-reset semantics."""
 
-    def __init__(self, kind, n_envs, seed=0, env_id0=0, randomize=RAND_NONE, half_width=0.0, nthreads=1, auto_reset=True):
+    def __init__(self, kind, n_envs, seed=0, env_id0=0, randomize=RAND_NONE, half_width=0.0, nthreads=1, auto_reset=True,
+                 id_stride=1, params=None):
+        """id_stride > 1: env i carries the global id env_id0 + i * id_stride (a strided sample of a larger batch).
+        params: dict of qo_params overrides (or a Params); None = the reference's literals."""
         if isinstance(kind, str):
             kind = KINDS[kind]
         self.kind, self.n, self.nthreads = kind, int(n_envs), int(nthreads)
-        cfg = _Config(kind, self.n, seed, env_id0, randomize, half_width, int(auto_reset))
+        self.params = params if isinstance(params, Params) else (make_params(kind, params) if params else None)
+        cfg = _Config(kind, self.n, seed, env_id0, randomize, half_width, int(auto_reset), int(id_stride),
+                      C.pointer(self.params) if self.params is not None else None)
         self._h = lib().qo_vec_create(C.byref(cfg))
         self.obs_dim = lib().qo_vec_obs_dim(self._h)
 

@@ -11,15 +11,21 @@
 #include <stdlib.h>
 #include <string.h>
 
-/* ---- constants: dynamics/quadrotor.py:10-63 ---- */
-#define QO_DT 0.02
-#define QO_G 9.81
-#define QO_MASS 0.18
-#define QO_L 0.086
-static const double QO_I[3] = {0.00025, 0.000232, 0.0003738};
-#define QO_KF 6.11e-8
-#define QO_KM 1.5e-9
+/* ---- constants: dynamics/quadrotor.py:10-63, controller/PIDController.py:10-44 and the envs' __init__ literals, as a
+ * parameter block (qo_params, quadsim_oracle.h) so that the parity tests can also run the model with non-default mass /
+ * inertia / gains / thresholds (the CUDA library's qs_env_params_t).  Every function takes the block explicitly; the public
+ * leaf functions use the reference's literals. ---- */
 #define QO_PI 3.141592653589793
+static const qo_params QO_DEF = {
+    0.02, 9.81, 0.18, 0.086, {0.00025, 0.000232, 0.0003738}, 1.5e-9 / 6.11e-8, {85, 85, 175},
+    {-10.0, -10.0, -9.5}, {5.1, 5.1, 4.0}, {-1.0, -1.0, 50.0}, {-1.65, -1.65, 8.0}, {-0.7, -0.7, 1.0},
+    {8, -50, 5}, {10, -50, 5}, {10, -50, 5}, {0, 0, 0}, 0.1, 0.1, 0.1, 10, 0, 0.1, 600, 0};
+void qo_default_params(int kind, qo_params* out) {
+  *out = QO_DEF;
+  if (kind == QO_HOVER) { out->chaser_ini_pos[0] = 0; out->chaser_ini_pos[1] = 0; out->chaser_ini_pos[2] = 5; out->range_limit = 100; }
+  else if (kind == QO_DOCK_V0) out->range_limit = 3;
+  else { out->range_limit = 10; out->target_des_vel[0] = 0.2; }
+}
 
 /* utils/transform.py:143-144  deg2rad(angle) = angle * np.pi / 180 */
 static double deg2rad(double a) { return a * QO_PI / 180; }
@@ -79,8 +85,9 @@ void qo_rot2euler(const double R[9], double e[3]) {
 }
 
 /* dynamics/quadrotor.py:171-187 (A = :47-50, B = :52-54; F_max/4 == mass*gravity exactly) */
-void qo_u_limit(const double u[4], double out[4]) {
-  const double hl = 0.5 / QO_L, fmax = 4 * QO_MASS * QO_G / 4, fmin = 0.0;
+static void u_limit_p(const qo_params* P, const double u[4], double out[4]) {
+  const double QO_L = P->arm_length;
+  const double hl = 0.5 / QO_L, fmax = 4 * P->mass * P->gravity / 4, fmin = 0.0;
   double p[4];
   p[0] = 0.25 * u[0] + 0 * u[1] + (-hl) * u[2];
   p[1] = 0.25 * u[0] + hl * u[1] + 0 * u[2];
@@ -95,9 +102,12 @@ void qo_u_limit(const double u[4], double out[4]) {
   out[2] = (-QO_L) * p[0] + 0 * p[1] + QO_L * p[2] + 0 * p[3];
   out[3] = u[3];
 }
+void qo_u_limit(const double u[4], double out[4]) { u_limit_p(&QO_DEF, u, out); }
 
 /* dynamics/quadrotor.py:80-113 */
-void qo_df(const double s[13], const double u[4], double ds[13]) {
+static void df_p(const qo_params* P, const double s[13], const double u[4], double ds[13]) {
+  const double QO_MASS = P->mass, QO_G = P->gravity;
+  const double* QO_I = P->inertia;
   double F = u[0];
   double M[3] = {QO_I[0] * u[1], QO_I[1] * u[2], QO_I[2] * u[3]};
   const double* q = s + 6;
@@ -119,29 +129,31 @@ void qo_df(const double s[13], const double u[4], double ds[13]) {
   for (int i = 0; i < 3; i++) ds[10 + i] = (1.0 / QO_I[i]) * (M[i] - cr[i]);
   ds[0] = s[3]; ds[1] = s[4]; ds[2] = s[5];
 }
+void qo_df(const double s[13], const double u[4], double ds[13]) { df_p(&QO_DEF, s, u, ds); }
 
 /* dynamics/quadrotor.py:126-144 with :115-124 -- SURVEY Q1/Q2: SciPy RK45 integrates a constant RHS
  * df(state_at_step_start, u_prev), i.e. one explicit Euler step of length dt; the new command is stored
  * only AFTER the integration (one-step latency).  attitude_limit: quadrotor.py:146-168. */
-void qo_drone_step(double s[13], double u_prev[4], const double u_cmd[4]) {
+static void drone_step_p(const qo_params* P, double s[13], double u_prev[4], const double u_cmd[4]) {
   double ds[13];
-  qo_df(s, u_prev, ds);
-  for (int i = 0; i < 13; i++) s[i] = s[i] + QO_DT * ds[i];
+  df_p(P, s, u_prev, ds);
+  for (int i = 0; i < 13; i++) s[i] = s[i] + P->dt * ds[i];
   double e[3], lim[4], tmp[3];
   int flag = 0;
   qo_quat2euler(s + 6, e);
   double r = e[0], p = e[1], y = e[2];
-  const double d85 = deg2rad(85), d175 = deg2rad(175);
-  if (fabs(r) >= d85) { tmp[0] = sgn(r) * d85; tmp[1] = p; tmp[2] = y; qo_euler2quat(tmp, lim); flag = 1; }
-  if (fabs(p) >= d85) { tmp[0] = r; tmp[1] = sgn(p) * d85; tmp[2] = y; qo_euler2quat(tmp, lim); flag = 1; }
-  if (fabs(y) >= d175) { tmp[0] = r; tmp[1] = p; tmp[2] = sgn(y) * d175; qo_euler2quat(tmp, lim); flag = 1; }
-  if (fabs(r) <= d85 && fabs(p) <= d85 && fabs(y) <= d175) flag = 0;
+  const double dr = deg2rad(P->att_limit_deg[0]), dp = deg2rad(P->att_limit_deg[1]), dy = deg2rad(P->att_limit_deg[2]);
+  if (fabs(r) >= dr) { tmp[0] = sgn(r) * dr; tmp[1] = p; tmp[2] = y; qo_euler2quat(tmp, lim); flag = 1; }
+  if (fabs(p) >= dp) { tmp[0] = r; tmp[1] = sgn(p) * dp; tmp[2] = y; qo_euler2quat(tmp, lim); flag = 1; }
+  if (fabs(y) >= dy) { tmp[0] = r; tmp[1] = p; tmp[2] = sgn(y) * dy; qo_euler2quat(tmp, lim); flag = 1; }
+  if (fabs(r) <= dr && fabs(p) <= dp && fabs(y) <= dy) flag = 0;
   if (flag) {
     for (int i = 0; i < 4; i++) s[6 + i] = lim[i];
     s[10] = s[11] = s[12] = 0.0;
   }
-  qo_u_limit(u_cmd, u_prev);
+  u_limit_p(P, u_cmd, u_prev);
 }
+void qo_drone_step(double s[13], double u_prev[4], const double u_cmd[4]) { drone_step_p(&QO_DEF, s, u_prev, u_cmd); }
 
 /* dynamics/quadrotor.py:213-224 with dock_port_inB_pos = [d,0,0]; only 'pos' and 'vel' are ever read */
 void qo_dock_port(const double s[13], double d, double pos[3], double vel[3]) {
@@ -155,42 +167,28 @@ void qo_dock_port(const double s[13], double d, double pos[3], double vel[3]) {
   vel[2] = s[5] + (-w[1] * r[0] + w[0] * r[1] + 0 * r[2]);
 }
 
-/* controller/PIDController.py:10-44 gains */
-#define KP_ROLL (-10.0)
-#define KP_PITCH (-10.0)
-#define KP_YAW (-9.5)
-#define KD_ROLL 5.1
-#define KD_PITCH 5.1
-#define KD_YAW 4.0
+/* controller/PIDController.py:10-44 gains: qo_params.kp_att / kd_att / kp_pos / kd_pos / kp_vel; the rest are fixed */
 #define FF_YAW 0.0
-#define KP_X (-1.0)
-#define KP_Y (-1.0)
-#define KP_Z 50.0
-#define KD_X (-1.65)
-#define KD_Y (-1.65)
-#define KD_Z 8.0
-#define KP_VX (-0.7)
-#define KP_VY (-0.7)
 #define KD_VX 0.0
 #define KD_VY 0.0
-#define KP_VZ 1.0
 #define KD_VZ 0.1
 
 /* controller/PIDController.py:52-74 */
-static void attitude_controller(const double des[13], const double now[13], double M[3]) {
+static void attitude_controller(const qo_params* P, const double des[13], const double now[13], double M[3]) {
   double ad[3], an[3];
   qo_quat2euler(des + 6, ad);
   qo_quat2euler(now + 6, an);
   double ea[3], er[3];
   for (int i = 0; i < 3; i++) { ea[i] = ad[i] - an[i]; er[i] = des[10 + i] - now[10 + i]; }
-  M[0] = KP_ROLL * ea[0] + KD_ROLL * er[0];
-  M[1] = KP_PITCH * ea[1] + KD_PITCH * er[1];
-  M[2] = FF_YAW + KP_YAW * ea[2] + KD_YAW * er[2];
+  M[0] = P->kp_att[0] * ea[0] + P->kd_att[0] * er[0];
+  M[1] = P->kp_att[1] * ea[1] + P->kd_att[1] * er[1];
+  M[2] = FF_YAW + P->kp_att[2] * ea[2] + P->kd_att[2] * er[2];
 }
 
 /* shared tail of hover_controller (PIDController.py:87-104) and vel_controller (:119-134):
  * acc_des -> F, desired attitude; OVERWRITES des[6:10], des[10], des[11] */
-static double acc2att(const double acc[3], double des[13]) {
+static double acc2att(const qo_params* P, const double acc[3], double des[13]) {
+  const double QO_MASS = P->mass, QO_G = P->gravity;
   double F = QO_MASS * QO_G + QO_MASS * acc[2];
   double att[3];
   qo_quat2euler(des + 6, att);
@@ -204,24 +202,26 @@ static double acc2att(const double acc[3], double des[13]) {
 }
 
 /* controller/PIDController.py:179-185 (hover_controller :76-104 then attitude_controller) */
-void qo_pid(double des[13], const double now[13], double u[4]) {
+static void pid_p(const qo_params* P, double des[13], const double now[13], double u[4]) {
   double acc[3];
-  acc[0] = KP_X * (des[0] - now[0]) + KD_X * (des[3] - now[3]);
-  acc[1] = KP_Y * (des[1] - now[1]) + KD_Y * (des[4] - now[4]);
-  acc[2] = KP_Z * (des[2] - now[2]) + KD_Z * (des[5] - now[5]);
-  u[0] = acc2att(acc, des);
-  attitude_controller(des, now, u + 1);
+  acc[0] = P->kp_pos[0] * (des[0] - now[0]) + P->kd_pos[0] * (des[3] - now[3]);
+  acc[1] = P->kp_pos[1] * (des[1] - now[1]) + P->kd_pos[1] * (des[4] - now[4]);
+  acc[2] = P->kp_pos[2] * (des[2] - now[2]) + P->kd_pos[2] * (des[5] - now[5]);
+  u[0] = acc2att(P, acc, des);
+  attitude_controller(P, des, now, u + 1);
 }
+void qo_pid(double des[13], const double now[13], double u[4]) { pid_p(&QO_DEF, des, now, u); }
 
 /* controller/PIDController.py:106-141 */
-void qo_vel_controller(double des[13], const double now[13], const double last[13], double u[4]) {
+static void vel_controller_p(const qo_params* P, double des[13], const double now[13], const double last[13], double u[4]) {
   double acc[3];
-  acc[0] = KP_VX * (des[3] - now[3]) + KD_VX * (now[3] - last[3]);
-  acc[1] = KP_VY * (des[4] - now[4]) + KD_VY * (now[4] - last[4]);
-  acc[2] = KP_VZ * (des[5] - now[5]) + KD_VZ * (now[5] - last[5]);
-  u[0] = acc2att(acc, des);
-  attitude_controller(des, now, u + 1);
+  acc[0] = P->kp_vel[0] * (des[3] - now[3]) + KD_VX * (now[3] - last[3]);
+  acc[1] = P->kp_vel[1] * (des[4] - now[4]) + KD_VY * (now[4] - last[4]);
+  acc[2] = P->kp_vel[2] * (des[5] - now[5]) + KD_VZ * (now[5] - last[5]);
+  u[0] = acc2att(P, acc, des);
+  attitude_controller(P, des, now, u + 1);
 }
+void qo_vel_controller(double des[13], const double now[13], const double last[13], double u[4]) { vel_controller_p(&QO_DEF, des, now, last, u); }
 
 /* The PID expert of the imitation-learning scripts: run_expert_policy.py:44-69 == run_expert_record.py:40-139.
  *   des_vel = kp * (env.state_target[0:3] + [-0.2,0,0] - env.state_chaser[0:3]) + kd * (-env.state_chaser[3:6])   (:133-134)
@@ -273,11 +273,11 @@ static void mat3vec(const double A[9], const double x[3], double y[3]) {
 
 /* gym_docking/envs/docking_env.py:257-295 (== moving_docking_env.py:222-260), with the env's dock ports
  * chaser [+0.1,0,0] (docking_env.py:38) and target [-0.1,0,0] (:51) */
-void qo_state2rel(const double sc[13], const double st[13], double rel[12]) {
+static void state2rel_p(const qo_params* P, const double sc[13], const double st[13], double rel[12]) {
   double RB[9], RA[9], RAt[9], RAB[9], RABA[9];
   double pc[3], vc[3], pt[3], vt[3];
-  qo_dock_port(sc, 0.1, pc, vc);
-  qo_dock_port(st, -0.1, pt, vt);
+  qo_dock_port(sc, P->dock_port, pc, vc);
+  qo_dock_port(st, -P->dock_port, pt, vt);
   qo_quat2rot(st + 6, RB);
   qo_quat2rot(sc + 6, RA);
   for (int i = 0; i < 3; i++)
@@ -295,6 +295,7 @@ void qo_state2rel(const double sc[13], const double st[13], double rel[12]) {
   rel[10] = q - tan(phi) * (r * cos(theta) - p * sin(theta));
   rel[11] = (r * cos(theta) - p * sin(theta)) / cos(phi);
 }
+void qo_state2rel(const double sc[13], const double st[13], double rel[12]) { state2rel_p(&QO_DEF, sc, st, rel); }
 
 /* Philox4x32-10, Salmon et al. SC'11 (Random123).  Not in the reference: the north star's specified
  * extension for randomised auto-reset (SURVEY section 0.1 closing note). */
@@ -325,34 +326,40 @@ void qo_philox_jitter3(uint64_t seed, uint64_t env_id, uint32_t episode, uint32_
 /* ------------------------------------------------------------------------------------------------ */
 struct qo_vec {
   qo_config cfg;
+  qo_params P;
   int obs_dim;
   double *chaser, *target, *uc, *ut, *desq, *last_shaping, *ep_return;
   int64_t *t, *episode;
   double stats[5];
 };
 
+/* global id of env i: env_id0 + i * id_stride (id_stride > 1: a strided SAMPLE of a larger batch, for the parity tests at
+ * sizes the oracle cannot step in full) */
+static uint64_t env_gid(const qo_vec* v, int64_t i) { return v->cfg.env_id0 + (uint64_t)i * (uint64_t)(v->cfg.id_stride > 1 ? v->cfg.id_stride : 1); }
+
 static void dock_ini(const qo_vec* v, int64_t i, double sc[13], double st[13]) {
   /* docking_env.py:34-57 / moving_docking_env.py:33-56 ; jitter = the commented-out U(-0.5,0.5)^3 (:34) */
   memset(sc, 0, 13 * sizeof(double));
   memset(st, 0, 13 * sizeof(double));
-  float base[3] = {8.f, -50.f, 5.f}, j[3] = {0, 0, 0};
+  float base[3] = {(float)v->P.chaser_ini_pos[0], (float)v->P.chaser_ini_pos[1], (float)v->P.chaser_ini_pos[2]}, j[3] = {0, 0, 0};
   if (v->cfg.randomize != QO_RAND_NONE) {
     uint32_t ep = v->cfg.randomize == QO_RAND_ONCE ? 0u : (uint32_t)v->episode[i];
-    qo_philox_jitter3(v->cfg.seed, v->cfg.env_id0 + (uint64_t)i, ep, 0, (float)(2 * v->cfg.half_width), j);
+    qo_philox_jitter3(v->cfg.seed, env_gid(v, i), ep, 0, (float)(2 * v->cfg.half_width), j);
   }
   for (int k = 0; k < 3; k++) { volatile float p = base[k] + j[k]; sc[k] = (double)p; }
   sc[6] = 1.0;
-  st[0] = 10; st[1] = -50; st[2] = 5; st[6] = 1.0;
+  for (int k = 0; k < 3; k++) st[k] = (double)(float)v->P.target_ini_pos[k];
+  st[6] = 1.0;
 }
 
 static void hover_ini(const qo_vec* v, int64_t i, double s[13]) {
   /* hovering_env.py:23-29: pos [0,0,5]+U(-1,1)^3, euler U(-0.2,0.2)^3, sampled once per env */
   memset(s, 0, 13 * sizeof(double));
-  float base[3] = {0.f, 0.f, 5.f}, jp[3] = {0, 0, 0}, je[3] = {0, 0, 0};
+  float base[3] = {(float)v->P.chaser_ini_pos[0], (float)v->P.chaser_ini_pos[1], (float)v->P.chaser_ini_pos[2]}, jp[3] = {0, 0, 0}, je[3] = {0, 0, 0};
   if (v->cfg.randomize != QO_RAND_NONE) {
     uint32_t ep = v->cfg.randomize == QO_RAND_ONCE ? 0u : (uint32_t)v->episode[i];
-    qo_philox_jitter3(v->cfg.seed, v->cfg.env_id0 + (uint64_t)i, ep, 0, (float)(2 * v->cfg.half_width), jp);
-    qo_philox_jitter3(v->cfg.seed, v->cfg.env_id0 + (uint64_t)i, ep, 1, 0.4f, je);
+    qo_philox_jitter3(v->cfg.seed, env_gid(v, i), ep, 0, (float)(2 * v->cfg.half_width), jp);
+    qo_philox_jitter3(v->cfg.seed, env_gid(v, i), ep, 1, 0.4f, je);
   }
   for (int k = 0; k < 3; k++) { volatile float p = base[k] + jp[k]; s[k] = (double)p; }
   double e[3] = {(double)je[0], (double)je[1], (double)je[2]};
@@ -370,7 +377,7 @@ static void env_seat(qo_vec* v, int64_t i, double* obs) {
     dock_ini(v, i, v->chaser + 13 * i, v->target + 13 * i);
     memset(v->uc + 4 * i, 0, 4 * sizeof(double));
     memset(v->ut + 4 * i, 0, 4 * sizeof(double));
-    if (obs) qo_state2rel(v->chaser + 13 * i, v->target + 13 * i, obs);
+    if (obs) state2rel_p(&v->P, v->chaser + 13 * i, v->target + 13 * i, obs);
   }
   v->t[i] = 0;
   v->last_shaping[i] = 0.0;
@@ -380,6 +387,8 @@ static void env_seat(qo_vec* v, int64_t i, double* obs) {
 qo_vec* qo_vec_create(const qo_config* cfg) {
   qo_vec* v = (qo_vec*)calloc(1, sizeof(qo_vec));
   v->cfg = *cfg;
+  if (cfg->params) v->P = *cfg->params; else qo_default_params(cfg->kind, &v->P);
+  v->cfg.params = NULL;
   if (v->cfg.half_width <= 0) v->cfg.half_width = cfg->kind == QO_HOVER ? 1.0 : 0.5;
   v->obs_dim = cfg->kind == QO_HOVER ? 13 : 12;
   int64_t n = cfg->n_envs;
@@ -438,11 +447,13 @@ typedef struct { double ret, len, neps, ndock, nnonfinite; } acc_t;
 static void dock_step_one(qo_vec* v, int64_t i, const double* a, double* obs, double* reward, uint8_t* done,
                           uint8_t* info, double* term_obs, acc_t* acc) {
   const int v2 = v->cfg.kind == QO_DOCK_V2;
+  const qo_params* P = &v->P;
+  const double QO_MASS = P->mass, QO_G = P->gravity, QO_L = P->arm_length;
   double* sc = v->chaser + 13 * i;
   double* st = v->target + 13 * i;
   v->t[i] += 1; /* docking_env.py:108 */
   /* docking_env.py:98-99,115: rotor2control @ (action_std*a + action_mean); rotor2control quadrotor.py:56-59 */
-  const double half = 1.0 * QO_MASS * QO_G / 2.0, lam = QO_KM / QO_KF;
+  const double half = 1.0 * QO_MASS * QO_G / 2.0, lam = P->motor_lambda;
   double f[4], u_c[4], u_t[4];
   for (int k = 0; k < 4; k++) f[k] = half * a[k] + half;
   u_c[0] = f[0] + f[1] + f[2] + f[3];
@@ -450,20 +461,21 @@ static void dock_step_one(qo_vec* v, int64_t i, const double* a, double* obs, do
   u_c[2] = (-QO_L) * f[0] + 0 * f[1] + QO_L * f[2] + 0 * f[3];
   u_c[3] = lam * f[0] + (-lam) * f[1] + lam * f[2] + (-lam) * f[3];
   /* target_state_des: docking_env.py:60-64 / moving_docking_env.py:59-66 ; des[6:10] persists (Q4) */
-  double des[13] = {10, -50, 5, v2 ? 0.2 : 0.0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double des[13] = {P->target_des_pos[0], P->target_des_pos[1], P->target_des_pos[2], P->target_des_vel[0], P->target_des_vel[1],
+                    P->target_des_vel[2], 0, 0, 0, 0, 0, 0, 0};
   memcpy(des + 6, v->desq + 4 * i, 4 * sizeof(double));
-  if (v2) qo_vel_controller(des, st, st, u_t); /* moving_docking_env.py:117,126 -- last IS now (Q5) */
-  else qo_pid(des, st, u_t);                   /* docking_env.py:119 */
+  if (v2) vel_controller_p(P, des, st, st, u_t); /* moving_docking_env.py:117,126 -- last IS now (Q5) */
+  else pid_p(P, des, st, u_t);                   /* docking_env.py:119 */
   memcpy(v->desq + 4 * i, des + 6, 4 * sizeof(double));
-  qo_drone_step(st, v->ut + 4 * i, u_t); /* :120 */
-  qo_drone_step(sc, v->uc + 4 * i, u_c); /* :121 */
+  drone_step_p(P, st, v->ut + 4 * i, u_t); /* :120 */
+  drone_step_p(P, sc, v->uc + 4 * i, u_c); /* :121 */
   double rel[12];
-  qo_state2rel(sc, st, rel); /* :124-127 */
-  const double d10 = deg2rad(10);
-  int docking = norm3(rel) < 0.1 && norm3(rel + 3) < 0.1 && fabs(rel[6]) < d10 && fabs(rel[7]) < d10 && fabs(rel[8]) < d10;
-  const double radius = v2 ? 10.0 : 3.0; /* docking_env.py:141 / moving_docking_env.py:148 */
-  int overlimit = norm3(rel) >= radius || sc[2] <= 0.1;
-  int overtime = v->t[i] >= 600;
+  state2rel_p(P, sc, st, rel); /* :124-127 */
+  const double d10 = deg2rad(P->dock_angle_deg);
+  int docking = norm3(rel) < P->dock_pos_tol && norm3(rel + 3) < P->dock_vel_tol && fabs(rel[6]) < d10 && fabs(rel[7]) < d10 && fabs(rel[8]) < d10;
+  const double radius = P->range_limit; /* docking_env.py:141 (3) / moving_docking_env.py:148 (10) */
+  int overlimit = norm3(rel) >= radius || sc[2] <= P->min_altitude;
+  int overtime = v->t[i] >= P->max_steps;
   int dn = overlimit || overtime;
   double ra = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3]);
   double x[3], y[3];
@@ -496,15 +508,17 @@ static void dock_step_one(qo_vec* v, int64_t i, const double* a, double* obs, do
 static void hover_step_one(qo_vec* v, int64_t i, const double* a, double* obs, double* reward, uint8_t* done,
                            uint8_t* info, double* term_obs, acc_t* acc) {
   double* s = v->chaser + 13 * i;
+  const qo_params* P = &v->P;
+  const double QO_MASS = P->mass, QO_G = P->gravity, QO_L = P->arm_length;
   v->t[i] += 1;
-  const double amax = 1.0 * QO_MASS * QO_G, lam = QO_KM / QO_KF;
+  const double amax = 1.0 * QO_MASS * QO_G, lam = P->motor_lambda;
   double f[4], u[4];
   for (int k = 0; k < 4; k++) f[k] = amax * a[k];
   u[0] = f[0] + f[1] + f[2] + f[3];
   u[1] = 0 * f[0] + QO_L * f[1] + 0 * f[2] + (-QO_L) * f[3];
   u[2] = (-QO_L) * f[0] + 0 * f[1] + QO_L * f[2] + 0 * f[3];
   u[3] = lam * f[0] + (-lam) * f[1] + lam * f[2] + (-lam) * f[3];
-  qo_drone_step(s, v->uc + 4 * i, u);
+  drone_step_p(P, s, v->uc + 4 * i, u);
   const double des_p[3] = {0, 0, 5};
   double pe[3], ve[3], ae[3], we[3], ed[3], en[3];
   const double qd[4] = {1, 0, 0, 0};
@@ -512,7 +526,7 @@ static void hover_step_one(qo_vec* v, int64_t i, const double* a, double* obs, d
   qo_quat2euler(s + 6, en);
   for (int k = 0; k < 3; k++) { pe[k] = des_p[k] - s[k]; ve[k] = 0 - s[3 + k]; ae[k] = ed[k] - en[k]; we[k] = 0 - s[10 + k]; }
   double r_thre = (norm3(pe) < 0.1 && norm3(ve) < 0.1) ? 1.0 : 0.0;
-  int dn = norm3(s) > 100 || norm3(s + 3) > 100;
+  int dn = norm3(s) > P->range_limit || norm3(s + 3) > P->range_limit;
   double r;
   if (!dn) r = r_thre + 0.1 - 0.01 * norm3(pe) - 0.001 * norm3(ve) - 0.01 * norm3(ae) - 0.001 * norm3(we);
   else r = -0.1;

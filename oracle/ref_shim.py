@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE ONLY -- import shim for the *unmodified* reference (sd196821/QuadSim).
 
-Only usable where ``/root/reference`` exists (the build container, never the GPU box).  It is used by
-``tests/golden/make_golden.py`` (to generate the committed fixtures) and by the optional
-``tests/test_oracle_vs_live_reference.py`` (skipped when the reference tree is absent).  Nothing in
-``quadsim_b200/`` may import this module.
+Usable where ``/root/reference`` exists (the build container) or where ``oracle/make_ref.py`` has staged the six
+hot-path files under ``oracle/_ref/`` (git-ignored; it travels to the GPU box with the snapshot, so bench.py's
+cpu_baseline leg can time the unmodified reference there).  It is used by ``tests/golden/make_golden.py`` (to generate
+the committed fixtures), by ``oracle/ref_bench.py`` and by the live-reference tests (skipped when neither tree is
+present).  Nothing in ``quadsim_b200/`` may import this module.
 
 The reference's env modules ``import gym`` / ``evdev`` / ``server.pub_server`` at import time
 (gym-docking/gym_docking/envs/docking_env.py:1-3, controller/__init__.py:2,
@@ -16,11 +17,24 @@ import types
 
 import numpy as np
 
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 REF_ROOT = os.environ.get("QUADSIM_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "dynamics")) and os.path.isdir(os.path.join(STAGED_ROOT, "dynamics")):
+    REF_ROOT = STAGED_ROOT  # the GPU box: only the staged copy of the hot-path files exists
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "dynamics"))
+
+
+def use_staged():
+    """Point the shim at oracle/_ref/ even where the full tree exists (bench.py: measure the same files everywhere)."""
+    global REF_ROOT
+    if _installed:
+        raise RuntimeError("ref_shim.use_staged() must be called before install()")
+    if not os.path.isdir(os.path.join(STAGED_ROOT, "dynamics")):
+        raise RuntimeError("oracle/_ref is not staged: run `python oracle/make_ref.py` where /root/reference exists")
+    REF_ROOT = STAGED_ROOT
 
 
 def _mod(name, **attrs):
@@ -67,6 +81,8 @@ def install():
     srv = _mod("server", pub_server=pub)
     srv.__path__ = []
     sys.path[:0] = [REF_ROOT, os.path.join(REF_ROOT, "gym-docking")]
+    for name in [m for m in sys.modules if m == "gym_docking" or m.startswith("gym_docking.")]:
+        del sys.modules[name]  # this repository ships a drop-in of the same name: the reference's must be the one imported
     _installed = True
 
 

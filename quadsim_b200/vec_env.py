@@ -160,15 +160,21 @@ class QuadVecEnv:
         return VecInfo(self, bits, term, tc, tt) if (bits is not None or term is not None or tc is not None) else None
 
     def _out(self):
+        """Output tensors of the next step.  reuse_buffers: False = fresh tensors every step; True / 1 = one set overwritten
+        in place; k > 1 = k sets used round-robin (a result stays valid for k - 1 further steps)."""
         if not self.reuse_buffers:
             return self._new_bufs()
         if self._bufs is None:
-            self._bufs = self._new_bufs()
-            obs, rew, done, bits, term, tc, tt, extras = self._bufs
-            ret = (obs, rew, done.view(torch.bool), self._info(bits, term, tc, tt))
-            self._fast = ((self.num_envs, 4), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
-                          C.byref(extras) if extras is not None else None, ret)
-        return self._bufs
+            self._bufs, self._fast, self._turn = [], [], 0
+            for _ in range(max(int(self.reuse_buffers), 1)):
+                b = self._new_bufs()
+                obs, rew, done, bits, term, tc, tt, extras = b
+                ret = (obs, rew, done.view(torch.bool), self._info(bits, term, tc, tt))
+                self._bufs.append(b)
+                self._fast.append(((self.num_envs, 4), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                   C.byref(extras) if extras is not None else None, ret))
+        self._turn = (self._turn + 1) % len(self._bufs)
+        return self._bufs[self._turn]
 
     @staticmethod
     def _ptr(t):
@@ -218,6 +224,9 @@ class QuadVecEnv:
         # straight to the C ABI -- the python side of a step drops from ~35 us to ~10 us, which is what bounds small batches
         # and the 35 us hover kernel
         f = self._fast
+        if f is not None:
+            self._turn = (self._turn + 1) % len(f)
+            f = f[self._turn]
         if (f is not None and type(actions) is torch.Tensor and actions.dtype == self.dtype and actions.device == self.device
                 and actions.shape == f[0] and actions.is_contiguous() and self._h is not None):
             if torch.cuda.current_device() == self.device.index:

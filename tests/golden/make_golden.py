@@ -23,6 +23,13 @@ Fixtures
   expert_v0.npz      the PID expert loop of run_expert_record.py:103-160 (generate_PID_expert_traj) on docking-v0, two episodes
                      (crosses a reset, so the scripts' state_des = env.chaser_ini_state aliasing is exercised)
   gae_numpy.npz      the GAE loop of Runner._run (ppo2.py:511-521) transcribed and run by numpy on float32 buffers
+  dock_v2_rand64.npz    64 envs x 160 steps of docking-v2 (observation-level record only): the fp32 flag-flip budget against
+                        the reference itself needs more than two envs
+  dock_v{0,2}_params.npz  tapes with NON-DEFAULT model parameters (mass, inertia, arm length, dt, gravity, motor constant,
+                        controller gains, set-points, start positions, dock-port offset) set on the unmodified reference's
+                        objects after construction -- pins the EnvParams path of the library (qs_env_params_t)
+  clamp_freerun.npz     H2 measured: docking-v2 envs started at attitudes that drive the chaser into the +-85 deg clamp, free
+                        running for 50 steps; records when the reference's clamp fired
 """
 import io
 import json
@@ -186,21 +193,58 @@ def gen_sim_pid():
 DOCK_BASE_C = np.array([8.0, -50.0, 5.0])
 
 
+def apply_params(env, prm):
+    """Set non-default model parameters on an UNMODIFIED reference env after construction: everything the reference keeps as
+    an attribute (Drone.__init__ quadrotor.py:10-63, controller.__init__ PIDController.py:10-44, DockingEnv.__init__
+    docking_env.py:34-99).  Derived attributes are recomputed with the reference's own expressions.  (Thresholds that are
+    literals inside step() -- range limit, docking tolerances, 600 steps, the 85/175 degree clamp -- cannot be changed
+    without editing the reference; those members of qs_env_params_t are checked against the C oracle only.)"""
+    for d in (env.chaser, env.target):
+        d.dt, d.gravity, d.mass, d.arm_length = prm["dt"], prm["gravity"], prm["mass"], prm["arm_length"]
+        d.Inertia = np.diag(prm["inertia"]).astype(np.float64)
+        d.F_max = 4 * d.mass * d.gravity                                    # quadrotor.py:21
+        d.motor_lambda = prm["motor_lambda"]                                # quadrotor.py:45
+        L, lam = d.arm_length, d.motor_lambda
+        d.A = np.array([[0.25, 0, -0.5 / L], [0.25, 0.5 / L, 0], [0.25, 0, 0.5 / L], [0.25, -0.5 / L, 0]])   # :47-50
+        d.B = np.array([[1, 1, 1, 1], [0, L, 0, -L], [-L, 0, L, 0]])                                            # :52-54
+        d.rotor2control = np.array([[1, 1, 1, 1], [0, L, 0, -L], [-L, 0, L, 0], [lam, -lam, lam, -lam]])       # :56-59
+    c = env.target_controller
+    c.kp_roll, c.kp_pitch, c.kp_yaw = prm["kp_att"]
+    c.kd_roll, c.kd_pitch, c.kd_yaw = prm["kd_att"]
+    c.kp_x, c.kp_y, c.kp_z = prm["kp_pos"]
+    c.kd_x, c.kd_y, c.kd_z = prm["kd_pos"]
+    c.kp_vx, c.kp_vy, c.kp_vz = prm["kp_vel"]
+    c.kd_vz = 0.0  # multiplied by (now - last) == 0 in the envs (SURVEY Q5); zeroed so the record cannot depend on it
+    c.g, c.mass = prm["gravity"], prm["mass"]                               # PIDController.py:43-44
+    env.action_mean = np.ones(4) * env.chaser.mass * env.chaser.gravity / 2.0   # docking_env.py:98-99
+    env.action_std = np.ones(4) * env.chaser.mass * env.chaser.gravity / 2.0
+    env.chaser_dock_port = np.array([prm["dock_port"], 0.0, 0.0])            # docking_env.py:38
+    env.target_dock_port = np.array([-prm["dock_port"], 0.0, 0.0])           # :51
+    env.target_ini_state[0:3] = prm["target_ini_pos"]                        # :47
+    env.target_state_des[0:3] = prm["target_des_pos"]                        # :59
+    env.target_state_des[3:6] = prm["target_des_vel"]                        # moving_docking_env.py:62-66
+
+
 class DockTape:
     """Drive reference docking envs with an action source; record everything per step."""
 
-    def __init__(self, kind, K, seed=None, env_id0=0, half_width=0.5):
+    def __init__(self, kind, K, seed=None, env_id0=0, half_width=0.5, params=None, light=False):
         self.kind = kind
         self.cls = R.DockingEnv if kind == 0 else R.MovingDockingEnv
         self.K, self.seed, self.env_id0, self.hw = K, seed, env_id0, half_width
         self.envs = [self.cls() for _ in range(K)]
         self.episode = [0] * K
+        self.params, self.light = params, light
+        self.base_c = DOCK_BASE_C.copy() if params is None else np.asarray(params["chaser_ini_pos"], dtype=np.float64)
+        if params is not None:
+            for e in self.envs:
+                apply_params(e, params)
 
     def ini_pos(self, k):
         if self.seed is None:
-            return DOCK_BASE_C.copy()
+            return self.base_c.copy()
         j = philox_jitter3(self.seed, self.env_id0 + k, self.episode[k], 0, 2 * self.hw)
-        return (DOCK_BASE_C.astype(np.float32) + j).astype(np.float64)
+        return (self.base_c.astype(np.float32) + j).astype(np.float64)
 
     def reset(self, k):
         env = self.envs[k]
@@ -237,6 +281,10 @@ class DockTape:
                     self.episode[k] += 1
                     obs, rec["ini_pos"][k, t] = self.reset(k)
                 rec["obs"][k, t] = obs
+        if self.light:
+            for k in ("chaser", "target", "u_c", "u_t", "des_q"):
+                del rec[k]
+            rec["actions"] = rec["actions"].astype(np.float32)  # float32-representable by construction
         rec["kind"] = np.int64(self.kind)
         rec["seed"] = np.int64(-1 if self.seed is None else self.seed)
         rec["env_id0"] = np.int64(self.env_id0)
@@ -258,6 +306,75 @@ def gen_dock_rand(kind, K=2, T=1000, seed=1234, env_id0=7):
     acts = rng.uniform(-1, 1, size=(K, T, 4)).astype(np.float32)
     tape = DockTape(kind, K, seed=seed, env_id0=env_id0)
     return tape.run(T, lambda k, t, o: acts[k, t])
+
+
+def gen_dock_rand64(kind=1, K=64, T=160, seed=4321, env_id0=1000):
+    rng = np.random.RandomState(300 + kind)
+    acts = rng.uniform(-1, 1, size=(K, T, 4)).astype(np.float32)
+    tape = DockTape(kind, K, seed=seed, env_id0=env_id0, light=True)
+    return tape.run(T, lambda k, t, o: acts[k, t])
+
+
+# non-default model parameters: every member of qs_env_params_t the reference keeps as an attribute
+PARAMS_ALT = dict(dt=0.015, gravity=9.5, mass=0.25, arm_length=0.1, inertia=[0.0003, 0.00028, 0.00045], motor_lambda=0.03,
+                  kp_att=[-8.0, -9.0, -7.5], kd_att=[4.0, 4.5, 3.0], kp_pos=[-1.2, -0.9, 40.0], kd_pos=[-1.5, -1.8, 7.0],
+                  kp_vel=[-0.6, -0.8, 1.2], chaser_ini_pos=[7.5, -49.0, 6.0], target_ini_pos=[10.5, -49.5, 5.5],
+                  target_des_pos=[10.0, -49.0, 5.0], target_des_vel=[0.15, 0.05, 0.0], dock_port=0.12)
+
+
+def gen_dock_params(kind, K=3, T=250, seed=77, env_id0=11):
+    prm = dict(PARAMS_ALT)
+    if kind == 0:
+        prm["target_des_vel"] = [0.0, 0.0, 0.0]  # docking-v0 keeps des vel 0 (docking_env.py:60-64)
+    rng = np.random.RandomState(400 + kind)
+    acts = rng.uniform(-1, 1, size=(K, T, 4)).astype(np.float32)
+    tape = DockTape(kind, K, seed=seed, env_id0=env_id0, params=prm)
+    rec = tape.run(T, lambda k, t, o: acts[k, t])
+    for k, v in prm.items():
+        rec["param_" + k] = np.asarray(v, dtype=np.float64)
+    assert rec["done"].sum() >= K  # every env crosses at least one auto-reset
+    return rec
+
+
+def gen_clamp_freerun(K=160, T=50, seed=5):
+    """SURVEY H2, measured: docking-v2 envs whose chaser starts at a large roll / pitch with a body rate pushing it through
+    the +-85 degree clamp (quadrotor.py:146-168).  After a clamp the state sits exactly ON the threshold and the reference's
+    own next decision is taken by the last ulp of quat2euler(euler2quat(.)); the record keeps, per step, whether the clamp
+    fired, so a test can measure how long an independent implementation stays on the reference's trajectory."""
+    rng = np.random.RandomState(seed)
+    T_ = R.transform
+    rec = dict(in_chaser=np.zeros((K, 13)), actions=np.zeros((K, T, 4), np.float32), chaser=np.zeros((K, T, 13)), clamp=np.zeros((K, T), np.uint8),
+               done=np.zeros((K, T), np.uint8))
+    for k in range(K):
+        env = R.MovingDockingEnv()
+        sc = np.zeros(13)
+        sc[0:3] = [8.0, -50.0, 5.0]
+        axis = k % 2
+        e = np.zeros(3)
+        e[axis] = rng.choice([-1, 1]) * np.deg2rad(rng.uniform(60, 84))
+        e[1 - axis] = np.deg2rad(rng.uniform(-20, 20))
+        e[2] = np.deg2rad(rng.uniform(-30, 30))
+        sc[6:10] = T_.euler2quat(e)
+        sc[10 + axis] = -np.sign(e[axis]) * rng.uniform(0.5, 4.0)  # the reference's kinematics (quadrotor.py:98-103): -w grows the angle
+        env.chaser_ini_state[:] = sc
+        env.reset()
+        rec["in_chaser"][k] = sc
+        acts = f32(rng.uniform(-0.2, 0.2, size=(T, 4)))
+        alive = True
+        for t in range(T):
+            if alive:
+                with np.errstate(invalid="ignore"):
+                    y = env.chaser.state + env.chaser.dt * env.chaser.df(env.chaser.state, env.chaser.u)
+                    ee = T_.quat2euler(y[6:10])
+                    fired = not (abs(ee[0]) <= np.deg2rad(85) and abs(ee[1]) <= np.deg2rad(85) and abs(ee[2]) <= np.deg2rad(175))
+                    o, r, d, info = env.step(acts[t])
+                rec["clamp"][k, t] = fired
+                rec["chaser"][k, t], rec["done"][k, t] = env.chaser.state, d
+                if d:
+                    alive = False  # no auto-reset here: the record ends with the episode
+            rec["actions"][k, t] = acts[t]
+    assert rec["clamp"].any(axis=1).mean() > 0.5
+    return rec
 
 
 def gen_dock_docked():
@@ -508,6 +625,10 @@ def main():
         "expert_v0": gen_expert_v0,
         "gae_numpy": gen_gae_numpy,
         "policy_v0": gen_policy_v0,
+        "dock_v2_rand64": gen_dock_rand64,
+        "dock_v0_params": lambda: gen_dock_params(0),
+        "dock_v2_params": lambda: gen_dock_params(1),
+        "clamp_freerun": gen_clamp_freerun,
     }
     only = sys.argv[1:]
     for name, fn in jobs.items():

@@ -14,6 +14,12 @@ def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
 
 
+def golden_params(g):
+    """The non-default model parameters a *_params fixture was recorded with (dict for OracleVecEnv / QuadVecEnv), or None."""
+    prm = {k[len("param_"):]: (v.tolist() if v.ndim else float(v)) for k, v in g.items() if k.startswith("param_")}
+    return prm or None
+
+
 def close(a, b, tol):
     a, b = np.asarray(a), np.asarray(b)
     assert a.shape == b.shape, (a.shape, b.shape)

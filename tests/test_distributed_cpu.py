@@ -23,6 +23,10 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     r, lr, w = D.init_from_env(backend="gloo")
     lo, hi = D.shard_range(1000, r, w)
+    # unequal shards (5 envs over 2 ranks = 3 / 2): the default global id of a rank's env 0 is the exclusive prefix sum of the
+    # ranks' env counts -- rank * num_envs would give rank 1 id0 = 2 and overlap rank 0's env 2
+    ulo, uhi = D.shard_range(5, r, w)
+    assert D.default_env_id0(uhi - ulo) == ulo == (0, 3)[r]
     stats = torch.tensor([1.5 * (r + 1), 10.0 * (r + 1), float(r + 1), 0.0, float(hi - lo)], dtype=torch.float64)
     red = D.all_reduce_stats(stats)
     mx = D.max_over_ranks(0.1 * (r + 1))

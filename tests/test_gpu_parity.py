@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from qs_testutil import close, load_golden
+from qs_testutil import close, golden_params, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -154,16 +154,17 @@ def _replay_tape(name, dtype, tol, flags_exact=True):
     env_id = {0: "docking-v0", 1: "docking-v2"}[int(g["kind"])]
     K, Tn = g["actions"].shape[:2]
     seed = int(g["seed"])
+    light = "chaser" not in g  # observation-level record only (dock_v2_rand64)
     env = qs.make_vec(env_id, K, dtype=dtype, seed=max(seed, 0), env_id0=int(g["env_id0"]),
                       randomize="episode" if seed >= 0 else "none", half_width=float(g["half_width"]),
-                      want_info=True, want_terminal_obs=True)
+                      want_info=True, want_terminal_obs=True, want_terminal_state=True, params=golden_params(g))
     obs0 = N(env.reset())
     assert rel_err(obs0, g["obs0"]) <= tol
     st = env.get_state()
     assert np.array_equal(N(st["chaser"])[:, :3], g["ini_pos0"])  # Philox start positions are bit-identical
     worst, alive = 0.0, np.ones(K, bool)
     for t in range(Tn):
-        obs, rew, done, info = env.step(T(g["actions"][:, t], dtype))
+        obs, rew, done, info = env.step(T(g["actions"][:, t].astype(np.float64), dtype))
         done = done.cpu().numpy()
         if flags_exact:
             assert np.array_equal(done, g["done"][:, t] != 0), t
@@ -176,11 +177,16 @@ def _replay_tape(name, dtype, tol, flags_exact=True):
         a = alive
         st = env.get_state()
         e = max(rel_err(N(obs)[a], g["obs"][a, t]), rel_err(N(info.terminal_observation)[a], g["term_obs"][a, t]),
-                rel_err(N(rew)[a], g["reward"][a, t]), rel_err(N(st["des_q"])[a], g["des_q"][a, t]))
+                rel_err(N(rew)[a], g["reward"][a, t]))
+        if not light:
+            e = max(e, rel_err(N(st["des_q"])[a], g["des_q"][a, t]))
         nd = a & ~done
-        if nd.any():
+        if nd.any() and not light:
             e = max(e, rel_err(N(st["chaser"])[nd], g["chaser"][nd, t]), rel_err(N(st["target"])[nd], g["target"][nd, t]),
                     rel_err(N(st["u_chaser"])[nd], g["u_c"][nd, t]), rel_err(N(st["u_target"])[nd], g["u_t"][nd, t]))
+        fin = a & done
+        if fin.any() and not light:  # info['chaser'] / info['target'] of the terminal step: the kernel's terminal_* rows
+            e = max(e, rel_err(N(info.terminal_chaser)[fin], g["chaser"][fin, t]), rel_err(N(info.terminal_target)[fin], g["target"][fin, t]))
         for k in np.nonzero(done & a)[0]:
             assert np.array_equal(N(st["chaser"])[k, :3], g["ini_pos"][k, t]), (k, t)
         worst = max(worst, e)
@@ -189,17 +195,27 @@ def _replay_tape(name, dtype, tol, flags_exact=True):
     return worst, alive
 
 
-@pytest.mark.parametrize("name", ["dock_v0_kat", "dock_v2_kat", "dock_v0_rand", "dock_v2_rand", "dock_v0_docked"])
+TAPES = ["dock_v0_kat", "dock_v2_kat", "dock_v0_rand", "dock_v2_rand", "dock_v0_docked", "dock_v2_rand64"]
+
+
+@pytest.mark.parametrize("name", TAPES)
 def test_reference_tapes_fp64(name):
     worst, _ = _replay_tape(name, torch.float64, 1e-9)
     print(name, "fp64 worst err", worst)
 
 
-@pytest.mark.parametrize("name", ["dock_v0_kat", "dock_v2_kat", "dock_v0_rand", "dock_v2_rand", "dock_v0_docked"])
+@pytest.mark.parametrize("name", TAPES)
 def test_reference_tapes_fp32(name):
+    """fp32 against the reference's own tapes with an explicit flag-flip budget: an env whose done flag differs from the
+    reference's at any step counts as one flip (and is out of phase from then on); at most 1e-4 of the tape's env-steps may
+    flip -- zero for the 1- and 2-env tapes, one for the 64-env x 160-step tape (a flip needs the fp64 state
+    within fp32 rounding of a threshold, ~4e-5 per episode end)."""
+    g = load_golden(name)
+    K, Tn = g["actions"].shape[:2]
     worst, alive = _replay_tape(name, torch.float32, 1e-4, flags_exact=False)
-    print(name, "fp32 worst rel err", worst, "envs still in phase", alive.sum(), "/", alive.size)
-    assert alive.any()
+    flips = int((~alive).sum())
+    print(name, "fp32 worst rel err", worst, "flag flips", flips, "of", K, "envs x", Tn, "steps")
+    assert flips <= int(1e-4 * K * Tn), (flips, K, Tn)
 
 
 @pytest.mark.parametrize("v", [0, 2])

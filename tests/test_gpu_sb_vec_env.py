@@ -20,6 +20,11 @@ def test_sb_vec_env_replays_reference_tape(name, env_id):
     K, T = g["actions"].shape[:2]
     env = SBVecEnv(env_id, K, seed=int(g["seed"]), env_id0=int(g["env_id0"]), randomize="episode", half_width=float(g["half_width"]))
     assert env.num_envs == K and env.observation_space.shape == (12,) and env.action_space.shape == (4,)
+    # the Box bounds themselves, not only the shapes: docking_env.py:84-95
+    lo = np.array([-np.inf, -np.inf, -np.inf, -100, -100, -100, -np.pi, -np.pi / 2, -np.pi, -10 * np.pi, -10 * np.pi, -10 * np.pi], np.float32)
+    assert np.array_equal(env.observation_space.low, lo) and np.array_equal(env.observation_space.high, -lo)
+    assert env.observation_space.dtype == np.float32 and env.action_space.dtype == np.float32
+    assert np.array_equal(env.action_space.low, -np.ones(4, np.float32)) and np.array_equal(env.action_space.high, np.ones(4, np.float32))
     obs = env.reset()
     assert obs.dtype == np.float32 and obs.shape == (K, 12) and np.allclose(obs, g["obs0"], atol=1e-6)
     n_done = 0
@@ -35,7 +40,9 @@ def test_sb_vec_env_replays_reference_tape(name, env_id):
             if done[k]:
                 n_done += 1
                 assert np.allclose(info["terminal_observation"], g["term_obs"][k, t], atol=2e-6, rtol=1e-6)
-                assert np.array_equal(info["chaser"][:3], g["ini_pos"][k, t])  # re-seated (documented in sb_vec_env.py)
+                # like the reference's, the info dict of a finished env describes the TERMINAL step (docking_env.py:226-229):
+                # the pre-reset 13-states come from the kernel's terminal_chaser / terminal_target rows
+                assert np.max(np.abs(info["chaser"] - g["chaser"][k, t])) < 1e-9 and np.max(np.abs(info["target"] - g["target"][k, t])) < 1e-9
             else:
                 assert np.max(np.abs(info["chaser"] - g["chaser"][k, t])) < 1e-9 and np.max(np.abs(info["target"] - g["target"][k, t])) < 1e-9
     assert n_done >= 4
@@ -61,4 +68,15 @@ def test_sb_vec_env_monitor_episode_info():
                 assert infos[k]["episode"]["l"] == length[k] and abs(infos[k]["episode"]["r"] - ret[k]) < 1e-6
                 ret[k], length[k], seen = 0.0, 0, seen + 1
     assert seen >= 4
+    env.close()
+
+
+def test_hover_spaces_match_reference():
+    """hovering-v0: observation Box = Drone.state_lim_low/high (dynamics/quadrotor.py:35-39 via hovering_env.py:36-40), action
+    Box = [0, 1]^4 (hovering_env.py:42)."""
+    env = SBVecEnv("hovering-v0", 4)
+    lo = np.array([-100, -100, 0, -100, -100, -100, -100, -100, -100, -100, -10 * 2 * np.pi, -10 * 2 * np.pi, -10 * 2 * np.pi], np.float32)
+    hi = np.array([100] * 10 + [10 * 2 * np.pi] * 3, np.float32)
+    assert np.array_equal(env.observation_space.low, lo) and np.array_equal(env.observation_space.high, hi)
+    assert np.array_equal(env.action_space.low, np.zeros(4, np.float32)) and np.array_equal(env.action_space.high, np.ones(4, np.float32))
     env.close()

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from qs_testutil import GOLDEN, close, load_golden
+from qs_testutil import GOLDEN, close, golden_params, load_golden
 
 
 @pytest.fixture(scope="module")
@@ -94,8 +94,10 @@ def _replay_dock(name, tol=1e-9):
     kind = {0: O.DOCK_V0, 1: O.DOCK_V2}[int(g["kind"])]
     K, T = g["actions"].shape[:2]
     seed = int(g["seed"])
+    light = "chaser" not in g  # observation-level record only (dock_v2_rand64)
     env = O.OracleVecEnv(kind, K, seed=max(seed, 0), env_id0=int(g["env_id0"]),
-                         randomize=O.RAND_EPISODE if seed >= 0 else O.RAND_NONE, half_width=float(g["half_width"]))
+                         randomize=O.RAND_EPISODE if seed >= 0 else O.RAND_NONE, half_width=float(g["half_width"]),
+                         params=golden_params(g))
     obs0 = env.reset()
     close(obs0, g["obs0"], 1e-13)
     close(env.field("chaser")[:, :3], g["ini_pos0"], 0.0)
@@ -106,9 +108,11 @@ def _replay_dock(name, tol=1e-9):
         assert np.array_equal((info & O.INFO_DOCKING) != 0, g["docking"][:, t] != 0), t
         assert np.array_equal((info & O.INFO_OVERLIMIT) != 0, g["overlimit"][:, t] != 0), t
         e = max(np.max(np.abs(obs - g["obs"][:, t])), np.max(np.abs(term - g["term_obs"][:, t])),
-                np.max(np.abs(rew - g["reward"][:, t])), np.max(np.abs(env.field("des_q") - g["des_q"][:, t])))
+                np.max(np.abs(rew - g["reward"][:, t])))
+        if not light:
+            e = max(e, np.max(np.abs(env.field("des_q") - g["des_q"][:, t])))
         nd = done == 0  # after a done the oracle holds the re-seated state, the tape the terminal one
-        if nd.any():
+        if nd.any() and not light:
             e = max(e, np.max(np.abs(env.field("chaser")[nd] - g["chaser"][nd, t])),
                     np.max(np.abs(env.field("target")[nd] - g["target"][nd, t])),
                     np.max(np.abs(env.field("u_c")[nd] - g["u_c"][nd, t])),
@@ -120,10 +124,15 @@ def _replay_dock(name, tol=1e-9):
     return g, worst
 
 
-@pytest.mark.parametrize("name", ["dock_v0_kat", "dock_v2_kat", "dock_v0_rand", "dock_v2_rand", "dock_v0_docked"])
+@pytest.mark.parametrize("name", ["dock_v0_kat", "dock_v2_kat", "dock_v0_rand", "dock_v2_rand", "dock_v0_docked", "dock_v2_rand64",
+                                  "dock_v0_params", "dock_v2_params"])
 def test_dock_tapes(name):
+    """`*_params`: tapes recorded with NON-default mass / inertia / arm length / dt / gravity / motor constant / gains /
+    set-points / start positions / dock-port offset on the unmodified reference (make_golden.apply_params)."""
     g, worst = _replay_dock(name)
     print(name, "worst abs err", worst)
+    if name.endswith("_params"):
+        assert golden_params(g)["mass"] == 0.25 and g["done"].sum() >= g["actions"].shape[0]
     if name == "dock_v0_docked":
         assert g["docking"].sum() == 183 and g["done"][0, 599] == 1  # docked + overtime branches exercised
 
@@ -151,6 +160,36 @@ def test_dock_wild_single_step(v):
     close(env.field("u_c")[nd], g["out_u_c"][nd], 1e-12)
     close(env.field("u_t")[nd], g["out_u_t"][nd], 1e-10)
     assert done.sum() > 20 and (info & O.INFO_DOCKING).astype(bool).sum() > 10
+
+
+def test_clamp_freerun_h2_measured():
+    """SURVEY H2, measured instead of argued.  160 docking-v2 envs are driven into the +-85 degree attitude clamp
+    (quadrotor.py:146-168).  Until an env's first clamp the oracle must sit on the reference's trajectory (1e-9); from then
+    on the clamped state lies exactly ON the threshold and the reference's own next decision is taken by the last ulp of
+    numpy's arctan2/arcsin (SVML) -- the fraction of envs that leave the reference's trajectory afterwards is reported, and
+    must be what makes H2 a limitation: neither zero (then there would be nothing to document) nor everything."""
+    g = load_golden("clamp_freerun")
+    K, T = g["actions"].shape[:2]
+    env = O.OracleVecEnv(O.DOCK_V2, K, auto_reset=False)
+    env.reset()
+    env.field("chaser")[...] = g["in_chaser"]
+    first = np.where(g["clamp"].any(axis=1), g["clamp"].argmax(axis=1), T)
+    alive = np.ones(K, bool)
+    diverged_at = np.full(K, -1)
+    for t in range(T):
+        env.step(g["actions"][:, t].astype(np.float64))
+        err = np.max(np.abs(env.field("chaser") - g["chaser"][:, t]), axis=1)
+        pre = alive & (t < first)
+        assert err[pre].max(initial=0.0) <= 1e-9, (t, err[pre].max())
+        new = alive & (t >= first) & (err > 1e-6) & (diverged_at < 0)
+        diverged_at[new] = t
+        alive &= g["done"][:, t] == 0
+    clamped = first < T
+    frac = float((diverged_at >= 0)[clamped].mean())
+    print("H2: %d of %d envs clamp; %.1f %% of those leave the reference's trajectory within %d steps (first clamp at step %.1f on average)"
+          % (clamped.sum(), K, 100 * frac, T, first[clamped].mean()))
+    assert clamped.sum() >= K // 2
+    assert 0.0 <= frac < 0.9
 
 
 def test_hover_tape():
