@@ -22,6 +22,8 @@
 #include <stdint.h>
 #include <math.h>
 
+#include "../../include/quadsim_b200.h"  // qs_env_params_t
+
 #if defined(__CUDACC__)
 #define QS_HD __host__ __device__ __forceinline__
 #else
@@ -30,7 +32,18 @@
 
 namespace qs {
 
+template <typename T> constexpr bool is_f32_v() { return sizeof(T) == 4; }
+
 // ---- physical constants: dynamics/quadrotor.py:10-63 ; gains: controller/PIDController.py:10-44 ----
+// K<T>: the reference's literals.  Only pi is read from it directly; everything a caller may override goes through a
+// *parameter provider* P (first argument of every model function below):
+//   DefaultParams<T, KIND>  every member a static constexpr -> the literals end up as immediates, exactly as before
+//                           parameters existed (handles created with use_params = 0);
+//   RuntimeParams<T>        the same member names as plain data, filled on the host from qs_env_params_t
+//                           (make_runtime_params) and handed to the kernel as a __grid_constant__ parameter, i.e. read
+//                           from the constant bank as an instruction operand (handles created with use_params = 1).
+// Both spell `p.mass`, so the model code is written once.  Derived members (reciprocals, m*g, thresholds of the
+// transcendental-free clamp pre-test ...) are part of the provider so that the division / sin / tan happens once on the host.
 template <typename T> struct K {
   static constexpr T dt = T(0.02), g = T(9.81), mass = T(0.18), L = T(0.086);
   static constexpr T I0 = T(0.00025), I1 = T(0.000232), I2 = T(0.0003738);
@@ -44,6 +57,102 @@ template <typename T> struct K {
   static constexpr T kp_x = T(-1), kp_y = T(-1), kp_z = T(50), kd_x = T(-1.65), kd_y = T(-1.65), kd_z = T(8);
   static constexpr T kp_vx = T(-0.7), kp_vy = T(-0.7), kp_vz = T(1);
 };
+
+constexpr int kHover = 0, kDockV0 = 1, kDockV2 = 2;                 // == qs_env_kind
+
+// Docking positions are ~50 m from the world origin (y = -50) while everything the env computes from them is a
+// difference of a few metres.  The fp32 path therefore keeps both drones' positions RELATIVE to the fixed point
+// O = the target's start (10,-50,5) (== docking-v0 set-point, docking_env.py:47,59): the dynamics are translation invariant,
+// so this is the same trajectory with ~10x smaller position rounding.  The fp64 path stays in world coordinates
+// (literal).  State export/import (always float64) converts, exactly, at the boundary.
+template <typename T> struct Origin { static constexpr T x = T(0), y = T(0), z = T(0); };
+#ifndef QS_LITERAL32
+template <> struct Origin<float> { static constexpr float x = 10.f, y = -50.f, z = 5.f; };
+#endif
+
+// arithmetic type the constants of a provider are folded in (sdouble, the speculative fp64 type below, folds in double)
+struct sdouble;
+template <typename T> struct Arith { using type = T; };
+template <> struct Arith<sdouble> { using type = double; };
+
+template <typename T, int KIND = kDockV2> struct DefaultParams {
+  using A = typename Arith<T>::type;
+  using C = K<A>;
+  using O = Origin<A>;
+  static constexpr bool custom = false;
+  // plant (quadrotor.py:10-63)
+  static constexpr T dt = T(C::dt), mass = T(C::mass), g = T(C::g), L = T(C::L), lam = T(C::lam), mg = T(C::mg);
+  static constexpr T inv_m = T(A(1.0) / C::mass), mass_x_g = T(C::mass * C::g), inv_g = T(A(1) / C::g), hl = T(A(0.5 / 0.086));
+  static constexpr T I0 = T(C::I0), I1 = T(C::I1), I2 = T(C::I2), inv_I0 = T(A(1) / C::I0), inv_I1 = T(A(1) / C::I1), inv_I2 = T(A(1) / C::I2);
+  // attitude_limit (quadrotor.py:146-168): limits in radians; sin / tan forms for the transcendental-free pre-test
+  static constexpr T lim_roll = T(C::d85), lim_pitch = T(C::d85), lim_yaw = T(C::d175);
+  static constexpr T s_roll = T(A(0.99619469809174555)), t_pitch = T(A(11.430052302761343)), t_yaw = T(A(0.087488663525924007));
+  // controller gains (PIDController.py:10-44)
+  static constexpr T kp_roll = T(C::kp_roll), kp_pitch = T(C::kp_pitch), kp_yaw = T(C::kp_yaw);
+  static constexpr T kd_roll = T(C::kd_roll), kd_pitch = T(C::kd_pitch), kd_yaw = T(C::kd_yaw);
+  static constexpr T kp_x = T(C::kp_x), kp_y = T(C::kp_y), kp_z = T(C::kp_z), kd_x = T(C::kd_x), kd_y = T(C::kd_y), kd_z = T(C::kd_z);
+  static constexpr T kp_vx = T(C::kp_vx), kp_vy = T(C::kp_vy), kp_vz = T(C::kp_vz);
+  // environment (docking_env.py:34-99,130-152 ; moving_docking_env.py:62-66,148 ; hovering_env.py:23,42,68)
+  static constexpr T half = T(A(1.0 * 0.18 * 9.81 / 2.0));                // action_mean = action_std = m g / 2
+  static constexpr T port = T(A(0.1)), port2 = T(A(-0.2));                // chaser port +d, target port -d; -d - d
+  static constexpr T tol_pos = T(A(0.1)), tol_vel = T(A(0.1)), d10 = T(C::d10);
+  static constexpr T radius = T(KIND == kHover ? A(100) : (KIND == kDockV0 ? A(3) : A(10)));
+  static constexpr T ten_over_radius = T(A(10) / (KIND == kDockV0 ? A(3) : A(10)));
+  static constexpr T z_floor = T(A(0.1 - (double)O::z));
+  static constexpr int max_steps = 600;
+  static constexpr T ox = T(O::x), oy = T(O::y), oz = T(O::z);
+  static constexpr float cini_x = KIND == kHover ? 0.f : 8.f, cini_y = KIND == kHover ? 0.f : -50.f, cini_z = 5.f;
+  static constexpr T tini_x = T(A(10) - O::x), tini_y = T(A(-50) - O::y), tini_z = T(A(5) - O::z);
+  static constexpr T des_px = T(A(10) - O::x), des_py = T(A(-50) - O::y), des_pz = T(A(5) - O::z);
+  static constexpr T des_vx = T(KIND == kDockV2 ? A(0.2) : A(0)), des_vy = T(A(0)), des_vz = T(A(0));
+};
+
+template <typename T> struct RuntimeParams {
+  static constexpr bool custom = true;
+  T dt, mass, g, L, lam, mg, inv_m, mass_x_g, inv_g, hl, I0, I1, I2, inv_I0, inv_I1, inv_I2;
+  T lim_roll, lim_pitch, lim_yaw, s_roll, t_pitch, t_yaw;
+  T kp_roll, kp_pitch, kp_yaw, kd_roll, kd_pitch, kd_yaw, kp_x, kp_y, kp_z, kd_x, kd_y, kd_z, kp_vx, kp_vy, kp_vz;
+  T half, port, port2, tol_pos, tol_vel, d10, radius, ten_over_radius, z_floor;
+  T ox, oy, oz, tini_x, tini_y, tini_z, des_px, des_py, des_pz, des_vx, des_vy, des_vz;
+  float cini_x, cini_y, cini_z;
+  int max_steps;
+};
+
+// Host side: qs_env_params_t -> RuntimeParams<T>.  Every derived member is formed the way the constexpr provider forms it
+// (products of doubles rounded once to T where the literal was a double expression; T arithmetic where it was T arithmetic),
+// so a RuntimeParams built from qs_default_params() reproduces the compiled-in constants bit for bit -- except the three
+// pre-test thresholds, which come from libm here and are pulled in by 2^-20 so that the pre-test can only over-trigger
+// the exact (out-of-line) clamp, never miss it.
+template <typename T> inline void make_runtime_params(const qs_env_params_t& in, int kind, RuntimeParams<T>& p) {
+  const double pi = 3.141592653589793;
+  p.dt = T(in.dt); p.mass = T(in.mass); p.g = T(in.gravity); p.L = T(in.arm_length); p.lam = T(in.motor_lambda);
+  p.mg = T(in.mass * in.gravity);
+  p.inv_m = T(1.0) / p.mass; p.mass_x_g = p.mass * p.g; p.inv_g = T(1) / p.g; p.hl = T(0.5 / in.arm_length);
+  p.I0 = T(in.inertia[0]); p.I1 = T(in.inertia[1]); p.I2 = T(in.inertia[2]);
+  p.inv_I0 = T(1) / p.I0; p.inv_I1 = T(1) / p.I1; p.inv_I2 = T(1) / p.I2;
+  const double lr = in.att_limit_deg[0] * pi / 180, lp = in.att_limit_deg[1] * pi / 180, ly = in.att_limit_deg[2] * pi / 180;
+  p.lim_roll = T(lr); p.lim_pitch = T(lp); p.lim_yaw = T(ly);
+  const double shrink = 1.0 - 9.5367431640625e-07;
+  p.s_roll = T(sin(lr) * shrink); p.t_pitch = T(tan(lp) * shrink); p.t_yaw = T(tan(pi - ly) / shrink);
+  p.kp_roll = T(in.kp_att[0]); p.kp_pitch = T(in.kp_att[1]); p.kp_yaw = T(in.kp_att[2]);
+  p.kd_roll = T(in.kd_att[0]); p.kd_pitch = T(in.kd_att[1]); p.kd_yaw = T(in.kd_att[2]);
+  p.kp_x = T(in.kp_pos[0]); p.kp_y = T(in.kp_pos[1]); p.kp_z = T(in.kp_pos[2]);
+  p.kd_x = T(in.kd_pos[0]); p.kd_y = T(in.kd_pos[1]); p.kd_z = T(in.kd_pos[2]);
+  p.kp_vx = T(in.kp_vel[0]); p.kp_vy = T(in.kp_vel[1]); p.kp_vz = T(in.kp_vel[2]);
+  p.half = T(1.0 * in.mass * in.gravity / 2.0);
+  p.port = T(in.dock_port); p.port2 = -p.port - p.port;
+  p.tol_pos = T(in.dock_pos_tol); p.tol_vel = T(in.dock_vel_tol); p.d10 = T(in.dock_angle_deg * pi / 180);
+  p.radius = T(in.range_limit); p.ten_over_radius = T(10) / p.radius;
+  const bool shifted = is_f32_v<T>() && kind != kHover;  // the fp32 docking layout is relative to the target's start position
+  const float o[3] = {shifted ? (float)in.target_ini_pos[0] : 0.f, shifted ? (float)in.target_ini_pos[1] : 0.f, shifted ? (float)in.target_ini_pos[2] : 0.f};
+  p.ox = T(o[0]); p.oy = T(o[1]); p.oz = T(o[2]);
+  p.z_floor = T(in.min_altitude - (double)o[2]);
+  p.cini_x = (float)in.chaser_ini_pos[0]; p.cini_y = (float)in.chaser_ini_pos[1]; p.cini_z = (float)in.chaser_ini_pos[2];
+  p.tini_x = T((float)in.target_ini_pos[0]) - p.ox; p.tini_y = T((float)in.target_ini_pos[1]) - p.oy; p.tini_z = T((float)in.target_ini_pos[2]) - p.oz;
+  p.des_px = T(in.target_des_pos[0]) - p.ox; p.des_py = T(in.target_des_pos[1]) - p.oy; p.des_pz = T(in.target_des_pos[2]) - p.oz;
+  p.des_vx = T(in.target_des_vel[0]); p.des_vy = T(in.target_des_vel[1]); p.des_vz = T(in.target_des_vel[2]);
+  p.max_steps = in.max_steps;
+}
 
 template <typename T> struct is_f32 { static constexpr bool value = false; };
 template <> struct is_f32<float> { static constexpr bool value = true; };
@@ -494,8 +603,8 @@ template <typename T> QS_HD Euler<T> rot2euler(T r12, T r10, T r11, T r02, T r22
 }
 
 // dynamics/quadrotor.py:171-187  u_limit: per-rotor thrust A@[F,Mx,My] clamped to [0, F_max/4 = m*g], Mz untouched
-template <typename T> QS_HD void u_limit(T F, T Mx, T My, T Mz, T& o0, T& o1, T& o2, T& o3) {
-  const T hl = T(0.5 / 0.086), L = K<T>::L, fmax = K<T>::mg;
+template <typename T, typename P> QS_HD void u_limit(const P& p, T F, T Mx, T My, T Mz, T& o0, T& o1, T& o2, T& o3) {
+  const T hl = p.hl, L = p.L, fmax = p.mg;
   T p0 = T(0.25) * F - hl * My;
   T p1 = T(0.25) * F + hl * Mx;
   T p2 = T(0.25) * F + hl * My;
@@ -509,10 +618,13 @@ template <typename T> QS_HD void u_limit(T F, T Mx, T My, T Mz, T& o0, T& o1, T&
   o2 = L * p2 - L * p0;
   o3 = Mz;
 }
+template <typename T> QS_HD void u_limit(T F, T Mx, T My, T Mz, T& o0, T& o1, T& o2, T& o3) {
+  u_limit(DefaultParams<T>{}, F, Mx, My, Mz, o0, o1, o2, o3);
+}
 
 // rotor thrusts -> [F, Mx, My, Mz]: rotor2control, dynamics/quadrotor.py:56-59
-template <typename T> QS_HD void rotor2control(T f0, T f1, T f2, T f3, T& F, T& Mx, T& My, T& Mz) {
-  const T L = K<T>::L, lam = K<T>::lam;
+template <typename T, typename P> QS_HD void rotor2control(const P& p, T f0, T f1, T f2, T f3, T& F, T& Mx, T& My, T& Mz) {
+  const T L = p.L, lam = p.lam;
   F = ((f0 + f1) + f2) + f3;
   Mx = L * f1 - L * f3;
   My = L * f2 - L * f0;
@@ -533,8 +645,8 @@ inline
 Quat<T> euler2quat_cold(T roll, T pitch, T yaw) { return euler2quat(roll, pitch, yaw); }
 
 template <typename T> struct ClampResult { T w, x, y, z; bool fired; };
-template <typename T> QS_HD ClampResult<T> attitude_clamp(T q0, T q1, T q2, T q3) {
-  using C = K<T>;
+template <typename T, typename P> QS_HD ClampResult<T> attitude_clamp(const P& p_, T q0, T q1, T q2, T q3) {
+  const T d85r = p_.lim_roll, d85p = p_.lim_pitch, d175 = p_.lim_yaw;
   ClampResult<T> out = {q0, q1, q2, q3, false};
   Euler<T> e = quat2euler(q0, q1, q2, q3);
   const T r = e.phi, p = e.theta, y = e.psi;
@@ -542,32 +654,31 @@ template <typename T> QS_HD ClampResult<T> attitude_clamp(T q0, T q1, T q2, T q3
     out.w = out.x = out.y = out.z = r + p + y; out.fired = true;
     return out;
   }
-  const bool cr = m_abs(r) >= C::d85, cp = m_abs(p) >= C::d85, cy = m_abs(y) >= C::d175;
-  const bool inside = m_abs(r) <= C::d85 && m_abs(p) <= C::d85 && m_abs(y) <= C::d175;
+  const bool cr = m_abs(r) >= d85r, cp = m_abs(p) >= d85p, cy = m_abs(y) >= d175;
+  const bool inside = m_abs(r) <= d85r && m_abs(p) <= d85p && m_abs(y) <= d175;
   if (!(cr || cp || cy) || inside) return out;
   T lr = r, lp = p, ly = y;
-  if (cy) ly = m_sign(y) * C::d175;
-  else if (cp) lp = m_sign(p) * C::d85;
-  else lr = m_sign(r) * C::d85;
+  if (cy) ly = m_sign(y) * d175;
+  else if (cp) lp = m_sign(p) * d85p;
+  else lr = m_sign(r) * d85r;
   Quat<T> lim = euler2quat_cold(lr, lp, ly);
   out.w = lim.w; out.x = lim.x; out.y = lim.y; out.z = lim.z; out.fired = true;
   return out;
 }
 // out-of-line copy for the fp32 fast path, where the clamp is a cold branch behind a transcendental-free pre-test
 // (by-value in/out so the caller's drone state never has to live in local memory)
-template <typename T>
+template <typename T, typename P>
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
 #else
 inline
 #endif
-ClampResult<T> attitude_clamp_cold(T q0, T q1, T q2, T q3) { return attitude_clamp(q0, q1, q2, q3); }
+ClampResult<T> attitude_clamp_cold(const P& p, T q0, T q1, T q2, T q3) { return attitude_clamp(p, q0, q1, q2, q3); }
 
 // dynamics/quadrotor.py:126-144  Drone.step(u_cmd): Euler step with frozen RHS df(state, u_prev) (:80-113),
 // attitude_limit (:146-168), then u_prev <- u_limit(u_cmd).  Returns true if the attitude clamp fired.
-template <typename T> QS_HD bool drone_step(Drone<T>& d, T c0, T c1, T c2, T c3) {
-  using C = K<T>;
-  const T dt = C::dt;
+template <typename T, typename P> QS_HD bool drone_step(const P& p, Drone<T>& d, T c0, T c1, T c2, T c3) {
+  const T dt = p.dt;
   // --- df: quadrotor.py:80-113 ---
   T ss = d.q0 * d.q0 + d.q1 * d.q1 + d.q2 * d.q2 + d.q3 * d.q3;
   T n1, n2;
@@ -575,8 +686,8 @@ template <typename T> QS_HD bool drone_step(Drone<T>& d, T c0, T c1, T c2, T c3)
   else { T n = m_sqrt(ss); n1 = d.q1 / n; n2 = d.q2 / n; }
   T w2 = T(2) * d.q0;
   T r20 = (T(2) * n2) * n2 - w2 * n2, r21 = (T(2) * n1) * n1 + w2 * n1;
-  const T inv_m = T(1.0) / C::mass;
-  T ax = inv_m * (r20 * d.u0), ay = inv_m * (r21 * d.u0), az = inv_m * (d.u0 - C::mg);
+  const T inv_m = p.inv_m;
+  T ax = inv_m * (r20 * d.u0), ay = inv_m * (r21 * d.u0), az = inv_m * (d.u0 - p.mg);
   T e2 = T(2) * (T(1) - ss);  // K_quat * e_quat, quadrotor.py:96-97
   T sk0 = -d.wx * d.q1 - d.wy * d.q2 - d.wz * d.q3;  // q_sk @ q, quadrotor.py:98-103
   T sk1 = d.wx * d.q0 - d.wy * d.q2 + d.wz * d.q3;
@@ -585,10 +696,10 @@ template <typename T> QS_HD bool drone_step(Drone<T>& d, T c0, T c1, T c2, T c3)
   T dq0 = T(-0.5) * sk0 + e2 * d.q0, dq1 = T(-0.5) * sk1 + e2 * d.q1;
   T dq2 = T(-0.5) * sk2 + e2 * d.q2, dq3 = T(-0.5) * sk3 + e2 * d.q3;
   // inv(I) @ (I@u[1:] - w x (I w)), quadrotor.py:83,105
-  T Iw0 = C::I0 * d.wx, Iw1 = C::I1 * d.wy, Iw2 = C::I2 * d.wz;
-  T aw0 = (T(1) / C::I0) * (C::I0 * d.u1 - (d.wy * Iw2 - d.wz * Iw1));
-  T aw1 = (T(1) / C::I1) * (C::I1 * d.u2 - (d.wz * Iw0 - d.wx * Iw2));
-  T aw2 = (T(1) / C::I2) * (C::I2 * d.u3 - (d.wx * Iw1 - d.wy * Iw0));
+  T Iw0 = p.I0 * d.wx, Iw1 = p.I1 * d.wy, Iw2 = p.I2 * d.wz;
+  T aw0 = p.inv_I0 * (p.I0 * d.u1 - (d.wy * Iw2 - d.wz * Iw1));
+  T aw1 = p.inv_I1 * (p.I1 * d.u2 - (d.wz * Iw0 - d.wx * Iw2));
+  T aw2 = p.inv_I2 * (p.I2 * d.u3 - (d.wx * Iw1 - d.wy * Iw0));
   // --- y = s + dt * f (Q1) ---
   d.px += dt * d.vx; d.py += dt * d.vy; d.pz += dt * d.vz;
   d.vx += dt * ax; d.vy += dt * ay; d.vz += dt * az;
@@ -602,7 +713,7 @@ template <typename T> QS_HD bool drone_step(Drone<T>& d, T c0, T c1, T c2, T c3)
     T w = d.q0, x = d.q1, y = d.q2, z = d.q3;
     T r10 = T(2) * (x * y - w * z), r11 = w * w - x * x + y * y - z * z, r12 = T(2) * (w * x + y * z);
     T r02 = T(2) * (x * z - w * y), r22 = w * w - x * x - y * y + z * z;
-    const T s85 = T(0.99619469809174555), t85 = T(11.430052302761343), t5 = T(0.087488663525924007);
+    const T s85 = p.s_roll, t85 = p.t_pitch, t5 = p.t_yaw;
     bool in_phi = m_abs(r12) < s85;
     bool in_theta = (r22 > T(0)) && (m_abs(r02) < r22 * t85);
     bool in_psi = !((r11 < T(0)) && (m_abs(r10) <= -r11 * t5));
@@ -612,7 +723,7 @@ template <typename T> QS_HD bool drone_step(Drone<T>& d, T c0, T c1, T c2, T c3)
     clamp = true;
   }
   if (clamp) {
-    ClampResult<T> cr = kFast<T> ? attitude_clamp_cold(d.q0, d.q1, d.q2, d.q3) : attitude_clamp(d.q0, d.q1, d.q2, d.q3);
+    ClampResult<T> cr = kFast<T> ? attitude_clamp_cold(p, d.q0, d.q1, d.q2, d.q3) : attitude_clamp(p, d.q0, d.q1, d.q2, d.q3);
     clamp = cr.fired;
     if (cr.fired) {
       d.q0 = cr.w; d.q1 = cr.x; d.q2 = cr.y; d.q3 = cr.z;
@@ -620,15 +731,15 @@ template <typename T> QS_HD bool drone_step(Drone<T>& d, T c0, T c1, T c2, T c3)
     }
   }
   // --- u_prev <- u_limit(u_cmd) (Q2) ---
-  u_limit(c0, c1, c2, c3, d.u0, d.u1, d.u2, d.u3);
+  u_limit(p, c0, c1, c2, c3, d.u0, d.u1, d.u2, d.u3);
   return clamp;
 }
+template <typename T> QS_HD bool drone_step(Drone<T>& d, T c0, T c1, T c2, T c3) { return drone_step(DefaultParams<T>{}, d, c0, c1, c2, c3); }
 
 // Shared tail of hover_controller (PIDController.py:87-104) and vel_controller (:119-134) followed by
 // attitude_controller (:52-74): acc_des -> u = [F, M].  des_q is read (psi_des) and OVERWRITTEN (Q4).
-template <typename T> QS_HD void acc2cmd(T ax, T ay, T az, Quat<T>& dq, const Drone<T>& now, T& F, T& M0, T& M1, T& M2) {
-  using C = K<T>;
-  F = C::mass * C::g + C::mass * az;
+template <typename T, typename P> QS_HD void acc2cmd(const P& p, T ax, T ay, T az, Quat<T>& dq, const Drone<T>& now, T& F, T& M0, T& M1, T& M2) {
+  F = p.mass_x_g + p.mass * az;
   T phi_d, theta_d, psi_d, sp, cp;
   {
     // psi_des = quat2euler(des_q)[2]
@@ -647,11 +758,11 @@ template <typename T> QS_HD void acc2cmd(T ax, T ay, T az, Quat<T>& dq, const Dr
     }
   }
   if (kFast<T> && !is_f32<T>::value) {
-    phi_d = (ax * sp - ay * cp) * (T(1) / C::g);
-    theta_d = (ax * cp + ay * sp) * (T(1) / C::g);
+    phi_d = (ax * sp - ay * cp) * p.inv_g;
+    theta_d = (ax * cp + ay * sp) * p.inv_g;
   } else {
-    phi_d = (ax * sp - ay * cp) / C::g;
-    theta_d = (ax * cp + ay * sp) / C::g;
+    phi_d = (ax * sp - ay * cp) / p.g;
+    theta_d = (ax * cp + ay * sp) / p.g;
   }
   dq = euler2quat(phi_d, theta_d, psi_d);
   // attitude_controller re-extracts the desired angles from the quaternion it was just given
@@ -665,39 +776,43 @@ template <typename T> QS_HD void acc2cmd(T ax, T ay, T az, Quat<T>& dq, const Dr
   }
   Euler<T> en = quat2euler(now.q0, now.q1, now.q2, now.q3);
   // des rates: des[10]=des[11]=0 (written), des[12]=0 (never set)
-  M0 = C::kp_roll * (ed.phi - en.phi) + C::kd_roll * (T(0) - now.wx);
-  M1 = C::kp_pitch * (ed.theta - en.theta) + C::kd_pitch * (T(0) - now.wy);
-  M2 = C::kp_yaw * (ed.psi - en.psi) + C::kd_yaw * (T(0) - now.wz);
+  M0 = p.kp_roll * (ed.phi - en.phi) + p.kd_roll * (T(0) - now.wx);
+  M1 = p.kp_pitch * (ed.theta - en.theta) + p.kd_pitch * (T(0) - now.wy);
+  M2 = p.kp_yaw * (ed.psi - en.psi) + p.kd_yaw * (T(0) - now.wz);
 }
 
 // controller/PIDController.py:179-185  PID(des, now) with des pos/vel given explicitly
-template <typename T> QS_HD void pid(T dpx, T dpy, T dpz, T dvx, T dvy, T dvz, Quat<T>& dq, const Drone<T>& now,
-                                     T& F, T& M0, T& M1, T& M2) {
-  using C = K<T>;
-  T ax = C::kp_x * (dpx - now.px) + C::kd_x * (dvx - now.vx);
-  T ay = C::kp_y * (dpy - now.py) + C::kd_y * (dvy - now.vy);
-  T az = C::kp_z * (dpz - now.pz) + C::kd_z * (dvz - now.vz);
-  acc2cmd(ax, ay, az, dq, now, F, M0, M1, M2);
+template <typename T, typename P> QS_HD void pid(const P& p, T dpx, T dpy, T dpz, T dvx, T dvy, T dvz, Quat<T>& dq, const Drone<T>& now,
+                                                 T& F, T& M0, T& M1, T& M2) {
+  T ax = p.kp_x * (dpx - now.px) + p.kd_x * (dvx - now.vx);
+  T ay = p.kp_y * (dpy - now.py) + p.kd_y * (dvy - now.vy);
+  T az = p.kp_z * (dpz - now.pz) + p.kd_z * (dvz - now.vz);
+  acc2cmd(p, ax, ay, az, dq, now, F, M0, M1, M2);
+}
+template <typename T> QS_HD void pid(T dpx, T dpy, T dpz, T dvx, T dvy, T dvz, Quat<T>& dq, const Drone<T>& now, T& F, T& M0, T& M1, T& M2) {
+  pid(DefaultParams<T>{}, dpx, dpy, dpz, dvx, dvy, dvz, dq, now, F, M0, M1, M2);
 }
 
 // controller/PIDController.py:106-141  vel_controller(des, now, last) with last == now (Q5): the kd_v* terms vanish
-template <typename T> QS_HD void vel_controller(T dvx, T dvy, T dvz, Quat<T>& dq, const Drone<T>& now, T& F, T& M0,
-                                                T& M1, T& M2) {
-  using C = K<T>;
-  T ax = C::kp_vx * (dvx - now.vx);
-  T ay = C::kp_vy * (dvy - now.vy);
-  T az = C::kp_vz * (dvz - now.vz);
-  acc2cmd(ax, ay, az, dq, now, F, M0, M1, M2);
+template <typename T, typename P> QS_HD void vel_controller(const P& p, T dvx, T dvy, T dvz, Quat<T>& dq, const Drone<T>& now, T& F, T& M0,
+                                                            T& M1, T& M2) {
+  T ax = p.kp_vx * (dvx - now.vx);
+  T ay = p.kp_vy * (dvy - now.vy);
+  T az = p.kp_vz * (dvz - now.vz);
+  acc2cmd(p, ax, ay, az, dq, now, F, M0, M1, M2);
+}
+template <typename T> QS_HD void vel_controller(T dvx, T dvy, T dvz, Quat<T>& dq, const Drone<T>& now, T& F, T& M0, T& M1, T& M2) {
+  vel_controller(DefaultParams<T>{}, dvx, dvy, dvz, dq, now, F, M0, M1, M2);
 }
 
 // gym_docking/envs/docking_env.py:257-295 state2rel, with get_dock_port_state (quadrotor.py:213-224) folded in for
 // the ports the envs use: chaser [+0.1,0,0] (docking_env.py:38), target [-0.1,0,0] (:51).
 // c = chaser (drone A), t = target (drone B).  rel = [dp(3), dv(3), euler(3), euler rates(3)].
-template <typename T> QS_HD void state2rel(const Drone<T>& c, const Drone<T>& t, T rel[12]) {
+template <typename T, typename P> QS_HD void state2rel(const P& p_, const Drone<T>& c, const Drone<T>& t, T rel[12]) {
   Rot<T> A = quat2rot(c.q0, c.q1, c.q2, c.q3);  // R_I2A
   Rot<T> B = quat2rot(t.q0, t.q1, t.q2, t.q3);  // R_I2B
   // dock ports: r = R^T @ [d,0,0] = d * (1, R01, R02); pos = p + r; vel = v + w x r
-  const T dc = T(0.1), dt_ = T(-0.1);
+  const T dc = p_.port, dt_ = -p_.port;
   T rc0 = dc, rc1 = A.r01 * dc, rc2 = A.r02 * dc;
   T rt0 = dt_, rt1 = B.r01 * dt_, rt2 = B.r02 * dt_;
   if (kFast<T>) {
@@ -761,6 +876,7 @@ template <typename T> QS_HD void state2rel(const Drone<T>& c, const Drone<T>& t,
   if (kSpec<T>) rel[11] = rc_ps * icphi;
   else rel[11] = (icphi != T(0)) ? rc_ps * icphi : rc_ps / cphi;
 }
+template <typename T> QS_HD void state2rel(const Drone<T>& c, const Drone<T>& t, T rel[12]) { state2rel(DefaultParams<T>{}, c, t, rel); }
 
 // ---- Philox4x32-10 (Salmon et al., SC'11).  Not in the reference: the north star's counter-based per-env RNG
 // for the randomised auto-reset (docking_env.py:34 has the distribution commented out). ----
@@ -806,21 +922,10 @@ QS_HD void philox_jitter3(uint64_t seed, uint64_t env_id, uint32_t episode, uint
 // =========================================================================================================
 // Environment level: one env's step / (re)seat in registers.  The CUDA kernels (qs_lib.cu) are load -> these -> store.
 // =========================================================================================================
-constexpr int kHover = 0, kDockV0 = 1, kDockV2 = 2;                 // == qs_env_kind
 constexpr int kRandNone = 0, kRandEpisode = 1, kRandOnce = 2;       // == qs_randomize
 constexpr int kInfoDone = 1, kInfoOverlimit = 2, kInfoDocking = 4, kInfoOvertime = 8;  // == QS_INFO_*
 
 struct RngCfg { uint64_t seed, env_id0; int randomize; float jitter_scale; };
-
-// Docking positions are ~50 m from the world origin (y = -50) while everything the env computes from them is a
-// difference of a few metres.  The fp32 path therefore keeps both drones' positions RELATIVE to the fixed point
-// O = (10,-50,5) (target start == docking-v0 set-point, docking_env.py:47,59): the dynamics are translation invariant, so
-// this is the same trajectory with ~10x smaller position rounding.  The fp64 path stays in world coordinates
-// (literal).  State export/import (always float64) converts, exactly, at the boundary.
-template <typename T> struct Origin { static constexpr T x = T(0), y = T(0), z = T(0); };
-#ifndef QS_LITERAL32
-template <> struct Origin<float> { static constexpr float x = 10.f, y = -50.f, z = 5.f; };
-#endif
 
 template <typename T> struct DockEnv {
   Drone<T> c, t;        // chaser (drone A), target (drone B)
@@ -848,50 +953,50 @@ template <typename T> QS_HD Drone<T> drone_at(T x, T y, T z) {
 // target_state_des (dq) is NOT re-initialised (Q4).  Chaser ini [8,-50,5] + Philox jitter U(-hw,hw)^3 (the distribution
 // commented out at docking_env.py:34), target ini [10,-50,5].  obs = state2rel of the seated states, which for identity
 // attitudes and zero rates is (dp, 0, ..., 0).
-template <typename T> QS_HD void dock_env_seat(DockEnv<T>& e, const RngCfg& rng, int64_t i, T obs[12]) {
+template <typename T, typename P> QS_HD void dock_env_seat(const P& p, DockEnv<T>& e, const RngCfg& rng, int64_t i, T obs[12]) {
   float j[3] = {0.f, 0.f, 0.f};
   if (rng.randomize != kRandNone)
     philox_jitter3(rng.seed, rng.env_id0 + (uint64_t)i, rng.randomize == kRandOnce ? 0u : (uint32_t)e.episode, 0u, rng.jitter_scale, j);
-  using O = Origin<T>;  // the fp32 subtractions below are exact (result has fewer significant bits than the minuend)
-  e.c = drone_at<T>(T(f_add(8.f, j[0])) - O::x, T(f_add(-50.f, j[1])) - O::y, T(f_add(5.f, j[2])) - O::z);
-  e.t = drone_at<T>(T(10) - O::x, T(-50) - O::y, T(5) - O::z);
+  // the fp32 subtractions of the origin below are exact (the result has fewer significant bits than the minuend)
+  e.c = drone_at<T>(T(f_add(p.cini_x, j[0])) - p.ox, T(f_add(p.cini_y, j[1])) - p.oy, T(f_add(p.cini_z, j[2])) - p.oz);
+  e.t = drone_at<T>(p.tini_x, p.tini_y, p.tini_z);
   e.tt = 0; e.last_shaping = T(0);
-  if (kFast<T>) obs[0] = (e.t.px - e.c.px) + T(-0.2);
-  else obs[0] = (e.t.px + T(-0.1)) - (e.c.px + T(0.1));
+  if (kFast<T>) obs[0] = (e.t.px - e.c.px) + p.port2;
+  else obs[0] = (e.t.px + (-p.port)) - (e.c.px + p.port);
   obs[1] = e.t.py - e.c.py; obs[2] = e.t.pz - e.c.pz;
 #pragma unroll
   for (int k = 3; k < 12; k++) obs[k] = T(0);
 }
+template <typename T> QS_HD void dock_env_seat(DockEnv<T>& e, const RngCfg& rng, int64_t i, T obs[12]) { dock_env_seat(DefaultParams<T>{}, e, rng, i, obs); }
 
 // gym_docking/envs/docking_env.py:104-231 (KIND = kDockV0) / moving_docking_env.py:111-192 (KIND = kDockV2).
 // rel = the step's observation (terminal observation if done); the caller applies the auto-reset.
-template <typename T, int KIND> QS_HD void dock_env_step(DockEnv<T>& e, const T act[4], T rel[12], StepOut<T>& o) {
+template <typename T, int KIND, typename P> QS_HD void dock_env_step(const P& p, DockEnv<T>& e, const T act[4], T rel[12], StepOut<T>& o) {
   using C = K<T>;
   e.tt += 1;  // docking_env.py:108
   // chaser command: rotor2control @ (action_std * a + action_mean), action_std = action_mean = m*g/2 (docking_env.py:98-99,115)
-  const T half = T(1.0 * 0.18 * 9.81 / 2.0);
+  const T half = p.half;
   T uc0, uc1, uc2, uc3;
-  rotor2control(half * act[0] + half, half * act[1] + half, half * act[2] + half, half * act[3] + half, uc0, uc1, uc2, uc3);
+  rotor2control(p, half * act[0] + half, half * act[1] + half, half * act[2] + half, half * act[3] + half, uc0, uc1, uc2, uc3);
   // target command from the target state BEFORE stepping (docking_env.py:119 / moving_docking_env.py:126)
   T ut0, ut1, ut2, ut3;
-  using O = Origin<T>;
-  if (KIND == kDockV0) pid(T(10) - O::x, T(-50) - O::y, T(5) - O::z, T(0), T(0), T(0), e.dq, e.t, ut0, ut1, ut2, ut3);  // des: docking_env.py:60-64
-  else vel_controller(T(0.2), T(0), T(0), e.dq, e.t, ut0, ut1, ut2, ut3);                         // des vel: moving_docking_env.py:62-66
-  drone_step(e.t, ut0, ut1, ut2, ut3);  // docking_env.py:120
-  drone_step(e.c, uc0, uc1, uc2, uc3);  // docking_env.py:121
-  state2rel(e.c, e.t, rel);             // docking_env.py:124-127
+  if (KIND == kDockV0) pid(p, p.des_px, p.des_py, p.des_pz, T(0), T(0), T(0), e.dq, e.t, ut0, ut1, ut2, ut3);  // des: docking_env.py:60-64
+  else vel_controller(p, p.des_vx, p.des_vy, p.des_vz, e.dq, e.t, ut0, ut1, ut2, ut3);       // des vel: moving_docking_env.py:62-66
+  drone_step(p, e.t, ut0, ut1, ut2, ut3);  // docking_env.py:120
+  drone_step(p, e.c, uc0, uc1, uc2, uc3);  // docking_env.py:121
+  state2rel(p, e.c, e.t, rel);             // docking_env.py:124-127
   // flags: docking_env.py:130-152 / moving_docking_env.py:137-157
-  const T radius = KIND == kDockV0 ? T(3) : T(10);
+  const T radius = p.radius;
   T np_ = norm3(rel[0], rel[1], rel[2]), nv = norm3(rel[3], rel[4], rel[5]);
-  o.docking = (np_ < T(0.1)) && (nv < T(0.1)) && (m_abs(rel[6]) < C::d10) && (m_abs(rel[7]) < C::d10) && (m_abs(rel[8]) < C::d10);
-  o.overlimit = (np_ >= radius) || (e.c.pz <= T(0.1 - (double)O::z));
-  o.overtime = e.tt >= 600;
+  o.docking = (np_ < p.tol_pos) && (nv < p.tol_vel) && (m_abs(rel[6]) < p.d10) && (m_abs(rel[7]) < p.d10) && (m_abs(rel[8]) < p.d10);
+  o.overlimit = (np_ >= radius) || (e.c.pz <= p.z_floor);
+  o.overtime = e.tt >= p.max_steps;
   o.done = o.overlimit || o.overtime;
   // shaping / reward: docking_env.py:215-222 / moving_docking_env.py:176-183
   T na = m_sqrt(act[0] * act[0] + act[1] * act[1] + act[2] * act[2] + act[3] * act[3]);
   T shaping;
   if (kFast<T>) {
-    shaping = -(T(10) / radius) * np_ - nv - T(10.0 / 3.141592653589793) * norm3(rel[6], rel[7], rel[8]) -
+    shaping = -p.ten_over_radius * np_ - nv - T(10.0 / 3.141592653589793) * norm3(rel[6], rel[7], rel[8]) -
               norm3(rel[9], rel[10], rel[11]) - T(0.1) * na + (o.docking ? T(1) : T(0));
   } else {
     shaping = T(-10) * norm3(rel[0] / radius, rel[1] / radius, rel[2] / radius) - T(1) * nv -
@@ -904,6 +1009,9 @@ template <typename T, int KIND> QS_HD void dock_env_step(DockEnv<T>& e, const T 
 #pragma unroll
   for (int k = 0; k < 12; k++) fsum += m_abs(rel[k]);
   o.nonfinite = !m_finite(fsum);
+}
+template <typename T, int KIND> QS_HD void dock_env_step(DockEnv<T>& e, const T act[4], T rel[12], StepOut<T>& o) {
+  dock_env_step<T, KIND>(DefaultParams<T, KIND>{}, e, act, rel, o);
 }
 
 // Speculative fp64 step (see sdouble): returns false if the step has to be redone from the ORIGINAL state with the
@@ -928,7 +1036,7 @@ template <int KIND> QS_HD bool dock_env_step_spec(DockEnv<double>& e, const doub
   const sdouble a[4] = {sdouble(act[0]), sdouble(act[1]), sdouble(act[2]), sdouble(act[3])};
   sdouble r[12];
   StepOut<sdouble> so;
-  dock_env_step<sdouble, KIND>(s, a, r, so);
+  dock_env_step<sdouble, KIND>(DefaultParams<sdouble, KIND>{}, s, a, r, so);
   const double hidden = ((s.t.u0.v + s.t.u1.v) + (s.t.u2.v + s.t.u3.v)) + ((s.dq.w.v + s.dq.x.v) + (s.dq.y.v + s.dq.z.v));
   const bool ok = !so.nonfinite && (hidden - hidden == 0.0);
   e.c = from_spec(s.c); e.t = from_spec(s.t);
@@ -970,8 +1078,7 @@ template <typename T> QS_HD bool pid_expert_reseat(Drone<T>& c, const ExpertMem<
 }
 
 // second half of the aliased first step, after the caller has taken the reset observation from the re-seated chaser
-template <typename T> QS_HD void pid_expert_cmd(Drone<T>& c, const Drone<T>& t, ExpertMem<T>& m, bool first, bool alias, T act[4]) {
-  using C = K<T>;
+template <typename T, typename P> QS_HD void pid_expert_cmd(const P& p, Drone<T>& c, const Drone<T>& t, ExpertMem<T>& m, bool first, bool alias, T act[4]) {
   T F, M0, M1, M2;
   if (first && alias) {
     // vel_controller(des, now, last) on ONE array: e_vel == 0 -> acc_des = 0 -> att_des = (0, 0, psi_des); the write of
@@ -980,7 +1087,7 @@ template <typename T> QS_HD void pid_expert_cmd(Drone<T>& c, const Drone<T>& t, 
     m.dq = euler2quat(T(0), T(0), m_atan2(-r10, r11));
     c.q0 = m.dq.w; c.q1 = m.dq.x; c.q2 = m.dq.y; c.q3 = m.dq.z;
     c.wx = T(0); c.wy = T(0);
-    F = C::mass * C::g + C::mass * T(0); M0 = T(0); M1 = T(0); M2 = T(0);
+    F = p.mass_x_g + p.mass * T(0); M0 = T(0); M1 = T(0); M2 = T(0);
   } else {
     if (!first) {
       const T kp = T(0.35), kd = T(0);
@@ -988,13 +1095,16 @@ template <typename T> QS_HD void pid_expert_cmd(Drone<T>& c, const Drone<T>& t, 
       m.dvy = kp * ((t.py + T(0)) - c.py) + kd * (-c.vy);
       m.dvz = kp * ((t.pz + T(0)) - c.pz) + kd * (-c.vz);
     }
-    vel_controller(m.dvx, m.dvy, m.dvz, m.dq, c, F, M0, M1, M2);
+    vel_controller(p, m.dvx, m.dvy, m.dvz, m.dq, c, F, M0, M1, M2);
   }
   // inv(rotor2control) (quadrotor.py:56-59) in closed form, then the env's action normalisation (docking_env.py:98-99)
-  const T hl = T(0.5 / 0.086), ql = T(0.25 / (1.5e-9 / 6.11e-8)), half = T(1.0 * 0.18 * 9.81 / 2.0);
+  const T hl = p.hl, ql = P::custom ? T(0.25) / p.lam : T(0.25 / (1.5e-9 / 6.11e-8)), half = p.half;
   const T f0 = (T(0.25) * F - hl * M1) + ql * M2, f1 = (T(0.25) * F + hl * M0) - ql * M2;
   const T f2 = (T(0.25) * F + hl * M1) + ql * M2, f3 = (T(0.25) * F - hl * M0) - ql * M2;
   act[0] = (f0 - half) / half; act[1] = (f1 - half) / half; act[2] = (f2 - half) / half; act[3] = (f3 - half) / half;
+}
+template <typename T> QS_HD void pid_expert_cmd(Drone<T>& c, const Drone<T>& t, ExpertMem<T>& m, bool first, bool alias, T act[4]) {
+  pid_expert_cmd(DefaultParams<T>{}, c, t, m, first, alias, act);
 }
 
 template <typename T> QS_HD void drone_to_obs13(const Drone<T>& d, T o[13]) {
@@ -1003,7 +1113,7 @@ template <typename T> QS_HD void drone_to_obs13(const Drone<T>& d, T o[13]) {
 }
 
 // hover (re)seat: hovering_env.py:23-29, :80-82 -- pos [0,0,5] + U(-hw,hw)^3, euler U(-0.2,0.2)^3, zero rates, u <- 0
-template <typename T> QS_HD void hover_env_seat(HoverEnv<T>& e, const RngCfg& rng, int64_t i, T obs[13]) {
+template <typename T, typename P> QS_HD void hover_env_seat(const P& p, HoverEnv<T>& e, const RngCfg& rng, int64_t i, T obs[13]) {
   float jp[3] = {0.f, 0.f, 0.f}, je[3] = {0.f, 0.f, 0.f};
   if (rng.randomize != kRandNone) {
     uint32_t ep = rng.randomize == kRandOnce ? 0u : (uint32_t)e.episode;
@@ -1011,26 +1121,27 @@ template <typename T> QS_HD void hover_env_seat(HoverEnv<T>& e, const RngCfg& rn
     philox_jitter3(rng.seed, rng.env_id0 + (uint64_t)i, ep, 1u, 0.4f, je);
   }
   Quat<T> q = euler2quat(T(je[0]), T(je[1]), T(je[2]));
-  e.d = drone_at<T>(T(f_add(0.f, jp[0])), T(f_add(0.f, jp[1])), T(f_add(5.f, jp[2])));
+  e.d = drone_at<T>(T(f_add(p.cini_x, jp[0])), T(f_add(p.cini_y, jp[1])), T(f_add(p.cini_z, jp[2])));
   e.d.q0 = q.w; e.d.q1 = q.x; e.d.q2 = q.y; e.d.q3 = q.z;
   e.tt = 0; e.ep_return = T(0);
   drone_to_obs13(e.d, obs);
 }
+template <typename T> QS_HD void hover_env_seat(HoverEnv<T>& e, const RngCfg& rng, int64_t i, T obs[13]) { hover_env_seat(DefaultParams<T, kHover>{}, e, rng, i, obs); }
 
 // hovering-v0 step: gym_docking/envs/hovering_env.py:47-78
-template <typename T> QS_HD void hover_env_step(HoverEnv<T>& e, const T act[4], T obs[13], StepOut<T>& o) {
+template <typename T, typename P> QS_HD void hover_env_step(const P& p, HoverEnv<T>& e, const T act[4], T obs[13], StepOut<T>& o) {
   Drone<T>& d = e.d;
   e.tt += 1;
-  const T amax = T(1.0 * 0.18 * 9.81);  // action_max = m*g per rotor, hovering_env.py:42
+  const T amax = p.mg;  // action_max = m*g per rotor, hovering_env.py:42
   T u0, u1, u2, u3;
-  rotor2control(amax * act[0], amax * act[1], amax * act[2], amax * act[3], u0, u1, u2, u3);  // :51
-  drone_step(d, u0, u1, u2, u3);                                                               // :52
+  rotor2control(p, amax * act[0], amax * act[1], amax * act[2], amax * act[3], u0, u1, u2, u3);  // :51
+  drone_step(p, d, u0, u1, u2, u3);                                                               // :52
   // errors w.r.t. state_des = [0,0,5, 0.., q=identity, 0..] (hovering_env.py:31-35, :57-60); quat2euler(identity) = 0
   Euler<T> en = quat2euler(d.q0, d.q1, d.q2, d.q3);
   T pe = norm3(T(0) - d.px, T(0) - d.py, T(5) - d.pz), ve = norm3(d.vx, d.vy, d.vz);
   T ae = norm3(en.phi, en.theta, en.psi), we = norm3(d.wx, d.wy, d.wz);
   T r_thre = (pe < T(0.1) && ve < T(0.1)) ? T(1) : T(0);                                      // :62-66
-  o.done = (norm3(d.px, d.py, d.pz) > T(100)) || (ve > T(100));                                // :68
+  o.done = (norm3(d.px, d.py, d.pz) > p.radius) || (ve > p.radius);                            // :68
   o.overlimit = o.done; o.overtime = false; o.docking = r_thre > T(0);
   o.reward = o.done ? T(-0.1) : (r_thre + T(0.1) - T(0.01) * pe - T(0.001) * ve - T(0.01) * ae - T(0.001) * we);  // :70-76
   e.ep_return += o.reward;
@@ -1040,5 +1151,6 @@ template <typename T> QS_HD void hover_env_step(HoverEnv<T>& e, const T act[4], 
   for (int k = 0; k < 13; k++) fsum += m_abs(obs[k]);
   o.nonfinite = !m_finite(fsum);
 }
+template <typename T> QS_HD void hover_env_step(HoverEnv<T>& e, const T act[4], T obs[13], StepOut<T>& o) { hover_env_step(DefaultParams<T, kHover>{}, e, act, obs, o); }
 
 }  // namespace qs

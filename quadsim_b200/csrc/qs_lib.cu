@@ -265,9 +265,8 @@ template <typename T> __device__ __forceinline__ void store_obs13_tile(T* stage,
 
 // info['chaser'] / info['target'] of an episode's last step (docking_env.py:226-229): the 13-state in float64 world
 // coordinates, written before the auto-reset re-seats the env.  Cold: ~1.4 % of env-steps under random actions.
-template <typename T> __device__ __forceinline__ void store_terminal_state(double* out, int64_t i, const Drone<T>& d, bool shifted) {
+template <typename T> __device__ __forceinline__ void store_terminal_state(double* out, int64_t i, const Drone<T>& d, double ox, double oy, double oz) {
   double* o = out + i * 13;
-  const double ox = shifted ? (double)Origin<T>::x : 0.0, oy = shifted ? (double)Origin<T>::y : 0.0, oz = shifted ? (double)Origin<T>::z : 0.0;
   o[0] = (double)d.px + ox; o[1] = (double)d.py + oy; o[2] = (double)d.pz + oz;
   o[3] = (double)d.vx; o[4] = (double)d.vy; o[5] = (double)d.vz;
   o[6] = (double)d.q0; o[7] = (double)d.q1; o[8] = (double)d.q2; o[9] = (double)d.q3;
@@ -289,12 +288,16 @@ constexpr bool kSpec64 = kFast64;  // -DQS_NO_SPEC64: the guarded fp64 arithmeti
 #endif
 
 template <int KIND> __device__ __noinline__ StepTail dock_step_replay(const StepArgs& a, int64_t i);
+// kernel-parameter type of the model constants: DefaultParams (empty: every constant an immediate) or RuntimeParams (the
+// handle's qs_env_params_t, read from the constant bank)
+template <typename T, int KIND, bool CUSTOM> struct PrmSel { using type = DefaultParams<T, KIND>; };
+template <typename T, int KIND> struct PrmSel<T, KIND, true> { using type = RuntimeParams<T>; };
 
 // step -> outputs -> auto-reset -> store for one env whose state words and action are in registers.  SPEC (fp64 only):
 // the speculative straight-line step (qs::sdouble); an env that fails its check is replayed out of line from its state
 // in HBM, which nothing has overwritten yet.
-template <typename T, int KIND, bool SPEC>
-__device__ __forceinline__ StepTail dock_step_loaded(const StepArgs& a, int64_t i, T (&w)[dock_words<T>()], const T (&act)[4]) {
+template <typename T, int KIND, bool SPEC, typename P>
+__device__ __forceinline__ StepTail dock_step_loaded(const StepArgs& a, const P& prm, int64_t i, T (&w)[dock_words<T>()], const T (&act)[4]) {
   constexpr int NW = dock_words<T>();
   DockEnv<T> e;
   words_to_dock<T, NW>(w, e);
@@ -303,7 +306,7 @@ __device__ __forceinline__ StepTail dock_step_loaded(const StepArgs& a, int64_t 
   if constexpr (SPEC) {
     if (!dock_env_step_spec<KIND>(e, act, rel, o)) return dock_step_replay<KIND>(a, i);
   } else {
-    dock_env_step<T, KIND>(e, act, rel, o);
+    dock_env_step<T, KIND>(prm, e, act, rel, o);
   }
   reinterpret_cast<T*>(a.reward)[i] = o.reward;
   a.done[i] = o.done ? 1 : 0;
@@ -311,11 +314,11 @@ __device__ __forceinline__ StepTail dock_step_loaded(const StepArgs& a, int64_t 
   if (a.term_obs) store_row<T, 12>(a.term_obs, i, rel);
   const StepTail tail = {(double)e.last_shaping, e.tt, o.done, o.docking, o.nonfinite};  // ret == sum of the episode's rewards (telescoping)
   if (o.done) {
-    if (a.term_chaser) store_terminal_state<T>(a.term_chaser, i, e.c, true);
-    if (a.term_target) store_terminal_state<T>(a.term_target, i, e.t, true);
+    if (a.term_chaser) store_terminal_state<T>(a.term_chaser, i, e.c, (double)prm.ox, (double)prm.oy, (double)prm.oz);
+    if (a.term_target) store_terminal_state<T>(a.term_target, i, e.t, (double)prm.ox, (double)prm.oy, (double)prm.oz);
     if (a.auto_reset) {
       e.episode += 1;
-      dock_env_seat<T>(e, a.rng, i, rel);
+      dock_env_seat<T>(prm, e, a.rng, i, rel);
     }
   }
   store_row<T, 12>(a.obs, i, rel);
@@ -328,12 +331,12 @@ template <int KIND> __device__ __noinline__ StepTail dock_step_replay(const Step
   double w[NW], act[4];
   load_words<double, NW>(a.state, i, w);
   load_action<double>(a.actions, i, act);
-  return dock_step_loaded<double, KIND, false>(a, i, w, act);
+  return dock_step_loaded<double, KIND, false>(a, DefaultParams<double, KIND>{}, i, w, act);  // only the compiled-in constants speculate
 }
-template <typename T> constexpr bool dock_spec() { return !is_f32<T>::value && kSpec64; }
+template <typename T, typename P> constexpr bool dock_spec() { return !is_f32<T>::value && kSpec64 && !P::custom; }
 
-template <typename T, int KIND>
-__global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_kernel(const __grid_constant__ StepArgs a) {
+template <typename T, int KIND, typename P>
+__global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ P prm) {
   pdl_prologue();
   constexpr int NW = dock_words<T>();
   const int64_t i = a.first + (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_kernel(cons
   T w[NW], act[4];
   load_words<T, NW>(a.state, i, w);
   load_action<T>(a.actions, i, act);
-  const StepTail tail = dock_step_loaded<T, KIND, dock_spec<T>()>(a, i, w, act);
+  const StepTail tail = dock_step_loaded<T, KIND, dock_spec<T, P>()>(a, prm, i, w, act);
   warp_stats_update(a.warp_stats, i, mask, tail.done, tail.docking, tail.nonfinite, tail.ret, tail.len);
 }
 
@@ -440,7 +443,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_pipe_kernel
     }
     const unsigned mask = __ballot_sync(0xffffffffu, active);
     if (active) {
-      const StepTail tail = dock_step_loaded<T, KIND, dock_spec<T>()>(a, i, w, act);
+      const StepTail tail = dock_step_loaded<T, KIND, dock_spec<T, DefaultParams<T, KIND>>()>(a, DefaultParams<T, KIND>{}, i, w, act);
       warp_stats_update(a.warp_stats, i, mask, tail.done, tail.docking, tail.nonfinite, tail.ret, tail.len);
     }
   }
@@ -454,8 +457,8 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_pipe_kernel
 // =========================================================================================================
 // hovering-v0 step: gym_docking/envs/hovering_env.py:47-78 + auto-reset to the per-env initial state (:80-82)
 // =========================================================================================================
-template <typename T>
-__global__ void __launch_bounds__(kBlock) hover_step_kernel(const StepArgs a) {
+template <typename T, typename P>
+__global__ void __launch_bounds__(kBlock) hover_step_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ P prm) {
   pdl_prologue();
   __shared__ T stage[kBlock * 13];
   const int64_t tile0 = a.first + (int64_t)blockIdx.x * kBlock;
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(kBlock) hover_step_kernel(const StepArgs a) {
     T act[4];
     load_action<T>(a.actions, i, act);
     words_to_hover<T>(w, e);
-    hover_env_step<T>(e, act, obs, o);
+    hover_env_step<T>(prm, e, act, obs, o);
     reinterpret_cast<T*>(a.reward)[i] = o.reward;
     a.done[i] = o.done ? 1 : 0;
     if (a.info) a.info[i] = (uint8_t)o.info();
@@ -485,10 +488,10 @@ __global__ void __launch_bounds__(kBlock) hover_step_kernel(const StepArgs a) {
   }
   if (a.term_obs) store_obs13_tile<T>(stage, a.term_obs, tile0, cnt, obs, active);
   if (active && o.done) {
-    if (a.term_chaser) store_terminal_state<T>(a.term_chaser, i, e.d, false);
+    if (a.term_chaser) store_terminal_state<T>(a.term_chaser, i, e.d, 0.0, 0.0, 0.0);
     if (a.auto_reset) {
       e.episode += 1;
-      hover_env_seat<T>(e, a.rng, i, obs);
+      hover_env_seat<T>(prm, e, a.rng, i, obs);
     }
   }
   store_obs13_tile<T>(stage, a.obs, tile0, cnt, obs, active);
@@ -505,8 +508,8 @@ __global__ void __launch_bounds__(kBlock) hover_step_kernel(const StepArgs a) {
 // across the T steps (no state traffic between steps, no launch per step) and stores it once; per step it reads 4 action
 // words and writes the step's observation / reward / done.  Same arithmetic (qs_core.cuh) as the single-step kernels.
 // =========================================================================================================
-template <typename T, int KIND>
-__global__ void __launch_bounds__(kBlock, min_blocks<T>()) multi_step_kernel(const StepArgs a, int64_t n_steps) {
+template <typename T, int KIND, typename P>
+__global__ void __launch_bounds__(kBlock, min_blocks<T>()) multi_step_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ P prm, int64_t n_steps) {
   constexpr bool HOVER = KIND == QS_HOVER;
   constexpr int NW = HOVER ? kHoverWords : dock_words<T>();
   constexpr int OD = HOVER ? 13 : 12;
@@ -535,17 +538,17 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T>()) multi_step_kernel(con
       T act[4];
       load_action<T>(a.actions, row0 + i, act);
       if constexpr (HOVER) {
-        hover_env_step<T>(he, act, obs, o);
+        hover_env_step<T>(prm, he, act, obs, o);
         stat_ret = (double)he.ep_return; stat_len = he.tt;
       } else {
-        dock_env_step<T, KIND>(de, act, obs, o);
+        dock_env_step<T, KIND>(prm, de, act, obs, o);
         stat_ret = (double)de.last_shaping; stat_len = de.tt;
       }
       reinterpret_cast<T*>(a.reward)[row0 + i] = o.reward;
       a.done[row0 + i] = o.done ? 1 : 0;
       if (o.done && a.auto_reset) {
-        if constexpr (HOVER) { he.episode += 1; hover_env_seat<T>(he, a.rng, i, obs); }
-        else { de.episode += 1; dock_env_seat<T>(de, a.rng, i, obs); }
+        if constexpr (HOVER) { he.episode += 1; hover_env_seat<T>(prm, he, a.rng, i, obs); }
+        else { de.episode += 1; dock_env_seat<T>(prm, de, a.rng, i, obs); }
       }
     }
     if constexpr (HOVER) store_obs13_tile<T>(stage, a.obs, row0 + tile0, cnt, obs, active);
@@ -563,8 +566,8 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T>()) multi_step_kernel(con
 //   mode 0: construct -- episode 0, des_q = identity (docking_env.py:60-63), u = 0
 //   mode 1: reset()   -- envs with t != 0 start their next episode; des_q survives (Q4)
 // =========================================================================================================
-template <typename T, int KIND>
-__global__ void __launch_bounds__(kBlock) seat_kernel(const StepArgs a, int mode) {
+template <typename T, int KIND, typename P>
+__global__ void __launch_bounds__(kBlock) seat_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ P prm, int mode) {
   const int64_t i = a.first + (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= a.first + a.n) return;
   if (KIND == QS_HOVER) {
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(kBlock) seat_kernel(const StepArgs a, int mode
       e.episode += e.tt != 0 ? 1 : 0;
     }
     T obs[13];
-    hover_env_seat<T>(e, a.rng, i, obs);
+    hover_env_seat<T>(prm, e, a.rng, i, obs);
     hover_to_words<T>(e, w);
     store_words<T, kHoverWords>(a.state, i, w);
     if (a.obs) store_obs13<T>(a.obs, i, obs);
@@ -593,7 +596,7 @@ __global__ void __launch_bounds__(kBlock) seat_kernel(const StepArgs a, int mode
       e.episode += e.tt != 0 ? 1 : 0;
     }
     T obs[12];
-    dock_env_seat<T>(e, a.rng, i, obs);
+    dock_env_seat<T>(prm, e, a.rng, i, obs);
     dock_to_words<T, NW>(e, w);
     store_words<T, NW>(a.state, i, w);
     if (a.obs) store_row<T, 12>(a.obs, i, obs);
@@ -606,15 +609,16 @@ __global__ void __launch_bounds__(kBlock) seat_kernel(const StepArgs a, int mode
 struct StateArrays { void *chaser, *target, *uc, *ut, *desq, *last_shaping, *ep_return; int32_t *t, *episode; };
 
 template <typename T, bool HOVER, bool IMPORT>
-__global__ void __launch_bounds__(kBlock) state_io_kernel(void* state, int64_t stride, int64_t n, StateArrays s) {
+__global__ void __launch_bounds__(kBlock) state_io_kernel(void* state, int64_t stride, int64_t n, StateArrays s, double ox, double oy, double oz) {
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
   constexpr int NW = HOVER ? kHoverWords : dock_words<T>();
   T w[NW];
   load_words<T, NW>(state, i, w);
-  // word index of state[k] (k = 0..12) relative to a drone's base word; positions (k < 3) are stored relative to Origin<T>
+  // word index of state[k] (k = 0..12) relative to a drone's base word; positions (k < 3) are stored relative to the handle's
+  // origin (fp32 docking: the target's start position; otherwise 0)
   const int sidx[13] = {0, 1, 2, 4, 5, 6, 8, 9, 10, 11, 3, 7, -1};
-  const double org[3] = {HOVER ? 0.0 : (double)Origin<T>::x, HOVER ? 0.0 : (double)Origin<T>::y, HOVER ? 0.0 : (double)Origin<T>::z};
+  const double org[3] = {ox, oy, oz};
   double* ch = reinterpret_cast<double*>(s.chaser);
   double* tg = reinterpret_cast<double*>(s.target);
   double* uc = reinterpret_cast<double*>(s.uc);
@@ -798,9 +802,9 @@ __global__ void __launch_bounds__(256) gae_kernel(int64_t T, int64_t n, const fl
 // reads the env state rows, keeps its own [N,8] memory (des vel xyz, pad, des q wxyz).  In alias mode the first step of an
 // episode re-seats the chaser from that memory (the scripts' state_des IS env.chaser_ini_state) and rewrites the reset
 // observation the caller is about to record.
-template <typename T>
+template <typename T, typename P>
 __global__ void __launch_bounds__(kBlock) expert_kernel(void* state, int64_t n, T* __restrict__ mem, int alias, T* __restrict__ actions,
-                                                        void* obs) {
+                                                        void* obs, const __grid_constant__ P prm) {
   constexpr int NW = dock_words<T>();
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
@@ -813,11 +817,11 @@ __global__ void __launch_bounds__(kBlock) expert_kernel(void* state, int64_t n, 
   const bool reseated = pid_expert_reseat(e.c, m, first, alias != 0);
   if (reseated && obs) {  // env.reset()'s observation of the re-seated chaser (docking_env.py:240-244)
     T rel[12];
-    state2rel(e.c, e.t, rel);
+    state2rel(prm, e.c, e.t, rel);
     store_row<T, 12>(obs, i, rel);
   }
   T act[4];
-  pid_expert_cmd(e.c, e.t, m, first, alias != 0, act);
+  pid_expert_cmd(prm, e.c, e.t, m, first, alias != 0, act);
   if (reseated) {
     dock_to_words<T, NW>(e, w);
     store_words<T, NW>(state, i, w);
@@ -831,7 +835,8 @@ __global__ void __launch_bounds__(kBlock) expert_kernel(void* state, int64_t n, 
 // A few envs' drone states for an observer (the Unity bridge, server/pub_server.py:25-36): gather k env ids into
 // [k,13] float64 world-coordinate rows (chaser / single drone, and target for docking).  t_out: env.t (the sim step).
 template <typename T, bool HOVER>
-__global__ void peek_state_kernel(const void* state, int64_t n, const int64_t* ids, int64_t k, double* chaser, double* target, int32_t* t_out) {
+__global__ void peek_state_kernel(const void* state, int64_t n, const int64_t* ids, int64_t k, double* chaser, double* target, int32_t* t_out,
+                                  double ox, double oy, double oz) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= k) return;
   const int64_t i = ids[j];
@@ -840,7 +845,7 @@ __global__ void peek_state_kernel(const void* state, int64_t n, const int64_t* i
   T w[NW];
   load_words<T, NW>(state, i, w);
   const int sidx[13] = {0, 1, 2, 4, 5, 6, 8, 9, 10, 11, 3, 7, -1};
-  const double org[3] = {HOVER ? 0.0 : (double)Origin<T>::x, HOVER ? 0.0 : (double)Origin<T>::y, HOVER ? 0.0 : (double)Origin<T>::z};
+  const double org[3] = {ox, oy, oz};
 #pragma unroll
   for (int c = 0; c < 13; c++) {
     const double o = c < 3 ? org[c] : 0.0;
@@ -883,6 +888,13 @@ struct qs_env {
   int pipe_grid = 0;
   unsigned int* sched = nullptr;  // [kHostStreams + 1][2] tile counters (one pair per stream slot)
   int* import_flag = nullptr;     // device word set by the import validation kernel (fp32 counter ranges)
+  // model parameters: custom = handle created with use_params (kernels read prm_f / prm_d from the constant bank); origin =
+  // what the state rows' positions are relative to (fp32 docking: the target's start position; otherwise 0)
+  bool custom = false;
+  qs_env_params_t params;
+  RuntimeParams<float> prm_f;
+  RuntimeParams<double> prm_d;
+  double origin[3] = {0, 0, 0};
   // qs_step_host pipeline
   cudaEvent_t ev_fork = nullptr;  // recorded on the caller's stream, waited on by every internal stream
   cudaStream_t hstreams[kHostStreams] = {};
@@ -902,37 +914,50 @@ StepArgs make_args(qs_env* e, int64_t first, int64_t n) {
   return a;
 }
 
-template <typename T> int launch_step_t(qs_env* e, const StepArgs& a, cudaStream_t st) {
-  const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
-  // QUADSIM_B200_PDL=0 launches without programmatic dependent launch (A/B)
-  static const bool pdl = [] { const char* v = getenv("QUADSIM_B200_PDL"); return !(v && v[0] == '0'); }();
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  switch (e->cfg.env_kind) {
-    case QS_HOVER: QS_CUDA(cudaLaunchKernelEx(&cfg, hover_step_kernel<T>, a)); break;
-    case QS_DOCK_V0: QS_CUDA(cudaLaunchKernelEx(&cfg, dock_step_kernel<T, QS_DOCK_V0>, a)); break;
-    default: QS_CUDA(cudaLaunchKernelEx(&cfg, dock_step_kernel<T, QS_DOCK_V2>, a)); break;
+// ---- dispatch on (dtype, env kind, compiled-in vs runtime parameters): f(TypeTag<T>, IntTag<KIND>, prm) with prm the
+// kernel-parameter object of the model constants
+template <typename T> struct TypeTag { using type = T; };
+template <int V> struct IntTag { static constexpr int value = V; };
+template <typename T> const RuntimeParams<T>& runtime_prm(const qs_env* e);
+template <> const RuntimeParams<float>& runtime_prm<float>(const qs_env* e) { return e->prm_f; }
+template <> const RuntimeParams<double>& runtime_prm<double>(const qs_env* e) { return e->prm_d; }
+
+template <typename T, typename F> int dispatch_kind(const qs_env* e, F&& f) {
+  if (e->custom) {
+    switch (e->cfg.env_kind) {
+      case QS_HOVER: return f(TypeTag<T>{}, IntTag<QS_HOVER>{}, runtime_prm<T>(e));
+      case QS_DOCK_V0: return f(TypeTag<T>{}, IntTag<QS_DOCK_V0>{}, runtime_prm<T>(e));
+      default: return f(TypeTag<T>{}, IntTag<QS_DOCK_V2>{}, runtime_prm<T>(e));
+    }
   }
-  return QS_OK;
+  switch (e->cfg.env_kind) {
+    case QS_HOVER: return f(TypeTag<T>{}, IntTag<QS_HOVER>{}, DefaultParams<T, QS_HOVER>{});
+    case QS_DOCK_V0: return f(TypeTag<T>{}, IntTag<QS_DOCK_V0>{}, DefaultParams<T, QS_DOCK_V0>{});
+    default: return f(TypeTag<T>{}, IntTag<QS_DOCK_V2>{}, DefaultParams<T, QS_DOCK_V2>{});
+  }
 }
+template <typename F> int dispatch_env(const qs_env* e, F&& f) {
+  return e->cfg.dtype == QS_F32 ? dispatch_kind<float>(e, f) : dispatch_kind<double>(e, f);
+}
+
+bool use_pdl() {  // QUADSIM_B200_PDL=0 launches without programmatic dependent launch (A/B)
+  static const bool pdl = [] { const char* v = getenv("QUADSIM_B200_PDL"); return !(v && v[0] == '0'); }();
+  return pdl;
+}
+
 // slot >= 0: the scheduler-counter pair of the persistent pipelined kernel to use (launches that may run concurrently need
 // different slots); slot < 0: always the direct kernel (qs_step_range: callers may step slices on any number of streams).
 int launch_step(qs_env* e, const StepArgs& a, cudaStream_t st, int slot = 0) {
   if (a.n <= 0) return QS_OK;
-  if (e->use_pipe && slot >= 0) {
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kBlock); cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 1 : 0;
+  if (e->use_pipe && slot >= 0) {  // never with runtime parameters (qs_create)
     const int tiles = (int)((a.n + kBlock - 1) / kBlock);
     unsigned int* sched = e->sched + 2 * slot;
-    static const bool pdl = [] { const char* v = getenv("QUADSIM_B200_PDL"); return !(v && v[0] == '0'); }();
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(tiles < e->pipe_grid ? tiles : e->pipe_grid)); cfg.blockDim = dim3(kBlock); cfg.stream = st;
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cfg.gridDim = dim3((unsigned)(tiles < e->pipe_grid ? tiles : e->pipe_grid));
     const bool v0 = e->cfg.env_kind == QS_DOCK_V0;
     if (e->cfg.dtype == QS_F32) {
       cfg.dynamicSmemBytes = pipe_smem_bytes<float>();
@@ -945,30 +970,35 @@ int launch_step(qs_env* e, const StepArgs& a, cudaStream_t st, int slot = 0) {
     }
     return QS_OK;
   }
-  return e->cfg.dtype == QS_F32 ? launch_step_t<float>(e, a, st) : launch_step_t<double>(e, a, st);
+  cfg.gridDim = dim3((unsigned)((a.n + kBlock - 1) / kBlock));
+  return dispatch_env(e, [&](auto tt, auto kind, auto prm) -> int {
+    using T = typename decltype(tt)::type;
+    using P = decltype(prm);
+    constexpr int KIND = decltype(kind)::value;
+    if constexpr (KIND == QS_HOVER) QS_CUDA(cudaLaunchKernelEx(&cfg, hover_step_kernel<T, P>, a, prm));
+    else QS_CUDA(cudaLaunchKernelEx(&cfg, dock_step_kernel<T, KIND, P>, a, prm));
+    return QS_OK;
+  });
 }
 
-template <typename T> int launch_seat_t(qs_env* e, const StepArgs& a, int mode, cudaStream_t st) {
-  const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
-  switch (e->cfg.env_kind) {
-    case QS_HOVER: seat_kernel<T, QS_HOVER><<<grid, kBlock, 0, st>>>(a, mode); break;
-    case QS_DOCK_V0: seat_kernel<T, QS_DOCK_V0><<<grid, kBlock, 0, st>>>(a, mode); break;
-    default: seat_kernel<T, QS_DOCK_V2><<<grid, kBlock, 0, st>>>(a, mode); break;
-  }
-  QS_CUDA(cudaGetLastError());
-  return QS_OK;
-}
 int launch_seat(qs_env* e, void* obs, int mode, cudaStream_t st) {
   StepArgs a = make_args(e, 0, e->cfg.n_envs);
   a.obs = obs;
-  return e->cfg.dtype == QS_F32 ? launch_seat_t<float>(e, a, mode, st) : launch_seat_t<double>(e, a, mode, st);
+  const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
+  return dispatch_env(e, [&](auto tt, auto kind, auto prm) -> int {
+    using T = typename decltype(tt)::type;
+    seat_kernel<T, decltype(kind)::value, decltype(prm)><<<grid, kBlock, 0, st>>>(a, prm, mode);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+  });
 }
 
 template <typename T, bool IMPORT> int launch_state_io(qs_env* e, const qs_state_arrays_t* s, cudaStream_t st) {
   StateArrays sa = {s->chaser, s->target, s->u_chaser, s->u_target, s->des_q, s->last_shaping, s->ep_return, s->t, s->episode};
   const unsigned grid = (unsigned)((e->cfg.n_envs + kBlock - 1) / kBlock);
-  if (e->cfg.env_kind == QS_HOVER) state_io_kernel<T, true, IMPORT><<<grid, kBlock, 0, st>>>(e->state, e->stride, e->cfg.n_envs, sa);
-  else state_io_kernel<T, false, IMPORT><<<grid, kBlock, 0, st>>>(e->state, e->stride, e->cfg.n_envs, sa);
+  const double* o = e->origin;
+  if (e->cfg.env_kind == QS_HOVER) state_io_kernel<T, true, IMPORT><<<grid, kBlock, 0, st>>>(e->state, e->stride, e->cfg.n_envs, sa, o[0], o[1], o[2]);
+  else state_io_kernel<T, false, IMPORT><<<grid, kBlock, 0, st>>>(e->state, e->stride, e->cfg.n_envs, sa, o[0], o[1], o[2]);
   QS_CUDA(cudaGetLastError());
   return QS_OK;
 }
@@ -1014,9 +1044,15 @@ int qs_create(qs_env_t** out, const qs_config_t* cfg) {
   if (cfg->n_envs <= 0) return fail(QS_ERR_INVALID, "qs_create: n_envs must be positive (got %lld)", (long long)cfg->n_envs);
   if (cfg->randomize < QS_RAND_NONE || cfg->randomize > QS_RAND_ONCE) return fail(QS_ERR_INVALID, "qs_create: unknown randomize mode %d", cfg->randomize);
   if (cfg->use_params) {
-    qs_env_params_t d;
-    qs_default_params(cfg->env_kind, &d);
-    if (memcmp(&d, &cfg->params, sizeof d) != 0) return fail(QS_ERR_INVALID, "qs_create: non-default params not wired yet");
+    const qs_env_params_t& q = cfg->params;
+    const bool pos = q.dt > 0 && q.gravity > 0 && q.mass > 0 && q.arm_length > 0 && q.inertia[0] > 0 && q.inertia[1] > 0 && q.inertia[2] > 0 &&
+                     q.motor_lambda > 0 && q.range_limit > 0 && q.dock_port >= 0 && q.dock_pos_tol >= 0 && q.dock_vel_tol >= 0 && q.dock_angle_deg >= 0;
+    if (!pos) return fail(QS_ERR_INVALID, "qs_create: params: dt, gravity, mass, arm_length, inertia, motor_lambda and range_limit must be positive, tolerances non-negative");
+    // the clamp pre-test is written for the reference's geometry: roll / pitch limits below 90 degrees, yaw limit above
+    if (!(q.att_limit_deg[0] > 0 && q.att_limit_deg[0] < 90 && q.att_limit_deg[1] > 0 && q.att_limit_deg[1] < 90 && q.att_limit_deg[2] > 90 && q.att_limit_deg[2] <= 180))
+      return fail(QS_ERR_INVALID, "qs_create: params.att_limit_deg must satisfy 0 < roll, pitch < 90 and 90 < yaw <= 180 (reference: 85, 85, 175)");
+    if (q.max_steps < 1 || (cfg->dtype == QS_F32 && cfg->env_kind != QS_HOVER && q.max_steps > 1023))
+      return fail(QS_ERR_INVALID, "qs_create: params.max_steps must be >= 1 (and <= 1023 for float32 docking handles: t is a 10-bit field)");
   }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -1028,6 +1064,16 @@ int qs_create(qs_env_t** out, const qs_config_t* cfg) {
   qs_env* e = new (std::nothrow) qs_env();
   if (!e) return fail(QS_ERR_ALLOC, "qs_create: out of host memory");
   e->cfg = *cfg;
+  e->custom = cfg->use_params != 0;
+  if (e->custom) e->params = cfg->params; else qs_default_params(cfg->env_kind, &e->params);
+  make_runtime_params<float>(e->params, cfg->env_kind, e->prm_f);
+  make_runtime_params<double>(e->params, cfg->env_kind, e->prm_d);
+  if (cfg->env_kind != QS_HOVER) {
+    if (cfg->dtype == QS_F32) { e->origin[0] = (double)e->prm_f.ox; e->origin[1] = (double)e->prm_f.oy; e->origin[2] = (double)e->prm_f.oz; }
+#ifdef QS_LITERAL32
+    e->origin[0] = e->origin[1] = e->origin[2] = 0.0;  // the literal fp32 build keeps world coordinates
+#endif
+  }
   if (e->cfg.half_width <= 0) e->cfg.half_width = cfg->env_kind == QS_HOVER ? 1.0 : 0.5;
   e->jitter_scale = (float)(2.0 * e->cfg.half_width);
   e->obs_dim = cfg->env_kind == QS_HOVER ? 13 : 12;
@@ -1052,7 +1098,7 @@ int qs_create(qs_env_t** out, const qs_config_t* cfg) {
   // QUADSIM_B200_KERNEL=pipe|direct overrides.
   e->use_pipe = e->cfg.dtype == QS_F64;
   if (const char* k = getenv("QUADSIM_B200_KERNEL")) e->use_pipe = strcmp(k, "pipe") == 0 ? 1 : (strcmp(k, "direct") == 0 ? 0 : e->use_pipe);
-  if (e->cfg.env_kind == QS_HOVER) e->use_pipe = 0;
+  if (e->cfg.env_kind == QS_HOVER || e->custom) e->use_pipe = 0;  // runtime parameters: the direct kernel only
   if (e->use_pipe) {
     cudaDeviceProp prop;
     int per_sm = 0;
@@ -1150,20 +1196,12 @@ int qs_step_n(qs_env_t* e, int64_t n_steps, const void* actions, void* obs_out, 
   a.actions = actions; a.obs = obs_out; a.reward = reward_out; a.done = done_out;
   const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
   cudaStream_t st = (cudaStream_t)stream;
-  const bool f32 = e->cfg.dtype == QS_F32;
-  switch (e->cfg.env_kind) {
-    case QS_HOVER:
-      if (f32) multi_step_kernel<float, QS_HOVER><<<grid, kBlock, 0, st>>>(a, n_steps); else multi_step_kernel<double, QS_HOVER><<<grid, kBlock, 0, st>>>(a, n_steps);
-      break;
-    case QS_DOCK_V0:
-      if (f32) multi_step_kernel<float, QS_DOCK_V0><<<grid, kBlock, 0, st>>>(a, n_steps); else multi_step_kernel<double, QS_DOCK_V0><<<grid, kBlock, 0, st>>>(a, n_steps);
-      break;
-    default:
-      if (f32) multi_step_kernel<float, QS_DOCK_V2><<<grid, kBlock, 0, st>>>(a, n_steps); else multi_step_kernel<double, QS_DOCK_V2><<<grid, kBlock, 0, st>>>(a, n_steps);
-      break;
-  }
-  QS_CUDA(cudaGetLastError());
-  return QS_OK;
+  return dispatch_env(e, [&](auto tt, auto kind, auto prm) -> int {
+    using T = typename decltype(tt)::type;
+    multi_step_kernel<T, decltype(kind)::value, decltype(prm)><<<grid, kBlock, 0, st>>>(a, prm, n_steps);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+  });
 }
 
 int qs_step(qs_env_t* e, const void* actions, void* obs_out, void* reward_out, uint8_t* done_out, void* stream) {
@@ -1319,12 +1357,14 @@ int qs_expert_action(qs_env_t* e, void* expert_mem, int alias_ini_state, void* a
   DeviceGuard g(e->cfg.device);
   const int64_t n = e->cfg.n_envs;
   const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
-  if (e->cfg.dtype == QS_F32)
-    expert_kernel<float><<<grid, kBlock, 0, (cudaStream_t)stream>>>(e->state, n, (float*)expert_mem, alias_ini_state, (float*)actions_out, obs_inout);
-  else
-    expert_kernel<double><<<grid, kBlock, 0, (cudaStream_t)stream>>>(e->state, n, (double*)expert_mem, alias_ini_state, (double*)actions_out, obs_inout);
-  QS_CUDA(cudaGetLastError());
-  return QS_OK;
+  return dispatch_env(e, [&](auto tt, auto kind, auto prm) -> int {
+    using T = typename decltype(tt)::type;
+    if constexpr (decltype(kind)::value != QS_HOVER) {
+      expert_kernel<T, decltype(prm)><<<grid, kBlock, 0, (cudaStream_t)stream>>>(e->state, n, (T*)expert_mem, alias_ini_state, (T*)actions_out, obs_inout, prm);
+      QS_CUDA(cudaGetLastError());
+    }
+    return QS_OK;
+  });
 }
 
 int qs_peek_state(qs_env_t* e, const int64_t* env_ids, int64_t k, double* chaser_out, double* target_out, int32_t* t_out, void* stream) {
@@ -1334,12 +1374,13 @@ int qs_peek_state(qs_env_t* e, const int64_t* env_ids, int64_t k, double* chaser
   const unsigned grid = (unsigned)((k + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
   const bool hover = e->cfg.env_kind == QS_HOVER;
+  const double* o = e->origin;
   if (e->cfg.dtype == QS_F32) {
-    if (hover) peek_state_kernel<float, true><<<grid, 128, 0, st>>>(e->state, e->cfg.n_envs, env_ids, k, chaser_out, target_out, t_out);
-    else peek_state_kernel<float, false><<<grid, 128, 0, st>>>(e->state, e->cfg.n_envs, env_ids, k, chaser_out, target_out, t_out);
+    if (hover) peek_state_kernel<float, true><<<grid, 128, 0, st>>>(e->state, e->cfg.n_envs, env_ids, k, chaser_out, target_out, t_out, o[0], o[1], o[2]);
+    else peek_state_kernel<float, false><<<grid, 128, 0, st>>>(e->state, e->cfg.n_envs, env_ids, k, chaser_out, target_out, t_out, o[0], o[1], o[2]);
   } else {
-    if (hover) peek_state_kernel<double, true><<<grid, 128, 0, st>>>(e->state, e->cfg.n_envs, env_ids, k, chaser_out, target_out, t_out);
-    else peek_state_kernel<double, false><<<grid, 128, 0, st>>>(e->state, e->cfg.n_envs, env_ids, k, chaser_out, target_out, t_out);
+    if (hover) peek_state_kernel<double, true><<<grid, 128, 0, st>>>(e->state, e->cfg.n_envs, env_ids, k, chaser_out, target_out, t_out, o[0], o[1], o[2]);
+    else peek_state_kernel<double, false><<<grid, 128, 0, st>>>(e->state, e->cfg.n_envs, env_ids, k, chaser_out, target_out, t_out, o[0], o[1], o[2]);
   }
   QS_CUDA(cudaGetLastError());
   return QS_OK;

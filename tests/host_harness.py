@@ -7,7 +7,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_build", "libqs_host_harness.so")
-SRC = [os.path.join(HERE, "host_harness.cpp"), os.path.join(HERE, "..", "quadsim_b200", "csrc", "qs_core.cuh")]
+SRC = [os.path.join(HERE, "host_harness.cpp"), os.path.join(HERE, "..", "quadsim_b200", "csrc", "qs_core.cuh"),
+       os.path.join(HERE, "..", "include", "quadsim_b200.h")]
 KINDS = {"hovering-v0": 0, "docking-v0": 1, "docking-v2": 2}
 _lib = None
 
@@ -22,7 +23,7 @@ def lib():
                                    "-o", LIB, SRC[0]])
         L = C.CDLL(LIB)
         L.hh_create.restype = C.c_void_p
-        L.hh_create.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_int]
+        L.hh_create.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_int, C.c_void_p]
         L.hh_destroy.argtypes = [C.c_int, C.c_void_p]
         L.hh_reset.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.hh_step.argtypes = [C.c_int, C.c_void_p] + [C.c_void_p] * 6
@@ -50,11 +51,19 @@ def _p(a):
 
 
 class HostVecEnv:
-    def __init__(self, env_id, n, dtype=np.float32, seed=0, env_id0=0, randomize=0, half_width=0.0, auto_reset=True):
+    def __init__(self, env_id, n, dtype=np.float32, seed=0, env_id0=0, randomize=0, half_width=0.0, auto_reset=True, params=None,
+                 runtime_params=False):
+        """params: dict of qs_env_params_t overrides -> the RuntimeParams arithmetic (what use_params = 1 handles run);
+        runtime_params=True takes that path with the reference's literals (it must then equal the compiled-in constants)."""
         self.kind, self.n, self.dtype = KINDS[env_id], n, np.dtype(dtype)
         self.f64 = int(self.dtype == np.float64)
         self.obs_dim = 13 if self.kind == 0 else 12
-        self._h = lib().hh_create(self.f64, self.kind, n, seed, env_id0, randomize, half_width, int(auto_reset))
+        self._params = None
+        if params or runtime_params:
+            from oracle import oracle as O  # the oracle's Params mirrors qs_env_params_t field for field (test infrastructure)
+            self._params = O.make_params(self.kind, params or {})
+        self._h = lib().hh_create(self.f64, self.kind, n, seed, env_id0, randomize, half_width, int(auto_reset),
+                                  C.cast(C.pointer(self._params), C.c_void_p) if self._params is not None else None)
 
     def reset(self):
         obs = np.zeros((self.n, self.obs_dim), self.dtype)

@@ -7,7 +7,7 @@ import pytest
 
 from host_harness import HostVecEnv
 from oracle import oracle as O
-from qs_testutil import load_golden
+from qs_testutil import golden_params, load_golden
 
 
 def rel_err(a, ref):
@@ -16,14 +16,17 @@ def rel_err(a, ref):
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 1e-4)])
-@pytest.mark.parametrize("name", ["dock_v0_kat", "dock_v2_kat", "dock_v0_rand", "dock_v2_rand", "dock_v0_docked"])
+@pytest.mark.parametrize("name", ["dock_v0_kat", "dock_v2_kat", "dock_v0_rand", "dock_v2_rand", "dock_v0_docked", "dock_v0_params", "dock_v2_params"])
 def test_reference_tapes(name, dtype, tol):
+    """`*_params`: the tapes recorded on the unmodified reference with NON-default mass / inertia / arm length / dt / gravity /
+    motor constant / gains / set-points / start positions / dock-port offset, replayed through the RuntimeParams arithmetic
+    (what a handle created with use_params = 1 runs on the GPU)."""
     g = load_golden(name)
     env_id = {0: "docking-v0", 1: "docking-v2"}[int(g["kind"])]
     K, Tn = g["actions"].shape[:2]
     seed = int(g["seed"])
     env = HostVecEnv(env_id, K, dtype, seed=max(seed, 0), env_id0=int(g["env_id0"]), randomize=1 if seed >= 0 else 0,
-                     half_width=float(g["half_width"]))
+                     half_width=float(g["half_width"]), params=golden_params(g))
     assert rel_err(env.reset(), g["obs0"]) <= (1e-13 if dtype == np.float64 else 1e-6)
     assert np.array_equal(env.get_state()["chaser"][:, :3], g["ini_pos0"])
     for t in range(Tn):
@@ -41,6 +44,67 @@ def test_reference_tapes(name, dtype, tol):
         for k in np.nonzero(done)[0]:
             assert np.array_equal(st["chaser"][k, :3], g["ini_pos"][k, t])
     env.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("env_id", ["docking-v0", "docking-v2", "hovering-v0"])
+def test_runtime_params_with_default_values_equal_the_compiled_in_constants(env_id, dtype):
+    """make_runtime_params(qs_default_params) must reproduce DefaultParams: the same trajectories bit for bit (the three
+    pre-test thresholds of the attitude clamp are the one deliberate difference, and they only decide whether the exact,
+    out-of-line clamp is consulted).  fp64 compares the guarded arithmetic on both sides (runtime parameters never
+    speculate)."""
+    n, steps = 256, 300
+    rand = 2 if env_id.startswith("hover") else 1
+    a = HostVecEnv(env_id, n, dtype, seed=4, randomize=rand)
+    b = HostVecEnv(env_id, n, dtype, seed=4, randomize=rand, runtime_params=True)
+    a.set_speculative(False)
+    assert np.array_equal(a.reset(), b.reset())
+    rng = np.random.RandomState(0)
+    lo = 0.0 if env_id.startswith("hover") else -1.0
+    n_done = 0
+    for t in range(steps):
+        act = rng.uniform(lo, 1, (n, 4)).astype(np.float32)
+        ra, rb = a.step(act), b.step(act)
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x, y), t
+        n_done += int(ra[2].sum())
+    sa, sb = a.get_state(), b.get_state()
+    assert all(np.array_equal(sa[k], sb[k]) for k in sa) and (n_done > n or env_id.startswith("hover"))
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 1e-4)])
+@pytest.mark.parametrize("env_id", ["docking-v0", "docking-v2", "hovering-v0"])
+def test_runtime_params_thresholds_vs_oracle(env_id, dtype, tol):
+    """The members of qs_env_params_t that are literals inside the reference's step() -- range limit, docking tolerances,
+    altitude floor, step limit, attitude clamp angles -- cannot be varied on the live reference; the RuntimeParams arithmetic
+    is checked against the parametrised oracle instead (itself pinned to the reference on every attribute-level parameter by
+    the *_params tapes): 400 steps, flags exact in fp64."""
+    n, steps = 512, 400
+    hover = env_id.startswith("hover")
+    prm = dict(range_limit=30.0 if hover else (2.5 if env_id == "docking-v0" else 6.0), max_steps=25, min_altitude=0.4, dock_pos_tol=2.1,
+               dock_vel_tol=0.6, dock_angle_deg=25.0, att_limit_deg=[70.0, 60.0, 150.0], mass=0.2, dt=0.025)
+    rand = 2 if hover else 1
+    env = HostVecEnv(env_id, n, dtype, seed=8, randomize=rand, params=prm)
+    ora = O.OracleVecEnv(env_id, n, seed=8, randomize=rand, params=prm)
+    assert rel_err(env.reset(), ora.reset()) <= (1e-13 if dtype == np.float64 else 1e-6)
+    rng = np.random.RandomState(1)
+    alive = np.ones(n, bool)
+    docked = overtime = 0
+    for t in range(steps):
+        act = rng.uniform(0.0 if hover else -1.0, 1, (n, 4)).astype(np.float32)
+        obs, rew, done, info, term = env.step(act)
+        o_obs, o_rew, o_done, o_info, o_term = ora.step(act.astype(np.float64), want_term_obs=True)
+        if dtype == np.float64:
+            assert np.array_equal(done, o_done) and np.array_equal(info, o_info), t
+        alive &= done == o_done
+        assert max(rel_err(obs[alive], o_obs[alive]), rel_err(rew[alive], o_rew[alive]), rel_err(term[alive], o_term[alive])) <= tol, t
+        docked += int(((o_info & 4) != 0).sum())
+        overtime += int(((o_info & 8) != 0).sum())
+    assert (~alive).sum() <= 2
+    if not hover:
+        assert docked > 0 and overtime > 0  # the widened docking tolerances and the 25-step limit were both exercised
+    env.close(); ora.close()
 
 
 def test_f64_scalar_math_polynomials():

@@ -195,7 +195,9 @@ def _replay_tape(name, dtype, tol, flags_exact=True):
     return worst, alive
 
 
-TAPES = ["dock_v0_kat", "dock_v2_kat", "dock_v0_rand", "dock_v2_rand", "dock_v0_docked", "dock_v2_rand64"]
+# *_params: recorded on the unmodified reference with NON-default mass / inertia / arm length / dt / gravity / motor constant /
+# gains / set-points / start positions / dock-port offset (make_golden.apply_params) -> the library's qs_env_params_t path
+TAPES = ["dock_v0_kat", "dock_v2_kat", "dock_v0_rand", "dock_v2_rand", "dock_v0_docked", "dock_v2_rand64", "dock_v0_params", "dock_v2_params"]
 
 
 @pytest.mark.parametrize("name", TAPES)
@@ -216,6 +218,87 @@ def test_reference_tapes_fp32(name):
     flips = int((~alive).sum())
     print(name, "fp32 worst rel err", worst, "flag flips", flips, "of", K, "envs x", Tn, "steps")
     assert flips <= int(1e-4 * K * Tn), (flips, K, Tn)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("env_id", ["docking-v0", "docking-v2", "hovering-v0"])
+def test_runtime_params_with_default_values_equal_the_compiled_in_constants(env_id, dtype):
+    """A handle created with use_params = 1 but the reference's own literals runs the RuntimeParams kernels (constants read from
+    the constant bank) and must reproduce the compiled-in-constant kernels bit for bit: outputs, state and statistics over 300
+    steps with auto-resets on a ragged env count."""
+    n = 128 * 40 + 17
+    rand = "once" if env_id.startswith("hover") else "episode"
+    a = qs.make_vec(env_id, n, dtype=dtype, seed=4, randomize=rand, want_info=True, want_terminal_obs=True)
+    b = qs.make_vec(env_id, n, dtype=dtype, seed=4, randomize=rand, want_info=True, want_terminal_obs=True, params={"mass": 0.18})
+    assert torch.equal(a.reset(), b.reset())
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    lo = 0.0 if env_id.startswith("hover") else -1.0
+    for t in range(300):
+        act = (torch.rand((n, 4), generator=gen, device=DEV) * (1 - lo) + lo).to(dtype)
+        ra, rb = a.step(act), b.step(act)
+        assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1]) and torch.equal(ra[2], rb[2]), t
+        assert torch.equal(ra[3].bits, rb[3].bits) and torch.equal(ra[3].terminal_observation, rb[3].terminal_observation), t
+    sa, sb = a.get_state(), b.get_state()
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    assert a.stats() == b.stats()
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-4)])
+@pytest.mark.parametrize("env_id", ["docking-v0", "docking-v2", "hovering-v0"])
+def test_runtime_params_thresholds_vs_oracle(env_id, dtype, tol):
+    """The members of qs_env_params_t that are literals inside the reference's step() (range limit, docking tolerances, altitude
+    floor, step limit, clamp angles) cannot be varied on the live reference: the kernels are checked against the parametrised
+    oracle (pinned to the reference on every attribute-level parameter by the *_params tapes).  Also through qs_step_n."""
+    n, steps = 4096 + 11, 300
+    hover = env_id.startswith("hover")
+    prm = dict(range_limit=30.0 if hover else (2.5 if env_id == "docking-v0" else 6.0), max_steps=25, min_altitude=0.4, dock_pos_tol=2.1,
+               dock_vel_tol=0.6, dock_angle_deg=25.0, att_limit_deg=[70.0, 60.0, 150.0], mass=0.2, dt=0.025)
+    rand = "once" if hover else "episode"
+    env = qs.make_vec(env_id, n, dtype=dtype, seed=8, randomize=rand, want_info=True, want_terminal_obs=True, params=prm)
+    twin = qs.make_vec(env_id, n, dtype=dtype, seed=8, randomize=rand, params=prm)  # stepped T steps per launch
+    ora = O.OracleVecEnv(env_id, n, seed=8, randomize=RAND[rand], params=prm, nthreads=8)
+    assert rel_err(N(env.reset()), ora.reset()) <= (1e-13 if dtype == torch.float64 else 1e-6)
+    twin.reset()
+    gen = torch.Generator().manual_seed(1)
+    alive = np.ones(n, bool)
+    tape, outs = [], []
+    docked = overtime = 0
+    for t in range(steps):
+        a = (torch.rand((n, 4), generator=gen) * (1 if hover else 2) - (0 if hover else 1)).float()
+        tape.append(a)
+        obs, rew, done, info = env.step(a.to(DEV, dtype))
+        o_obs, o_rew, o_done, o_info, o_term = ora.step(a.double().numpy(), want_term_obs=True)
+        if dtype == torch.float64:
+            assert np.array_equal(done.cpu().numpy(), o_done != 0) and np.array_equal(info.bits.cpu().numpy(), o_info), t
+        alive &= done.cpu().numpy() == (o_done != 0)
+        assert max(rel_err(N(obs)[alive], o_obs[alive]), rel_err(N(rew)[alive], o_rew[alive]), rel_err(N(info.terminal_observation)[alive], o_term[alive])) <= tol, t
+        outs.append((obs.clone(), rew.clone(), done.clone()))
+        docked += int(((o_info & 4) != 0).sum())
+        overtime += int(((o_info & 8) != 0).sum())
+    assert (~alive).sum() <= n * steps * 1e-4
+    if not hover:
+        assert docked > 0 and overtime > 0
+    m_obs, m_rew, m_done = twin.step_many(torch.stack(tape).to(DEV, dtype))
+    ok = torch.ones(n, dtype=torch.bool, device=DEV)  # qs_step_n is a separate compilation: last-bit differences may flip an fp32 flag
+    for t in range(steps):
+        if dtype == torch.float64:
+            assert torch.equal(m_done[t], outs[t][2]), t
+        ok &= m_done[t] == outs[t][2]
+        assert float((m_obs[t] - outs[t][0])[ok].abs().max()) <= tol and float((m_rew[t] - outs[t][1])[ok].abs().max()) <= tol, t
+    assert int((~ok).sum()) <= n * steps * 1e-4
+    env.close(); twin.close(); ora.close()
+
+
+def test_invalid_params_are_refused():
+    for bad in ({"mass": 0.0}, {"att_limit_deg": [85, 95, 175]}, {"att_limit_deg": [85, 85, 60]}, {"max_steps": 0}, {"inertia": [1e-4, -1.0, 1e-4]}):
+        with pytest.raises(qs.QuadSimError):
+            qs.make_vec("docking-v2", 16, params=bad)
+    with pytest.raises(qs.QuadSimError, match="1023"):
+        qs.make_vec("docking-v2", 16, dtype=torch.float32, params={"max_steps": 5000})
+    qs.make_vec("docking-v2", 16, dtype=torch.float64, params={"max_steps": 5000}).close()
+    with pytest.raises(ValueError):
+        qs.make_vec("docking-v2", 16, params={"no_such_parameter": 1.0})
 
 
 @pytest.mark.parametrize("v", [0, 2])
