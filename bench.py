@@ -305,11 +305,13 @@ def config2_record(args, rank, dev, D):
         for k in range(T):
             env.step(acts[k])
         ev[1].record()
-        env.step_many(acts[:8])  # warm the multi-step kernel
+        env.step_many(acts)  # untimed: warms the multi-step kernel and the allocator (T x N x 13 outputs)
+        torch.cuda.synchronize(dev)
         ev[2].record()
         env.step_many(acts)
         ev[3].record()
         torch.cuda.synchronize(dev)
+        out["binding"] = "PyTorch extension (csrc/qs_torch_ext.cpp)" if env._bound is not None else "ctypes"
         out[dtype] = {"per_launch_us_per_step": 1e3 * ev[0].elapsed_time(ev[1]) / T, "step_n_us_per_step": 1e3 * ev[2].elapsed_time(ev[3]) / T,
                       "step_n_env_steps_per_s": n * T / (ev[2].elapsed_time(ev[3]) * 1e-3), "steps": T}
         env.close()

@@ -138,6 +138,38 @@ def load():
     return L
 
 
+_ext = False  # False: not tried yet; None: unavailable
+
+
+def load_ext():
+    """The PyTorch-extension face of the library (csrc/qs_torch_ext.cpp: tensors in, PyTorch's current stream, plain pointers
+    to the C ABI) used on the per-step path, or None when it is neither built nor buildable here -- the ctypes binding above
+    reaches the same entry points, only with a higher per-call cost."""
+    global _ext
+    if _ext is False:
+        _ext = None
+        if os.environ.get("QUADSIM_B200_NO_EXT") != "1":
+            try:
+                import importlib.util
+                import torch  # noqa: F401  (libc10 / libtorch must be loaded first)
+                load()
+                path = _build.ext_path()
+                if not _build.ext_up_to_date():
+                    try:
+                        path = _build.build_ext()
+                    except Exception:
+                        if not os.path.exists(path):
+                            raise
+                spec = importlib.util.spec_from_file_location(_build.EXT_NAME, path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                if mod.abi_version() == ABI_VERSION:
+                    _ext = mod
+            except Exception:
+                _ext = None
+    return _ext
+
+
 def default_params(kind):
     """EnvParams filled with the reference's literals for `kind` (qs_default_params)."""
     p = EnvParams()

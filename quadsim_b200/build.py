@@ -61,5 +61,52 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
     return target
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# The PyTorch-extension face (csrc/qs_torch_ext.cpp): host-only C++ (pybind11 + ATen), links libquadsim_b200.so by rpath.
+EXT_NAME = "_qs_torch_ext"
+EXT_SRC = os.path.join(CSRC, "qs_torch_ext.cpp")
+
+
+def ext_path():
+    import sysconfig
+    return os.path.join(LIB_DIR, EXT_NAME + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def ext_up_to_date():
+    p = ext_path()
+    deps = [EXT_SRC, os.path.join(ROOT, "include", "quadsim_b200.h")]
+    return os.path.exists(p) and all(os.path.getmtime(p) >= os.path.getmtime(d) for d in deps)
+
+
+def build_ext(force=False, verbose=False):
+    """g++ -> quadsim_b200/_lib/_qs_torch_ext.<abi>.so (in-tree, travels to the GPU box like the CUDA library)."""
+    if not force and ext_up_to_date():
+        return ext_path()
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension as E
+    build(force=False)  # the extension links the CUDA library
+    cuda_home = os.environ.get("CUDA_HOME") or "/usr/local/cuda"
+    inc = E.include_paths() + [sysconfig.get_paths()["include"], os.path.join(cuda_home, "include"), os.path.join(ROOT, "include")]
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DTORCH_EXTENSION_NAME=" + EXT_NAME,
+           "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)]
+    for i in inc:
+        cmd += ["-isystem", i]
+    cmd += [EXT_SRC, "-o", ext_path(), "-L" + LIB_DIR, "-lquadsim_b200", "-Wl,-rpath,$ORIGIN"]
+    for lp in E.library_paths():
+        cmd += ["-L" + lp, "-Wl,-rpath," + lp]
+    cmd += ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(os.path.join(LIB_DIR, "build_ext.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + res.stdout)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+    if res.returncode != 0:
+        raise RuntimeError("building the PyTorch extension failed (exit %d); see %s" % (res.returncode, os.path.join(LIB_DIR, "build_ext.log")))
+    return ext_path()
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_ext(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

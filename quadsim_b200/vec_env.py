@@ -124,6 +124,9 @@ class QuadVecEnv:
         _capi.check(self.lib.qs_create(C.byref(h), C.byref(cfg)))
         self._h = h
         self.obs_dim = self.lib.qs_obs_dim(self._h)
+        # per-step path: the PyTorch extension (tensors + current stream -> C ABI) when built, else ctypes
+        self._ext = _capi.load_ext()
+        self._bound = self._ext.bind(h.value) if self._ext is not None else None
         lo, hi, alo, ahi = _space_bounds(kind)
         self.observation_space = make_box(lo, hi, np.float32)
         self.action_space = make_box(alo, ahi, np.float32)
@@ -172,7 +175,8 @@ class QuadVecEnv:
                 ret = (obs, rew, done.view(torch.bool), self._info(bits, term, tc, tt))
                 self._bufs.append(b)
                 self._fast.append(((self.num_envs, 4), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
-                                   C.byref(extras) if extras is not None else None, ret))
+                                   C.byref(extras) if extras is not None else None, ret,
+                                   obs, rew, done, C.addressof(extras) if extras is not None else 0))
         self._turn = (self._turn + 1) % len(self._bufs)
         return self._bufs[self._turn]
 
@@ -227,6 +231,16 @@ class QuadVecEnv:
         if f is not None:
             self._turn = (self._turn + 1) % len(f)
             f = f[self._turn]
+        if f is not None and self._bound is not None and type(actions) is torch.Tensor and actions.dtype == self.dtype and actions.is_cuda:
+            # the extension checks device / shape / contiguity itself and takes PyTorch's current stream of the handle's device
+            try:
+                rc = self._ext.step(self._bound, actions, f[6], f[7], f[8], f[9])
+            except RuntimeError:
+                rc = None  # another device / a view / a wrong shape: the general path below converts or explains
+            if rc is not None:
+                if rc != 0:
+                    _capi.check(rc)
+                return f[5]
         if (f is not None and type(actions) is torch.Tensor and actions.dtype == self.dtype and actions.device == self.device
                 and actions.shape == f[0] and actions.is_contiguous() and self._h is not None):
             if torch.cuda.current_device() == self.device.index:
@@ -297,6 +311,9 @@ class QuadVecEnv:
 
     def close(self):
         if getattr(self, "_h", None) is not None:
+            if getattr(self, "_bound", None) is not None:
+                self._ext.unbind(self._bound)
+                self._bound = None
             self.lib.qs_destroy(self._h)
             self._h = None
 
