@@ -135,7 +135,7 @@ def cpu_baseline(args):
     threads = os.cpu_count() or 1
     os.environ["OMP_NUM_THREADS"] = str(threads)
     os.environ.setdefault("OMP_PROC_BIND", "false")
-    port = cpu_port_run(args.env, 1 << 17, 8, 2, min_seconds=args.port_seconds, threads=threads)
+    port = cpu_port_run(args.env, args.envs_per_gpu, 4, 2, min_seconds=args.port_seconds, threads=threads)  # the reference arm's own sample
     port_rec = {"value": port["value"], "unit": "env-steps/s", "cores": threads, "kind": "port",
                 "sample": "%d envs x %d steps of %s (%.1f s), fp64 C restatement of the reference (oracle/), OpenMP" % (port["envs"], port["steps"], args.env, port["seconds"])}
     try:
