@@ -108,7 +108,7 @@ template <typename T, int KIND = kDockV2> struct DefaultParams {
 };
 
 template <typename T> struct RuntimeParams {
-  static constexpr bool custom = true;
+  static constexpr bool custom = true;  // "not the compiled-in immediates"
   T dt, mass, g, L, lam, mg, inv_m, mass_x_g, inv_g, hl, I0, I1, I2, inv_I0, inv_I1, inv_I2;
   T lim_roll, lim_pitch, lim_yaw, s_roll, t_pitch, t_yaw;
   T kp_roll, kp_pitch, kp_yaw, kd_roll, kd_pitch, kd_yaw, kp_x, kp_y, kp_z, kd_x, kd_y, kd_z, kp_vx, kp_vy, kp_vz;
@@ -1028,7 +1028,9 @@ QS_HD Drone<double> from_spec(const Drone<sdouble>& d) {
   return Drone<double>{d.px.v, d.py.v, d.pz.v, d.vx.v, d.vy.v, d.vz.v, d.q0.v, d.q1.v, d.q2.v, d.q3.v, d.wx.v, d.wy.v, d.wz.v,
                        d.u0.v, d.u1.v, d.u2.v, d.u3.v};
 }
-template <int KIND> QS_HD bool dock_env_step_spec(DockEnv<double>& e, const double act[4], double rel[12], StepOut<double>& o) {
+// Speculative evaluation reads its constants from the same provider: the compiled-in ones folded for sdouble, or the very
+// same runtime block viewed as sdouble members (sdouble is a struct of one double: identical layout).
+template <int KIND, typename P> QS_HD bool dock_env_step_spec(const P& p, DockEnv<double>& e, const double act[4], double rel[12], StepOut<double>& o) {
   DockEnv<sdouble> s;
   s.c = to_spec(e.c); s.t = to_spec(e.t);
   s.dq = Quat<sdouble>{sdouble(e.dq.w), sdouble(e.dq.x), sdouble(e.dq.y), sdouble(e.dq.z)};
@@ -1036,7 +1038,8 @@ template <int KIND> QS_HD bool dock_env_step_spec(DockEnv<double>& e, const doub
   const sdouble a[4] = {sdouble(act[0]), sdouble(act[1]), sdouble(act[2]), sdouble(act[3])};
   sdouble r[12];
   StepOut<sdouble> so;
-  dock_env_step<sdouble, KIND>(DefaultParams<sdouble, KIND>{}, s, a, r, so);
+  if constexpr (P::custom) dock_env_step<sdouble, KIND>(reinterpret_cast<const RuntimeParams<sdouble>&>(p), s, a, r, so);
+  else dock_env_step<sdouble, KIND>(DefaultParams<sdouble, KIND>{}, s, a, r, so);
   const double hidden = ((s.t.u0.v + s.t.u1.v) + (s.t.u2.v + s.t.u3.v)) + ((s.dq.w.v + s.dq.x.v) + (s.dq.y.v + s.dq.z.v));
   const bool ok = !so.nonfinite && (hidden - hidden == 0.0);
   e.c = from_spec(s.c); e.t = from_spec(s.t);
@@ -1047,6 +1050,9 @@ template <int KIND> QS_HD bool dock_env_step_spec(DockEnv<double>& e, const doub
   o.reward = so.reward.v; o.done = so.done; o.docking = so.docking; o.overlimit = so.overlimit; o.overtime = so.overtime;
   o.nonfinite = so.nonfinite;
   return ok;
+}
+template <int KIND> QS_HD bool dock_env_step_spec(DockEnv<double>& e, const double act[4], double rel[12], StepOut<double>& o) {
+  return dock_env_step_spec<KIND>(DefaultParams<double, KIND>{}, e, act, rel, o);
 }
 
 // =========================================================================================================

@@ -287,7 +287,7 @@ constexpr bool kSpec64 = false;
 constexpr bool kSpec64 = kFast64;  // -DQS_NO_SPEC64: the guarded fp64 arithmetic on the main path (A/B)
 #endif
 
-template <int KIND> __device__ __noinline__ StepTail dock_step_replay(const StepArgs& a, int64_t i);
+template <int KIND, typename P> __device__ __noinline__ StepTail dock_step_replay(const StepArgs& a, const P& prm, int64_t i);
 // kernel-parameter type of the model constants: DefaultParams (empty: every constant an immediate) or RuntimeParams (the
 // handle's qs_env_params_t, read from the constant bank)
 template <typename T, int KIND, bool CUSTOM> struct PrmSel { using type = DefaultParams<T, KIND>; };
@@ -304,7 +304,7 @@ __device__ __forceinline__ StepTail dock_step_loaded(const StepArgs& a, const P&
   T rel[12];
   StepOut<T> o;
   if constexpr (SPEC) {
-    if (!dock_env_step_spec<KIND>(e, act, rel, o)) return dock_step_replay<KIND>(a, i);
+    if (!dock_env_step_spec<KIND>(prm, e, act, rel, o)) return dock_step_replay<KIND, P>(a, prm, i);
   } else {
     dock_env_step<T, KIND>(prm, e, act, rel, o);
   }
@@ -326,14 +326,14 @@ __device__ __forceinline__ StepTail dock_step_loaded(const StepArgs& a, const P&
   store_words<T, NW>(a.state, i, w);
   return tail;
 }
-template <int KIND> __device__ __noinline__ StepTail dock_step_replay(const StepArgs& a, int64_t i) {
+template <int KIND, typename P> __device__ __noinline__ StepTail dock_step_replay(const StepArgs& a, const P& prm, int64_t i) {
   constexpr int NW = dock_words<double>();
   double w[NW], act[4];
   load_words<double, NW>(a.state, i, w);
   load_action<double>(a.actions, i, act);
-  return dock_step_loaded<double, KIND, false>(a, DefaultParams<double, KIND>{}, i, w, act);  // only the compiled-in constants speculate
+  return dock_step_loaded<double, KIND, false, P>(a, prm, i, w, act);
 }
-template <typename T, typename P> constexpr bool dock_spec() { return !is_f32<T>::value && kSpec64 && !P::custom; }
+template <typename T, typename P> constexpr bool dock_spec() { return !is_f32<T>::value && kSpec64; }
 
 template <typename T, int KIND, typename P>
 __global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ P prm) {
@@ -387,8 +387,8 @@ template <typename T> constexpr int pipe_smem_bytes() { return pipe_rows<T>() * 
 
 // (A warp-granular version -- every warp its own stage, mbarrier and work counter, no CTA barrier, a unit = 20 copies of
 // 512 B -- was measured slower: 158 vs 134 us fp64, 83 vs 73 us fp32.  One 40 KB copy per tile is what the copy engine likes.)
-template <typename T, int KIND>
-__global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_pipe_kernel(const __grid_constant__ StepArgs a, unsigned int* sched) {
+template <typename T, int KIND, typename P>
+__global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_pipe_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ P prm, unsigned int* sched) {
   using V = typename Row<T>::V;
   constexpr int NW = dock_words<T>(), W = Row<T>::W, NR = NW / W, AR = 4 / W;  // AR: 16-byte rows per action
   pdl_prologue();
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T>()) dock_step_pipe_kernel
     }
     const unsigned mask = __ballot_sync(0xffffffffu, active);
     if (active) {
-      const StepTail tail = dock_step_loaded<T, KIND, dock_spec<T, DefaultParams<T, KIND>>()>(a, DefaultParams<T, KIND>{}, i, w, act);
+      const StepTail tail = dock_step_loaded<T, KIND, dock_spec<T, P>()>(a, prm, i, w, act);
       warp_stats_update(a.warp_stats, i, mask, tail.done, tail.docking, tail.nonfinite, tail.ret, tail.len);
     }
   }
@@ -954,21 +954,19 @@ int launch_step(qs_env* e, const StepArgs& a, cudaStream_t st, int slot = 0) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kBlock); cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 1 : 0;
-  if (e->use_pipe && slot >= 0) {  // never with runtime parameters (qs_create)
+  if (e->use_pipe && slot >= 0) {
     const int tiles = (int)((a.n + kBlock - 1) / kBlock);
     unsigned int* sched = e->sched + 2 * slot;
     cfg.gridDim = dim3((unsigned)(tiles < e->pipe_grid ? tiles : e->pipe_grid));
-    const bool v0 = e->cfg.env_kind == QS_DOCK_V0;
-    if (e->cfg.dtype == QS_F32) {
-      cfg.dynamicSmemBytes = pipe_smem_bytes<float>();
-      if (v0) QS_CUDA(cudaLaunchKernelEx(&cfg, dock_step_pipe_kernel<float, QS_DOCK_V0>, a, sched));
-      else QS_CUDA(cudaLaunchKernelEx(&cfg, dock_step_pipe_kernel<float, QS_DOCK_V2>, a, sched));
-    } else {
-      cfg.dynamicSmemBytes = pipe_smem_bytes<double>();
-      if (v0) QS_CUDA(cudaLaunchKernelEx(&cfg, dock_step_pipe_kernel<double, QS_DOCK_V0>, a, sched));
-      else QS_CUDA(cudaLaunchKernelEx(&cfg, dock_step_pipe_kernel<double, QS_DOCK_V2>, a, sched));
-    }
-    return QS_OK;
+    return dispatch_env(e, [&](auto tt, auto kind, auto prm) -> int {
+      using T = typename decltype(tt)::type;
+      constexpr int KIND = decltype(kind)::value;
+      if constexpr (KIND != QS_HOVER) {
+        cfg.dynamicSmemBytes = pipe_smem_bytes<T>();
+        QS_CUDA(cudaLaunchKernelEx(&cfg, dock_step_pipe_kernel<T, KIND, decltype(prm)>, a, prm, sched));
+      }
+      return QS_OK;
+    });
   }
   cfg.gridDim = dim3((unsigned)((a.n + kBlock - 1) / kBlock));
   return dispatch_env(e, [&](auto tt, auto kind, auto prm) -> int {
@@ -1098,19 +1096,27 @@ int qs_create(qs_env_t** out, const qs_config_t* cfg) {
   // QUADSIM_B200_KERNEL=pipe|direct overrides.
   e->use_pipe = e->cfg.dtype == QS_F64;
   if (const char* k = getenv("QUADSIM_B200_KERNEL")) e->use_pipe = strcmp(k, "pipe") == 0 ? 1 : (strcmp(k, "direct") == 0 ? 0 : e->use_pipe);
-  if (e->cfg.env_kind == QS_HOVER || e->custom) e->use_pipe = 0;  // runtime parameters: the direct kernel only
+  if (e->cfg.env_kind == QS_HOVER) e->use_pipe = 0;
+  // QUADSIM_B200_CONSTS=bank: run even default handles on the RuntimeParams kernels (constants as constant-bank operands
+  // instead of immediates -- an A/B switch: 64-bit immediates cost the fp64 kernel an extra instruction each)
+  if (const char* c = getenv("QUADSIM_B200_CONSTS")) { if (strcmp(c, "bank") == 0) e->custom = true; }
   if (e->use_pipe) {
     cudaDeviceProp prop;
     int per_sm = 0;
-    const bool f32 = e->cfg.dtype == QS_F32;
-    const int smem = f32 ? pipe_smem_bytes<float>() : pipe_smem_bytes<double>();
-    const void* k0 = f32 ? (const void*)dock_step_pipe_kernel<float, QS_DOCK_V0> : (const void*)dock_step_pipe_kernel<double, QS_DOCK_V0>;
-    const void* k2 = f32 ? (const void*)dock_step_pipe_kernel<float, QS_DOCK_V2> : (const void*)dock_step_pipe_kernel<double, QS_DOCK_V2>;
-    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess ||
-        cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, kBlock, smem) != cudaSuccess ||
-        per_sm < 1 || cudaMalloc(&e->sched, (kHostStreams + 1) * 2 * sizeof(unsigned int)) != cudaSuccess ||
+    cudaError_t perr = cudaGetDeviceProperties(&prop, cfg->device);
+    if (perr == cudaSuccess) {
+      dispatch_env(e, [&](auto tt, auto kind, auto prm) -> int {
+        using T = typename decltype(tt)::type;
+        constexpr int KIND = decltype(kind)::value;
+        if constexpr (KIND != QS_HOVER) {
+          auto kfn = dock_step_pipe_kernel<T, KIND, decltype(prm)>;
+          perr = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem_bytes<T>());
+          if (perr == cudaSuccess) perr = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kBlock, pipe_smem_bytes<T>());
+        }
+        return QS_OK;
+      });
+    }
+    if (perr != cudaSuccess || per_sm < 1 || cudaMalloc(&e->sched, (kHostStreams + 1) * 2 * sizeof(unsigned int)) != cudaSuccess ||
         cudaMemset(e->sched, 0, (kHostStreams + 1) * 2 * sizeof(unsigned int)) != cudaSuccess) {
       int rc = fail(QS_ERR_CUDA, "qs_create: pipelined kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
       qs_destroy(e);

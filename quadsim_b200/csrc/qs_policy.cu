@@ -600,7 +600,7 @@ __device__ __forceinline__ void pdl_prologue() {
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
-__global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const StepArgs a) {
+__device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a) {
   pdl_prologue();
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -828,6 +828,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const Step
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
 }
+__global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const StepArgs a) { policy_fwd_ws_body(a); }
+// Register-capped builds of the same kernel for the sliced rollout: a policy CTA at 128 registers x 320 threads leaves an SM
+// room for ONE 128-thread env CTA (80 registers) next to it, at 80 registers for three -- and it is the env kernel's occupancy
+// that decides how much of its HBM time hides under the other slice's policy kernel.  The cap costs ~100 bytes of spills.
+template <int REGS> __global__ void __maxnreg__(REGS) policy_fwd_ws_kernel_capped(const StepArgs a) { policy_fwd_ws_body(a); }
 
 }  // namespace
 
@@ -837,6 +842,7 @@ struct NvtxRange {  // see qs_lib.cu
 };
 
 constexpr int kMaxSlices = 8;
+constexpr int kDefaultPolicyRegs = 128;  // per-thread register build of the rollout forward kernel (see policy_fwd_ws_kernel_capped)
 struct qs_policy {
   int device = 0;
   unsigned char* packed = nullptr;
@@ -874,6 +880,9 @@ int qs_policy_create(qs_policy_t** out, int device) {
       (err = cudaFuncSetAttribute(policy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
+      (err = cudaFuncSetAttribute(policy_fwd_ws_kernel_capped<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
+      (err = cudaFuncSetAttribute(policy_fwd_ws_kernel_capped<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
+      (err = cudaFuncSetAttribute(policy_fwd_ws_kernel_capped<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
       (err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, policy_kernel<true>, kThreads, kSmemBytes)) != cudaSuccess) {
     int rc = qs_fail_(QS_ERR_CUDA, "qs_policy_create: %s", cudaGetErrorString(err));
     cudaFree(p->packed);
@@ -972,7 +981,12 @@ int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, u
     const int ws_ctas = (int)(((n + kTileRows - 1) / kTileRows + kWsGroups - 1) / kWsGroups);
     cfg.gridDim = dim3(ws_ctas < p->grid ? ws_ctas : p->grid); cfg.blockDim = dim3(kWsThreads); cfg.dynamicSmemBytes = kWsSmemBytes;
     cfg.stream = (cudaStream_t)stream; cfg.attrs = attr; cfg.numAttrs = na;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, policy_fwd_ws_kernel, a);
+    // QUADSIM_B200_POLICY_REGS = 128 (uncapped build) | 96 | 80 | 72: see policy_fwd_ws_kernel_capped
+    static const int regs = [] { const char* v = getenv("QUADSIM_B200_POLICY_REGS"); return v ? atoi(v) : kDefaultPolicyRegs; }();
+    cudaError_t le = regs == 96   ? cudaLaunchKernelEx(&cfg, policy_fwd_ws_kernel_capped<96>, a)
+                     : regs == 80 ? cudaLaunchKernelEx(&cfg, policy_fwd_ws_kernel_capped<80>, a)
+                     : regs == 72 ? cudaLaunchKernelEx(&cfg, policy_fwd_ws_kernel_capped<72>, a)
+                                  : cudaLaunchKernelEx(&cfg, policy_fwd_ws_kernel, a);
     if (le != cudaSuccess) { cudaSetDevice(prev); return qs_fail_(QS_ERR_CUDA, "qs_policy_step: %s", cudaGetErrorString(le)); }
   }
   cudaError_t e = cudaGetLastError();

@@ -61,9 +61,9 @@ template <typename P> inline void dock_step_like_kernel(const P& prm, int kind, 
   else dock_env_step<float, kDockV2>(prm, e, act, rel, o);
 }
 template <typename P> inline void dock_step_like_kernel(const P& prm, int kind, DockEnv<double>& e, const double* act, double* rel, StepOut<double>& o, int64_t& replays, int spec) {
-  if (kFast64 && spec && !P::custom) {  // runtime parameters never take the speculative path (qs_lib.cu: dock_spec)
+  if (kFast64 && spec) {
     const DockEnv<double> e0 = e;
-    const bool ok = kind == kDockV0 ? dock_env_step_spec<kDockV0>(e, act, rel, o) : dock_env_step_spec<kDockV2>(e, act, rel, o);
+    const bool ok = kind == kDockV0 ? dock_env_step_spec<kDockV0>(prm, e, act, rel, o) : dock_env_step_spec<kDockV2>(prm, e, act, rel, o);
     if (ok) return;
     e = e0;
     replays++;
