@@ -264,27 +264,52 @@ int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, u
                    void* stream);
 
 
-/* ---- PPO2 minibatch gradient: forward + loss + backward through the activations in one kernel -------------------------
+/* ---- PPO2 minibatch gradient: forward + loss + backward through the activations in one kernel, weight gradients in a second
  * The loss graph of the reference's PPO2 (rl_baselines/ppo2/ppo2.py:138-189: clipped surrogate on normalised advantages
- * (:265-266), clipped value loss, entropy bonus) for the minibatch rows idx[0..batch) of a flat rollout.  Per 128-sample
- * tile the kernel runs the policy forward, evaluates the per-sample loss and d loss / d (mean, value, logstd) in fp32, and
- * pushes the gradient back through the two hidden layers on the tensor cores.  It writes the operands of the weight-
- * gradient GEMMs -- which reduce over the whole minibatch and are the caller's (a library GEMM per layer):
- *     d W1  = dz1^T . a1   ([128,32]: columns 0-11 + 16-27 = the two halves of the hi/lo input split; column 12 = d b1)
- *     d [Wp;Wv | bp;bv] = dz2^T . h   (h rows are [h(128), 1, 1, 0...]: column 128 of the product = d bias)
- *     d [W3p;w3v] = dOut^T . hpv,  d (b3p, b3v) = column sums of dOut,  d logstd = column sums of per_sample[:, 8:12]
- * per_sample[i] = (dOut: d mean 0-3, d value, 0,0,0 | d logstd 0-3 | pg_loss_i, vf_loss_i, approxkl_i, clipfrac_i); the
- * gradients already carry the 1/batch of the mean and vf_coef; the entropy term (-ent_coef per logstd) is the caller's. */
+ * (:265-266), clipped value loss, entropy bonus) for the minibatch rows idx[0..batch) of a flat rollout.  Kernel 1: per
+ * 128-sample tile the policy forward, the per-sample loss and d loss / d (mean, value, logstd) in fp32, and the gradient pushed
+ * back through the two hidden layers on the tensor cores; it leaves the bf16 operands of the weight-gradient contraction in
+ * the caller's workspace as ready-made tensor-core operand images (opaque; sizes below) and adds the column sums of the
+ * per-sample block to col_sums.  Kernel 2 (split-K over the minibatch, accumulators in tensor memory) reduces them to
+ *     g1[128,32]  = dz1^T . a1        columns 0-11 + 16-27 = d W1 (the two halves of the hi/lo input split), column 12 = d b1
+ *     g2[256,144] = dz2^T . [h|1 1 0] rows 0-127 = d Wp, rows 128-255 = d Wv, column 128 = d bias
+ *     g3[256,16]  = [hp|hv]^T . dOut  rows 0-127, columns 0-3 = d W3p^T; rows 128-255, column 4 = d w3v
+ * per_sample[i] (optional) = (dOut: d mean 0-3, d value, 0,0,0 | d logstd 0-3 | pg_loss_i, vf_loss_i, approxkl_i, clipfrac_i);
+ * col_sums[16] = its column sums: d (b3p, b3v) = [0..4], d logstd = [8..11], the logged loss terms = [12..15].  The gradients
+ * already carry the 1/batch of the mean and vf_coef; the entropy term (-ent_coef per logstd) is the caller's.
+ * Workspace bytes for a minibatch of `batch` samples, T = ceil(batch / 128) tiles: a1 T*8192, h T*36864, hpv T*65536,
+ * dz2 T*65536, dz1 T*32768, dout T*4096. */
 typedef struct {
   const float *obs, *actions, *returns, *values, *neglogp; /* the rollout, flat: [M,12], [M,4], [M], [M], [M] */
   const int64_t* idx;      /* [batch] row numbers, or NULL for rows 0..batch-1 */
   int64_t batch;
   const float* adv_stats;  /* device [2]: mean and 1/(std + 1e-8) of (returns - values) over the minibatch (ppo2.py:265-266) */
   float cliprange, cliprange_vf, vf_coef; /* cliprange_vf < 0: unclipped value loss */
-  void *a1, *h, *hpv, *dz2, *dz1;         /* bf16 rows out: [batch,32], [batch,144], [batch,256], [batch,256], [batch,128] */
-  float* per_sample;                      /* [batch,16] out */
+  void *a1, *h, *hpv, *dz2, *dz1, *dout;  /* workspace (operand images, see above) */
+  float* per_sample;                      /* [batch,16] out, or NULL */
+  float* col_sums;                        /* [16] out */
+  float *g1, *g2, *g3;                    /* [128,32], [256,144], [256,16] out */
 } qs_ppo_grad_t;
 int qs_policy_ppo_grad(qs_policy_t* p, const qs_ppo_grad_t* g, void* stream);
+
+/* The optimiser step of the update in one launch: tf.clip_by_global_norm(grads, max_grad_norm) followed by
+ * tf.train.AdamOptimizer(learning_rate, epsilon=1e-5).apply_gradients (rl_baselines/ppo2/ppo2.py:200-207), TensorFlow's
+ * formulation: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t); m += (1 - b1)(g - m); v += (1 - b2)(g^2 - v); p -= lr_t m / (sqrt(v) + eps).
+ * Up to 16 float32 device tensors; `step` counts from 1 -- or, with a device-resident int64 `step_counter` (nullable), the
+ * kernel increments that counter and derives lr_t from it (what a captured CUDA graph needs: nothing step-dependent is baked
+ * into the launch); max_grad_norm <= 0 disables clipping; grad_norm_out (device [1], nullable) receives the unclipped norm. */
+typedef struct {
+  float* param;
+  const float* grad;
+  float *m, *v;
+  int64_t n;
+} qs_adam_tensor_t;
+int qs_adam_step(const qs_adam_tensor_t* tensors, int n_tensors, float lr, float beta1, float beta2, float eps, int64_t step,
+                 int64_t* step_counter, float max_grad_norm, float* grad_norm_out, void* stream);
+
+/* The minibatch shuffle of the update (np.random.shuffle(inds), rl_baselines/ppo2/ppo2.py:350-352): out[0..n) = a permutation
+ * of 0..n-1 determined by `seed` (a keyed Feistel bijection with cycle walking: no sort, every entry independent). */
+int qs_permutation(int64_t n, uint64_t seed, int64_t* out, void* stream);
 
 /* ---- device-resident rollout: the step loop of Runner._run (rl_baselines/ppo2/ppo2.py:471-510) ------------------------
  * for t in 0..T-1:  actions, values, neglogp = model.step(obs[t]);  obs[t+1], rewards[t], dones[t+1] = env.step(clip(actions))

@@ -37,6 +37,7 @@
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -228,9 +229,15 @@ struct TrainArgs {
   const int64_t* idx;                                  // [n] or null (rows 0..n-1)
   const float* adv_stats;                              // device [2]: mean and 1/(std + 1e-8) of (returns - values) over the minibatch
   float cliprange, cliprange_vf, vf_coef, inv_batch;
-  uint4 *a1, *h, *hpv, *dz2, *dz1;                     // bf16 rows: [n,32], [n,144], [n,256], [n,256], [n,128]
-  float4* per_sample;                                  // [n,16] fp32
+  // bf16 operand IMAGES of the weight-gradient contraction (dw_kernel below): per 128-sample tile and operand one block in
+  // the canonical no-swizzle MN-major UMMA layout -- the 16-byte chunk (8 features b*8..b*8+7) of sample row r sits at
+  // tile * F * 256 + (b * 16 + (r >> 3)) * 128 + (r & 7) * 16 -- F = 32, 144, 256, 256, 128, 16 features
+  uint4 *a1, *h, *hpv, *dz2, *dz1, *dout;
+  float4* per_sample;                                  // [n,16] fp32 (optional: NULL skips the store)
+  float* col_sums;                                     // [16] fp32: column sums of per_sample over the minibatch (atomics)
 };
+// where the 16-byte chunk `b` of tile row `r` of an F-feature operand image lives (in uint4 units)
+__device__ __forceinline__ int64_t img_chunk(int64_t tile, int F, int r, int b) { return tile * (F * 16) + (b * 16 + (r >> 3)) * 8 + (r & 7); }
 
 struct ObsRow { float4 a, b, c; };
 __device__ __forceinline__ ObsRow load_obs(const float* obs, int64_t i, int64_t n, const int64_t* idx) {
@@ -314,7 +321,11 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
       *reinterpret_cast<uint4*>(a_row + 1 * 2048) = q1;
       *reinterpret_cast<uint4*>(a_row + 2 * 2048) = q2;
       *reinterpret_cast<uint4*>(a_row + 3 * 2048) = q3;
-      if (TRAIN && active) { uint4* dst = t.a1 + i * 4; dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3; }
+      if (TRAIN) {  // rows past the minibatch (last tile) are stored as zeros: they must not contribute to the contraction
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        t.a1[img_chunk(tile, 32, row, 0)] = active ? q0 : z4; t.a1[img_chunk(tile, 32, row, 1)] = active ? q1 : z4;
+        t.a1[img_chunk(tile, 32, row, 2)] = active ? q2 : z4; t.a1[img_chunk(tile, 32, row, 3)] = active ? q3 : z4;
+      }
     }
     proxy_fence();       // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     tc_fence_before();   // orders the previous tile's tcgen05.ld before the barrier (TMEM columns are reused)
@@ -354,14 +365,14 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
         w.z = relu_pack_bf16(r[8 * j + 4], r[8 * j + 5]);
         w.w = relu_pack_bf16(r[8 * j + 6], r[8 * j + 7]);
         *reinterpret_cast<uint4*>(a_row + ((c0 >> 3) + j) * 2048) = w;
-        if (TRAIN && active) t.h[i * 18 + (c0 >> 3) + j] = w;
+        if (TRAIN) t.h[img_chunk(tile, 144, row, (c0 >> 3) + j)] = active ? w : make_uint4(0u, 0u, 0u, 0u);
       }
     }
     *reinterpret_cast<uint4*>(a_row + 16 * 2048) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(a_row + 17 * 2048) = make_uint4(0u, 0u, 0u, 0u);
-    if (TRAIN && active) {  // the bias block goes out with h: dz2^T . [h | 1 1 0...] carries d bias in column 128
-      t.h[i * 18 + 16] = make_uint4(0x3F803F80u, 0u, 0u, 0u);
-      t.h[i * 18 + 17] = make_uint4(0u, 0u, 0u, 0u);
+    if (TRAIN) {  // the bias block goes out with h: dz2^T . [h | 1 1 0...] carries d bias in column 128
+      t.h[img_chunk(tile, 144, row, 16)] = active ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+      t.h[img_chunk(tile, 144, row, 17)] = make_uint4(0u, 0u, 0u, 0u);
     }
     proxy_fence();
     tc_fence_before();
@@ -389,9 +400,10 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
       for (int j = 0; j < 32; j++) w[j] = relu_pack_bf16(r[2 * j], r[2 * j + 1]);
       tmem_st16(trow + (c0 >> 1), w);
       tmem_st16(trow + (c0 >> 1) + 16, w + 16);
-      if (TRAIN && active) {
+      if (TRAIN) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) t.hpv[i * 32 + (c0 >> 3) + j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        for (int j = 0; j < 8; j++)
+          t.hpv[img_chunk(tile, 256, row, (c0 >> 3) + j)] = active ? make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]) : make_uint4(0u, 0u, 0u, 0u);
       }
     }
     tmem_wait_st();
@@ -471,9 +483,28 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
         dval = t.vf_coef * t.inv_batch * (v1 >= v2 ? e1 : e2 * inside);
         kl = 0.5f * (nlp - oldnlp) * (nlp - oldnlp);
         cf = fabsf(ratio - 1.f) > t.cliprange ? 1.f : 0.f;
-        float4* ps = t.per_sample + i * 4;
-        ps[0] = make_float4(dm0, dm1, dm2, dm3); ps[1] = make_float4(dval, 0.f, 0.f, 0.f);
-        ps[2] = make_float4(dl0, dl1, dl2, dl3); ps[3] = make_float4(pg, vf, kl, cf);
+        if (t.per_sample) {
+          float4* ps = t.per_sample + i * 4;
+          ps[0] = make_float4(dm0, dm1, dm2, dm3); ps[1] = make_float4(dval, 0.f, 0.f, 0.f);
+          ps[2] = make_float4(dl0, dl1, dl2, dl3); ps[3] = make_float4(pg, vf, kl, cf);
+        }
+      }
+      {  // column sums over the minibatch (bias gradients of the heads, d logstd, the logged loss terms): warp tree, one
+         // atomic per warp and column (rows past the minibatch hold zeros)
+        float cs[13] = {dm0, dm1, dm2, dm3, dval, dl0, dl1, dl2, dl3, pg, vf, kl, cf};
+#pragma unroll
+        for (int k = 0; k < 13; k++) {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], off);
+        }
+        if ((tid & 31) == 0) {
+#pragma unroll
+          for (int k = 0; k < 13; k++) atomicAdd(t.col_sums + (k < 5 ? k : k + 3), cs[k]);
+        }
+      }
+      {  // dOut as a bf16 operand image row (16 features: d mean 0-3, d value, zeros) for d [W3p; w3v] = hpv^T . dOut
+        t.dout[img_chunk(tile, 16, row, 0)] = make_uint4(pack_bf16(dm0, dm1), pack_bf16(dm2, dm3), pack_bf16(dval, 0.f), 0u);
+        t.dout[img_chunk(tile, 16, row, 1)] = make_uint4(0u, 0u, 0u, 0u);
       }
       // dOut as the A operand of the first backward MMAs: [128 x 16] bf16 in k-blocks 16-17 of the A buffer (the bias block,
       // rewritten every tile); h stays intact in k-blocks 0-15: its zeros are relu' for the last step
@@ -505,10 +536,9 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
 #pragma unroll
           for (int j = 0; j < 16; j++) w[j] = relu_grad_pack_bf16(r[2 * j], r[2 * j + 1], act[j]);
           tmem_st16(trow + 64 * half + (c0 >> 1), w);
-          if (active) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) t.dz2[i * 32 + 16 * half + (c0 >> 3) + j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-          }
+          for (int j = 0; j < 4; j++)  // rows past the minibatch carry dOut = 0, hence zeros here
+            t.dz2[img_chunk(tile, 256, row, 16 * half + (c0 >> 3) + j)] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
         }
         tmem_wait_st();
       }
@@ -540,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
           w.y = relu_grad_pack_bf16(r[8 * j + 2], r[8 * j + 3], hw.y);
           w.z = relu_grad_pack_bf16(r[8 * j + 4], r[8 * j + 5], hw.z);
           w.w = relu_grad_pack_bf16(r[8 * j + 6], r[8 * j + 7], hw.w);
-          if (active) t.dz1[i * 16 + (c0 >> 3) + j] = w;
+          t.dz1[img_chunk(tile, 128, row, (c0 >> 3) + j)] = w;
         }
       }
     }
@@ -548,6 +578,224 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
+}
+
+
+// =========================================================================================================
+// Weight-gradient contraction of the PPO2 update (the "dW GEMMs"): for a minibatch of B samples
+//     d [Wp;Wv | bias]  g2[256 x 144] = dZ2^T . [h | 1 1 0...]        d W1 (hi | bias | lo)  g1[128 x 32] = dZ1^T . A1
+//     d [W3p ; w3v]     g3[256 x 16]  = [hp|hv]^T . dOut
+// All three reduce over the SAMPLE index (K = B ~ 1.7 M): split-K over one persistent CTA per SM, each walking a contiguous
+// range of 128-sample tiles; fp32 accumulators live in tensor memory for the CTA's whole range (352 of 512 columns) and are
+// added to the global results once at the end (red.global.add.f32).  Both operands of every product are stored
+// sample-major, i.e. MN-major for the tensor core: policy_kernel<true> writes them as ready-made canonical no-swizzle UMMA
+// images per tile, so a tile's operand is ONE contiguous block that an elected thread pulls in with cp.async.bulk (SASS
+// UBLKCP) and the MMAs read through fixed descriptors (instruction-descriptor bits 15/16: A and B MN-major).
+// The kernel is HBM-bound by construction: 208 KB of operands per tile against 40 tcgen05.mma (~2.2 k tensor-pipe clocks).
+// Two shared-memory stages of ~100 KB each hold half a tile's operands (stage 0: dZ2 + h -> g2; stage 1: hpv + dOut + dZ1 + A1 ->
+// g3, g1): warp 0 produces, warp 1 issues, tcgen05.commit hands a stage back to the producer.
+// Replaces three library GEMMs (cuBLASLt nvjet_tss_* + splitKreduce in profiles/r1_launches_bench_final.txt).
+// =========================================================================================================
+constexpr int kDwImgDz2 = 256 * 256, kDwImgH = kK2 * 256, kDwImgHpv = 256 * 256, kDwImgDout = 16 * 256, kDwImgDz1 = 128 * 256, kDwImgA1 = kK1 * 256;
+constexpr int kDwStage0 = kDwImgDz2 + kDwImgH;                           // 102400 B
+constexpr int kDwStage1 = kDwImgHpv + kDwImgDout + kDwImgDz1 + kDwImgA1; // 110592 B
+constexpr int kDwOff1 = kDwStage0;
+constexpr int kDwOffBar = kDwOff1 + kDwStage1;
+constexpr int kDwSmemBytes = kDwOffBar + 64;
+static_assert(kDwSmemBytes <= 227 * 1024, "shared memory budget of dw_kernel");
+constexpr uint32_t kDwColG2 = 0, kDwColG1 = 288, kDwColG3 = 320;  // g2: two M=128 halves x 144 columns; g1: 32; g3: two halves x 16
+
+struct DwArgs {
+  const unsigned char *a1, *h, *hpv, *dz2, *dz1, *dout;  // operand images (see TrainArgs)
+  int tiles;
+  float *g1, *g2, *g3;  // [128,32], [256,144], [256,16] fp32, zeroed by the caller
+};
+
+__host__ __device__ constexpr uint32_t umma_idesc_mn(int M, int N) {  // D = f32, A = B = bf16, both MN-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(128, 1) dw_kernel(const DwArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_full = sbase + kDwOffBar, bar_empty = sbase + kDwOffBar + 16, bar_done = sbase + kDwOffBar + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kDwOffBar + 40);
+  // this CTA's contiguous range of tiles
+  const int lo = (int)((int64_t)a.tiles * blockIdx.x / gridDim.x), hi = (int)((int64_t)a.tiles * (blockIdx.x + 1) / gridDim.x);
+  if (lo >= hi) return;  // (the launch never uses more CTAs than tiles)
+  if (tid == 0) {
+    for (int s = 0; s < 2; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------------------------------------------------------- producer: two bulk-copy stages per tile
+    auto pull = [&](uint32_t dst, const unsigned char* src, int bytes, uint32_t bar) {
+      for (int off = 0; off < bytes; off += 16384) bulk_g2s(dst + off, src + off, bytes - off < 16384 ? bytes - off : 16384, bar);
+    };
+    for (int j = lo, n = 0; j < hi; j++, n++) {
+      const uint32_t par = (n & 1) ^ 1;  // a fresh barrier passes a wait on parity 1: both stages start out empty
+      mbar_wait(bar_empty, par);
+      mbar_expect_tx(bar_full, kDwStage0);
+      pull(sbase, a.dz2 + (int64_t)j * kDwImgDz2, kDwImgDz2, bar_full);
+      pull(sbase + kDwImgDz2, a.h + (int64_t)j * kDwImgH, kDwImgH, bar_full);
+      mbar_wait(bar_empty + 8, par);
+      mbar_expect_tx(bar_full + 8, kDwStage1);
+      uint32_t d = sbase + kDwOff1;
+      pull(d, a.hpv + (int64_t)j * kDwImgHpv, kDwImgHpv, bar_full + 8); d += kDwImgHpv;
+      pull(d, a.dout + (int64_t)j * kDwImgDout, kDwImgDout, bar_full + 8); d += kDwImgDout;
+      pull(d, a.dz1 + (int64_t)j * kDwImgDz1, kDwImgDz1, bar_full + 8); d += kDwImgDz1;
+      pull(d, a.a1 + (int64_t)j * kDwImgA1, kDwImgA1, bar_full + 8);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer
+    // MN-major images: 8 features x 8 samples per 128-byte core matrix; next 8 samples (LBO) = 128 B, next 8 features (SBO) =
+    // 16 core matrices = 2048 B.  One K = 16 step = 16 samples = 256 B further into the image; an M = 128 half = 16 * 2048 B.
+    constexpr uint32_t id_g2 = umma_idesc_mn(128, kK2), id_g1 = umma_idesc_mn(128, kK1), id_g3 = umma_idesc_mn(128, 16);
+    for (int j = lo, n = 0; j < hi; j++, n++) {
+      const uint32_t par = n & 1, acc0 = n > 0;
+      mbar_wait(bar_full, par);
+      tc_fence_after();
+      {
+        const uint32_t dz2 = sbase, hh = sbase + kDwImgDz2;
+#pragma unroll
+        for (int half = 0; half < 2; half++)
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++)
+            umma_ss(tmem + kDwColG2 + half * kK2, umma_desc(dz2 + half * 16 * 2048 + ks * 256, 128, 2048), umma_desc(hh + ks * 256, 128, 2048), id_g2, acc0 | (ks > 0));
+      }
+      umma_commit(bar_empty);  // stage 0 may be refilled once these MMAs have read it
+      mbar_wait(bar_full + 8, par);
+      tc_fence_after();
+      {
+        const uint32_t hpv = sbase + kDwOff1, dout = hpv + kDwImgHpv, dz1 = dout + kDwImgDout, a1 = dz1 + kDwImgDz1;
+#pragma unroll
+        for (int half = 0; half < 2; half++)
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++)
+            umma_ss(tmem + kDwColG3 + half * 16, umma_desc(hpv + half * 16 * 2048 + ks * 256, 128, 2048), umma_desc(dout + ks * 256, 128, 2048), id_g3, acc0 | (ks > 0));
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++)
+          umma_ss(tmem + kDwColG1, umma_desc(dz1 + ks * 256, 128, 2048), umma_desc(a1 + ks * 256, 128, 2048), id_g1, acc0 | (ks > 0));
+      }
+      umma_commit(bar_empty + 8);
+    }
+    umma_commit(bar_done);  // arrives when every MMA issued above has completed
+  }
+  __syncwarp();
+  // ---------------------------------------------------------------- read-out: TMEM lane = feature row of the result
+  mbar_wait(bar_done, 0);
+  tc_fence_after();
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const int m = warp * 32 + lane;
+  auto flush = [&](uint32_t col, int ncols, float* dst, int ld) {  // dst[(m) * ld + c] += D[m][col + c]
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(trow + col + c0, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int c = 0; c < 16; c++) atomicAdd(dst + (int64_t)m * ld + c0 + c, __uint_as_float(r[c]));
+    }
+  };
+  flush(kDwColG2, kK2, a.g2, kK2);
+  flush(kDwColG2 + kK2, kK2, a.g2 + 128 * kK2, kK2);
+  flush(kDwColG1, kK1, a.g1, kK1);
+  flush(kDwColG3, 16, a.g3, 16);
+  flush(kDwColG3 + 16, 16, a.g3 + 128 * 16, 16);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
+}
+
+// =========================================================================================================
+// The optimiser step of the PPO2 update in ONE launch: tf.clip_by_global_norm + tf.train.AdamOptimizer(epsilon=1e-5)
+// (rl_baselines/ppo2/ppo2.py:200-207) over the policy's ~35 k parameters.  One CTA: phase 1 = global gradient norm
+// (fixed-order tree: bit-reproducible), phase 2 = clip and Adam in TensorFlow's formulation
+//     lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  m += (1 - b1)(g - m);  v += (1 - b2)(g^2 - v);  p -= lr_t * m / (sqrt(v) + eps)
+// =========================================================================================================
+constexpr int kAdamMaxTensors = 16;
+struct AdamArgs {
+  float* param[kAdamMaxTensors];
+  const float* grad[kAdamMaxTensors];
+  float *m[kAdamMaxTensors], *v[kAdamMaxTensors];
+  int n[kAdamMaxTensors];
+  int count;
+  float lr_t, lr, beta1, beta2, eps, max_norm;
+  float* norm_out;      // [1], may be null
+  long long* step_dev;  // may be null: the step count lives on the device (graph replay), lr_t is derived in the kernel
+};
+__global__ void __launch_bounds__(1024, 1) adam_kernel(const __grid_constant__ AdamArgs a) {
+  __shared__ float red[1024];
+  __shared__ float s_scale, s_lr_t;
+  float ss = 0.f;
+  for (int k = 0; k < a.count; k++)
+    for (int i = threadIdx.x; i < a.n[k]; i += 1024) { const float g = a.grad[k][i]; ss = fmaf(g, g, ss); }
+  red[threadIdx.x] = ss;
+  __syncthreads();
+  for (int off = 512; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float norm = sqrtf(red[0]);
+    // tf.clip_by_global_norm: g * clip / max(norm, clip); max_norm <= 0: no clipping
+    s_scale = a.max_norm > 0.f ? a.max_norm / fmaxf(norm, a.max_norm) : 1.f;
+    if (a.norm_out) *a.norm_out = norm;
+    s_lr_t = a.lr_t;
+    if (a.step_dev) {
+      const long long t = *a.step_dev + 1;
+      *a.step_dev = t;
+      s_lr_t = (float)((double)a.lr * sqrt(1.0 - pow((double)a.beta2, (double)t)) / (1.0 - pow((double)a.beta1, (double)t)));
+    }
+  }
+  __syncthreads();
+  const float scale = s_scale, b1 = a.beta1, b2 = a.beta2, lr_t = s_lr_t;
+  for (int k = 0; k < a.count; k++)
+    for (int i = threadIdx.x; i < a.n[k]; i += 1024) {
+      const float g = a.grad[k][i] * scale;
+      const float m = a.m[k][i] + (1.f - b1) * (g - a.m[k][i]);
+      const float v = a.v[k][i] + (1.f - b2) * (g * g - a.v[k][i]);
+      a.m[k][i] = m; a.v[k][i] = v;
+      a.param[k][i] -= lr_t * m / (sqrtf(v) + a.eps);
+    }
+}
+
+// =========================================================================================================
+// Minibatch shuffle of the PPO2 update (np.random.shuffle(inds), rl_baselines/ppo2/ppo2.py:350-352) without a sort: a keyed
+// bijection of [0, n) -- a 4-round Feistel network on the next power of four above n, cycle-walked back into range -- so
+// index i of the permutation is computed independently by one thread (torch.randperm = a radix sort of n random keys).
+// =========================================================================================================
+__device__ __forceinline__ uint32_t feistel_round(uint32_t x, uint32_t k) {
+  x = (x ^ k) * 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
+  return x;
+}
+__global__ void __launch_bounds__(256) permutation_kernel(int64_t n, int half_bits, uint64_t seed, int64_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t mask = (1u << half_bits) - 1u;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint64_t x = (uint64_t)i;
+  do {  // cycle walking: the domain is at most 4x the range, so this loops 1-4 times on average
+    uint32_t l = (uint32_t)(x >> half_bits) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+    for (int rnd = 0; rnd < 4; rnd++) {
+      const uint32_t f = feistel_round(r, (rnd & 1 ? k1 : k0) + 0x632BE5ABu * (uint32_t)(rnd + 1)) & mask;
+      const uint32_t nl = r;
+      r = l ^ f; l = nl;
+    }
+    x = ((uint64_t)l << half_bits) | r;
+  } while (x >= (uint64_t)n);
+  out[i] = (int64_t)x;
 }
 
 // =========================================================================================================
@@ -879,6 +1127,7 @@ int qs_policy_create(qs_policy_t** out, int device) {
   if ((err = cudaGetDeviceProperties(&prop, device)) != cudaSuccess || (err = cudaMalloc(&p->packed, kPackedBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
+      (err = cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_fwd_ws_kernel_capped<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_fwd_ws_kernel_capped<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
@@ -999,21 +1248,70 @@ int qs_policy_ppo_grad(qs_policy_t* p, const qs_ppo_grad_t* g, void* stream) {
   if (!p || !g) return qs_fail_(QS_ERR_INVALID, "qs_policy_ppo_grad: null argument");
   if (!p->have_weights) return qs_fail_(QS_ERR_INVALID, "qs_policy_ppo_grad: qs_policy_set_weights has not been called");
   if (!g->obs || !g->actions || !g->returns || !g->values || !g->neglogp || !g->adv_stats || !g->a1 || !g->h || !g->hpv || !g->dz2 || !g->dz1 ||
-      !g->per_sample)
+      !g->dout || !g->col_sums || !g->g1 || !g->g2 || !g->g3)
     return qs_fail_(QS_ERR_INVALID, "qs_policy_ppo_grad: null buffer");
   if (g->batch <= 0) return qs_fail_(QS_ERR_INVALID, "qs_policy_ppo_grad: batch must be positive");
   NvtxRange nv("qs_policy_ppo_grad");
   int prev = 0;
   QSP_CUDA(cudaGetDevice(&prev));
   QSP_CUDA(cudaSetDevice(p->device));
-  StepArgs a = {p->packed, g->obs, g->batch, 0, 0, 0, 1, nullptr, nullptr, nullptr, nullptr};
-  TrainArgs t = {g->actions, g->returns, g->values, g->neglogp, g->idx, g->adv_stats, g->cliprange, g->cliprange_vf, g->vf_coef,
-                 (float)(1.0 / (double)g->batch), (uint4*)g->a1, (uint4*)g->h, (uint4*)g->hpv, (uint4*)g->dz2, (uint4*)g->dz1, (float4*)g->per_sample};
-  const int ctas = (int)(((g->batch + kTileRows - 1) / kTileRows + kGroups - 1) / kGroups);
-  policy_kernel<true><<<ctas < p->grid ? ctas : p->grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, t);
-  cudaError_t e = cudaGetLastError();
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tiles = (int)((g->batch + kTileRows - 1) / kTileRows);
+  cudaError_t e = cudaMemsetAsync(g->col_sums, 0, 16 * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(g->g1, 0, (size_t)kHid * kK1 * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(g->g2, 0, (size_t)2 * kHid * kK2 * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(g->g3, 0, (size_t)2 * kHid * 16 * sizeof(float), st);
+  if (e == cudaSuccess) {
+    StepArgs a = {p->packed, g->obs, g->batch, 0, 0, 0, 1, nullptr, nullptr, nullptr, nullptr};
+    TrainArgs t = {g->actions, g->returns, g->values, g->neglogp, g->idx, g->adv_stats, g->cliprange, g->cliprange_vf, g->vf_coef,
+                   (float)(1.0 / (double)g->batch), (uint4*)g->a1, (uint4*)g->h, (uint4*)g->hpv, (uint4*)g->dz2, (uint4*)g->dz1, (uint4*)g->dout,
+                   (float4*)g->per_sample, g->col_sums};
+    const int ctas = (tiles + kGroups - 1) / kGroups;
+    policy_kernel<true><<<ctas < p->grid ? ctas : p->grid, kThreads, kSmemBytes, st>>>(a, t);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) {
+    DwArgs d = {(const unsigned char*)g->a1, (const unsigned char*)g->h, (const unsigned char*)g->hpv, (const unsigned char*)g->dz2,
+                (const unsigned char*)g->dz1, (const unsigned char*)g->dout, tiles, g->g1, g->g2, g->g3};
+    dw_kernel<<<tiles < p->grid ? tiles : p->grid, 128, kDwSmemBytes, st>>>(d);
+    e = cudaGetLastError();
+  }
   cudaSetDevice(prev);
   if (e != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_policy_ppo_grad: %s", cudaGetErrorString(e));
+  return QS_OK;
+}
+
+int qs_adam_step(const qs_adam_tensor_t* tensors, int n_tensors, float lr, float beta1, float beta2, float eps, int64_t step, int64_t* step_counter,
+                 float max_grad_norm, float* grad_norm_out, void* stream) {
+  if (!tensors || n_tensors < 1 || n_tensors > kAdamMaxTensors) return qs_fail_(QS_ERR_INVALID, "qs_adam_step: 1..%d tensors", kAdamMaxTensors);
+  if (step < 1 && !step_counter) return qs_fail_(QS_ERR_INVALID, "qs_adam_step: step counts from 1 (or pass a device step counter)");
+  if (step < 1) step = 1;
+  AdamArgs a;
+  memset(&a, 0, sizeof a);
+  for (int k = 0; k < n_tensors; k++) {
+    const qs_adam_tensor_t& t = tensors[k];
+    if (!t.param || !t.grad || !t.m || !t.v || t.n < 0 || t.n > (int64_t)1 << 30) return qs_fail_(QS_ERR_INVALID, "qs_adam_step: bad tensor %d", k);
+    a.param[k] = t.param; a.grad[k] = t.grad; a.m[k] = t.m; a.v[k] = t.v; a.n[k] = (int)t.n;
+  }
+  a.count = n_tensors;
+  // tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), evaluated in double on the host
+  a.lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step)));
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_grad_norm; a.norm_out = grad_norm_out;
+  a.step_dev = reinterpret_cast<long long*>(step_counter);
+  adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_adam_step: %s", cudaGetErrorString(e));
+  return QS_OK;
+}
+
+int qs_permutation(int64_t n, uint64_t seed, int64_t* out, void* stream) {
+  if (n <= 0 || !out) return qs_fail_(QS_ERR_INVALID, "qs_permutation: n must be positive and out non-null");
+  if (n > (int64_t)1 << 40) return qs_fail_(QS_ERR_INVALID, "qs_permutation: n too large");
+  int bits = 2;
+  while (((int64_t)1 << bits) < n) bits += 2;  // an even number of bits: two equal Feistel halves
+  permutation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, bits / 2, seed, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_permutation: %s", cudaGetErrorString(e));
   return QS_OK;
 }
 

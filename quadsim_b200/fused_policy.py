@@ -69,50 +69,90 @@ class FusedPolicy:
     def _workspace(self, batch):
         ws = getattr(self, "_ws", None)
         if ws is None or ws["batch"] < batch:
-            bf = dict(dtype=torch.bfloat16, device=self.device)
-            ws = dict(batch=batch, a1=torch.empty((batch, 32), **bf), h=torch.empty((batch, 144), **bf), hpv=torch.empty((batch, 256), **bf),
-                      dz2=torch.empty((batch, 256), **bf), dz1=torch.empty((batch, 128), **bf),
-                      per_sample=torch.empty((batch, 16), dtype=torch.float32, device=self.device))
+            tiles = (batch + 127) // 128
+            raw = lambda nbytes: torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            f32 = dict(dtype=torch.float32, device=self.device)
+            # operand images of the weight-gradient contraction: opaque, sized per 128-sample tile (include/quadsim_b200.h)
+            ws = dict(batch=batch, a1=raw(tiles * 8192), h=raw(tiles * 36864), hpv=raw(tiles * 65536), dz2=raw(tiles * 65536),
+                      dz1=raw(tiles * 32768), dout=raw(tiles * 4096), per_sample=torch.empty((batch, 16), **f32),
+                      col=torch.empty(16, **f32), g1=torch.empty((128, 32), **f32), g2=torch.empty((256, 144), **f32),
+                      g3=torch.empty((256, 16), **f32), stats=torch.empty(2, **f32))
             self._ws = ws
         return ws
 
     @torch.no_grad()
-    def ppo_grad(self, batch, idx, cliprange=0.2, cliprange_vf=None, vf_coef=0.5, ent_coef=0.0):
+    def ppo_grad(self, batch, idx, cliprange=0.2, cliprange_vf=None, vf_coef=0.5, ent_coef=0.0, want_per_sample=True):
         """Gradient of PPO2's loss (ppo2.py:138-189) over the minibatch rows `idx` of the flat rollout `batch` (the dict
-        DeviceRunner.run returns).  One kernel does forward + per-sample loss + the backward pass through the activations
-        on the tensor cores and leaves bf16 operand rows in a workspace; the weight gradients are then one library GEMM per
-        layer over the whole minibatch (K = batch, fp32 out).  Returns ({param: grad} in the module's layouts, logs)."""
+        DeviceRunner.run returns), all in hand-written kernels behind ONE C call: forward + per-sample loss + backward
+        through the activations on the tensor cores, then the weight-gradient contraction over the whole minibatch
+        (split-K, accumulators in tensor memory).  Returns ({param: grad} in the module's layouts, logs)."""
         m, B = self.module, int(idx.shape[0])
         ws = self._workspace(B)
         ret, val = batch["returns"], batch["values"]
         # PPO2.update leaves returns - values of the whole rollout in batch["adv_raw"]: one gather per minibatch instead of two
         adv = batch["adv_raw"][idx] if "adv_raw" in batch else ret[idx] - val[idx]
-        stats = torch.stack([adv.mean(), 1.0 / (adv.std(unbiased=False) + 1e-8)]).float()  # ppo2.py:265-266 (population std)
+        std, mean = torch.std_mean(adv, unbiased=False)  # ppo2.py:265-266 (numpy's population std)
+        stats = ws["stats"]
+        stats[0] = mean
+        stats[1] = 1.0 / (std + 1e-8)
         p = lambda t: t.data_ptr()
-        g = _capi.PPOGrad(p(batch["obs"]), p(batch["actions"]), p(ret), p(val), p(batch["neglogp"]), p(idx), B, p(stats),
-                          float(cliprange), float(-1.0 if cliprange_vf is None or cliprange_vf < 0 else cliprange_vf), float(vf_coef),
-                          p(ws["a1"]), p(ws["h"]), p(ws["hpv"]), p(ws["dz2"]), p(ws["dz1"]), p(ws["per_sample"]))
         for k in ("obs", "actions", "returns", "values", "neglogp"):
             t = batch[k]
             if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
                 raise ValueError("rollout tensor %r must be contiguous float32 on %s" % (k, self.device))
         if idx.dtype != torch.int64 or not idx.is_contiguous():
             raise ValueError("idx must be a contiguous int64 tensor")
+        g = _capi.PPOGrad(p(batch["obs"]), p(batch["actions"]), p(ret), p(val), p(batch["neglogp"]), p(idx), B, p(stats),
+                          float(cliprange), float(-1.0 if cliprange_vf is None or cliprange_vf < 0 else cliprange_vf), float(vf_coef),
+                          p(ws["a1"]), p(ws["h"]), p(ws["hpv"]), p(ws["dz2"]), p(ws["dz1"]), p(ws["dout"]),
+                          p(ws["per_sample"]) if want_per_sample else None, p(ws["col"]), p(ws["g1"]), p(ws["g2"]), p(ws["g3"]))
         with torch.cuda.device(self.device):
             _capi.check(self.lib.qs_policy_ppo_grad(self._h, C.byref(g), self._stream()))
-        a1, h, hpv, dz2, dz1, ps = (ws[k][:B] for k in ("a1", "h", "hpv", "dz2", "dz1", "per_sample"))
-        f32 = torch.float32
-        col = ps.sum(0)                                                       # [16]: dOut / d logstd / logged terms, summed
-        g3 = torch.mm(ps[:, :8].to(torch.bfloat16).t(), hpv, out_dtype=f32)  # [8,256]: rows 0-3 pi over hp, row 4 vf over hv
-        g2 = torch.mm(dz2.t(), h, out_dtype=f32)                             # [256,144]: h rows carry (1, 1, 0...) after the 128 features
+        return self.grads_from_workspace(ent_coef, B)
+
+    def grads_from_workspace(self, ent_coef, B):
+        """({param: grad}, logs) as views of the result buffers the gradient kernels filled (g1, g2, g3, column sums)."""
+        m, ws = self.module, self._ws
+        col, g1, g2, g3 = ws["col"], ws["g1"], ws["g2"], ws["g3"]
         b2 = g2[:, 128]
-        g1 = torch.mm(dz1.t(), a1, out_dtype=f32)                            # [128,32]: hi half | 1 1 0 0 | lo half | 0...
         grads = {m.shared_fc0.weight: g1[:, 0:12] + g1[:, 16:28], m.shared_fc0.bias: g1[:, 12],
                  m.pi_fc0.weight: g2[:128, :128], m.pi_fc0.bias: b2[:128], m.vf_fc0.weight: g2[128:, :128], m.vf_fc0.bias: b2[128:],
-                 m.pi.weight: g3[0:4, :128], m.pi.bias: col[0:4], m.vf.weight: g3[4:5, 128:], m.vf.bias: col[4:5],
+                 m.pi.weight: g3[:128, 0:4].t(), m.pi.bias: col[0:4], m.vf.weight: g3[128:, 4:5].t(), m.vf.bias: col[4:5],
                  m.logstd: (col[8:12] - ent_coef).view_as(m.logstd)}
         logs = dict(pg_loss=col[12] / B, vf_loss=col[13] / B, approxkl=col[14] / B, clipfrac=col[15] / B, entropy=m.entropy().detach())
         return grads, logs
+
+    # ------------------------------------------------------------------ optimiser step and shuffle (qs_adam_step, qs_permutation)
+    def adam_step(self, grads, state, lr, max_grad_norm=0.5, beta1=0.9, beta2=0.999, eps=1e-5):
+        """tf.clip_by_global_norm + tf.train.AdamOptimizer(epsilon=1e-5) (ppo2.py:200-207) over `grads` ({param: grad}) in ONE
+        launch.  `state` is a dict the caller keeps (moments per parameter, the step count -- held on the device, so that a
+        captured CUDA graph of the step replays correctly); the parameters are updated in place."""
+        if "step" not in state:
+            state.update(step=0, m={}, v={}, norm=torch.zeros(1, dtype=torch.float32, device=self.device),
+                         step_dev=torch.zeros(1, dtype=torch.int64, device=self.device))
+        params = list(grads.keys())
+        gc = [grads[prm] if grads[prm].is_contiguous() else grads[prm].contiguous() for prm in params]
+        for prm in params:
+            if prm not in state["m"]:
+                state["m"][prm] = torch.zeros_like(prm)
+                state["v"][prm] = torch.zeros_like(prm)
+        tab = (_capi.AdamTensor * len(params))()
+        for k, (prm, gk) in enumerate(zip(params, gc)):
+            tab[k] = _capi.AdamTensor(prm.data_ptr(), gk.data_ptr(), state["m"][prm].data_ptr(), state["v"][prm].data_ptr(), prm.numel())
+        state["step"] += 1
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.qs_adam_step(tab, len(params), float(lr), float(beta1), float(beta2), float(eps), state["step"],
+                                              state["step_dev"].data_ptr(), float(max_grad_norm if max_grad_norm is not None else 0.0),
+                                              state["norm"].data_ptr(), self._stream()))
+        state["keep"] = gc  # the gradient views must outlive the launch
+        return state["norm"]
+
+    def permutation(self, n, seed, out=None):
+        """np.random.shuffle(inds) of the update (ppo2.py:350-352) as a keyed bijection of [0, n): int64 device tensor."""
+        out = torch.empty(n, dtype=torch.int64, device=self.device) if out is None else out
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.qs_permutation(int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, out.data_ptr(), self._stream()))
+        return out
 
     def close(self):
         if getattr(self, "_h", None) is not None:

@@ -228,7 +228,9 @@ class PPO2:
         if fused_policy:
             from .fused_policy import FusedPolicy
             self.fused = FusedPolicy(self.policy, seed=seed, env_id0=getattr(env, "env_id0", 0))
-        # fused_update: gradients from qs_policy_ppo_grad (tensor-core forward/backward + library GEMMs) instead of autograd
+        # fused_update: the whole minibatch step in hand-written kernels -- qs_policy_ppo_grad (tensor-core forward / backward and the
+        # weight-gradient contraction), qs_adam_step (global-norm clip + Adam in TensorFlow's formulation, as the reference
+        # trains: ppo2.py:200-207), qs_permutation (the shuffle) -- instead of autograd + torch.optim.Adam + torch.randperm
         self.fused_update = bool(fused_policy) if fused_update is None else bool(fused_update)
         if self.fused_update and self.fused is None:
             raise ValueError("fused_update needs fused_policy=True")
@@ -247,7 +249,10 @@ class PPO2:
         self.learning_rate = learning_rate
         self._cliprange_arg, self._cliprange_vf_arg = cliprange, cliprange_vf
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate(1.0) if callable(learning_rate) else learning_rate, eps=1e-5,
-                                    capturable=self.graph_update)
+                                    )  # the autograd path's optimiser; the fused update has its own (qs_adam_step)
+        self._adam = {}  # qs_adam_step state of the fused update (moments, device step counter)
+        self._shuffles = 0
+        self._seed = int(seed)
         self._set_schedules(1.0)
         self.num_timesteps = 0
 
@@ -256,9 +261,10 @@ class PPO2:
         self.cliprange = val(self._cliprange_arg)
         cv = val(self._cliprange_vf_arg)
         self.cliprange_vf = self.cliprange if cv is None else cv  # legacy default: same as the policy's (ppo2.py:152-156)
+        self.lr_now = float(self.learning_rate(frac)) if callable(self.learning_rate) else float(self.learning_rate)
         if hasattr(self, "opt") and callable(self.learning_rate):
             for grp in self.opt.param_groups:
-                grp["lr"] = float(self.learning_rate(frac))
+                grp["lr"] = self.lr_now
 
     def loss(self, mb):
         mean, vpred = self.policy.forward(mb["obs"])
@@ -282,16 +288,31 @@ class PPO2:
 
     @torch.no_grad()
     def _minibatch_fused(self, batch, idx):
-        grads, log = self.fused.ppo_grad(batch, idx, self.cliprange, self.cliprange_vf, self.vf_coef, self.ent_coef)
-        for prm, grad in grads.items():
-            if prm.grad is None:
-                prm.grad = torch.empty_like(prm)
-            prm.grad.copy_(grad)
-        if self.max_grad_norm is not None:
-            nn.utils.clip_grad_norm_(list(grads.keys()), self.max_grad_norm)
-        self.opt.step()
-        self.fused.sync_weights(sync=False)
+        """One minibatch step in hand-written kernels: gradient (two launches), optimiser (one), weight re-pack (one)."""
+        grads, log = self.fused.ppo_grad(batch, idx, self.cliprange, self.cliprange_vf, self.vf_coef, self.ent_coef, want_per_sample=False)
+        if self.dist:  # one flat bucket per minibatch: the four result buffers of the gradient kernels
+            ws = self.fused._ws
+            flat = torch.cat([ws[k].reshape(-1) for k in ("g1", "g2", "g3", "col")])
+            torch.distributed.all_reduce(flat)
+            flat /= torch.distributed.get_world_size()
+            off = 0
+            for k in ("g1", "g2", "g3", "col"):
+                n = ws[k].numel()
+                ws[k].copy_(flat[off:off + n].view_as(ws[k]))
+                off += n
+            grads, log = self.fused.grads_from_workspace(self.ent_coef, int(idx.shape[0]))
+        self.fused.adam_step(grads, self._adam, self.lr_now, self.max_grad_norm)
+        self.fused.sync_weights(sync=False)  # the next minibatch's forward uses the updated weights
         return log
+
+    def _shuffle(self, n_batch):
+        """np.random.shuffle(inds) (ppo2.py:350-352).  Fused update: qs_permutation, keyed by (seed, rank, shuffle count);
+        otherwise torch.randperm."""
+        if self.fused_update:
+            self._shuffles += 1
+            rank = torch.distributed.get_rank() if self.dist else 0
+            return self.fused.permutation(n_batch, (self._seed * 1000003 + rank) * 1000003 + self._shuffles)
+        return torch.randperm(n_batch, device=self.device, generator=self.gen)
 
     def _graph_step(self, batch, idx):
         """Replay the captured minibatch step on `idx` (copied into the graph's static index buffer)."""
@@ -302,30 +323,38 @@ class PPO2:
                 raise _capi.QuadSimError("graph_update is single-process: the gradient all-reduce is not captured")
             static_idx = idx.clone()
             params = list(self.policy.parameters())
-            # One eager step first (outside capture: workspaces, GEMM heuristics and Adam's state tensors are created lazily),
-            # then parameters and optimiser state are put back, so the captured step below is the first one that counts.
+            # One eager step first (outside capture: workspaces and the optimiser's moment tensors are created lazily), then
+            # parameters and optimiser state are put back, so the captured step below is the first one that counts.
             snap_p = [prm.detach().clone() for prm in params]
-            snap_s = {prm: {k: v.clone() for k, v in self.opt.state[prm].items() if torch.is_tensor(v)} for prm in params if prm in self.opt.state}
-            for prm in params:  # the unused q head keeps grad None; everything else gets a static grad tensor
-                prm.grad = None
+            had_state = "step" in self._adam
+            snap_a = {k: {prm: t.clone() for prm, t in self._adam[k].items()} for k in ("m", "v")} if had_state else None
+            snap_step = (self._adam["step"], self._adam["step_dev"].clone()) if had_state else None
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side), torch.no_grad():
                 self._minibatch_fused(batch, static_idx)
                 for prm, p0 in zip(params, snap_p):
                     prm.copy_(p0)
-                    for k, v in self.opt.state.get(prm, {}).items():
-                        if torch.is_tensor(v):
-                            v.copy_(snap_s[prm][k]) if prm in snap_s else v.zero_()
+                for k in ("m", "v"):
+                    for prm, t in self._adam[k].items():
+                        t.copy_(snap_a[k][prm]) if had_state and prm in snap_a[k] else t.zero_()
+                if had_state:
+                    self._adam["step"] = snap_step[0]
+                    self._adam["step_dev"].copy_(snap_step[1])
+                else:
+                    self._adam["step"] = 0
+                    self._adam["step_dev"].zero_()
                 self.fused.sync_weights(sync=False)
             torch.cuda.current_stream(self.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph), torch.no_grad():
                 log = self._minibatch_fused(batch, static_idx)
+            self._adam["step"] -= 1  # the capture counted a step that has not run yet
             self._graph = (key, graph, static_idx, log)
         _, graph, static_idx, log = self._graph
         static_idx.copy_(idx)
         graph.replay()
+        self._adam["step"] += 1  # host mirror of the device step counter the captured optimiser kernel increments
         return {k: v.clone() for k, v in log.items()}
 
     def update(self, batch):
@@ -342,29 +371,24 @@ class PPO2:
             torch.sub(batch["returns"], batch["values"], out=buf)
             batch = dict(batch, adv_raw=buf)
         for _ in range(self.noptepochs):
-            perm = torch.randperm(n_batch, device=self.device, generator=self.gen)
+            perm = self._shuffle(n_batch)
             for start in range(0, mb_size * self.nminibatches, mb_size):
                 idx = perm[start:start + mb_size]
                 if self.graph_update:
                     logs.append(self._graph_step(batch, idx))
                     continue
                 if self.fused_update:
-                    grads, log = self.fused.ppo_grad(batch, idx, self.cliprange, self.cliprange_vf, self.vf_coef, self.ent_coef)
-                    self.opt.zero_grad(set_to_none=True)
-                    for prm, grad in grads.items():
-                        prm.grad = grad.contiguous()
-                else:
-                    mb = {k: batch[k][idx] for k in keys}
-                    total, log = self.loss(mb)
-                    self.opt.zero_grad(set_to_none=True)
-                    total.backward()
+                    logs.append(self._minibatch_fused(batch, idx))
+                    continue
+                mb = {k: batch[k][idx] for k in keys}
+                total, log = self.loss(mb)
+                self.opt.zero_grad(set_to_none=True)
+                total.backward()
                 if self.dist:
                     all_reduce_mean_grads(self.policy.parameters())  # one flat bucket per minibatch
                 if self.max_grad_norm is not None:
                     nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)  # tf.clip_by_global_norm
                 self.opt.step()
-                if self.fused_update:
-                    self.fused.sync_weights(sync=False)  # the next minibatch's forward uses the updated weights
                 logs.append(log)
         if self.fused is not None:
             self.fused.sync_weights()  # re-pack the updated parameters into the tensor-core operand images

@@ -45,6 +45,7 @@ int main(void) {
          offsetof(qs_env_params_t, max_steps));
   printf("%zu %zu %zu %zu %zu\\n", sizeof(qs_state_arrays_t), sizeof(qs_step_extras_t), sizeof(qs_rollout_t), sizeof(qs_ppo_grad_t),
          sizeof(qs_policy_weights_t));
+  printf("%zu\\n", sizeof(qs_adam_tensor_t));
   return 0;
 }
 """)
@@ -57,6 +58,7 @@ int main(void) {
     assert rows[1] == [Prm.inertia.offset, Prm.kp_vel.offset, Prm.dock_port.offset, Prm.max_steps.offset]
     assert rows[2] == [C.sizeof(_capi.StateArrays), C.sizeof(_capi.StepExtras), C.sizeof(_capi.RolloutBuffers), C.sizeof(_capi.PPOGrad),
                        C.sizeof(_capi.PolicyWeights)]
+    assert rows[3] == [C.sizeof(_capi.AdamTensor)]
 
 
 def test_default_params_are_the_reference_literals():
@@ -104,7 +106,9 @@ def test_invalid_arguments_return_status_not_crash():
     assert L.qs_gae(0, 4, None, None, None, None, None, 0.99, 0.95, None, None, None) == -1
     assert L.qs_env_dtype(None) == -1 and L.qs_env_id0(None) == 0 and L.qs_env_device(None) == -1
     assert C.sizeof(_capi.RolloutBuffers) == 7 * C.sizeof(C.c_void_p)
-    assert C.sizeof(_capi.PPOGrad) == 6 * 8 + 8 + 8 + 3 * 4 + 4 + 6 * 8  # 12-byte float block padded to the next pointer
+    assert C.sizeof(_capi.PPOGrad) == 6 * 8 + 8 + 8 + 3 * 4 + 4 + 11 * 8  # 12-byte float block padded to the next pointer
+    assert L.qs_adam_step(None, 0, 3e-4, 0.9, 0.999, 1e-5, 1, None, 0.5, None, None) == -1 and b"qs_adam_step" in L.qs_last_error()
+    assert L.qs_permutation(0, 1, None, None) == -1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

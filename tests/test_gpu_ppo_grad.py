@@ -106,16 +106,91 @@ def test_ppo_grad_matches_autograd(B):
     env.close()
 
 
+def _unpack_image(img, F, B):
+    """An operand image of the weight-gradient contraction (include/quadsim_b200.h: per 128-sample tile, the 16-byte chunk b of
+    row r at (b * 16 + (r >> 3)) * 128 + (r & 7) * 16) -> the [B, F] bf16 matrix it holds."""
+    tiles = (B + 127) // 128
+    x = img[: tiles * F * 256].view(torch.bfloat16).view(tiles, F // 8, 16, 8, 8)  # [tile, b, r >> 3, r & 7, feature in chunk]
+    return x.permute(0, 2, 3, 1, 4).reshape(tiles * 128, F)[:B]
+
+
+@pytest.mark.parametrize("B", [128, 1000, 4096 * 3 + 77])
+def test_weight_gradient_contraction_kernel_vs_matmul(B):
+    """dw_kernel (tcgen05, both operands MN-major, split-K over CTAs, accumulators in tensor memory, red.global.add) against
+    torch.matmul on the very operand rows the gradient kernel left in the workspace: isolates the contraction from the rest
+    of the gradient path.  fp32 accumulation of bf16 products on both sides: agreement to accumulation order."""
+    env, algo, batch = _rollout()
+    idx = torch.randperm(batch["obs"].shape[0], device="cuda")[:B].contiguous()
+    algo.fused.ppo_grad(batch, idx, algo.cliprange, algo.cliprange_vf, algo.vf_coef, algo.ent_coef)
+    ws = algo.fused._ws
+    a1, h, hpv = _unpack_image(ws["a1"], 32, B).float(), _unpack_image(ws["h"], 144, B).float(), _unpack_image(ws["hpv"], 256, B).float()
+    dz2, dz1, dout = _unpack_image(ws["dz2"], 256, B).float(), _unpack_image(ws["dz1"], 128, B).float(), _unpack_image(ws["dout"], 16, B).float()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for name, got, ref in (("g1", ws["g1"], dz1.t() @ a1), ("g2", ws["g2"], dz2.t() @ h), ("g3", ws["g3"], hpv.t() @ dout)):
+        scale = float(ref.abs().max())
+        assert scale > 0 and float((got - ref).abs().max()) <= 2e-4 * scale + 1e-7, (name, float((got - ref).abs().max()), scale)
+    # the bias block of h really is (1, 1, 0, ...) on every row, the per-sample block's column sums are the kernel's col_sums,
+    # and the dOut image is the bf16 rounding of the per-sample output gradients
+    assert torch.equal(h[:, 128:130], torch.ones(B, 2, device="cuda")) and float(h[:, 130:].abs().max()) == 0.0
+    ps = ws["per_sample"][:B]
+    assert torch.allclose(ws["col"], ps.double().sum(0).float(), rtol=2e-4, atol=1e-5)
+    assert torch.equal(dout[:, :5], ps[:, :5].to(torch.bfloat16).float()) and float(dout[:, 5:].abs().max()) == 0.0
+    env.close()
+
+
+def test_adam_step_kernel_matches_tensorflow_formula():
+    """qs_adam_step: tf.clip_by_global_norm + tf.train.AdamOptimizer(epsilon=1e-5) (ppo2.py:200-207) in one launch, against
+    the same formulas in torch float64; the device step counter makes consecutive calls advance the bias correction."""
+    torch.manual_seed(0)
+    pol = ppo.MlpPolicy().cuda()
+    fused = FusedPolicy(pol)
+    params = [p for n, p in pol.named_parameters() if not n.startswith("q.")]
+    ref_p = [p.detach().double().clone() for p in params]
+    ref_m = [torch.zeros_like(p) for p in ref_p]
+    ref_v = [torch.zeros_like(p) for p in ref_p]
+    state, lr, b1, b2, eps, clip = {}, 3e-4, 0.9, 0.999, 1e-5, 0.5
+    for step in range(1, 6):
+        grads = {p: torch.randn_like(p) * (0.3 if step % 2 else 0.001) for p in params}  # clipped on odd steps, not on even ones
+        norm = fused.adam_step(grads, state, lr, clip)
+        gn = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values()))
+        assert abs(float(norm) - float(gn)) < 1e-4 * float(gn)
+        scale = clip / max(float(gn), clip)
+        lr_t = lr * (1 - b2 ** step) ** 0.5 / (1 - b1 ** step)
+        for k, p in enumerate(params):
+            g = grads[p].double() * scale
+            ref_m[k] += (1 - b1) * (g - ref_m[k])
+            ref_v[k] += (1 - b2) * (g * g - ref_v[k])
+            ref_p[k] -= lr_t * ref_m[k] / (ref_v[k].sqrt() + eps)
+            assert float((p.detach().double() - ref_p[k]).abs().max()) < 2e-6, (step, k)
+    assert int(state["step_dev"]) == 5 and state["step"] == 5
+
+
+@pytest.mark.parametrize("n", [1, 7, 4096, 16 * 1048576, 1000003])
+def test_permutation_kernel_is_a_keyed_bijection(n):
+    """qs_permutation (the update's minibatch shuffle, ppo2.py:350-352): a bijection of [0, n) for any n, reproducible per seed,
+    different across seeds, and well mixed (neighbouring positions land far apart)."""
+    pol = ppo.MlpPolicy().cuda()
+    fused = FusedPolicy(pol)
+    a, b, c = fused.permutation(n, 5), fused.permutation(n, 5), fused.permutation(n, 6)
+    assert a.dtype == torch.int64 and torch.equal(a, b)
+    assert torch.equal(torch.sort(a).values, torch.arange(n, device="cuda"))
+    if n > 100:
+        assert not torch.equal(a, c) and float((a == torch.arange(n, device="cuda")).float().mean()) < 0.01
+        d = (a[1:] - a[:-1]).abs().double()
+        assert float(d.mean()) > 0.2 * n  # a uniform shuffle gives n / 3
+
+
 def test_fused_update_tracks_autograd_update():
     env, algo, batch = _rollout(n=2048, T=16, seed=2)
     state = {k: v.clone() for k, v in algo.policy.state_dict().items()}
-    opt_state = algo.opt.state_dict()
-    gen_state = algo.gen.get_state()
+    perms = [torch.randperm(batch["obs"].shape[0], device="cuda") for _ in range(algo.noptepochs)]
+    feed = list(perms)
+    algo._shuffle = lambda n: feed.pop(0)  # both passes see the same minibatches
     log_f = algo.update(batch)
     after_f = [p.detach().clone() for p in algo.policy.parameters()]
     algo.policy.load_state_dict(state)
     algo.opt = torch.optim.Adam(algo.policy.parameters(), lr=3e-4, eps=1e-5)
-    algo.gen.set_state(gen_state)
+    feed = list(perms)
     algo.fused_update = False
     log_a = algo.update(batch)
     moved = [float((a - s).norm()) for a, s in zip(after_f, state.values())]
@@ -145,7 +220,7 @@ def test_graph_captured_update_equals_eager_fused_update():
         results.append(([p.detach().clone() for p in algo.policy.parameters()], logs))
         env.close()
     (p_eager, l_eager), (p_graph, l_graph) = results
-    for a, b in zip(p_eager, p_graph):  # 16 Adam steps of 3e-4 each; the library GEMMs may pick another split-K under capture
+    for a, b in zip(p_eager, p_graph):  # 16 Adam steps of 3e-4 each; the split-K partial sums are added in a different order
         assert torch.allclose(a, b, rtol=1e-4, atol=3e-5), float((a - b).abs().max())
     for le, lg in zip(l_eager, l_graph):
         for k in ("pg_loss", "vf_loss", "approxkl", "clipfrac"):
