@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
   constexpr uint32_t idesc1 = umma_idesc(128, kHid), idesc2 = umma_idesc(128, 2 * kHid), idesc3 = umma_idesc(128, kN3);
   constexpr uint32_t idesc4 = umma_idesc(128, kHid, true), idesc5 = umma_idesc(128, kHid, true);  // B read MN-major
   uint32_t phase = 0;
+  float col_acc[13] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // TRAIN: this thread's share of col_sums
   for (int tile = tile0; tile < tiles; tile += tile_stride) {
     const int64_t i = (int64_t)tile * kTileRows + row;
     const bool active = i < a.n;
@@ -489,18 +490,12 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
           ps[2] = make_float4(dl0, dl1, dl2, dl3); ps[3] = make_float4(pg, vf, kl, cf);
         }
       }
-      {  // column sums over the minibatch (bias gradients of the heads, d logstd, the logged loss terms): warp tree, one
-         // atomic per warp and column (rows past the minibatch hold zeros)
-        float cs[13] = {dm0, dm1, dm2, dm3, dval, dl0, dl1, dl2, dl3, pg, vf, kl, cf};
+      {  // column sums over the minibatch (bias gradients of the heads, d logstd, the logged loss terms): summed per thread over
+         // its tiles here, reduced over the warp and added to global memory ONCE per warp after the tile loop (an atomic per
+         // tile and warp put 680 k same-address atomics into every minibatch: +60 % kernel time)
+        const float cs[13] = {dm0, dm1, dm2, dm3, dval, dl0, dl1, dl2, dl3, pg, vf, kl, cf};
 #pragma unroll
-        for (int k = 0; k < 13; k++) {
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], off);
-        }
-        if ((tid & 31) == 0) {
-#pragma unroll
-          for (int k = 0; k < 13; k++) atomicAdd(t.col_sums + (k < 5 ? k : k + 3), cs[k]);
-        }
+        for (int k = 0; k < 13; k++) col_acc[k] += cs[k];
       }
       {  // dOut as a bf16 operand image row (16 features: d mean 0-3, d value, zeros) for d [W3p; w3v] = hpv^T . dOut
         t.dout[img_chunk(tile, 16, row, 0)] = make_uint4(pack_bf16(dm0, dm1), pack_bf16(dm2, dm3), pack_bf16(dval, 0.f), 0u);
@@ -734,12 +729,25 @@ struct AdamArgs {
   float* norm_out;      // [1], may be null
   long long* step_dev;  // may be null: the step count lives on the device (graph replay), lr_t is derived in the kernel
 };
+constexpr int kAdamCtas = 16;
 __global__ void __launch_bounds__(1024, 1) adam_kernel(const __grid_constant__ AdamArgs a) {
+  // Every CTA computes the global norm itself (35 k gradient words, L2-resident: cheaper than a grid-wide reduction) and then
+  // updates its own share of the parameters.  Tensors are walked four elements per thread and iteration so that the loads
+  // of an iteration are independent (the single-CTA, one-element version was a 50 us chain of dependent global loads).
   __shared__ float red[1024];
   __shared__ float s_scale, s_lr_t;
   float ss = 0.f;
-  for (int k = 0; k < a.count; k++)
-    for (int i = threadIdx.x; i < a.n[k]; i += 1024) { const float g = a.grad[k][i]; ss = fmaf(g, g, ss); }
+  for (int k = 0; k < a.count; k++) {
+    const float* g = a.grad[k];
+    const int n = a.n[k];
+    for (int i = threadIdx.x * 4; i < n; i += 4096) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = i + j < n ? g[i + j] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; j++) ss = fmaf(v[j], v[j], ss);
+    }
+  }
   red[threadIdx.x] = ss;
   __syncthreads();
   for (int off = 512; off > 0; off >>= 1) {
@@ -750,25 +758,29 @@ __global__ void __launch_bounds__(1024, 1) adam_kernel(const __grid_constant__ A
     const float norm = sqrtf(red[0]);
     // tf.clip_by_global_norm: g * clip / max(norm, clip); max_norm <= 0: no clipping
     s_scale = a.max_norm > 0.f ? a.max_norm / fmaxf(norm, a.max_norm) : 1.f;
-    if (a.norm_out) *a.norm_out = norm;
+    if (a.norm_out && blockIdx.x == 0) *a.norm_out = norm;
     s_lr_t = a.lr_t;
-    if (a.step_dev) {
+    if (a.step_dev) {  // every CTA derives lr_t from the counter as it was at launch; CTA 0 advances it (nobody reads it later in this launch)
       const long long t = *a.step_dev + 1;
-      *a.step_dev = t;
       s_lr_t = (float)((double)a.lr * sqrt(1.0 - pow((double)a.beta2, (double)t)) / (1.0 - pow((double)a.beta1, (double)t)));
     }
   }
   __syncthreads();
   const float scale = s_scale, b1 = a.beta1, b2 = a.beta2, lr_t = s_lr_t;
-  for (int k = 0; k < a.count; k++)
-    for (int i = threadIdx.x; i < a.n[k]; i += 1024) {
+  for (int k = 0; k < a.count; k++) {
+    const int n = a.n[k];
+    for (int i = blockIdx.x * 1024 + threadIdx.x; i < n; i += gridDim.x * 1024) {
       const float g = a.grad[k][i] * scale;
       const float m = a.m[k][i] + (1.f - b1) * (g - a.m[k][i]);
       const float v = a.v[k][i] + (1.f - b2) * (g * g - a.v[k][i]);
       a.m[k][i] = m; a.v[k][i] = v;
       a.param[k][i] -= lr_t * m / (sqrtf(v) + a.eps);
     }
+  }
 }
+// the device step counter is advanced by its own tiny launch right behind adam_kernel (stream-ordered: no CTA of the
+// optimiser launch can still be reading it)
+__global__ void adam_advance_kernel(long long* step_dev) { *step_dev += 1; }
 
 // =========================================================================================================
 // Minibatch shuffle of the PPO2 update (np.random.shuffle(inds), rl_baselines/ppo2/ppo2.py:350-352) without a sort: a keyed
@@ -1298,7 +1310,8 @@ int qs_adam_step(const qs_adam_tensor_t* tensors, int n_tensors, float lr, float
   a.lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step)));
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_grad_norm; a.norm_out = grad_norm_out;
   a.step_dev = reinterpret_cast<long long*>(step_counter);
-  adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+  adam_kernel<<<kAdamCtas, 1024, 0, (cudaStream_t)stream>>>(a);
+  if (a.step_dev) adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a.step_dev);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_adam_step: %s", cudaGetErrorString(e));
   return QS_OK;
