@@ -570,6 +570,15 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
       }
     }
   }
+  if (TRAIN) {  // this thread's column sums -> warp tree -> one atomic per warp and column
+#pragma unroll
+    for (int k = 0; k < 13; k++) {
+      float v = col_acc[k];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if ((tid & 31) == 0) atomicAdd(t.col_sums + (k < 5 ? k : k + 3), v);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
