@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libquadsim_b200.so")
 SOURCES = [os.path.join(CSRC, "qs_lib.cu"), os.path.join(CSRC, "qs_policy.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "qs_core.cuh"), os.path.join(ROOT, "include", "quadsim_b200.h"), os.path.abspath(__file__)]
+DEPS = SOURCES + [os.path.join(CSRC, "qs_core.cuh"), os.path.join(CSRC, "qs_env_kernels.cuh"), os.path.join(ROOT, "include", "quadsim_b200.h"), os.path.abspath(__file__)]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

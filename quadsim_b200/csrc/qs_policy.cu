@@ -853,7 +853,10 @@ constexpr int kWsEpi = kTileRows * kWsSides;               // epilogue threads p
 constexpr int kWsThreads = kWsGroups * kWsEpi + 32 * kWsGroups; // + one issuer warp per group
 constexpr uint32_t kWsWindow = kWsGroups == 2 ? 256 : 144; // TMEM columns per group
 constexpr int kWsCols = kHid / kWsSides;                   // accumulator columns one thread reads out per 128-column phase
-constexpr int kWsChunk = kWsSides == 1 ? 64 : 32;          // ... per tcgen05.wait::ld (register budget: 576 threads x <= 112)
+#ifndef QS_POLICY_WS_CHUNK
+#define QS_POLICY_WS_CHUNK (QS_POLICY_WS_SIDES == 1 ? 64 : 32)
+#endif
+constexpr int kWsChunk = QS_POLICY_WS_CHUNK;          // ... per tcgen05.wait::ld (register budget: 576 threads x <= 112)
 static_assert(kWsSides == 1 || kWsSides == 2, "one or two epilogue warps per quadrant");
 constexpr int kWsOffBar = kOffA + kWsGroups * kABytes;
 constexpr int kWsBarBytes = 8 + kWsGroups * 64 + 8;        // weights | per group: full_a1, full_a2, full_a3p, full_a3v, done_1, done_p, done_v, done_3 | TMEM slot
