@@ -325,8 +325,11 @@ typedef struct {
   uint8_t* dones;   /* [T+1, N]      row 0 in; row t+1 = done flag returned by step t (== "done before step t+1") */
   float* clipped;   /* [N, 4]        scratch: the clipped actions handed to the env */
 } qs_rollout_t;
-/* Noise for step t uses Philox counter word step_idx0 + t (see qs_policy_step).  n_slices = 1: everything in order on
- * `stream`.  n_slices = 2..8: the envs are cut into that many slices (whole 128-env tiles) that run their step loops on
+/* Noise for step t uses Philox counter word step_idx0 + t (see qs_policy_step).  n_slices = 0: the FUSED step kernel -- one
+ * launch per step does model.step and env.step: the policy half of every CTA hands a tile's clipped actions to env warps of
+ * the same CTA through shared memory, and those run the env step kernel's own device code while the tensor pipe works on the
+ * next tile (float32 docking handles with the default model parameters; `clipped` is not used).  n_slices = 1: two launches
+ * per step, everything in order on `stream`.  n_slices = 2..8: the envs are cut into that many slices (whole 128-env tiles) that run their step loops on
  * internal streams (forked from and joined back into `stream`), so one slice's env kernel (HBM-bound) overlaps another's
  * policy kernel (tensor cores); results are bit-identical to n_slices = 1. */
 int qs_rollout(qs_env_t* env, qs_policy_t* policy, int64_t n_steps, const qs_rollout_t* buffers, uint64_t seed,

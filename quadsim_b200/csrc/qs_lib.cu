@@ -737,6 +737,17 @@ template <typename T, bool IMPORT> int launch_state_io(qs_env* e, const qs_state
 
 }  // namespace
 
+// internal (not part of the C ABI; used by qs_rollout in qs_policy.cu): the step arguments of the whole handle for the fused
+// policy-forward + env-step kernel -- float32 docking handles with the compiled-in constants only
+int qs_env_fused_args_(qs_env_t* e, void* out, size_t out_size, int* kind) {
+  if (!e || !out || out_size != sizeof(StepArgs) || !kind) return QS_ERR_INVALID;
+  if (e->cfg.dtype != QS_F32 || e->cfg.env_kind == QS_HOVER || e->custom) return QS_ERR_INVALID;
+  const StepArgs a = make_args(e, 0, e->cfg.n_envs);
+  memcpy(out, &a, sizeof a);
+  *kind = e->cfg.env_kind;
+  return QS_OK;
+}
+
 extern "C" {
 
 int qs_abi_version(void) { return QS_ABI_VERSION; }

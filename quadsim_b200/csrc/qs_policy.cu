@@ -46,8 +46,10 @@
 
 #include "../../include/quadsim_b200.h"
 #include "qs_core.cuh"
+#include "qs_env_kernels.cuh"
 
 extern int qs_fail_(int code, const char* fmt, ...);  // qs_lib.cu: sets the thread-local error string
+extern int qs_env_fused_args_(qs_env_t* e, void* out, size_t out_size, int* kind);  // qs_lib.cu: EnvStepArgs of a whole fp32 docking handle
 
 namespace {
 
@@ -863,22 +865,31 @@ constexpr int kWsBarBytes = 8 + kWsGroups * 64 + 8;        // weights | per grou
 constexpr int kWsSmemBytes = kWsOffBar + (kWsBarBytes + 63) / 64 * 64;
 static_assert(kWsSmemBytes <= 227 * 1024, "shared memory budget");
 enum { kFullA1 = 0, kFullA2, kFullA3p, kFullA3v, kDone1, kDoneP, kDoneV, kDone3 };
+// ---- fused policy-forward + env-step kernel (policy_env_step_kernel): the same CTA plus four ENV WARPS per group ----
+// The epilogue threads hand the clipped actions of a tile to the group's env warps through shared memory (two 2 KB slots per
+// group, full / empty mbarriers); the env warps hold the tile's state rows in registers by then (loads issued before the
+// wait) and run the very device code of dock_step_kernel (dock_step_loaded, qs_env_kernels.cuh) on them.  One launch per
+// rollout step does model.step AND env.step; the env warps use the issue slots the policy's dependency chain leaves idle
+// (issue-active 28 % for the policy kernel alone), instead of a second kernel that can only share SMs by accident.
+constexpr int kFuEnvThreads = kWsGroups * kTileRows;          // one env thread per accumulator row
+constexpr int kFuThreads = kWsThreads + kFuEnvThreads;        // 576
+constexpr int kFuOffAct = kWsSmemBytes;                       // [group][slot][128] float4
+constexpr int kFuOffBar = kFuOffAct + kWsGroups * 2 * kTileRows * 16;  // [group][slot]{full, empty}
+constexpr int kFuSmemBytes = kFuOffBar + kWsGroups * 2 * 16;
+static_assert(kFuSmemBytes <= 227 * 1024, "shared memory budget");
 
-// programmatic dependent launch, as in the env step kernels (qs_lib.cu): stage the next kernel early, wait for the previous one
-__device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-
+// programmatic dependent launch: pdl_prologue() of qs_env_kernels.cuh (stage the next kernel early, wait for the previous one)
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
-__device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a) {
+template <bool FUSED, int KIND>
+__device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvStepArgs& ea) {
   pdl_prologue();
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int kEpiWarps = kWsGroups * kWsEpi / 32;
-  const bool issuer = warp >= kEpiWarps;
-  const int g = issuer ? warp - kEpiWarps : tid / kWsEpi;  // group
+  const bool env_warp = FUSED && warp >= kEpiWarps + kWsGroups;   // FUSED: warps behind the issuers step the environments
+  const bool issuer = warp >= kEpiWarps && !env_warp;
+  const int g = env_warp ? (tid - kWsThreads) / kTileRows : (issuer ? warp - kEpiWarps : tid / kWsEpi);  // group
   const int side = issuer ? 0 : (tid % kWsEpi) / kTileRows; // which half of the columns this epilogue thread handles
   const int row = tid & 127;                               // epilogue threads: accumulator row == TMEM lane == env within the tile
   const uint32_t sbase = smem_u32(smem);
@@ -888,13 +899,19 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a) {
   const int tiles = (int)((a.n + kTileRows - 1) / kTileRows);
   const int tile0 = blockIdx.x * kWsGroups + g, tile_stride = gridDim.x * kWsGroups;
 
+  // FUSED: action hand-off slots of this group and their barriers
+  const uint32_t act_bar = sbase + kFuOffBar + g * 32;  // + slot * 16: full, + 8: empty
+  float4* act_buf = reinterpret_cast<float4*>(smem + kFuOffAct) + g * 2 * kTileRows;
+
   ObsRow o = {};
-  if (!issuer) o = load_obs(a.obs, (int64_t)tile0 * kTileRows + row, tile0 < tiles ? a.n : 0, nullptr);  // in flight during the set-up
+  if (!issuer && !env_warp) o = load_obs(a.obs, (int64_t)tile0 * kTileRows + row, tile0 < tiles ? a.n : 0, nullptr);  // in flight during the set-up
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
     for (int gg = 0; gg < kWsGroups; gg++)
       for (int j = 0; j < 8; j++) mbar_init(sbase + kWsOffBar + 8 + 64 * gg + 8 * j, j < kDone1 ? kWsEpi : 1);
+    if (FUSED)
+      for (int j = 0; j < kWsGroups * 4; j++) mbar_init(sbase + kFuOffBar + 8 * j, kTileRows);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(bar_w, kPackedBytes);
     for (int off = 0; off < kPackedBytes; off += 16384) {
@@ -915,7 +932,30 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a) {
   // two groups: D1 and the vf half at [128,256), D3 right behind side 0's packed A3 pi; three groups: everything at [0,128)
   constexpr uint32_t kColD1 = kWsGroups == 2 ? 128 : 0, kColD2v = kWsGroups == 2 ? 128 : 0, kColD3ws = kWsGroups == 2 ? kWsCols / 2 : 128;
 
-  if (issuer) {
+  if (env_warp) {
+    // ---------------------------------------------------------------- env warps (FUSED): thread = env, as in dock_step_kernel
+    if constexpr (FUSED) {
+      constexpr int NW = dock_words<float>();
+      const int er = (tid - kWsThreads) % kTileRows;
+      uint32_t it = 0;
+      for (int tile = tile0; tile < tiles; tile += tile_stride, it++) {
+        const int64_t i = ea.first + (int64_t)tile * kTileRows + er;
+        const bool active = i < ea.first + ea.n;
+        float w[NW];
+        if (active) load_words<float, NW>(ea.state, i, w);  // in flight while the policy half of the CTA computes this tile's actions
+        const uint32_t slot = it & 1, par = (it >> 1) & 1;
+        mbar_wait(act_bar + slot * 16, par);
+        const float4 c = act_buf[slot * kTileRows + er];
+        mbar_arrive(act_bar + slot * 16 + 8);  // the slot may be rewritten
+        const unsigned mask = __ballot_sync(0xffffffffu, active);
+        if (active) {
+          const float act[4] = {c.x, c.y, c.z, c.w};
+          const StepTail tl = dock_step_loaded<float, KIND, false>(ea, DefaultParams<float, KIND>{}, i, w, act);
+          warp_stats_update(ea.warp_stats, i, mask, tl.done, tl.docking, tl.nonfinite, tl.ret, tl.len);
+        }
+      }
+    }
+  } else if (issuer) {
     // ---------------------------------------------------------------- MMA issuer: one elected lane, the warp waits together
     mbar_wait(bar_w, 0);
     uint32_t it = 0;
@@ -1001,23 +1041,31 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a) {
       tmem_wait_ld();
       tc_fence_before();  // D3 is read before the next tile's pi half (ordered by our full_a2 arrival) overwrites it
     };
-    auto finish = [&](int64_t i, float z0, float z1, float z2, float z3) {
-      if (i >= a.n) return;
+    auto finish = [&](int64_t i, uint32_t it_of_i, float z0, float z1, float z2, float z3) {
+      const bool live = i < a.n;
       const float ls0 = tail[8], ls1 = tail[9], ls2 = tail[10], ls3 = tail[11];
       const float mu0 = __uint_as_float(d3[0]) + tail[0], mu1 = __uint_as_float(d3[1]) + tail[1];
       const float mu2 = __uint_as_float(d3[2]) + tail[2], mu3 = __uint_as_float(d3[3]) + tail[3];
       const float val = __uint_as_float(d3[4]) + tail[4];
+      const float a0 = fmaf(__expf(ls0), z0, mu0), a1 = fmaf(__expf(ls1), z1, mu1), a2 = fmaf(__expf(ls2), z2, mu2), a3 = fmaf(__expf(ls3), z3, mu3);
+      const float4 clipped = make_float4(fminf(fmaxf(a0, -1.f), 1.f), fminf(fmaxf(a1, -1.f), 1.f), fminf(fmaxf(a2, -1.f), 1.f), fminf(fmaxf(a3, -1.f), 1.f));
+      if (FUSED && (kWsSides == 1 || side == 0)) {  // hand the tile's clipped actions to the env warps (every row arrives: the barrier counts 128)
+        const uint32_t slot = it_of_i & 1, par = ((it_of_i >> 1) & 1) ^ 1;  // a fresh barrier passes a wait on parity 1: both slots start out empty
+        mbar_wait(act_bar + slot * 16 + 8, par);
+        act_buf[slot * kTileRows + row] = clipped;
+        mbar_arrive(act_bar + slot * 16);
+      }
+      if (!live) return;
       if (kWsSides == 1 || side == 0) {
-        const float a0 = fmaf(__expf(ls0), z0, mu0), a1 = fmaf(__expf(ls1), z1, mu1), a2 = fmaf(__expf(ls2), z2, mu2), a3 = fmaf(__expf(ls3), z3, mu3);
         // neglogp = 0.5 * sum(((a - mean)/std)^2) + 0.5*log(2 pi)*4 + sum(logstd); (a - mean)/std == the noise itself
         const float nlp = 0.5f * (z0 * z0 + z1 * z1 + z2 * z2 + z3 * z3) + 3.6757541328186907f + (ls0 + ls1 + ls2 + ls3);
         if (a.actions) reinterpret_cast<float4*>(a.actions)[i] = make_float4(a0, a1, a2, a3);
-        if (a.clipped)
-          reinterpret_cast<float4*>(a.clipped)[i] = make_float4(fminf(fmaxf(a0, -1.f), 1.f), fminf(fmaxf(a1, -1.f), 1.f), fminf(fmaxf(a2, -1.f), 1.f), fminf(fmaxf(a3, -1.f), 1.f));
+        if (a.clipped) reinterpret_cast<float4*>(a.clipped)[i] = clipped;
         if (a.neglogp) a.neglogp[i] = nlp;
       }
       if (kWsSides == 1 || side == 1) a.values[i] = val;
     };
+    uint32_t it_prev = 0;
     uint32_t it = 0;
     for (int tile = tile0; tile < tiles; tile += tile_stride, it++) {
       const uint32_t ph = it & 1;
@@ -1050,7 +1098,7 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a) {
       if (i_prev >= 0) read_d3(ph ^ 1);  // the previous tile's layer-3 result, before this tile's pi half lands on it
       tc_fence_before();  // D1 is read; the vf half of layer 2 will overwrite its columns
       mbar_arrive(bars + 8 * kFullA2);
-      if (i_prev >= 0) finish(i_prev, p0, p1, p2, p3);  // under this tile's layer 2
+      if (i_prev >= 0) finish(i_prev, it_prev, p0, p1, p2, p3);  // under this tile's layer 2
       // ---- relu(D2 half) -> bf16 pairs packed in place: A3 pi = [0,64), A3 vf = [128,192) ----
 #pragma unroll 1
       for (int half = 0; half < 2; half++) {
@@ -1090,21 +1138,27 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a) {
         n0 = r0 * c0_; n1 = r0 * s0; n2 = r1 * c1_; n3 = r1 * s1;  // Box-Muller
       }
       i_prev = i;
+      it_prev = it;
     }
     if (i_prev >= 0) {  // the last tile's tail
       read_d3((it - 1) & 1);
-      finish(i_prev, n0, n1, n2, n3);
+      finish(i_prev, it_prev, n0, n1, n2, n3);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
 }
-__global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const StepArgs a) { policy_fwd_ws_body(a); }
+__global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const StepArgs a) { policy_fwd_ws_body<false, kDockV2>(a, EnvStepArgs{}); }
+// model.step + env.step of one rollout step in ONE launch (see the kFu* constants above): rl_baselines/ppo2/ppo2.py:472-482
+template <int KIND>
+__global__ void __launch_bounds__(kFuThreads, 1) policy_env_step_kernel(const StepArgs a, const __grid_constant__ EnvStepArgs ea) {
+  policy_fwd_ws_body<true, KIND>(a, ea);
+}
 // Register-capped builds of the same kernel for the sliced rollout: a policy CTA at 128 registers x 320 threads leaves an SM
 // room for ONE 128-thread env CTA (80 registers) next to it, at 80 registers for three -- and it is the env kernel's occupancy
 // that decides how much of its HBM time hides under the other slice's policy kernel.  The cap costs ~100 bytes of spills.
-template <int REGS> __global__ void __maxnreg__(REGS) policy_fwd_ws_kernel_capped(const StepArgs a) { policy_fwd_ws_body(a); }
+template <int REGS> __global__ void __maxnreg__(REGS) policy_fwd_ws_kernel_capped(const StepArgs a) { policy_fwd_ws_body<false, kDockV2>(a, EnvStepArgs{}); }
 
 }  // namespace
 
@@ -1152,6 +1206,8 @@ int qs_policy_create(qs_policy_t** out, int device) {
       (err = cudaFuncSetAttribute(policy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes)) != cudaSuccess ||
+      (err = cudaFuncSetAttribute(policy_env_step_kernel<kDockV0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes)) != cudaSuccess ||
+      (err = cudaFuncSetAttribute(policy_env_step_kernel<kDockV2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_fwd_ws_kernel_capped<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_fwd_ws_kernel_capped<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
@@ -1344,7 +1400,7 @@ int qs_rollout(qs_env_t* env, qs_policy_t* pol, int64_t n_steps, const qs_rollou
                void* stream) {
   if (!env || !pol || !b || !b->obs || !b->actions || !b->values || !b->neglogp || !b->rewards || !b->dones || !b->clipped)
     return qs_fail_(QS_ERR_INVALID, "qs_rollout: null argument");
-  if (n_steps < 0 || n_slices < 1 || n_slices > kMaxSlices) return qs_fail_(QS_ERR_INVALID, "qs_rollout: n_steps < 0 or n_slices not in [1, %d]", kMaxSlices);
+  if (n_steps < 0 || n_slices < 0 || n_slices > kMaxSlices) return qs_fail_(QS_ERR_INVALID, "qs_rollout: n_steps < 0 or n_slices not in [0, %d]", kMaxSlices);
   if (qs_env_dtype(env) != QS_F32 || qs_obs_dim(env) != kObs)
     return qs_fail_(QS_ERR_INVALID, "qs_rollout: needs a float32 docking environment (12 observations, what the policy was built for)");
   if (qs_env_device(env) != pol->device)
@@ -1352,6 +1408,35 @@ int qs_rollout(qs_env_t* env, qs_policy_t* pol, int64_t n_steps, const qs_rollou
   NvtxRange nv("qs_rollout");
   const int64_t n = qs_num_envs(env);
   const uint64_t id0 = qs_env_id0(env);
+  if (n_slices == 0) {
+    // ---- fused: ONE launch per step does model.step and env.step (policy_env_step_kernel); then the bootstrap value pass
+    EnvStepArgs ea;
+    int kind = 0;
+    if (qs_env_fused_args_(env, &ea, sizeof ea, &kind) != QS_OK)
+      return qs_fail_(QS_ERR_INVALID, "qs_rollout: the fused step kernel (n_slices = 0) needs a float32 docking handle with the default model parameters");
+    if (!pol->have_weights) return qs_fail_(QS_ERR_INVALID, "qs_rollout: qs_policy_set_weights has not been called");
+    int prev = 0;
+    QSP_CUDA(cudaGetDevice(&prev));
+    QSP_CUDA(cudaSetDevice(pol->device));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = [] { const char* v = getenv("QUADSIM_B200_PDL"); return !(v && v[0] == '0'); }();
+    cudaLaunchConfig_t cfg = {};
+    const int ws_ctas = (int)(((n + kTileRows - 1) / kTileRows + kWsGroups - 1) / kWsGroups);
+    cfg.gridDim = dim3(ws_ctas < pol->grid ? ws_ctas : pol->grid); cfg.blockDim = dim3(kFuThreads); cfg.dynamicSmemBytes = kFuSmemBytes;
+    cfg.stream = (cudaStream_t)stream; cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t le = cudaSuccess;
+    for (int64_t t = 0; t < n_steps && le == cudaSuccess; t++) {
+      StepArgs a = {pol->packed, b->obs + t * n * kObs, n, seed, id0, step_idx0 + (uint32_t)t, 0, b->actions + t * n * kAct, nullptr,
+                    b->values + t * n, b->neglogp + t * n};
+      ea.actions = nullptr; ea.obs = b->obs + (t + 1) * n * kObs; ea.reward = b->rewards + t * n; ea.done = b->dones + (t + 1) * n;
+      le = kind == QS_DOCK_V0 ? cudaLaunchKernelEx(&cfg, policy_env_step_kernel<kDockV0>, a, ea) : cudaLaunchKernelEx(&cfg, policy_env_step_kernel<kDockV2>, a, ea);
+    }
+    cudaSetDevice(prev);
+    if (le != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_rollout: %s", cudaGetErrorString(le));
+    return qs_policy_step(pol, n, b->obs + n_steps * n * kObs, seed, id0, 0, 1, nullptr, nullptr, b->values + n_steps * n, nullptr, stream);
+  }
   // slice boundaries on whole 128-env tiles (the state layout's unit)
   int64_t first[kMaxSlices + 1];
   const int64_t tiles = (n + kTileRows - 1) / kTileRows;

@@ -140,7 +140,9 @@ class DeviceRunner:
     def __init__(self, env, policy, n_steps, gamma=0.99, lam=0.95, reset_each_rollout=False, generator=None, fused=None, n_slices=2):
         self.env, self.policy, self.n_steps, self.gamma, self.lam = env, policy, int(n_steps), gamma, lam
         self.fused = fused  # FusedPolicy (tcgen05 kernel) or None for the torch forward
-        self.n_slices = int(n_slices)  # qs_rollout: 2 = overlap one half's env kernel with the other half's policy kernel
+        # qs_rollout: 0 = the fused step kernel (one launch per step does model.step and env.step); 1 = two launches per step;
+        # 2..8 = env slices on separate streams (one slice's env kernel overlaps another's policy kernel)
+        self.n_slices = int(n_slices)
         self.reset_each_rollout = reset_each_rollout  # the in-tree fork's `self.obs = self.env.reset()` (ppo2.py:525)
         self.generator = generator
         n, dev = env.num_envs, env.device
@@ -161,6 +163,11 @@ class DeviceRunner:
         self._advs, self._returns = torch.empty((T, n), **f32), torch.empty((T, n), **f32)
         self.obs = env.reset().float()
         self.dones = torch.zeros(n, dtype=torch.uint8, device=dev)
+
+    def launches_per_rollout(self):
+        """Kernel launches of one in-place rollout incl. the bootstrap value pass and GAE."""
+        T = self.n_steps
+        return T + 2 if self.n_slices == 0 else max(self.n_slices, 1) * (2 * T + 1) + 1
 
     def _run_in_place(self):
         T, env = self.n_steps, self.env

@@ -139,6 +139,51 @@ def test_in_place_rollout_equals_stepwise_loop(n_slices):
     env_b.close()
 
 
+@pytest.mark.parametrize("env_id", ["docking-v2", "docking-v0"])
+def test_fused_step_kernel_rollout_equals_two_kernel_rollout(env_id):
+    """qs_rollout(n_slices=0) -- ONE launch per step: the policy half of every CTA hands the clipped actions to env warps of the
+    same CTA, which run the env step kernel's own device code -- against qs_rollout(n_slices=1) (two launches per step) on a
+    twin environment, five consecutive rollouts with auto-resets on a ragged env count.  The policy arithmetic is the same
+    instruction sequence (bit-identical actions / values / log-probs for identical observations); the env arithmetic is the
+    same source compiled into another kernel, so it is compared within 1e-5 relative, done flags exactly."""
+    from quadsim_b200.fused_policy import FusedPolicy
+    n, T = 128 * 9 + 77, 24
+    torch.manual_seed(0)
+    pol = ppo.MlpPolicy().cuda()
+    with torch.no_grad():
+        pol.logstd.fill_(0.5)
+        pol.pi.weight.mul_(20.0)
+    envs = [qs.make_vec(env_id, n, seed=5, randomize="episode", want_info=False) for _ in range(2)]
+    fps = [FusedPolicy(pol, seed=11) for _ in range(2)]
+    fused = ppo.DeviceRunner(envs[0], pol, T, fused=fps[0], n_slices=0)
+    plain = ppo.DeviceRunner(envs[1], pol, T, fused=fps[1], n_slices=1)
+    assert fused.in_place and plain.in_place and fused.launches_per_rollout() == T + 2 and plain.launches_per_rollout() == 2 * T + 2
+    close_ = lambda x, y: bool(((x - y).abs() <= 1e-5 * y.abs().clamp(min=1)).all())
+    identical, n_done = True, 0
+    for rollout in range(5):
+        ba, bb = fused.run(), plain.run()
+        n_done += int(fused._dones_all[1:].sum())
+        assert torch.equal(fused._dones_all, plain._dones_all), rollout
+        for name in ("_obs_all", "mb_rewards", "mb_actions", "_values_all", "mb_neglogp"):
+            x, y = getattr(fused, name), getattr(plain, name)
+            assert close_(x, y), (rollout, name, float((x - y).abs().max()))
+            identical &= torch.equal(x, y)
+        assert close_(ba["advs"], bb["advs"]) and close_(ba["returns"], bb["returns"])
+        # teacher-forced: the policy half alone, on the fused run's own observations, is bit-identical to qs_policy_step
+        for t in (0, T // 2, T - 1):
+            act, clip, val, nlp = fps[1].step(fused.mb_obs[t], step_idx=rollout * T + t)
+            assert torch.equal(act, fused.mb_actions[t]) and torch.equal(val, fused.mb_values[t]) and torch.equal(nlp, fused.mb_neglogp[t])
+    sa, sb = envs[0].get_state(), envs[1].get_state()
+    assert torch.equal(sa["t"], sb["t"]) and torch.equal(sa["episode"], sb["episode"]) and close_(sa["chaser"], sb["chaser"])
+    st_a, st_b = envs[0].stats(), envs[1].stats()
+    assert st_a["episodes"] == st_b["episodes"] == n_done > 0 and st_a["length_sum"] == st_b["length_sum"]
+    print(env_id, "fused step kernel vs two-kernel rollout: bit-identical =", identical, "episodes", n_done)
+    with pytest.raises(qs.QuadSimError):  # the fused kernel is built for the compiled-in model constants
+        ppo.DeviceRunner(qs.make_vec(env_id, 256, params={"mass": 0.2}), pol, 4, fused=fps[0], n_slices=0).run()
+    for e in envs:
+        e.close()
+
+
 def test_ppo2_learn_with_fused_policy():
     n = 4096
     env = qs.make_vec("docking-v2", n, seed=3, randomize="episode")
