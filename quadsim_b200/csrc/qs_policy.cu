@@ -885,12 +885,21 @@ template <bool FUSED, int KIND>
 __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvStepArgs& ea) {
   pdl_prologue();
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // FUSED: the env warps come FIRST (QS_FUSED_ENV_FIRST, default): the warp scheduler favours the higher warp slots, and it is
+  // the policy's dependency chain (epilogue -> issuer -> tensor pipe -> epilogue) that sets the step time -- the env warps are
+  // there to fill the issue slots that chain leaves idle, not to compete for them
+#ifndef QS_FUSED_ENV_FIRST
+#define QS_FUSED_ENV_FIRST 1
+#endif
+  constexpr int kEnvFirst = FUSED && QS_FUSED_ENV_FIRST ? kFuEnvThreads : 0;  // threads in front of the policy's
+  const int lane = threadIdx.x & 31, tid_hw = threadIdx.x;
+  const int tid = tid_hw - kEnvFirst, warp = tid >> 5;           // policy-relative ids (negative: env threads placed first)
   constexpr int kEpiWarps = kWsGroups * kWsEpi / 32;
-  const bool env_warp = FUSED && warp >= kEpiWarps + kWsGroups;   // FUSED: warps behind the issuers step the environments
-  const bool issuer = warp >= kEpiWarps && !env_warp;
-  const int g = env_warp ? (tid - kWsThreads) / kTileRows : (issuer ? warp - kEpiWarps : tid / kWsEpi);  // group
-  const int side = issuer ? 0 : (tid % kWsEpi) / kTileRows; // which half of the columns this epilogue thread handles
+  const bool env_warp = FUSED && (kEnvFirst ? tid < 0 : warp >= kEpiWarps + kWsGroups);
+  const int env_tid = kEnvFirst ? tid_hw : tid - kWsThreads;     // 0 .. kFuEnvThreads-1 for env threads
+  const bool issuer = !env_warp && warp >= kEpiWarps;
+  const int g = env_warp ? env_tid / kTileRows : (issuer ? warp - kEpiWarps : tid / kWsEpi);  // group
+  const int side = issuer || env_warp ? 0 : (tid % kWsEpi) / kTileRows; // which half of the columns this epilogue thread handles
   const int row = tid & 127;                               // epilogue threads: accumulator row == TMEM lane == env within the tile
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_w = sbase + kWsOffBar, bars = sbase + kWsOffBar + 8 + 64 * g;
@@ -906,7 +915,7 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
   ObsRow o = {};
   if (!issuer && !env_warp) o = load_obs(a.obs, (int64_t)tile0 * kTileRows + row, tile0 < tiles ? a.n : 0, nullptr);  // in flight during the set-up
 
-  if (tid == 0) {
+  if (tid_hw == 0) {
     mbar_init(bar_w, 1);
     for (int gg = 0; gg < kWsGroups; gg++)
       for (int j = 0; j < 8; j++) mbar_init(sbase + kWsOffBar + 8 + 64 * gg + 8 * j, j < kDone1 ? kWsEpi : 1);
@@ -919,7 +928,7 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
       bulk_g2s(sbase + kOffW1 + off, a.packed + off, bytes, bar_w);
     }
   }
-  if (warp == 0) {
+  if (tid_hw < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -936,7 +945,7 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
     // ---------------------------------------------------------------- env warps (FUSED): thread = env, as in dock_step_kernel
     if constexpr (FUSED) {
       constexpr int NW = dock_words<float>();
-      const int er = (tid - kWsThreads) % kTileRows;
+      const int er = env_tid % kTileRows;
       uint32_t it = 0;
       for (int tile = tile0; tile < tiles; tile += tile_stride, it++) {
         const int64_t i = ea.first + (int64_t)tile * kTileRows + er;
@@ -1147,7 +1156,7 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
+  if (tid_hw < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
 }
 __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const StepArgs a) { policy_fwd_ws_body<false, kDockV2>(a, EnvStepArgs{}); }
 // model.step + env.step of one rollout step in ONE launch (see the kFu* constants above): rl_baselines/ppo2/ppo2.py:472-482
