@@ -871,7 +871,14 @@ enum { kFullA1 = 0, kFullA2, kFullA3p, kFullA3v, kDone1, kDoneP, kDoneV, kDone3 
 // wait) and run the very device code of dock_step_kernel (dock_step_loaded, qs_env_kernels.cuh) on them.  One launch per
 // rollout step does model.step AND env.step; the env warps use the issue slots the policy's dependency chain leaves idle
 // (issue-active 28 % for the policy kernel alone), instead of a second kernel that can only share SMs by accident.
-constexpr int kFuEnvThreads = kWsGroups * kTileRows;          // one env thread per accumulator row
+#ifndef QS_FUSED_ENV_SETS
+#define QS_FUSED_ENV_SETS 2   // env warp-sets (4 warps each) per group = env tiles in flight per group: set s serves slot s, i.e.
+                              // every other tile of the group.  An env tile takes ~5 us from its first load to its last store
+                              // (HBM latency on both ends), the policy half hands one over every ~1.6 us per group.
+#endif
+constexpr int kFuSets = QS_FUSED_ENV_SETS;
+static_assert(kFuSets == 1 || kFuSets == 2, "one or two env warp-sets per group (two action slots)");
+constexpr int kFuEnvThreads = kWsGroups * kFuSets * kTileRows; // one env thread per accumulator row and set
 constexpr int kFuThreads = kWsThreads + kFuEnvThreads;        // 576
 constexpr int kFuOffAct = kWsSmemBytes;                       // [group][slot][128] float4
 constexpr int kFuOffBar = kFuOffAct + kWsGroups * 2 * kTileRows * 16;  // [group][slot]{full, empty}
@@ -898,7 +905,8 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
   const bool env_warp = FUSED && (kEnvFirst ? tid < 0 : warp >= kEpiWarps + kWsGroups);
   const int env_tid = kEnvFirst ? tid_hw : tid - kWsThreads;     // 0 .. kFuEnvThreads-1 for env threads
   const bool issuer = !env_warp && warp >= kEpiWarps;
-  const int g = env_warp ? env_tid / kTileRows : (issuer ? warp - kEpiWarps : tid / kWsEpi);  // group
+  const int g = env_warp ? env_tid / (kFuSets * kTileRows) : (issuer ? warp - kEpiWarps : tid / kWsEpi);  // group
+  const int env_set = env_warp ? (env_tid / kTileRows) % kFuSets : 0;
   const int side = issuer || env_warp ? 0 : (tid % kWsEpi) / kTileRows; // which half of the columns this epilogue thread handles
   const int row = tid & 127;                               // epilogue threads: accumulator row == TMEM lane == env within the tile
   const uint32_t sbase = smem_u32(smem);
@@ -946,8 +954,8 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
     if constexpr (FUSED) {
       constexpr int NW = dock_words<float>();
       const int er = env_tid % kTileRows;
-      uint32_t it = 0;
-      for (int tile = tile0; tile < tiles; tile += tile_stride, it++) {
+      for (uint32_t it = env_set; tile0 + (int64_t)it * tile_stride < tiles; it += kFuSets) {  // this set's share of the group's tiles
+        const int tile = tile0 + (int)it * tile_stride;
         const int64_t i = ea.first + (int64_t)tile * kTileRows + er;
         const bool active = i < ea.first + ea.n;
         float w[NW];

@@ -1,7 +1,7 @@
-mkdir -p gpurun_out/r2h
+mkdir -p gpurun_out/r2i
 cd $GRAFT_REPO_ROOT
-(timeout 300 python -m pytest tests/test_gpu_ppo.py -m gpu -x -q -s -k "fused_step_kernel" 2>&1 | tail -8) > gpurun_out/r2h/pytest_fused.log
-tail -5 gpurun_out/r2h/pytest_fused.log
-for s in 0 2; do timeout 200 python tools/rollout_bench.py --fused --n-steps 16 --slices $s 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('env warps first: slices', d['slices'], 'rollout_ms', round(d['rollout_ms'],3), 'env-steps/s %.3g' % d['rollout_env_steps_per_s'])" >> gpurun_out/r2h/fused_rollout.log; done
-QUADSIM_B200_NO_EXT=1 QUADSIM_B200_LIB=$PWD/variants/fused_env_last.so timeout 200 python tools/rollout_bench.py --fused --n-steps 16 --slices 0 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('env warps last: slices', d['slices'], 'rollout_ms', round(d['rollout_ms'],3), 'env-steps/s %.3g' % d['rollout_env_steps_per_s'])" >> gpurun_out/r2h/fused_rollout.log
-cat gpurun_out/r2h/fused_rollout.log
+(timeout 300 python -m pytest tests/test_gpu_ppo.py -m gpu -x -q -s -k "fused_step_kernel" 2>&1 | tail -8) > gpurun_out/r2i/pytest_fused.log
+tail -5 gpurun_out/r2i/pytest_fused.log
+for s in 0 2; do timeout 200 python tools/rollout_bench.py --fused --n-steps 16 --slices $s 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('sets2: slices', d['slices'], 'rollout_ms', round(d['rollout_ms'],3), 'env-steps/s %.3g' % d['rollout_env_steps_per_s'])" >> gpurun_out/r2i/fused_rollout.log; done
+QUADSIM_B200_NO_EXT=1 QUADSIM_B200_LIB=$PWD/variants/fused_sets1.so timeout 200 python tools/rollout_bench.py --fused --n-steps 16 --slices 0 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('sets1: slices', d['slices'], 'rollout_ms', round(d['rollout_ms'],3), 'env-steps/s %.3g' % d['rollout_env_steps_per_s'])" >> gpurun_out/r2i/fused_rollout.log
+cat gpurun_out/r2i/fused_rollout.log
