@@ -872,17 +872,20 @@ enum { kFullA1 = 0, kFullA2, kFullA3p, kFullA3v, kDone1, kDoneP, kDoneV, kDone3 
 // rollout step does model.step AND env.step; the env warps use the issue slots the policy's dependency chain leaves idle
 // (issue-active 28 % for the policy kernel alone), instead of a second kernel that can only share SMs by accident.
 #ifndef QS_FUSED_ENV_SETS
-#define QS_FUSED_ENV_SETS 2   // env warp-sets (4 warps each) per group = env tiles in flight per group: set s serves slot s, i.e.
-                              // every other tile of the group.  An env tile takes ~5 us from its first load to its last store
-                              // (HBM latency on both ends), the policy half hands one over every ~1.6 us per group.
+#define QS_FUSED_ENV_SETS 1   // env warp-sets (4 warps each) per group: set s serves action slot s, i.e. every kFuSets-th tile of the
+                              // group.  Two sets (measured with plain state loads: 2.80 vs 2.64 ms per 16-step rollout) lose
+                              // more to the 72-register cap of an 832-thread CTA than they gain, and their state stages do
+                              // not fit shared memory next to the policy's operands.
 #endif
 constexpr int kFuSets = QS_FUSED_ENV_SETS;
 static_assert(kFuSets == 1 || kFuSets == 2, "one or two env warp-sets per group (two action slots)");
 constexpr int kFuEnvThreads = kWsGroups * kFuSets * kTileRows; // one env thread per accumulator row and set
 constexpr int kFuThreads = kWsThreads + kFuEnvThreads;        // 576
 constexpr int kFuOffAct = kWsSmemBytes;                       // [group][slot][128] float4
-constexpr int kFuOffBar = kFuOffAct + kWsGroups * 2 * kTileRows * 16;  // [group][slot]{full, empty}
-constexpr int kFuSmemBytes = kFuOffBar + kWsGroups * 2 * 16;
+constexpr int kFuOffBar = kFuOffAct + kWsGroups * 2 * kTileRows * 16;  // [group][slot]{full, empty}, then [group][set] state-stage barrier
+constexpr int kFuStateBytes = (dock_words<float>() / 4) * kTileRows * 16;  // one tile's state rows: 20 KB, contiguous in HBM (tile-major layout)
+constexpr int kFuOffState = (kFuOffBar + kWsGroups * 2 * 16 + kWsGroups * 2 * 8 + 127) / 128 * 128;  // [group][set] stage
+constexpr int kFuSmemBytes = kFuOffState + kWsGroups * kFuSets * kFuStateBytes;
 static_assert(kFuSmemBytes <= 227 * 1024, "shared memory budget");
 
 // programmatic dependent launch: pdl_prologue() of qs_env_kernels.cuh (stage the next kernel early, wait for the previous one)
@@ -927,8 +930,10 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
     mbar_init(bar_w, 1);
     for (int gg = 0; gg < kWsGroups; gg++)
       for (int j = 0; j < 8; j++) mbar_init(sbase + kWsOffBar + 8 + 64 * gg + 8 * j, j < kDone1 ? kWsEpi : 1);
-    if (FUSED)
+    if (FUSED) {
       for (int j = 0; j < kWsGroups * 4; j++) mbar_init(sbase + kFuOffBar + 8 * j, kTileRows);
+      for (int j = 0; j < kWsGroups * 2; j++) mbar_init(sbase + kFuOffBar + kWsGroups * 32 + 8 * j, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(bar_w, kPackedBytes);
     for (int off = 0; off < kPackedBytes; off += 16384) {
@@ -952,14 +957,34 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
   if (env_warp) {
     // ---------------------------------------------------------------- env warps (FUSED): thread = env, as in dock_step_kernel
     if constexpr (FUSED) {
-      constexpr int NW = dock_words<float>();
+      constexpr int NW = dock_words<float>(), NR = NW / 4;
       const int er = env_tid % kTileRows;
-      for (uint32_t it = env_set; tile0 + (int64_t)it * tile_stride < tiles; it += kFuSets) {  // this set's share of the group's tiles
+      // The tile's state rows arrive by bulk copy (cp.async.bulk, one elected thread, completion on an mbarrier) into this
+      // set's 20 KB stage; the request for the set's NEXT tile goes out as soon as all 128 threads have moved the current one
+      // to registers -- its HBM latency hides under this tile's arithmetic (registers are the second buffer, as in
+      // dock_step_pipe_kernel).  With plain loads the env warps, not the policy chain, set the step time: 155 us vs ~90.
+      const float4* state_rows = reinterpret_cast<const float4*>(ea.state);
+      const uint32_t st_bar = sbase + kFuOffBar + kWsGroups * 32 + (g * 2 + env_set) * 8;
+      const float4* st_buf = reinterpret_cast<const float4*>(smem + kFuOffState + (g * kFuSets + env_set) * kFuStateBytes);
+      const uint32_t st_dst = sbase + kFuOffState + (g * kFuSets + env_set) * kFuStateBytes;
+      auto request = [&](uint32_t it_next) {
+        const int64_t env0 = ea.first + ((int64_t)tile0 + (int64_t)it_next * tile_stride) * kTileRows;
+        mbar_expect_tx(st_bar, kFuStateBytes);
+        for (int off = 0; off < kFuStateBytes; off += 10240)
+          bulk_g2s(st_dst + off, reinterpret_cast<const unsigned char*>(state_rows + (env0 / kTileRows) * (NR * kTileRows)) + off, 10240, st_bar);
+      };
+      if (er == 0 && tile0 + (int64_t)env_set * tile_stride < tiles) request(env_set);
+      uint32_t n_it = 0;
+      for (uint32_t it = env_set; tile0 + (int64_t)it * tile_stride < tiles; it += kFuSets, n_it++) {  // this set's share of the group's tiles
         const int tile = tile0 + (int)it * tile_stride;
         const int64_t i = ea.first + (int64_t)tile * kTileRows + er;
         const bool active = i < ea.first + ea.n;
+        mbar_wait(st_bar, n_it & 1);
         float w[NW];
-        if (active) load_words<float, NW>(ea.state, i, w);  // in flight while the policy half of the CTA computes this tile's actions
+#pragma unroll
+        for (int r = 0; r < NR; r++) unpack(st_buf[r * kTileRows + er], &w[r * 4]);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + g * kFuSets + env_set), "n"(kTileRows) : "memory");  // the stage is drained
+        if (er == 0 && tile0 + (int64_t)(it + kFuSets) * tile_stride < tiles) request(it + kFuSets);
         const uint32_t slot = it & 1, par = (it >> 1) & 1;
         mbar_wait(act_bar + slot * 16, par);
         const float4 c = act_buf[slot * kTileRows + er];
