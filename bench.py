@@ -463,13 +463,30 @@ def measure_callers(args, rank, dev, world, D, n_steps=16, rollouts=5):
     torch.cuda.synchronize(dev)
     roll_ms = D.max_over_ranks(ev[0].elapsed_time(ev[1]) / rollouts, dev)
     upd_ms = D.max_over_ranks(ev[1].elapsed_time(ev[2]), dev)
+    launches, slices = algo.runner.launches_per_rollout(), algo.runner.n_slices
+    # the same rollout through the fused step kernel (one launch per step: policy forward + env step in one CTA)
+    algo.runner.n_slices = 0
+    for _ in range(2):
+        algo.runner.run()
+    torch.cuda.synchronize(dev)
+    fe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    fe[0].record()
+    for _ in range(rollouts):
+        algo.runner.run()
+    fe[1].record()
+    torch.cuda.synchronize(dev)
+    fused_ms = D.max_over_ranks(fe[0].elapsed_time(fe[1]) / rollouts, dev)
+    fused_launches = algo.runner.launches_per_rollout()
     env.close()
     rec = {"what": "PPO2 %s rollout-in-the-loop, %d envs/GPU, %d-step rollouts (BASELINE config 5 shape): tcgen05 policy forward + "
-                   "fused env step written in place (qs_rollout) + qs_gae; then one epoch of the fused update" % (args.env, n, n_steps),
+                   "fused env step written in place (qs_rollout, two env slices on two streams) + qs_gae; then one epoch of the fused update" % (args.env, n, n_steps),
            "rollout_env_steps_per_s": world * n * n_steps / (roll_ms * 1e-3), "rollout_ms": roll_ms,
-           "gpu_launches_per_rollout": algo.runner.launches_per_rollout() if hasattr(algo.runner, "launches_per_rollout") else algo.runner.n_slices * (2 * n_steps + 1) + 1,
-           "env_slices": algo.runner.n_slices,
-           "update_samples_per_s": world * n * n_steps / (upd_ms * 1e-3), "update_epoch_ms": upd_ms}
+           "gpu_launches_per_rollout": launches, "env_slices": slices,
+           "fused_step_kernel": {"what": "qs_rollout(n_slices=0): one launch per step (policy_env_step_kernel: env warps inside the policy CTA)",
+                                 "rollout_env_steps_per_s": world * n * n_steps / (fused_ms * 1e-3), "rollout_ms": fused_ms,
+                                 "gpu_launches_per_rollout": fused_launches},
+           "update_samples_per_s": world * n * n_steps / (upd_ms * 1e-3), "update_epoch_ms": upd_ms,
+           "update": "hand-written kernels only: qs_permutation, qs_policy_ppo_grad (gradient + tcgen05 split-K weight-gradient contraction), qs_adam_step"}
     del algo, batch
     return rec
 

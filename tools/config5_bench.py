@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE config 5: PPO2 docking-v2 rollout-in-the-loop with device-resident obs/reward, 8 Mi envs per GPU, one rank per
 GPU (torchrun), gradients all-reduced over NCCL.  Per PPO iteration: a T-step rollout (qs_rollout: tcgen05 policy + fused env
-step, in place) + GAE + `--epochs` optimisation epochs of 10 minibatches (qs_policy_ppo_grad + library GEMMs + Adam).
+step, in place) + GAE + `--epochs` optimisation epochs of 10 minibatches (qs_policy_ppo_grad incl. the weight-gradient contraction + qs_adam_step).
 Prints one JSON line on rank 0; times are CUDA-event, max over ranks.
 
     python tools/config5_bench.py [--envs-per-gpu 8388608] [--n-steps 16] [--iters 3] [--epochs 1]
