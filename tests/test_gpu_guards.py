@@ -61,17 +61,25 @@ def test_policy_step_and_ppo_grad_stay_in_bounds(n):
     idx = torch.randperm(n, device="cuda")[:B].contiguous()
     ret, oldv, oldnlp = torch.randn(n, device="cuda"), torch.randn(n, device="cuda"), nlp.view.clone()
     stats = torch.tensor([0.0, 1.0], device="cuda")
-    bufs = dict(a1=Guarded(B, 32, bf16), h=Guarded(B, 144, bf16), hpv=Guarded(B, 256, bf16), dz2=Guarded(B, 256, bf16),
-                dz1=Guarded(B, 128, bf16), per_sample=Guarded(B, 16, f32))
+    tiles = (B + 127) // 128  # the operand images of the weight-gradient contraction are sized per 128-sample tile (header)
+    img = lambda F: Guarded(tiles * F * 256, 0, torch.uint8)
+    bufs = dict(a1=img(32), h=img(144), hpv=img(256), dz2=img(256), dz1=img(128), dout=img(16), per_sample=Guarded(B, 16, f32),
+                col_sums=Guarded(16, 0, f32), g1=Guarded(128, 32, f32), g2=Guarded(256, 144, f32), g3=Guarded(256, 16, f32))
     p = lambda t: t.data_ptr()
     g = _capi.PPOGrad(p(obs), p(act.view), p(ret), p(oldv), p(oldnlp), p(idx), B, p(stats), 0.2, 0.2, 0.5,
-                      *[bufs[k].view.data_ptr() for k in ("a1", "h", "hpv", "dz2", "dz1", "per_sample")])
+                      *[bufs[k].view.data_ptr() for k in ("a1", "h", "hpv", "dz2", "dz1", "dout", "per_sample", "col_sums", "g1", "g2", "g3")])
     _capi.check(L.qs_policy_ppo_grad(fused._h, C.byref(g), _stream()))
     torch.cuda.synchronize()
     for k, b in bufs.items():
         assert b.intact(), k
         assert b.written(), k
-    assert bool(torch.isfinite(bufs["per_sample"].view).all())
+    assert bool(torch.isfinite(bufs["per_sample"].view).all()) and bool(torch.isfinite(bufs["g2"].view).all())
+    # every byte of every image is written (rows past the minibatch as zeros): nothing of the sentinel survives inside
+    for k in ("a1", "h", "hpv", "dz2", "dz1", "dout"):
+        v = bufs[k].view.view(torch.bfloat16).float()
+        assert bool(torch.isfinite(v).all()), k
+    last_rows = bufs["hpv"].view.view(torch.bfloat16).view(tiles, 32, 16, 8, 8)[-1].permute(1, 2, 0, 3).reshape(128, 256)[B - (tiles - 1) * 128:]
+    assert float(last_rows.float().abs().max()) == 0.0 if last_rows.numel() else True
 
 
 @pytest.mark.parametrize("env_id,dtype", [("docking-v2", torch.float32), ("docking-v0", torch.float64), ("hovering-v0", torch.float32),
@@ -113,7 +121,7 @@ def test_rollout_stays_in_bounds():
     nlp, rew, done, clip = Guarded(T * n, 0, f32), Guarded(T * n, 0, f32), Guarded((T + 1) * n, 0, torch.uint8), Guarded(n, 4, f32)
     obs.view[:n].copy_(env.reset())
     done.view[:n].zero_()
-    for slices in (1, 2):
+    for slices in (1, 2, 0):  # 0: the fused step kernel (policy forward + env step in one launch)
         b = _capi.RolloutBuffers(*[x.view.data_ptr() for x in (obs, act, val, nlp, rew, done, clip)])
         _capi.check(env.lib.qs_rollout(env._h, fused._h, T, C.byref(b), 0, 0, slices, _stream()))
         torch.cuda.synchronize()
