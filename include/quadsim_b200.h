@@ -278,7 +278,7 @@ int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, u
  * col_sums[16] = its column sums: d (b3p, b3v) = [0..4], d logstd = [8..11], the logged loss terms = [12..15].  The gradients
  * already carry the 1/batch of the mean and vf_coef; the entropy term (-ent_coef per logstd) is the caller's.
  * Workspace bytes for a minibatch of `batch` samples, T = ceil(batch / 128) tiles: a1 T*8192, h T*36864, hpv T*65536,
- * dz2 T*65536, dz1 T*32768, dout T*4096. */
+ * dz2 T*65536, dz1 T*32768, dout T*4096; each 16-byte aligned (any CUDA allocation is). */
 typedef struct {
   const float *obs, *actions, *returns, *values, *neglogp; /* the rollout, flat: [M,12], [M,4], [M], [M], [M] */
   const int64_t* idx;      /* [batch] row numbers, or NULL for rows 0..batch-1 */

@@ -17,11 +17,12 @@ PAD = 257  # rows of sentinel on each side
 
 
 class Guarded:
-    def __init__(self, rows, cols, dtype):
+    def __init__(self, rows, cols, dtype, pad=PAD):
         self.sentinel = 123 if dtype == torch.uint8 else (-7777 if dtype in (torch.int32, torch.int64) else -12288.0)  # exactly representable in bfloat16
-        shape = (rows + 2 * PAD,) + ((cols,) if cols else ())
+        self.pad = pad  # (the default leaves byte buffers such as `done` at an odd address on purpose)
+        shape = (rows + 2 * pad,) + ((cols,) if cols else ())
         self.full = torch.full(shape, self.sentinel, dtype=dtype, device="cuda")
-        self.view = self.full[PAD:PAD + rows]
+        self.view = self.full[pad:pad + rows]
         self.rows = rows
 
     @property
@@ -29,7 +30,7 @@ class Guarded:
         return C.c_void_p(self.view.data_ptr())
 
     def intact(self):
-        lo, hi = self.full[:PAD], self.full[PAD + self.rows:]
+        lo, hi = self.full[:self.pad], self.full[self.pad + self.rows:]
         if self.full.dtype == torch.bfloat16:
             lo, hi = lo.float(), hi.float()
         return bool((lo == self.sentinel).all()) and bool((hi == self.sentinel).all())
@@ -62,7 +63,7 @@ def test_policy_step_and_ppo_grad_stay_in_bounds(n):
     ret, oldv, oldnlp = torch.randn(n, device="cuda"), torch.randn(n, device="cuda"), nlp.view.clone()
     stats = torch.tensor([0.0, 1.0], device="cuda")
     tiles = (B + 127) // 128  # the operand images of the weight-gradient contraction are sized per 128-sample tile (header)
-    img = lambda F: Guarded(tiles * F * 256, 0, torch.uint8)
+    img = lambda F: Guarded(tiles * F * 256, 0, torch.uint8, pad=4096)  # operand images must be 16-byte aligned
     bufs = dict(a1=img(32), h=img(144), hpv=img(256), dz2=img(256), dz1=img(128), dout=img(16), per_sample=Guarded(B, 16, f32),
                 col_sums=Guarded(16, 0, f32), g1=Guarded(128, 32, f32), g2=Guarded(256, 144, f32), g3=Guarded(256, 16, f32))
     p = lambda t: t.data_ptr()
