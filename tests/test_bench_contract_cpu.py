@@ -44,3 +44,30 @@ def test_multi_gpu_lines_are_whole_job_aggregates():
         d = _load(name)
         assert d["n_gpus"] == n and d["scaling"] == "weak"
         assert 0.9 * n * one < d["value"] < 1.1 * n * one  # no collective on the step path: linear within run-to-run noise
+
+
+def test_round2_line_is_self_contained_and_same_config():
+    """Round 2 (VERDICT r1 'Next round' 1-2): the one JSON line carries the reference's own precision, BASELINE configs 2 and 3
+    and the UNMODIFIED reference timed on the GPU box; the reference arm runs the GPU arm's own config for >= 2 s and agrees
+    with the same box's cpu_baseline.port."""
+    d, ref = _load("r2_bench_c_20steps.json"), _load("r2_bench_b_reference_arm.json")
+    r = d["roofline"]
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and abs(r["dram_frac"] - r["traffic"] / (r["kernel_ms"] * 1e-3) / 1e9 / r["peak"]) < 1e-9
+    assert "NOT measured in this run" in r["traffic_source"] and 0.7 < r["dram_frac"] < r["frac"] <= 1.1
+    f = d["fp64"]
+    assert f["dtype"] == "f64" and f["roofline"]["algorithmic_bytes_per_env_step"] == 793 and f["roofline"]["frac"] >= 0.90
+    assert abs(f["value"] - (1 << 20) / (f["ms_per_step"] * 1e-3)) < 1e-6 * f["value"]
+    c = d["configs"]
+    assert c["config3"]["env"] == "docking-v0" and c["config3"]["envs_per_gpu"] == 1 << 20 and c["config3"]["roofline"]["frac"] > 0.9
+    assert c["config2"]["envs"] == 4096 and c["config2"]["f32"]["per_launch_us_per_step"] <= 6.0 and c["config2"]["f32"]["step_n_us_per_step"] < 2.0
+    assert "PyTorch extension" in c["config2"]["binding"]
+    b = d["cpu_baseline"]
+    assert b["kind"] == "reference" and b["cores"] >= 1 and 100 < b["per_core"] < 5000 and abs(b["value"] - b["per_core"] * b["cores"]) < 1e-6 * b["value"]
+    assert b["port"]["kind"] == "port" and "1048576 envs" in b["port"]["sample"] and b["config1"]["steps_per_s"] > 100
+    assert abs(b["config1"]["final_pos"][0] + 0.2) < 1e-6  # run_sim_PID.py's scenario really converged to pos_des
+    # the reference arm: same config dict as the GPU arm (the driver's same_config), >= 2 s timed, within 15 % of the port leg
+    assert ref["impl"] == "reference" and ref["config"] == dict(d["config"], parallelism=ref["config"]["parallelism"])
+    assert ref["config"]["envs_per_gpu"] == 1 << 20 and ref["timed_seconds"] >= 2.0 and ref["timed_steps"] >= ref["steps"]
+    assert abs(ref["value"] - b["port"]["value"]) < 0.15 * b["port"]["value"]
+    k = d["callers"]
+    assert k["update_epoch_ms"] <= 15.0 and k["fused_step_kernel"]["gpu_launches_per_rollout"] == 18 and k["gpu_launches_per_rollout"] == 67
