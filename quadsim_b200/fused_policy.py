@@ -73,10 +73,12 @@ class FusedPolicy:
             raw = lambda nbytes: torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             f32 = dict(dtype=torch.float32, device=self.device)
             # operand images of the weight-gradient contraction: opaque, sized per 128-sample tile (include/quadsim_b200.h)
+            # the four result buffers live in ONE allocation: the multi-GPU update all-reduces it as a single bucket, in place
+            flat = torch.empty(128 * 32 + 256 * 144 + 256 * 16 + 16, **f32)
+            g1, g2, g3, col = (v.view(s) for v, s in zip(flat.split([4096, 36864, 4096, 16]), ((128, 32), (256, 144), (256, 16), (16,))))
             ws = dict(batch=batch, a1=raw(tiles * 8192), h=raw(tiles * 36864), hpv=raw(tiles * 65536), dz2=raw(tiles * 65536),
                       dz1=raw(tiles * 32768), dout=raw(tiles * 4096), per_sample=torch.empty((batch, 16), **f32),
-                      col=torch.empty(16, **f32), g1=torch.empty((128, 32), **f32), g2=torch.empty((256, 144), **f32),
-                      g3=torch.empty((256, 16), **f32), stats=torch.empty(2, **f32))
+                      flat=flat, col=col, g1=g1, g2=g2, g3=g3, stats=torch.empty(2, **f32))
             self._ws = ws
         return ws
 

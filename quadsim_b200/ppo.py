@@ -297,16 +297,10 @@ class PPO2:
     def _minibatch_fused(self, batch, idx):
         """One minibatch step in hand-written kernels: gradient (two launches), optimiser (one), weight re-pack (one)."""
         grads, log = self.fused.ppo_grad(batch, idx, self.cliprange, self.cliprange_vf, self.vf_coef, self.ent_coef, want_per_sample=False)
-        if self.dist:  # one flat bucket per minibatch: the four result buffers of the gradient kernels
-            ws = self.fused._ws
-            flat = torch.cat([ws[k].reshape(-1) for k in ("g1", "g2", "g3", "col")])
+        if self.dist:  # one bucket per minibatch, reduced in place: the four result buffers of the gradient kernels are one allocation
+            flat = self.fused._ws["flat"]
             torch.distributed.all_reduce(flat)
             flat /= torch.distributed.get_world_size()
-            off = 0
-            for k in ("g1", "g2", "g3", "col"):
-                n = ws[k].numel()
-                ws[k].copy_(flat[off:off + n].view_as(ws[k]))
-                off += n
             grads, log = self.fused.grads_from_workspace(self.ent_coef, int(idx.shape[0]))
         self.fused.adam_step(grads, self._adam, self.lr_now, self.max_grad_norm)
         self.fused.sync_weights(sync=False)  # the next minibatch's forward uses the updated weights
