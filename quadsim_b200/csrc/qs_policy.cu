@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
   unsigned char* a_row = smem + kOffA + g * kABytes + row * 16;      // canon_off(row, 0, 128) == row * 16
   const uint32_t a_base = sbase + kOffA + g * kABytes;
   mbar_wait(bar_w, 0);
-
+  // (a start skew between the groups, which takes 20 % off the rollout forward -- QS_POLICY_WS_SKEW -- measures no different
+  // here: 14.26 vs 14.28-14.32 ms per epoch with 4 k / 12 k / 24 k clocks; this kernel waits on its image stores, not the pipe)
   constexpr uint32_t idesc1 = umma_idesc(128, kHid), idesc2 = umma_idesc(128, 2 * kHid), idesc3 = umma_idesc(128, kN3);
   constexpr uint32_t idesc4 = umma_idesc(128, kHid, true), idesc5 = umma_idesc(128, kHid, true);  // B read MN-major
   uint32_t phase = 0;
@@ -839,11 +840,24 @@ __global__ void __launch_bounds__(256) permutation_kernel(int64_t n, int half_bi
 // packs A3 pi into its own first 32 columns [64s, 64s+32); D3 [32,48) | D2 vf [128,256) likewise -> A3 vf [128+64s, +32).
 // Every barrier completes exactly once per tile, so the wait parity is the tile counter's low bit.
 // =========================================================================================================
+#ifndef QS_EXP_L3_STEPS
+#define QS_EXP_L3_STEPS 8      // EXPERIMENT ONLY (results are wrong below 8): layer-3 K-steps issued per half
+#endif
 #ifndef QS_POLICY_WS_SIDES
 #define QS_POLICY_WS_SIDES 1   // epilogue warps per TMEM lane quadrant and group: 1 or 2 (each side takes half the columns);
                                // measured 90.8 us (1) vs 96.4 us (2) per 2^20 envs: the chain is sync latency, not ALU work
 #endif
 constexpr int kWsSides = QS_POLICY_WS_SIDES;
+#ifndef QS_POLICY_WS_SKEW
+#define QS_POLICY_WS_SKEW 2000 // SM clocks by which group g delays its first tile (x g).  The groups start together and contend
+                               // symmetrically for the in-order tensor pipe, which PRESERVES their relative phase: started in phase
+                               // they stay in phase -- both wait for the pipe at the same time, then both run their epilogues while
+                               // it idles (88 us per 2^20 envs).  Started half a tile apart, one group's epilogue runs under the
+                               // other's layer 2: 77.5 us (700 .. 2800 clocks measure alike), 69.4 us together with kEarlyL1.
+#endif
+#ifndef QS_POLICY_WS_EARLY_L1
+#define QS_POLICY_WS_EARLY_L1 1
+#endif
 #ifndef QS_POLICY_WS_GROUPS
 #define QS_POLICY_WS_GROUPS 2  // tiles in flight per SM.  2: 256 TMEM columns per group, both layer-2 halves in the tensor pipe
                                // at once.  3: 144 columns per group -- every accumulator of a tile lives in [0,128) (+ D3 in
@@ -886,10 +900,24 @@ constexpr int kFuOffBar = kFuOffAct + kWsGroups * 2 * kTileRows * 16;  // [group
 constexpr int kFuStateBytes = (dock_words<float>() / 4) * kTileRows * 16;  // one tile's state rows: 20 KB, contiguous in HBM (tile-major layout)
 constexpr int kFuOffState = (kFuOffBar + kWsGroups * 2 * 16 + kWsGroups * 2 * 8 + 127) / 128 * 128;  // [group][set] stage
 constexpr int kFuSmemBytes = kFuOffState + kWsGroups * kFuSets * kFuStateBytes;
-static_assert(kFuSmemBytes <= 227 * 1024, "shared memory budget");
+constexpr bool kFuFits = kFuSmemBytes <= 227 * 1024;  // three groups' state stages do not fit: the fused step kernel is then unavailable
+static_assert(kFuFits || kWsGroups == 3, "shared memory budget");
 
 // programmatic dependent launch: pdl_prologue() of qs_env_kernels.cuh (stage the next kernel early, wait for the previous one)
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+// EXPERIMENT ONLY (-DQS_WS_TRACE=1): SM-clock stamps of the first kTrTiles tiles of CTA 0 / group 0 -- epilogue thread 0 in
+// slots [0,16), the issuer's lane 0 in [16,24) -- read back with qs_debug_ws_trace (tools/ws_trace.py draws the timeline)
+#ifndef QS_WS_TRACE
+#define QS_WS_TRACE 0
+#endif
+#if QS_WS_TRACE
+constexpr int kTrTiles = 28, kTrSlots = 24;
+__device__ long long g_ws_trace[kTrTiles * kTrSlots];
+#define QS_TR(slot) do { if (trace_on && it < (uint32_t)kTrTiles) g_ws_trace[it * kTrSlots + (slot)] = clock64(); } while (0)
+#else
+#define QS_TR(slot) do { } while (0)
+#endif
 
 template <bool FUSED, int KIND>
 __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvStepArgs& ea) {
@@ -913,6 +941,9 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
   const int side = issuer || env_warp ? 0 : (tid % kWsEpi) / kTileRows; // which half of the columns this epilogue thread handles
   const int row = tid & 127;                               // epilogue threads: accumulator row == TMEM lane == env within the tile
   const uint32_t sbase = smem_u32(smem);
+#if QS_WS_TRACE
+  const bool trace_on = blockIdx.x == 0 && g == 0 && lane == 0 && !env_warp && (issuer || (tid % kWsEpi) == 0);
+#endif
   const uint32_t bar_w = sbase + kWsOffBar, bars = sbase + kWsOffBar + 8 + 64 * g;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kWsOffBar + 8 + kWsGroups * 64);
   const float* tail = reinterpret_cast<const float*>(smem + kOffTail);
@@ -952,7 +983,17 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
   const uint32_t a_base = sbase + kOffA + g * kABytes;
   constexpr uint32_t idesc_n128 = umma_idesc(128, kHid), idesc3 = umma_idesc(128, kN3);
   // two groups: D1 and the vf half at [128,256), D3 right behind side 0's packed A3 pi; three groups: everything at [0,128)
-  constexpr uint32_t kColD1 = kWsGroups == 2 ? 128 : 0, kColD2v = kWsGroups == 2 ? 128 : 0, kColD3ws = kWsGroups == 2 ? kWsCols / 2 : 128;
+  constexpr uint32_t kColD1 = kWsGroups == 2 ? 128 : 0, kColD2v = kWsGroups == 2 ? 128 : 0;
+  // kEarlyL1 (two groups, one side): the NEXT tile's layer 1 is issued BEFORE this tile's layer-3 vf steps, so that it is not
+  // queued behind them (the issuer blocks in every tcgen05.mma while the other group's layer 2 holds the pipe; measured
+  // with QS_WS_TRACE: the next tile's A1 waited ~850 clk for the issuer).  D1 must then avoid A3 vf [128,192) and D3, which
+  // layer 3 vf still uses: it is split into two N=64 halves, [0,64) (A3 pi, dead once layer 3 pi is in the pipe ahead of it)
+  // and [192,256) (the read-out part of D2 vf); D3 moves to [112,128), the tail of the consumed D2 pi columns.
+  constexpr bool kEarlyL1 = kWsGroups == 2 && kWsSides == 1 && QS_POLICY_WS_EARLY_L1;
+  static_assert(!kEarlyL1 || kWsChunk <= 64, "D1 is read in two 64-column pieces");
+  constexpr uint32_t kColD3ws = kEarlyL1 ? 112 : (kWsGroups == 2 ? kWsCols / 2 : 128);
+  auto d1_col = [](int c) -> uint32_t { return kEarlyL1 ? (uint32_t)(c < 64 ? c : 128 + c) : kColD1 + (uint32_t)c; };
+  constexpr uint32_t idesc_n64 = umma_idesc(128, 64);
 
   if (env_warp) {
     // ---------------------------------------------------------------- env warps (FUSED): thread = env, as in dock_step_kernel
@@ -1001,19 +1042,33 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
     // ---------------------------------------------------------------- MMA issuer: one elected lane, the warp waits together
     mbar_wait(bar_w, 0);
     uint32_t it = 0;
-    for (int tile = tile0; tile < tiles; tile += tile_stride, it++) {
-      const uint32_t ph = it & 1;
-      mbar_wait(bars + 8 * kFullA1, ph);
+    auto issue_l1 = [&](uint32_t parity) {  // layer 1 of the tile whose A1 completes FullA1's phase `parity`
+      mbar_wait(bars + 8 * kFullA1, parity);
       tc_fence_after();
+      QS_TR(16);
       if (lane == 0) {
 #pragma unroll
-        for (int ks = 0; ks < kK1 / 16; ks++)
-          umma_ss(tmem + kColD1, umma_desc(a_base + ks * 4096, 2048, 128), umma_desc(sbase + kOffW1 + ks * 4096, 2048, 128), idesc_n128, ks);
+        for (int ks = 0; ks < kK1 / 16; ks++) {
+          if (kEarlyL1) {
+#pragma unroll
+            for (int h = 0; h < 2; h++)  // W1 rows 64.. start 8 row-groups = 1024 B into each K chunk of the image
+              umma_ss(tmem + d1_col(64 * h), umma_desc(a_base + ks * 4096, 2048, 128), umma_desc(sbase + kOffW1 + h * 1024 + ks * 4096, 2048, 128), idesc_n64, ks);
+          } else {
+            umma_ss(tmem + kColD1, umma_desc(a_base + ks * 4096, 2048, 128), umma_desc(sbase + kOffW1 + ks * 4096, 2048, 128), idesc_n128, ks);
+          }
+        }
         umma_commit(bars + 8 * kDone1);
       }
       __syncwarp();
+      QS_TR(17);
+    };
+    if (kEarlyL1 && tile0 < tiles) issue_l1(0);
+    for (int tile = tile0; tile < tiles; tile += tile_stride, it++) {
+      const uint32_t ph = it & 1;
+      if (!kEarlyL1) issue_l1(ph);
       mbar_wait(bars + 8 * kFullA2, ph);
       tc_fence_after();
+      QS_TR(18);
       // layer 2 as two N=128 halves of the 256-row W2 image (rows 128.. start 16 row-groups = 2048 B in; LBO stays the image's
       // 4096 B), each with its own commit; layer 3's 8 K-steps of a half follow as soon as that half has been packed
       auto issue_l2 = [&](int half) {
@@ -1027,21 +1082,25 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
         if (kWsGroups == 2) issue_l2(1);  // the vf half has its own columns: both halves go into the pipe back to back
       }
       __syncwarp();
+      QS_TR(19);
 #pragma unroll
       for (int half = 0; half < 2; half++) {
+        if (kEarlyL1 && half == 1 && tile + tile_stride < tiles) issue_l1(ph ^ 1);  // the next tile's layer 1 goes ahead of our vf steps
         mbar_wait(bars + 8 * (half == 0 ? kFullA3p : kFullA3v), ph);
         tc_fence_after();
+        QS_TR(20 + 2 * half);
         if (lane == 0) {
-#pragma unroll
-          for (int k8 = 0; k8 < 8; k8++) {  // K-step k8 of this half: features 16 k8 .., packed by side (16 k8) / kWsCols
+  #pragma unroll
+          for (int k8 = 0; k8 < QS_EXP_L3_STEPS; k8++) {  // K-step k8 of this half: features 16 k8 .., packed by side (16 k8) / kWsCols
             const int ks = 8 * half + k8, sd = (16 * k8) / kWsCols, kk = (16 * k8) % kWsCols;
             umma_ts(tmem + kColD3ws, tmem + half * kColD2v + sd * kWsCols + kk / 2, umma_desc(sbase + kOffW3 + ks * 512, 256, 128), idesc3, ks);
           }
           if (half == 1) umma_commit(bars + 8 * kDone3);
           // three groups: the vf half reuses the pi half's columns -- in order behind the layer-3 steps that read A3 pi
           if (kWsGroups == 3 && half == 0) issue_l2(1);
-        }
+          }
         __syncwarp();
+        QS_TR(21 + 2 * half);
       }
     }
   } else {
@@ -1069,6 +1128,10 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
       mbar_arrive(bars + 8 * kFullA1);
     };
     mbar_wait(bar_w, 0);  // the fp32 tail (biases of the heads, logstd) is read from shared memory below
+    if (QS_POLICY_WS_SKEW > 0 && g > 0 && tile0 + tile_stride < tiles) {  // start the groups out of phase (see QS_POLICY_WS_SKEW)
+      const long long t_go = clock64() + (long long)QS_POLICY_WS_SKEW * g;
+      while (clock64() < t_go) { }
+    }
     if (tile0 < tiles) build_a1(o);
     // The tail of a tile (layer-3 read-out, sampling, stores) is deferred into the next iteration: D3 is read right before
     // the next tile's layer-2 operand is handed over (its pi half overwrites D3's columns), and the arithmetic and the
@@ -1113,15 +1176,17 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
       const uint32_t ph = it & 1;
       const int64_t i = (int64_t)tile * kTileRows + row;
       const bool more = tile + tile_stride < tiles;
+      QS_TR(0);
       o = load_obs(a.obs, i + (int64_t)tile_stride * kTileRows, a.n, nullptr);  // next tile's row, in flight under this tile's work
       // ---- h = relu(D1) -> A2[:, 0:128]; A2[:, 128:144] = (1, 1, 0, ...) carries layer 2's bias ----
       mbar_wait(bars + 8 * kDone1, ph);
       tc_fence_after();
+      QS_TR(1);
 #pragma unroll 1
       for (int c0 = kWsCols * side; c0 < kWsCols * (side + 1); c0 += kWsChunk) {
         uint32_t r[kWsChunk];
 #pragma unroll
-        for (int q = 0; q < kWsChunk; q += 32) tmem_ld32(trow + kColD1 + c0 + q, r + q);
+        for (int q = 0; q < kWsChunk; q += 32) tmem_ld32(trow + d1_col(c0) + q, r + q);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < kWsChunk / 8; j++) {
@@ -1135,17 +1200,23 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
       }
       if (kWsSides == 1 || side == 0) *reinterpret_cast<uint4*>(a_row + 16 * 2048) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
       if (kWsSides == 1 || side == 1) *reinterpret_cast<uint4*>(a_row + 17 * 2048) = make_uint4(0u, 0u, 0u, 0u);
+      QS_TR(2);
       proxy_fence();
+      QS_TR(3);
       const float p0 = n0, p1 = n1, p2 = n2, p3 = n3;
       if (i_prev >= 0) read_d3(ph ^ 1);  // the previous tile's layer-3 result, before this tile's pi half lands on it
+      QS_TR(4);
       tc_fence_before();  // D1 is read; the vf half of layer 2 will overwrite its columns
       mbar_arrive(bars + 8 * kFullA2);
+      QS_TR(5);
       if (i_prev >= 0) finish(i_prev, it_prev, p0, p1, p2, p3);  // under this tile's layer 2
+      QS_TR(6);
       // ---- relu(D2 half) -> bf16 pairs packed in place: A3 pi = [0,64), A3 vf = [128,192) ----
 #pragma unroll 1
       for (int half = 0; half < 2; half++) {
         mbar_wait(bars + 8 * (half == 0 ? kDoneP : kDoneV), ph);
         tc_fence_after();
+        QS_TR(7 + 3 * half);
         const uint32_t base = trow + half * kColD2v + kWsCols * side;  // this side's columns; its packed A3 lands at their start
 #pragma unroll 1
         for (int c0 = 0; c0 < kWsCols; c0 += kWsChunk) {
@@ -1158,12 +1229,15 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
 #pragma unroll
           for (int q = 0; q < kWsChunk / 2; q += 16) tmem_st16(base + (c0 >> 1) + q, w + q);
         }
+        QS_TR(8 + 3 * half);
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(bars + 8 * (half == 0 ? kFullA3p : kFullA3v));
+        QS_TR(9 + 3 * half);
       }
       // ---- the next tile's A1 (the A buffer is free: both layer-2 halves have completed) and its layer 1, under our tail ----
       if (more) build_a1(o);
+      QS_TR(13);
       // ---- Gaussian noise for this tile while its layer 3 and the next tile's layer 1 run (DiagGaussianProbability
       //      Distribution.sample) ----
       n0 = n1 = n2 = n3 = 0.f;
@@ -1179,6 +1253,7 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
         __sincosf(6.283185307179586f * u3, &s1, &c1_);
         n0 = r0 * c0_; n1 = r0 * s0; n2 = r1 * c1_; n3 = r1 * s1;  // Box-Muller
       }
+      QS_TR(14);
       i_prev = i;
       it_prev = it;
     }
@@ -1227,6 +1302,12 @@ struct qs_policy {
     if (e_ != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+#if QS_WS_TRACE
+extern "C" int qs_debug_ws_trace(long long* out, int max_words) {
+  const int n = kTrTiles * kTrSlots < max_words ? kTrTiles * kTrSlots : max_words;
+  return cudaMemcpyFromSymbol(out, g_ws_trace, n * sizeof(long long)) == cudaSuccess ? n : -1;
+}
+#endif
 extern "C" {
 
 int qs_policy_create(qs_policy_t** out, int device) {
@@ -1248,8 +1329,8 @@ int qs_policy_create(qs_policy_t** out, int device) {
       (err = cudaFuncSetAttribute(policy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes)) != cudaSuccess ||
-      (err = cudaFuncSetAttribute(policy_env_step_kernel<kDockV0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes)) != cudaSuccess ||
-      (err = cudaFuncSetAttribute(policy_env_step_kernel<kDockV2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes)) != cudaSuccess ||
+      (kFuFits && (err = cudaFuncSetAttribute(policy_env_step_kernel<kDockV0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes)) != cudaSuccess) ||
+      (kFuFits && (err = cudaFuncSetAttribute(policy_env_step_kernel<kDockV2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes)) != cudaSuccess) ||
       (err = cudaFuncSetAttribute(policy_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_fwd_ws_kernel_capped<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_fwd_ws_kernel_capped<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
@@ -1454,6 +1535,7 @@ int qs_rollout(qs_env_t* env, qs_policy_t* pol, int64_t n_steps, const qs_rollou
     // ---- fused: ONE launch per step does model.step and env.step (policy_env_step_kernel); then the bootstrap value pass
     EnvStepArgs ea;
     int kind = 0;
+    if (!kFuFits) return qs_fail_(QS_ERR_INVALID, "qs_rollout: this build has no fused step kernel (n_slices = 0)");
     if (qs_env_fused_args_(env, &ea, sizeof ea, &kind) != QS_OK)
       return qs_fail_(QS_ERR_INVALID, "qs_rollout: the fused step kernel (n_slices = 0) needs a float32 docking handle with the default model parameters");
     if (!pol->have_weights) return qs_fail_(QS_ERR_INVALID, "qs_rollout: qs_policy_set_weights has not been called");
