@@ -255,6 +255,15 @@ int qs_policy_create(qs_policy_t** out, int device);
 int qs_policy_destroy(qs_policy_t* p);
 /* Packs the weights into bf16 tensor-core operand images on the device; call again after every optimiser step. */
 int qs_policy_set_weights(qs_policy_t* p, const qs_policy_weights_t* w, void* stream);
+/* Arithmetic of the rollout forward (qs_policy_step, and qs_rollout with n_slices >= 1).  QS_POLICY_BF16 (default): bf16
+ * weights and hidden activations, fp32 accumulation, on the tensor cores (inputs and hidden biases keep ~16 mantissa bits):
+ * within 5e-2 of the fp32 policy on O(1) outputs, 69 us per 2^20 envs.  QS_POLICY_FP32: plain fp32 on the CUDA cores -- what
+ * the reference's TensorFlow policy computes (run_moving_docking_ppo2.py:88-91) to within summation order (1e-4), ~25x
+ * slower (1.76 ms per 2^20 envs, 58 % of the fp32 FMA peak); for evaluation and for checking the fast path.  The same (seed, env id, step) draws the same action noise in
+ * either mode.  qs_policy_ppo_grad always runs the tensor-core formulation. */
+#define QS_POLICY_BF16 0
+#define QS_POLICY_FP32 1
+int qs_policy_set_precision(qs_policy_t* p, int precision);
 /* actions = mean + exp(logstd) * N(0,1) (noise: Philox4x32-10 keyed by seed, counter (env_id0 + i, step_idx, stream 2),
  * Box-Muller), values, neglogp for obs[N,12]; clipped_out (nullable) = actions clamped to the action Box [-1,1]
  * (ppo2.py:478-481).  deterministic != 0 returns the mean (model.predict(deterministic=True)). */

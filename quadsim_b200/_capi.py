@@ -22,7 +22,8 @@ SYMBOLS = ["qs_abi_version", "qs_last_error", "qs_create", "qs_destroy", "qs_obs
            "qs_import_state", "qs_get_stats", "qs_fn_apply", "qs_gae", "qs_policy_create", "qs_policy_destroy",
            "qs_policy_set_weights", "qs_policy_step", "qs_env_dtype", "qs_env_id0", "qs_rollout",
            "qs_step_range", "qs_expert_action", "qs_peek_state", "qs_policy_ppo_grad", "qs_step_n", "qs_default_params",
-           "qs_env_device", "qs_adam_step", "qs_permutation"]
+           "qs_env_device", "qs_adam_step", "qs_permutation", "qs_policy_set_precision"]
+POLICY_BF16, POLICY_FP32 = 0, 1
 
 
 _D3 = C.c_double * 3
@@ -125,6 +126,7 @@ def load():
     L.qs_policy_create.argtypes = [C.POINTER(vp), C.c_int]
     L.qs_policy_destroy.argtypes = [vp]
     L.qs_policy_set_weights.argtypes = [vp, C.POINTER(PolicyWeights), vp]
+    L.qs_policy_set_precision.argtypes = [vp, C.c_int]
     L.qs_policy_step.argtypes = [vp, i64, vp, u64, u64, C.c_uint32, C.c_int, vp, vp, vp, vp, vp]
     L.qs_env_dtype.argtypes = [vp]
     L.qs_env_id0.argtypes = [vp]

@@ -177,8 +177,25 @@ struct RawWeights { const float *w1, *b1, *wp, *bp, *wv, *bv, *w3p, *b3p, *w3v, 
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
-__global__ void pack_kernel(RawWeights w, unsigned char* packed) {
+// fp32 image of the same weights for the accurate forward (policy_fwd_f32_kernel), in floats: K-major so that a warp reads
+// consecutive output features -- W1T [12][128] | b1 [128] | W2T [128][256] (columns 0-127 pi, 128-255 vf) | b2 [256] |
+// W3Q [256][4] (feature n < 128: W3p[0..3][n]; n >= 128: (w3v[n-128], 0, 0, 0)) | tail [16] as in the bf16 image
+constexpr int kF32W1T = 0, kF32B1 = kF32W1T + kObs * kHid, kF32W2T = kF32B1 + kHid, kF32B2 = kF32W2T + kHid * 2 * kHid;
+constexpr int kF32W3Q = kF32B2 + 2 * kHid, kF32Tail = kF32W3Q + 2 * kHid * 4, kF32Floats = kF32Tail + kTailFloats;
+static_assert(kF32Floats % 4 == 0, "the image is copied in 16-byte units");
+
+__global__ void pack_kernel(RawWeights w, unsigned char* packed, float* img32) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int i = tid; i < kF32Floats; i += nth) {
+    float v = 0.f;
+    if (i < kF32B1) { const int k = i / kHid, n = i % kHid; v = w.w1[n * kObs + k]; }
+    else if (i < kF32W2T) v = w.b1[i - kF32B1];
+    else if (i < kF32B2) { const int k = (i - kF32W2T) / (2 * kHid), n = (i - kF32W2T) % (2 * kHid); v = n < kHid ? w.wp[n * kHid + k] : w.wv[(n - kHid) * kHid + k]; }
+    else if (i < kF32W3Q) { const int n = i - kF32B2; v = n < kHid ? w.bp[n] : w.bv[n - kHid]; }
+    else if (i < kF32Tail) { const int n = (i - kF32W3Q) / 4, j = (i - kF32W3Q) % 4; v = n < kHid ? w.w3p[j * kHid + n] : (j == 0 ? w.w3v[n - kHid] : 0.f); }
+    else { const int t = i - kF32Tail; v = t < 4 ? w.b3p[t] : (t == 4 ? w.b3v[0] : (t >= 8 && t < 12 ? w.logstd[t - 8] : 0.f)); }
+    img32[i] = v;
+  }
   __nv_bfloat16* W1 = reinterpret_cast<__nv_bfloat16*>(packed + kOffW1);
   __nv_bfloat16* W2 = reinterpret_cast<__nv_bfloat16*>(packed + kOffW2);
   __nv_bfloat16* W3 = reinterpret_cast<__nv_bfloat16*>(packed + kOffW3);
@@ -1277,6 +1294,131 @@ __global__ void __launch_bounds__(kFuThreads, 1) policy_env_step_kernel(const St
 // that decides how much of its HBM time hides under the other slice's policy kernel.  The cap costs ~100 bytes of spills.
 template <int REGS> __global__ void __maxnreg__(REGS) policy_fwd_ws_kernel_capped(const StepArgs a) { policy_fwd_ws_body<false, kDockV2>(a, EnvStepArgs{}); }
 
+// =========================================================================================================
+// The accurate forward (qs_policy_set_precision(QS_POLICY_FP32)): the same model.step in plain fp32 on the CUDA cores --
+// fp32 weights, fp32 activations, fp32 accumulation, i.e. what the reference's TensorFlow policy computes
+// (run_moving_docking_ppo2.py:88-91), to within summation order.  For evaluation runs and for checking the bf16 tensor-core
+// path; ~25x slower than it: 1.76 ms per 2^20 envs = 58 % of the fp32 FMA peak (36.7 G FMA per 2^20 envs on the FMA pipe instead of the tensor pipe).
+// One 256-thread CTA per SM walks 64-env tiles; all weights (140 KB) stay in shared memory.  Layer 2 is register-tiled:
+// warp w owns rows 8w..8w+7, lane l the pi columns 4l..4l+3 and the vf columns 128+4l..: 64 accumulators per thread, per k
+// two broadcast float4 of activations and two conflict-free float4 of weights feed 64 FMAs.  Layer 3 is folded into the
+// same threads (each multiplies its 8 relu'd columns into 4 + 1 partial sums per row) and reduced over the warp.
+// Sampling, clipping and neglogp follow policy_fwd_ws_kernel instruction for instruction: the same (seed, env, step) draws
+// the same noise in either precision.
+// =========================================================================================================
+constexpr int kF32Rows = 64, kF32Threads = 256;
+constexpr int kF32OffObs = kF32Floats;                          // obsT [12][64]
+constexpr int kF32OffH = kF32OffObs + kObs * kF32Rows;          // hT [128][64]
+constexpr int kF32OffOut = kF32OffH + kHid * kF32Rows;          // out [64][8]: mean(4), value
+constexpr int kF32SmemBytes = (kF32OffOut + kF32Rows * 8) * 4;
+static_assert(kF32SmemBytes <= 227 * 1024 && kF32OffObs % 4 == 0 && kF32OffH % 4 == 0, "shared memory budget / alignment");
+
+__global__ void __launch_bounds__(kF32Threads, 1) policy_fwd_f32_kernel(const StepArgs a, const float* __restrict__ img) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kF32Floats / 4; i += kF32Threads) reinterpret_cast<float4*>(sm)[i] = reinterpret_cast<const float4*>(img)[i];
+  const float *W1T = sm + kF32W1T, *B1 = sm + kF32B1, *W2T = sm + kF32W2T, *B2 = sm + kF32B2, *W3Q = sm + kF32W3Q, *tail = sm + kF32Tail;
+  float *obsT = sm + kF32OffObs, *hT = sm + kF32OffH, *out = sm + kF32OffOut;
+  const int64_t tiles = (a.n + kF32Rows - 1) / kF32Rows;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t i0 = tile * kF32Rows;
+    __syncthreads();  // the previous tile's readers are done (and the weights are in place)
+    for (int e = tid; e < kF32Rows * kObs; e += kF32Threads) {  // coalesced read of the tile's [64][12] block, transposed into obsT
+      const int r = e / kObs, k = e % kObs;
+      obsT[k * kF32Rows + r] = i0 + r < a.n ? a.obs[(i0 + r) * kObs + k] : 0.f;
+    }
+    __syncthreads();
+    {  // layer 1: thread = (row r, 32 output features)
+      const int r = tid % kF32Rows, n0 = (tid / kF32Rows) * 32;
+      float x[kObs];
+#pragma unroll
+      for (int k = 0; k < kObs; k++) x[k] = obsT[k * kF32Rows + r];
+#pragma unroll 4
+      for (int n = n0; n < n0 + 32; n += 4) {
+        float4 acc = *reinterpret_cast<const float4*>(B1 + n);
+#pragma unroll
+        for (int k = 0; k < kObs; k++) {
+          const float4 w = *reinterpret_cast<const float4*>(W1T + k * kHid + n);
+          acc.x = fmaf(x[k], w.x, acc.x); acc.y = fmaf(x[k], w.y, acc.y); acc.z = fmaf(x[k], w.z, acc.z); acc.w = fmaf(x[k], w.w, acc.w);
+        }
+        hT[(n + 0) * kF32Rows + r] = fmaxf(acc.x, 0.f); hT[(n + 1) * kF32Rows + r] = fmaxf(acc.y, 0.f);
+        hT[(n + 2) * kF32Rows + r] = fmaxf(acc.z, 0.f); hT[(n + 3) * kF32Rows + r] = fmaxf(acc.w, 0.f);
+      }
+    }
+    __syncthreads();
+    {  // layers 2 and 3
+      const int r0 = warp * 8, cp = lane * 4, cv = kHid + lane * 4;
+      float acc[8][8];
+      {
+        const float4 bp = *reinterpret_cast<const float4*>(B2 + cp), bv = *reinterpret_cast<const float4*>(B2 + cv);
+#pragma unroll
+        for (int r = 0; r < 8; r++) { acc[r][0] = bp.x; acc[r][1] = bp.y; acc[r][2] = bp.z; acc[r][3] = bp.w; acc[r][4] = bv.x; acc[r][5] = bv.y; acc[r][6] = bv.z; acc[r][7] = bv.w; }
+      }
+#pragma unroll 2
+      for (int k = 0; k < kHid; k++) {
+        const float4 ha = *reinterpret_cast<const float4*>(hT + k * kF32Rows + r0), hb = *reinterpret_cast<const float4*>(hT + k * kF32Rows + r0 + 4);
+        const float4 wp = *reinterpret_cast<const float4*>(W2T + k * 2 * kHid + cp), wv = *reinterpret_cast<const float4*>(W2T + k * 2 * kHid + cv);
+        const float h[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+        const float w[8] = {wp.x, wp.y, wp.z, wp.w, wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+          for (int c = 0; c < 8; c++) acc[r][c] = fmaf(h[r], w[c], acc[r][c]);
+      }
+      float4 q[4];
+      float wvv[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) { q[c] = *reinterpret_cast<const float4*>(W3Q + (cp + c) * 4); wvv[c] = W3Q[(cv + c) * 4]; }
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, v = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const float hp = fmaxf(acc[r][c], 0.f), hv = fmaxf(acc[r][4 + c], 0.f);
+          m0 = fmaf(hp, q[c].x, m0); m1 = fmaf(hp, q[c].y, m1); m2 = fmaf(hp, q[c].z, m2); m3 = fmaf(hp, q[c].w, m3);
+          v = fmaf(hv, wvv[c], v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          m0 += __shfl_xor_sync(0xffffffffu, m0, o); m1 += __shfl_xor_sync(0xffffffffu, m1, o); m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+          m3 += __shfl_xor_sync(0xffffffffu, m3, o); v += __shfl_xor_sync(0xffffffffu, v, o);
+        }
+        if (lane == 0) {
+          float* o8 = out + (r0 + r) * 8;
+          o8[0] = m0; o8[1] = m1; o8[2] = m2; o8[3] = m3; o8[4] = v;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < kF32Rows && i0 + tid < a.n) {  // sampling and stores: one thread per env, as the epilogue of policy_fwd_ws_kernel
+      const int64_t i = i0 + tid;
+      const float* o8 = out + tid * 8;
+      float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+      if (!a.deterministic) {
+        qs::U4 c = {(uint32_t)(a.env_id0 + (uint64_t)i), (uint32_t)((a.env_id0 + (uint64_t)i) >> 32), a.step_idx, 2u};
+        qs::U4 x = qs::philox4x32_10(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        const float s = 5.9604644775390625e-08f;  // 2^-24; u in (0,1)
+        const float u0 = ((float)(x.x >> 8) + 0.5f) * s, u1 = ((float)(x.y >> 8) + 0.5f) * s;
+        const float u2 = ((float)(x.z >> 8) + 0.5f) * s, u3 = ((float)(x.w >> 8) + 0.5f) * s;
+        const float r0 = sqrtf(-2.f * __logf(u0)), r1 = sqrtf(-2.f * __logf(u2));
+        float s0, c0_, s1, c1_;
+        __sincosf(6.283185307179586f * u1, &s0, &c0_);
+        __sincosf(6.283185307179586f * u3, &s1, &c1_);
+        n0 = r0 * c0_; n1 = r0 * s0; n2 = r1 * c1_; n3 = r1 * s1;  // Box-Muller
+      }
+      const float ls0 = tail[8], ls1 = tail[9], ls2 = tail[10], ls3 = tail[11];
+      const float mu0 = o8[0] + tail[0], mu1 = o8[1] + tail[1], mu2 = o8[2] + tail[2], mu3 = o8[3] + tail[3], val = o8[4] + tail[4];
+      const float a0 = fmaf(__expf(ls0), n0, mu0), a1 = fmaf(__expf(ls1), n1, mu1), a2 = fmaf(__expf(ls2), n2, mu2), a3 = fmaf(__expf(ls3), n3, mu3);
+      const float nlp = 0.5f * (n0 * n0 + n1 * n1 + n2 * n2 + n3 * n3) + 3.6757541328186907f + (ls0 + ls1 + ls2 + ls3);
+      if (a.actions) reinterpret_cast<float4*>(a.actions)[i] = make_float4(a0, a1, a2, a3);
+      if (a.clipped) reinterpret_cast<float4*>(a.clipped)[i] = make_float4(fminf(fmaxf(a0, -1.f), 1.f), fminf(fmaxf(a1, -1.f), 1.f), fminf(fmaxf(a2, -1.f), 1.f), fminf(fmaxf(a3, -1.f), 1.f));
+      if (a.neglogp) a.neglogp[i] = nlp;
+      a.values[i] = val;
+    }
+  }
+}
+
 }  // namespace
 
 struct NvtxRange {  // see qs_lib.cu
@@ -1289,6 +1431,9 @@ constexpr int kDefaultPolicyRegs = 128;  // per-thread register build of the rol
 struct qs_policy {
   int device = 0;
   unsigned char* packed = nullptr;
+  float* img32 = nullptr;       // fp32 image of the weights (policy_fwd_f32_kernel)
+  int precision = QS_POLICY_BF16;
+  int sms = 0;
   int grid = 0;
   bool have_weights = false;
   // qs_rollout with n_slices > 1: one stream per env slice, forked from / joined into the caller's stream
@@ -1326,6 +1471,8 @@ int qs_policy_create(qs_policy_t** out, int device) {
   int per_sm = 0;
   cudaError_t err;
   if ((err = cudaGetDeviceProperties(&prop, device)) != cudaSuccess || (err = cudaMalloc(&p->packed, kPackedBytes)) != cudaSuccess ||
+      (err = cudaMalloc((void**)&p->img32, kF32Floats * sizeof(float))) != cudaSuccess ||
+      (err = cudaFuncSetAttribute(policy_fwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF32SmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes)) != cudaSuccess ||
@@ -1338,6 +1485,7 @@ int qs_policy_create(qs_policy_t** out, int device) {
       (err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, policy_kernel<true>, kThreads, kSmemBytes)) != cudaSuccess) {
     int rc = qs_fail_(QS_ERR_CUDA, "qs_policy_create: %s", cudaGetErrorString(err));
     cudaFree(p->packed);
+    cudaFree(p->img32);
     delete p;
     cudaSetDevice(prev);
     return rc;
@@ -1345,11 +1493,12 @@ int qs_policy_create(qs_policy_t** out, int device) {
   if (per_sm < 1) {
     int rc = qs_fail_(QS_ERR_CUDA, "qs_policy_create: the policy kernel does not fit an SM (%d B shared memory)", kSmemBytes);
     cudaFree(p->packed);
+    cudaFree(p->img32);
     delete p;
     cudaSetDevice(prev);
     return rc;
   }
-  p->grid = prop.multiProcessorCount;  // one persistent CTA per SM: it owns all 512 TMEM columns
+  p->grid = p->sms = prop.multiProcessorCount;  // one persistent CTA per SM: it owns all 512 TMEM columns
   // QUADSIM_B200_POLICY_CTAS=<n> runs the forward kernel on fewer SMs (A/B: a sliced rollout leaves the rest to the env kernel)
   if (const char* v = getenv("QUADSIM_B200_POLICY_CTAS")) { const int c = atoi(v); if (c > 0 && c < p->grid) p->grid = c; }
   cudaSetDevice(prev);
@@ -1363,6 +1512,7 @@ int qs_policy_destroy(qs_policy_t* p) {
   cudaGetDevice(&prev);
   cudaSetDevice(p->device);
   cudaFree(p->packed);
+  cudaFree(p->img32);
   for (int k = 0; k < kMaxSlices; k++) {
     if (p->slice_stream[k]) cudaStreamDestroy(p->slice_stream[k]);
     if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]);
@@ -1370,6 +1520,12 @@ int qs_policy_destroy(qs_policy_t* p) {
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   cudaSetDevice(prev);
   delete p;
+  return QS_OK;
+}
+
+int qs_policy_set_precision(qs_policy_t* p, int precision) {
+  if (!p || (precision != QS_POLICY_BF16 && precision != QS_POLICY_FP32)) return qs_fail_(QS_ERR_INVALID, "qs_policy_set_precision: expected QS_POLICY_BF16 or QS_POLICY_FP32");
+  p->precision = precision;
   return QS_OK;
 }
 
@@ -1382,7 +1538,7 @@ int qs_policy_set_weights(qs_policy_t* p, const qs_policy_weights_t* w, void* st
   QSP_CUDA(cudaGetDevice(&prev));
   QSP_CUDA(cudaSetDevice(p->device));
   RawWeights r = {w->shared_w, w->shared_b, w->pi_fc_w, w->pi_fc_b, w->vf_fc_w, w->vf_fc_b, w->pi_w, w->pi_b, w->vf_w, w->vf_b, w->logstd};
-  pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(r, p->packed);
+  pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(r, p->packed, p->img32);
   cudaError_t e = cudaGetLastError();
   cudaSetDevice(prev);
   if (e != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_policy_set_weights: %s", cudaGetErrorString(e));
@@ -1403,7 +1559,10 @@ int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, u
   const int ctas = (int)(((n + kTileRows - 1) / kTileRows + kGroups - 1) / kGroups);
   // QUADSIM_B200_POLICY=v3 selects the previous (leader-thread-in-group) forward kernel for A/B
   static const bool use_v3 = [] { const char* v = getenv("QUADSIM_B200_POLICY"); return v && strcmp(v, "v3") == 0; }();
-  if (use_v3) policy_kernel<false><<<ctas < p->grid ? ctas : p->grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, TrainArgs{});
+  if (p->precision == QS_POLICY_FP32) {
+    const int64_t t64 = (n + kF32Rows - 1) / kF32Rows;
+    policy_fwd_f32_kernel<<<(unsigned)(t64 < p->sms ? t64 : p->sms), kF32Threads, kF32SmemBytes, (cudaStream_t)stream>>>(a, p->img32);
+  } else if (use_v3) policy_kernel<false><<<ctas < p->grid ? ctas : p->grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, TrainArgs{});
   else {
     static const bool pdl = [] { const char* v = getenv("QUADSIM_B200_PDL"); return !(v && v[0] == '0'); }();
     // Launch priority: in a sliced rollout the policy kernel of one slice and the env kernel of the other become runnable at
@@ -1539,6 +1698,7 @@ int qs_rollout(qs_env_t* env, qs_policy_t* pol, int64_t n_steps, const qs_rollou
     if (qs_env_fused_args_(env, &ea, sizeof ea, &kind) != QS_OK)
       return qs_fail_(QS_ERR_INVALID, "qs_rollout: the fused step kernel (n_slices = 0) needs a float32 docking handle with the default model parameters");
     if (!pol->have_weights) return qs_fail_(QS_ERR_INVALID, "qs_rollout: qs_policy_set_weights has not been called");
+    if (pol->precision != QS_POLICY_BF16) return qs_fail_(QS_ERR_INVALID, "qs_rollout: the fused step kernel (n_slices = 0) runs the tensor-core forward only (QS_POLICY_BF16)");
     int prev = 0;
     QSP_CUDA(cudaGetDevice(&prev));
     QSP_CUDA(cudaSetDevice(pol->device));

@@ -12,7 +12,10 @@ from . import _capi
 
 
 class FusedPolicy:
-    def __init__(self, module, seed=0, env_id0=0):
+    def __init__(self, module, seed=0, env_id0=0, precision="bf16"):
+        """precision: "bf16" (tensor cores: bf16 weights / hidden activations, fp32 accumulation) or "fp32" (the accurate
+        forward on the CUDA cores, ~25x slower: evaluation runs, checks of the fast path).  Either way the same
+        (seed, env id, step) draws the same action noise.  The update (ppo_grad) always uses the tensor-core formulation."""
         p = next(module.parameters())
         if not p.is_cuda:
             raise _capi.QuadSimError("FusedPolicy needs the policy on a CUDA device: there is no CPU fallback")
@@ -24,10 +27,20 @@ class FusedPolicy:
         _capi.check(self.lib.qs_policy_create(C.byref(h), self.device.index))
         self._h = h
         self._step = 0
+        self.precision = None
+        self.set_precision(precision)
         self.sync_weights()
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_precision(self, precision):
+        """"bf16" | "fp32": arithmetic of step / predict and of the two-kernel rollout (qs_policy_set_precision)."""
+        modes = {"bf16": _capi.POLICY_BF16, "fp32": _capi.POLICY_FP32}
+        if precision not in modes:
+            raise ValueError("precision must be 'bf16' or 'fp32', got %r" % (precision,))
+        _capi.check(self.lib.qs_policy_set_precision(self._h, modes[precision]))
+        self.precision = precision
 
     def sync_weights(self, sync=True):
         """Re-pack the module's parameters into the kernel's operand images.  sync=False skips the stream synchronise and

@@ -219,7 +219,7 @@ class PPO2:
 
     def __init__(self, env, policy=None, n_steps=600, nminibatches=10, noptepochs=10, learning_rate=3e-4, gamma=0.99, lam=0.95,
                  cliprange=0.2, cliprange_vf=None, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, seed=0, reset_each_rollout=False,
-                 fused_policy=False, fused_update=None, graph_update=False):
+                 fused_policy=False, fused_update=None, graph_update=False, policy_precision="bf16"):
         self.env = env
         self.device = env.device
         torch.manual_seed(seed)
@@ -234,7 +234,9 @@ class PPO2:
         self.fused = None
         if fused_policy:
             from .fused_policy import FusedPolicy
-            self.fused = FusedPolicy(self.policy, seed=seed, env_id0=getattr(env, "env_id0", 0))
+            # policy_precision="fp32": the rollout forward in plain fp32 (qs_policy_set_precision), e.g. to evaluate a policy
+            # exactly as the reference's TensorFlow graph would; the default is the bf16 tensor-core forward
+            self.fused = FusedPolicy(self.policy, seed=seed, env_id0=getattr(env, "env_id0", 0), precision=policy_precision)
         # fused_update: the whole minibatch step in hand-written kernels -- qs_policy_ppo_grad (tensor-core forward / backward and the
         # weight-gradient contraction), qs_adam_step (global-norm clip + Adam in TensorFlow's formulation, as the reference
         # trains: ppo2.py:200-207), qs_permutation (the shuffle) -- instead of autograd + torch.optim.Adam + torch.randperm

@@ -93,3 +93,63 @@ def test_kernels_reproducible_under_concurrent_load():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_policy.py"), "--seconds", "4"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "stress ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 1000, 148 * 64 * 3 + 17])
+def test_fp32_forward_matches_torch_reference(n):
+    """qs_policy_set_precision(QS_POLICY_FP32): fp32 weights, activations and accumulation on the CUDA cores -- the
+    reference's TensorFlow policy to within summation order.  Tolerance 1e-4 absolute on O(1) outputs (the bf16
+    tensor-core mode is held to 5e-2 by test_fused_forward_matches_torch_reference)."""
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    pol = ppo.MlpPolicy().cuda()
+    with torch.no_grad():
+        pol.pi.weight.mul_(30.0)
+        pol.logstd.copy_(torch.tensor([[0.1, -0.3, 0.0, 0.2]]))
+    fused = FusedPolicy(pol, precision="fp32")
+    obs = torch.randn(n, 12, device="cuda") * torch.tensor([2, 2, 2, .5, .5, .5, .3, .3, .3, 1, 1, 1], device="cuda")
+    act, clip, val, nlp = fused.step(obs, deterministic=True)
+    with torch.no_grad():
+        mean_ref, val_ref = pol.forward(obs)
+    assert float((act - mean_ref).abs().max()) < 1e-4 and float((val - val_ref).abs().max()) < 1e-4
+    assert torch.equal(clip, act.clamp(-1, 1))
+    const = 0.5 * math.log(2 * math.pi) * 4 + float(pol.logstd.sum())
+    assert float((nlp - const).abs().max()) < 1e-5
+
+
+def test_fp32_and_bf16_modes_share_noise_and_switch_in_place():
+    """The same (seed, env id, step) draws the same noise in either precision; set_precision switches a live handle."""
+    torch.manual_seed(2)
+    pol = ppo.MlpPolicy().cuda()
+    with torch.no_grad():
+        pol.pi.weight.mul_(30.0)
+        pol.logstd.copy_(torch.tensor([[0.2, -0.5, 0.0, 0.4]]))
+    fused = FusedPolicy(pol, seed=11, env_id0=4096)
+    obs = torch.randn(5000, 12, device="cuda")
+    mean_b = fused.step(obs, deterministic=True)[0]
+    act_b, _, val_b, nlp_b = fused.step(obs, step_idx=7)
+    fused.set_precision("fp32")
+    mean_f = fused.step(obs, deterministic=True)[0]
+    act_f, clip_f, val_f, nlp_f = fused.step(obs, step_idx=7)
+    z_b, z_f = (act_b - mean_b) / pol.logstd.exp(), (act_f - mean_f) / pol.logstd.exp()
+    assert float((z_b - z_f).abs().max()) < 1e-4            # identical draws; the subtraction of the means is the only noise
+    assert float((nlp_b - nlp_f).abs().max()) < 1e-5        # neglogp depends on the draw only, not on the mean
+    assert float((mean_b - mean_f).abs().max()) < 5e-2 and float((val_b - val_f).abs().max()) < 5e-2
+    with torch.no_grad():
+        mean_ref, val_ref = pol.forward(obs)
+    assert float((mean_f - mean_ref).abs().max()) < 1e-4 and float((val_f - val_ref).abs().max()) < 1e-4
+    assert torch.equal(clip_f, act_f.clamp(-1, 1))
+    fused.set_precision("bf16")
+    assert torch.equal(fused.step(obs, step_idx=7)[0], act_b)
+    with pytest.raises(ValueError):
+        fused.set_precision("fp16")
+
+
+def test_fp32_policy_matches_shipped_policy_numpy():
+    """The shipped archive's parameters through the fp32 forward against the numpy forward recorded in the fixture."""
+    g = load_golden("policy_v0")
+    pol = ppo.MlpPolicy().load_sb_params({k: g["param::" + k] for k in g["param_order"]}).cuda()
+    fused = FusedPolicy(pol, precision="fp32")
+    act, clip, val, nlp = fused.step(torch.as_tensor(g["obs"], device="cuda"), deterministic=True)
+    assert np.max(np.abs(act.cpu().numpy() - g["mean"])) < 1e-4
+    assert np.max(np.abs(val.cpu().numpy() - g["value"])) < 1e-4 * max(1.0, float(np.abs(g["value"]).max()))

@@ -98,11 +98,11 @@ def test_ppo2_learn_runs_and_updates():
     env.close()
 
 
-@pytest.mark.parametrize("n_slices", [1, 2, 3, 8])
-def test_in_place_rollout_equals_stepwise_loop(n_slices):
+@pytest.mark.parametrize("n_slices,precision", [(1, "bf16"), (2, "bf16"), (3, "bf16"), (8, "bf16"), (2, "fp32")])
+def test_in_place_rollout_equals_stepwise_loop(n_slices, precision):
     """qs_rollout (policy + env kernels writing the rollout rows in place) against the same kernels driven step by step
     through the public objects on a twin environment: every stored quantity must be bit-identical, over two consecutive
-    rollouts (the second continues from row T of the first)."""
+    rollouts (the second continues from row T of the first).  Also with the fp32 forward (qs_policy_set_precision)."""
     from quadsim_b200.fused_policy import FusedPolicy
     n, T = 3000, 24  # ragged: 23.4 tiles
     torch.manual_seed(0)
@@ -112,7 +112,7 @@ def test_in_place_rollout_equals_stepwise_loop(n_slices):
         pol.pi.weight.mul_(20.0)
     env_a = qs.make_vec("docking-v2", n, seed=5, randomize="episode", want_info=False)
     env_b = qs.make_vec("docking-v2", n, seed=5, randomize="episode", want_info=False)
-    fa, fb = FusedPolicy(pol, seed=11), FusedPolicy(pol, seed=11)
+    fa, fb = FusedPolicy(pol, seed=11, precision=precision), FusedPolicy(pol, seed=11, precision=precision)
     runner = ppo.DeviceRunner(env_a, pol, T, fused=fa, n_slices=n_slices)
     assert runner.in_place
     obs = env_b.reset().float()
@@ -182,6 +182,17 @@ def test_fused_step_kernel_rollout_equals_two_kernel_rollout(env_id):
         ppo.DeviceRunner(qs.make_vec(env_id, 256, params={"mass": 0.2}), pol, 4, fused=fps[0], n_slices=0).run()
     for e in envs:
         e.close()
+
+
+def test_fused_step_kernel_refuses_fp32_policy():
+    from quadsim_b200 import _capi
+    from quadsim_b200.fused_policy import FusedPolicy
+    pol = ppo.MlpPolicy().cuda()
+    env = qs.make_vec("docking-v2", 512, seed=1, want_info=False)
+    runner = ppo.DeviceRunner(env, pol, 4, fused=FusedPolicy(pol, precision="fp32"), n_slices=0)
+    with pytest.raises(_capi.QuadSimError, match="QS_POLICY_BF16"):
+        runner.run()
+    env.close()
 
 
 def test_ppo2_learn_with_fused_policy():
