@@ -857,6 +857,9 @@ __global__ void __launch_bounds__(256) permutation_kernel(int64_t n, int half_bi
 // packs A3 pi into its own first 32 columns [64s, 64s+32); D3 [32,48) | D2 vf [128,256) likewise -> A3 vf [128+64s, +32).
 // Every barrier completes exactly once per tile, so the wait parity is the tile counter's low bit.
 // =========================================================================================================
+#ifndef QS_EXP_D3_SPLIT
+#define QS_EXP_D3_SPLIT 0
+#endif
 #ifndef QS_EXP_L3_STEPS
 #define QS_EXP_L3_STEPS 8      // EXPERIMENT ONLY (results are wrong below 8): layer-3 K-steps issued per half
 #endif
@@ -1110,7 +1113,12 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
   #pragma unroll
           for (int k8 = 0; k8 < QS_EXP_L3_STEPS; k8++) {  // K-step k8 of this half: features 16 k8 .., packed by side (16 k8) / kWsCols
             const int ks = 8 * half + k8, sd = (16 * k8) / kWsCols, kk = (16 * k8) % kWsCols;
+#if QS_EXP_D3_SPLIT
+            // EXPERIMENT: even / odd K-steps accumulate into two D3 tiles ([112,128) and [96,112)), summed by the epilogue
+            umma_ts(tmem + kColD3ws - 16 * (ks & 1), tmem + half * kColD2v + sd * kWsCols + kk / 2, umma_desc(sbase + kOffW3 + ks * 512, 256, 128), idesc3, ks >> 1);
+#else
             umma_ts(tmem + kColD3ws, tmem + half * kColD2v + sd * kWsCols + kk / 2, umma_desc(sbase + kOffW3 + ks * 512, 256, 128), idesc3, ks);
+#endif
           }
           if (half == 1) umma_commit(bars + 8 * kDone3);
           // three groups: the vf half reuses the pi half's columns -- in order behind the layer-3 steps that read A3 pi
@@ -1160,6 +1168,13 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
       mbar_wait(bars + 8 * kDone3, ph_prev);
       tc_fence_after();
       tmem_ld8(trow + kColD3ws, d3);
+#if QS_EXP_D3_SPLIT
+      uint32_t d3b[8];
+      tmem_ld8(trow + kColD3ws - 16, d3b);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 8; j++) d3[j] = __float_as_uint(__uint_as_float(d3[j]) + __uint_as_float(d3b[j]));
+#endif
       tmem_wait_ld();
       tc_fence_before();  // D3 is read before the next tile's pi half (ordered by our full_a2 arrival) overwrites it
     };
