@@ -292,7 +292,8 @@ typedef struct {
   const float *obs, *actions, *returns, *values, *neglogp; /* the rollout, flat: [M,12], [M,4], [M], [M], [M] */
   const int64_t* idx;      /* [batch] row numbers, or NULL for rows 0..batch-1 */
   int64_t batch;
-  const float* adv_stats;  /* device [2]: mean and 1/(std + 1e-8) of (returns - values) over the minibatch (ppo2.py:265-266) */
+  const float* adv_stats;  /* device [2]: mean and 1/(std + 1e-8) of (returns - values) over the minibatch (ppo2.py:265-266);
+                            * NULL: computed here, from returns - values over idx (population std, sums in double, one launch) */
   float cliprange, cliprange_vf, vf_coef; /* cliprange_vf < 0: unclipped value loss */
   void *a1, *h, *hpv, *dz2, *dz1, *dout;  /* workspace (operand images, see above) */
   float* per_sample;                      /* [batch,16] out, or NULL */

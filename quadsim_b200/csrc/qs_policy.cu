@@ -811,6 +811,66 @@ __global__ void __launch_bounds__(1024, 1) adam_kernel(const __grid_constant__ A
 // optimiser launch can still be reading it)
 __global__ void adam_advance_kernel(long long* step_dev) { *step_dev += 1; }
 
+// ---- advantage statistics of a minibatch (ppo2.py:265-266: advs = returns - values; (advs - advs.mean()) / (advs.std() + 1e-8)) ----
+// mean and 1 / (population std + 1e-8) of (returns - values)[idx] in ONE launch: per-block partial sums in double, and the last
+// block to finish (ticket counter) adds the partials in block order -- bit-reproducible -- writes the two floats the gradient
+// kernel reads, and re-arms the counter.  Replaces a gather, a Welford reduction and six elementwise launches of the caller.
+constexpr int kAdvBlocks = 1184;  // 8 per SM: the gathers are latency-bound, so many loads in flight
+__global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict__ ret, const float* __restrict__ val, const int64_t* __restrict__ idx,
+                                                        int64_t n, double* partial, unsigned int* ticket, float* stats) {
+  double s = 0.0, q = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {  // four independent gathers in flight per thread
+    int64_t j[4];
+    float a[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) j[u] = idx ? idx[i + u * stride] : i + u * stride;
+#pragma unroll
+    for (int u = 0; u < 4; u++) a[u] = ret[j[u]] - val[j[u]];  // float32, as the reference forms it
+#pragma unroll
+    for (int u = 0; u < 4; u++) { s += (double)a[u]; q += (double)a[u] * (double)a[u]; }
+  }
+  for (; i < n; i += stride) {
+    const int64_t j = idx ? idx[i] : i;
+    const float a = ret[j] - val[j];
+    s += (double)a;
+    q += (double)a * (double)a;
+  }
+  __shared__ double sh[2][8];
+  __shared__ bool last;
+  auto block_sum = [&](double& x, double& y) {  // fixed order: lanes by xor-shuffle, then the 8 warps in turn
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { x += __shfl_xor_sync(0xffffffffu, x, o); y += __shfl_xor_sync(0xffffffffu, y, o); }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = x; sh[1][threadIdx.x >> 5] = y; }
+    __syncthreads();
+    x = y = 0.0;
+    for (int w = 0; w < 8; w++) { x += sh[0][w]; y += sh[1][w]; }
+  };
+  block_sum(s, q);
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = s;
+    partial[2 * blockIdx.x + 1] = q;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();  // the last block to finish adds the partials, every thread a fixed subset, and publishes the statistics
+  double S = 0.0, Q = 0.0;
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += 256) { S += ((volatile double*)partial)[2 * b]; Q += ((volatile double*)partial)[2 * b + 1]; }
+  block_sum(S, Q);
+  if (threadIdx.x == 0) {
+    const double mean = S / (double)n;
+    double var = Q / (double)n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[0] = (float)mean;
+    stats[1] = 1.0f / ((float)sqrt(var) + 1e-8f);
+    *ticket = 0;
+  }
+}
+
 // =========================================================================================================
 // Minibatch shuffle of the PPO2 update (np.random.shuffle(inds), rl_baselines/ppo2/ppo2.py:350-352) without a sort: a keyed
 // bijection of [0, n) -- a 4-round Feistel network on the next power of four above n, cycle-walked back into range -- so
@@ -1447,6 +1507,7 @@ struct qs_policy {
   int device = 0;
   unsigned char* packed = nullptr;
   float* img32 = nullptr;       // fp32 image of the weights (policy_fwd_f32_kernel)
+  double* adv_ws = nullptr;     // adv_stats_kernel: [2 * kAdvBlocks] partial sums | ticket (4 B) | pad | stats (2 floats)
   int precision = QS_POLICY_BF16;
   int sms = 0;
   int grid = 0;
@@ -1487,6 +1548,8 @@ int qs_policy_create(qs_policy_t** out, int device) {
   cudaError_t err;
   if ((err = cudaGetDeviceProperties(&prop, device)) != cudaSuccess || (err = cudaMalloc(&p->packed, kPackedBytes)) != cudaSuccess ||
       (err = cudaMalloc((void**)&p->img32, kF32Floats * sizeof(float))) != cudaSuccess ||
+      (err = cudaMalloc((void**)&p->adv_ws, (2 * kAdvBlocks + 2) * sizeof(double))) != cudaSuccess ||
+      (err = cudaMemset(p->adv_ws, 0, (2 * kAdvBlocks + 2) * sizeof(double))) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_fwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF32SmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
@@ -1501,6 +1564,7 @@ int qs_policy_create(qs_policy_t** out, int device) {
     int rc = qs_fail_(QS_ERR_CUDA, "qs_policy_create: %s", cudaGetErrorString(err));
     cudaFree(p->packed);
     cudaFree(p->img32);
+    cudaFree(p->adv_ws);
     delete p;
     cudaSetDevice(prev);
     return rc;
@@ -1509,6 +1573,7 @@ int qs_policy_create(qs_policy_t** out, int device) {
     int rc = qs_fail_(QS_ERR_CUDA, "qs_policy_create: the policy kernel does not fit an SM (%d B shared memory)", kSmemBytes);
     cudaFree(p->packed);
     cudaFree(p->img32);
+    cudaFree(p->adv_ws);
     delete p;
     cudaSetDevice(prev);
     return rc;
@@ -1528,6 +1593,7 @@ int qs_policy_destroy(qs_policy_t* p) {
   cudaSetDevice(p->device);
   cudaFree(p->packed);
   cudaFree(p->img32);
+  cudaFree(p->adv_ws);
   for (int k = 0; k < kMaxSlices; k++) {
     if (p->slice_stream[k]) cudaStreamDestroy(p->slice_stream[k]);
     if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]);
@@ -1624,7 +1690,7 @@ int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, u
 int qs_policy_ppo_grad(qs_policy_t* p, const qs_ppo_grad_t* g, void* stream) {
   if (!p || !g) return qs_fail_(QS_ERR_INVALID, "qs_policy_ppo_grad: null argument");
   if (!p->have_weights) return qs_fail_(QS_ERR_INVALID, "qs_policy_ppo_grad: qs_policy_set_weights has not been called");
-  if (!g->obs || !g->actions || !g->returns || !g->values || !g->neglogp || !g->adv_stats || !g->a1 || !g->h || !g->hpv || !g->dz2 || !g->dz1 ||
+  if (!g->obs || !g->actions || !g->returns || !g->values || !g->neglogp || !g->a1 || !g->h || !g->hpv || !g->dz2 || !g->dz1 ||
       !g->dout || !g->col_sums || !g->g1 || !g->g2 || !g->g3)
     return qs_fail_(QS_ERR_INVALID, "qs_policy_ppo_grad: null buffer");
   if (g->batch <= 0) return qs_fail_(QS_ERR_INVALID, "qs_policy_ppo_grad: batch must be positive");
@@ -1634,13 +1700,26 @@ int qs_policy_ppo_grad(qs_policy_t* p, const qs_ppo_grad_t* g, void* stream) {
   QSP_CUDA(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int tiles = (int)((g->batch + kTileRows - 1) / kTileRows);
-  cudaError_t e = cudaMemsetAsync(g->col_sums, 0, 16 * sizeof(float), st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(g->g1, 0, (size_t)kHid * kK1 * sizeof(float), st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(g->g2, 0, (size_t)2 * kHid * kK2 * sizeof(float), st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(g->g3, 0, (size_t)2 * kHid * 16 * sizeof(float), st);
+  cudaError_t e = cudaSuccess;
+  constexpr size_t n1 = (size_t)kHid * kK1, n2 = (size_t)2 * kHid * kK2, n3 = (size_t)2 * kHid * 16;
+  if (g->g2 == g->g1 + n1 && g->g3 == g->g2 + n2 && g->col_sums == g->g3 + n3) {  // one allocation (the caller's all-reduce bucket): one memset
+    e = cudaMemsetAsync(g->g1, 0, (n1 + n2 + n3 + 16) * sizeof(float), st);
+  } else {
+    e = cudaMemsetAsync(g->col_sums, 0, 16 * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->g1, 0, n1 * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->g2, 0, n2 * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->g3, 0, n3 * sizeof(float), st);
+  }
+  const float* adv_stats = g->adv_stats;
+  if (e == cudaSuccess && !adv_stats) {  // the minibatch's advantage statistics, computed here (one launch)
+    float* stats = reinterpret_cast<float*>(p->adv_ws + 2 * kAdvBlocks + 1);
+    adv_stats_kernel<<<kAdvBlocks, 256, 0, st>>>(g->returns, g->values, g->idx, g->batch, p->adv_ws, reinterpret_cast<unsigned int*>(p->adv_ws + 2 * kAdvBlocks), stats);
+    e = cudaGetLastError();
+    adv_stats = stats;
+  }
   if (e == cudaSuccess) {
     StepArgs a = {p->packed, g->obs, g->batch, 0, 0, 0, 1, nullptr, nullptr, nullptr, nullptr};
-    TrainArgs t = {g->actions, g->returns, g->values, g->neglogp, g->idx, g->adv_stats, g->cliprange, g->cliprange_vf, g->vf_coef,
+    TrainArgs t = {g->actions, g->returns, g->values, g->neglogp, g->idx, adv_stats, g->cliprange, g->cliprange_vf, g->vf_coef,
                    (float)(1.0 / (double)g->batch), (uint4*)g->a1, (uint4*)g->h, (uint4*)g->hpv, (uint4*)g->dz2, (uint4*)g->dz1, (uint4*)g->dout,
                    (float4*)g->per_sample, g->col_sums};
     const int ctas = (tiles + kGroups - 1) / kGroups;

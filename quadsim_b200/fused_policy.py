@@ -96,20 +96,18 @@ class FusedPolicy:
         return ws
 
     @torch.no_grad()
-    def ppo_grad(self, batch, idx, cliprange=0.2, cliprange_vf=None, vf_coef=0.5, ent_coef=0.0, want_per_sample=True):
+    def ppo_grad(self, batch, idx, cliprange=0.2, cliprange_vf=None, vf_coef=0.5, ent_coef=0.0, want_per_sample=True, adv_stats=None):
         """Gradient of PPO2's loss (ppo2.py:138-189) over the minibatch rows `idx` of the flat rollout `batch` (the dict
         DeviceRunner.run returns), all in hand-written kernels behind ONE C call: forward + per-sample loss + backward
         through the activations on the tensor cores, then the weight-gradient contraction over the whole minibatch
-        (split-K, accumulators in tensor memory).  Returns ({param: grad} in the module's layouts, logs)."""
+        (split-K, accumulators in tensor memory).  Returns ({param: grad} in the module's layouts, logs).
+        adv_stats: optional device tensor (mean, 1 / (std + 1e-8)) of the minibatch's advantages; by default the library
+        computes it itself from returns - values over idx (ppo2.py:265-266), in one launch."""
         m, B = self.module, int(idx.shape[0])
         ws = self._workspace(B)
         ret, val = batch["returns"], batch["values"]
-        # PPO2.update leaves returns - values of the whole rollout in batch["adv_raw"]: one gather per minibatch instead of two
-        adv = batch["adv_raw"][idx] if "adv_raw" in batch else ret[idx] - val[idx]
-        std, mean = torch.std_mean(adv, unbiased=False)  # ppo2.py:265-266 (numpy's population std)
-        stats = ws["stats"]
-        stats[0] = mean
-        stats[1] = 1.0 / (std + 1e-8)
+        if adv_stats is not None and (adv_stats.dtype != torch.float32 or adv_stats.numel() != 2 or adv_stats.device != self.device):
+            raise ValueError("adv_stats must be two float32 values on %s" % (self.device,))
         p = lambda t: t.data_ptr()
         for k in ("obs", "actions", "returns", "values", "neglogp"):
             t = batch[k]
@@ -117,7 +115,7 @@ class FusedPolicy:
                 raise ValueError("rollout tensor %r must be contiguous float32 on %s" % (k, self.device))
         if idx.dtype != torch.int64 or not idx.is_contiguous():
             raise ValueError("idx must be a contiguous int64 tensor")
-        g = _capi.PPOGrad(p(batch["obs"]), p(batch["actions"]), p(ret), p(val), p(batch["neglogp"]), p(idx), B, p(stats),
+        g = _capi.PPOGrad(p(batch["obs"]), p(batch["actions"]), p(ret), p(val), p(batch["neglogp"]), p(idx), B, p(adv_stats) if adv_stats is not None else None,
                           float(cliprange), float(-1.0 if cliprange_vf is None or cliprange_vf < 0 else cliprange_vf), float(vf_coef),
                           p(ws["a1"]), p(ws["h"]), p(ws["hpv"]), p(ws["dz2"]), p(ws["dz1"]), p(ws["dout"]),
                           p(ws["per_sample"]) if want_per_sample else None, p(ws["col"]), p(ws["g1"]), p(ws["g2"]), p(ws["g3"]))

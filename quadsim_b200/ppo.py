@@ -320,7 +320,7 @@ class PPO2:
     def _graph_step(self, batch, idx):
         """Replay the captured minibatch step on `idx` (copied into the graph's static index buffer)."""
         key = (batch["obs"].data_ptr(), batch["returns"].data_ptr(), batch["actions"].data_ptr(), batch["values"].data_ptr(),
-               batch["neglogp"].data_ptr(), batch["adv_raw"].data_ptr() if "adv_raw" in batch else 0, idx.shape[0])
+               batch["neglogp"].data_ptr(), idx.shape[0])
         if self._graph is None or self._graph[0] != key:
             if self.dist:
                 raise _capi.QuadSimError("graph_update is single-process: the gradient all-reduce is not captured")
@@ -365,14 +365,6 @@ class PPO2:
         mb_size = n_batch // self.nminibatches
         keys = ("obs", "returns", "actions", "values", "neglogp")
         logs = []
-        if self.fused_update or self.graph_update:
-            # un-normalised advantages of the whole rollout, once per update, in a buffer whose address survives updates (the
-            # captured minibatch step of graph_update reads it)
-            buf = getattr(self, "_adv_raw", None)
-            if buf is None or buf.shape != batch["returns"].shape:
-                buf = self._adv_raw = torch.empty_like(batch["returns"])
-            torch.sub(batch["returns"], batch["values"], out=buf)
-            batch = dict(batch, adv_raw=buf)
         for _ in range(self.noptepochs):
             perm = self._shuffle(n_batch)
             for start in range(0, mb_size * self.nminibatches, mb_size):

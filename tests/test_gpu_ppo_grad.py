@@ -106,6 +106,35 @@ def test_ppo_grad_matches_autograd(B):
     env.close()
 
 
+def test_advantage_statistics_computed_by_the_library():
+    """qs_policy_ppo_grad with adv_stats = NULL computes mean and 1 / (std + 1e-8) of (returns - values)[idx] itself
+    (ppo2.py:265-266; sums in double, block partials added in a fixed order): same gradients as with statistics handed in
+    from a float64 torch reduction, and the per-sample results bit-reproducible from call to call."""
+    env, algo, batch = _rollout()
+    M = batch["obs"].shape[0]
+    idx = torch.randperm(M, device="cuda")[:5000].contiguous()
+    args = (algo.cliprange, algo.cliprange_vf, algo.vf_coef, algo.ent_coef)
+    snap = lambda gl: ({k: v.clone() for k, v in gl[0].items()}, {k: float(v) for k, v in gl[1].items()})
+    g_a, l_a = snap(algo.fused.ppo_grad(batch, idx, *args))
+    g_b, l_b = snap(algo.fused.ppo_grad(batch, idx, *args))
+    adv = (batch["returns"] - batch["values"])[idx].double()
+    stats = torch.stack([adv.mean(), 1.0 / (adv.std(unbiased=False) + 1e-8)]).float()
+    g_c, l_c = snap(algo.fused.ppo_grad(batch, idx, *args, adv_stats=stats))
+    for prm in g_a:
+        scale = float(g_c[prm].abs().max()) + 1e-12
+        assert float((g_a[prm] - g_b[prm]).abs().max()) < 1e-5 * scale  # the contraction's split-K adds land in any order
+        assert float((g_a[prm] - g_c[prm]).abs().max()) < 2e-4 * scale
+    assert abs(l_a["pg_loss"] - l_b["pg_loss"]) < 1e-6 and abs(l_a["pg_loss"] - l_c["pg_loss"]) < 1e-5
+    # the statistics themselves: per-sample normalised advantages reproduce from call to call bit for bit
+    algo.fused.ppo_grad(batch, idx, *args)
+    ps1 = algo.fused._ws["per_sample"][:5000].clone()
+    algo.fused.ppo_grad(batch, idx, *args)
+    assert torch.equal(ps1, algo.fused._ws["per_sample"][:5000])
+    with pytest.raises(ValueError):
+        algo.fused.ppo_grad(batch, idx, *args, adv_stats=torch.zeros(3, device="cuda"))
+    env.close()
+
+
 def _unpack_image(img, F, B):
     """An operand image of the weight-gradient contraction (include/quadsim_b200.h: per 128-sample tile, the 16-byte chunk b of
     row r at (b * 16 + (r >> 3)) * 128 + (r & 7) * 16) -> the [B, F] bf16 matrix it holds."""
