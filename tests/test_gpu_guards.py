@@ -57,6 +57,17 @@ def test_policy_step_and_ppo_grad_stay_in_bounds(n):
     torch.cuda.synchronize()
     for g in (act, clip, val, nlp):
         assert g.intact() and g.written()
+    # the fp32 forward (qs_policy_set_precision): 64-row tiles, a ragged last tile, an exactly sized obs allocation before it
+    fused.set_precision("fp32")
+    obs_g = Guarded(n, 12, f32)
+    obs_g.view.copy_(obs)
+    act2, clip2, val2, nlp2 = Guarded(n, 4, f32), Guarded(n, 4, f32), Guarded(n, 0, f32), Guarded(n, 0, f32)
+    _capi.check(L.qs_policy_step(fused._h, n, obs_g.ptr, 1, 0, 0, 0, act2.ptr, clip2.ptr, val2.ptr, nlp2.ptr, _stream()))
+    torch.cuda.synchronize()
+    for g in (obs_g, act2, clip2, val2, nlp2):
+        assert g.intact() and g.written()
+    assert float((act2.view - act.view).abs().max()) < 5e-2 and torch.equal(nlp2.view, nlp.view)  # same draws in both precisions
+    fused.set_precision("bf16")
     # minibatch gradient: B rows gathered from a rollout of n rows through idx
     B = max(1, (2 * n) // 3)
     idx = torch.randperm(n, device="cuda")[:B].contiguous()
