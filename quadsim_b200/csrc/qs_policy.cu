@@ -269,6 +269,16 @@ __device__ __forceinline__ ObsRow load_obs(const float* obs, int64_t i, int64_t 
   return o;
 }
 
+// the same through a row index that is already in a register (policy_kernel<TRAIN> keeps the minibatch indices one tile ahead)
+__device__ __forceinline__ ObsRow load_obs_at(const float* obs, int64_t src, bool valid) {
+  ObsRow o = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+  if (valid) {
+    const float4* p = reinterpret_cast<const float4*>(obs + src * kObs);
+    o.a = __ldg(p); o.b = __ldg(p + 1); o.c = __ldg(p + 2);
+  }
+  return o;
+}
+
 // One kernel, two instantiations.  TRAIN = false: model.step (rollout).  TRAIN = true: the same forward pass over a minibatch
 // gathered through idx, then PPO2's loss (rl_baselines/ppo2/ppo2.py:138-189) per sample and the backward pass through the
 // activations, on the tensor cores as well:
@@ -279,6 +289,21 @@ __device__ __forceinline__ ObsRow load_obs(const float* obs, int64_t i, int64_t 
 //   dZ1           = dA2 * relu'(h)
 // The operands of the weight-gradient GEMMs (A1, h, hp|hv, dZ2, dZ1 as bf16 rows, plus 16 fp32 per sample: dOut, d logstd
 // and the logged loss terms) go to HBM; those GEMMs reduce over the whole minibatch (K = batch) and are left to the caller.
+// EXPERIMENT ONLY (-DQS_WS_TRACE=1): SM-clock stamps of the first kTrTiles tiles of CTA 0 / group 0 -- epilogue thread 0 in
+// slots [0,16), the issuer's lane 0 in [16,24) -- read back with qs_debug_ws_trace (tools/ws_trace.py draws the timeline)
+#ifndef QS_WS_TRACE
+#define QS_WS_TRACE 0
+#endif
+#if QS_WS_TRACE
+constexpr int kTrTiles = 28, kTrSlots = 24;
+__device__ long long g_ws_trace[kTrTiles * kTrSlots];
+#define QS_TR(slot) do { if (trace_on && it < (uint32_t)kTrTiles) g_ws_trace[it * kTrSlots + (slot)] = clock64(); } while (0)
+#define QS_TRT(slot) do { if (TRAIN && trace_on && it < (uint32_t)kTrTiles) g_ws_trace[it * kTrSlots + (slot)] = clock64(); } while (0)
+#else
+#define QS_TR(slot) do { } while (0)
+#define QS_TRT(slot) do { } while (0)
+#endif
+
 template <bool TRAIN>
 __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const StepArgs a, const TrainArgs t) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -292,7 +317,24 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
   const int tile0 = blockIdx.x * kGroups + g, tile_stride = gridDim.x * kGroups;
   const int64_t* idx = TRAIN ? t.idx : nullptr;
 
-  ObsRow o = load_obs(a.obs, (int64_t)tile0 * kTileRows + row, tile0 < tiles ? a.n : 0, idx);  // in flight during the set-up
+  // Rows are gathered through idx (TRAIN): index -> row is a dependent pair of DRAM round trips (~3.5 k clocks each under this
+  // kernel's store load; the trace showed 7.2 k clocks per tile exposed right here).  So the indices run TWO tiles ahead of their
+  // use and the rows and records they select one tile ahead: nothing a tile needs is requested inside that tile.
+  const int64_t i_first = (int64_t)tile0 * kTileRows + row, i_step = (int64_t)tile_stride * kTileRows;
+  auto row_index = [&](int64_t i) -> int64_t { return i < a.n ? (idx ? __ldg(idx + i) : i) : 0; };
+  struct Rec { float4 act; float ret, oldv, oldnlp; };  // TRAIN: a sample's rollout record (ppo2.py:244-262 feeds)
+  auto load_rec = [&](int64_t src, bool valid) {
+    Rec r = {make_float4(0.f, 0.f, 0.f, 0.f), 0.f, 0.f, 0.f};
+    if (TRAIN && valid) {
+      r.act = __ldg(reinterpret_cast<const float4*>(t.actions) + src);
+      r.ret = __ldg(t.returns + src); r.oldv = __ldg(t.values + src); r.oldnlp = __ldg(t.neglogp + src);
+    }
+    return r;
+  };
+  const int64_t src_first = tile0 < tiles ? row_index(i_first) : 0;
+  int64_t src_next = tile0 < tiles ? row_index(i_first + i_step) : 0;
+  ObsRow o = load_obs_at(a.obs, src_first, tile0 < tiles && i_first < a.n);  // in flight during the set-up
+  Rec rec_next = load_rec(src_first, tile0 < tiles && i_first < a.n);        // rows AND records run one tile ahead of their use
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
@@ -323,7 +365,12 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
   constexpr uint32_t idesc4 = umma_idesc(128, kHid, true), idesc5 = umma_idesc(128, kHid, true);  // B read MN-major
   uint32_t phase = 0;
   float col_acc[13] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // TRAIN: this thread's share of col_sums
-  for (int tile = tile0; tile < tiles; tile += tile_stride) {
+#if QS_WS_TRACE
+  const bool trace_on = blockIdx.x == 0 && tid == 0;
+#endif
+  uint32_t it = 0;
+  for (int tile = tile0; tile < tiles; tile += tile_stride, it++) {
+    QS_TRT(0);
     const int64_t i = (int64_t)tile * kTileRows + row;
     const bool active = i < a.n;
     // ---- A1: the observation row split hi/lo, K = 32 = four 16-byte core-matrix rows ----
@@ -350,7 +397,9 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
     }
     proxy_fence();       // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     tc_fence_before();   // orders the previous tile's tcgen05.ld before the barrier (TMEM columns are reused)
+    QS_TRT(1);
     group_sync(g);
+    QS_TRT(2);
     if (row == 0) {
       tc_fence_after();
       // operand rows = 128 -> SBO = 128 B, LBO = 16 row-groups * 128 B = 2048 B; one K=16 step = two k-blocks = 4096 B
@@ -359,18 +408,17 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
         umma_ss(tmem, umma_desc(a_base + ks * 4096, 2048, 128), umma_desc(sbase + kOffW1 + ks * 4096, 2048, 128), idesc1, ks);
       umma_commit(bar_mma);
     }
-    o = load_obs(a.obs, i + (int64_t)tile_stride * kTileRows, a.n, idx);  // next tile's row, in flight under this tile's work
-    // TRAIN: this sample's rollout record (ppo2.py:244-262 feeds): action, return, old value, old neglogp
-    float4 act4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float ret = 0.f, oldv = 0.f, oldnlp = 0.f;
-    if (TRAIN && active) {
-      const int64_t src = idx ? __ldg(idx + i) : i;
-      act4 = __ldg(reinterpret_cast<const float4*>(t.actions) + src);
-      ret = __ldg(t.returns + src); oldv = __ldg(t.values + src); oldnlp = __ldg(t.neglogp + src);
-    }
+    // this sample's record was requested a tile ago; the next tile's row and record go out now, under this tile's work
+    const float4 act4 = rec_next.act;
+    const float ret = rec_next.ret, oldv = rec_next.oldv, oldnlp = rec_next.oldnlp;
+    o = load_obs_at(a.obs, src_next, i + i_step < a.n);
+    rec_next = load_rec(src_next, i + i_step < a.n);
+    src_next = row_index(i + 2 * i_step);  // consumed a whole tile from now
+    QS_TRT(3);
     mbar_wait(bar_mma, phase);
     phase ^= 1;
     tc_fence_after();
+    QS_TRT(4);
     // ---- epilogue 1: h = relu(D1) -> A2[:, 0:128]; A2[:, 128:144] = (1, 1, 0, ...) carries layer 2's bias ----
 #pragma unroll 1
     for (int c0 = 0; c0 < kHid; c0 += 64) {
@@ -397,7 +445,9 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
     }
     proxy_fence();
     tc_fence_before();
+    QS_TRT(5);
     group_sync(g);
+    QS_TRT(6);
     if (row == 0) {
       tc_fence_after();
       // B rows = 256 -> LBO = 32 row-groups * 128 B = 4096 B, one K step = 8192 B
@@ -409,6 +459,7 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
     mbar_wait(bar_mma, phase);
     phase ^= 1;
     tc_fence_after();
+    QS_TRT(7);
     // ---- epilogue 2: relu(D2) -> bf16 pairs written back over the columns they came from: A3 = columns [0,128).  Chunk c's
     //      packed columns land in columns this thread has already loaded, so nothing is overwritten before it is read. ----
 #pragma unroll 1
@@ -429,7 +480,9 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
     }
     tmem_wait_st();
     tc_fence_before();
+    QS_TRT(8);
     group_sync(g);
+    QS_TRT(9);
     if (row == 0) {
       tc_fence_after();
       // A from tensor memory: one K=16 step = 8 columns.  B rows = 16 -> LBO = 2 row-groups * 128 B = 256 B, one K step = 512 B
@@ -455,6 +508,7 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
     mbar_wait(bar_mma, phase);
     phase ^= 1;
     tc_fence_after();
+    QS_TRT(10);
     uint32_t d3[8];
     tmem_ld8(trow + kColD3, d3);
     tmem_wait_ld();
@@ -526,6 +580,7 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
       *reinterpret_cast<uint4*>(a_row + 16 * 2048) = make_uint4(pack_bf16(dm0, dm1), pack_bf16(dm2, dm3), pack_bf16(dval, 0.f), 0u);
       *reinterpret_cast<uint4*>(a_row + 17 * 2048) = make_uint4(0u, 0u, 0u, 0u);
       proxy_fence();
+      QS_TRT(11);
       // dZ2 = (dOut . W3) * relu'(hp|hv), one 128-feature half at a time: the half's dA3 lands in columns [128,256), its
       // forward activations (bf16 pairs) are still in TMEM at [64 half, 64 half + 64), and dZ2 is packed over them in place
 #pragma unroll 1
@@ -542,6 +597,7 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
         mbar_wait(bar_mma, phase);
         phase ^= 1;
         tc_fence_after();
+        QS_TRT(12 + 2 * half);
 #pragma unroll 1
         for (int c0 = 0; c0 < kHid; c0 += 32) {
           uint32_t r[32], act[16], w[16];
@@ -556,9 +612,11 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
             t.dz2[img_chunk(tile, 256, row, 16 * half + (c0 >> 3) + j)] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
         }
         tmem_wait_st();
+        QS_TRT(13 + 2 * half);
       }
       tc_fence_before();
       group_sync(g);
+      QS_TRT(16);
       if (row == 0) {
         tc_fence_after();
         // dA2[128 x 128] = dZ2[128 x 256] . [Wp;Wv]: A from TMEM (8 columns per K=16 step); B = the W2 image (256 rows x 144 k)
@@ -571,6 +629,7 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
       mbar_wait(bar_mma, phase);
       phase ^= 1;
       tc_fence_after();
+      QS_TRT(17);
       // ---- dZ1 = dA2 * relu'(h) -> bf16 rows in HBM; h is read back from this thread's row of the A buffer ----
 #pragma unroll 1
       for (int c0 = 0; c0 < kHid; c0 += 32) {
@@ -985,19 +1044,6 @@ static_assert(kFuFits || kWsGroups == 3, "shared memory budget");
 
 // programmatic dependent launch: pdl_prologue() of qs_env_kernels.cuh (stage the next kernel early, wait for the previous one)
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-
-// EXPERIMENT ONLY (-DQS_WS_TRACE=1): SM-clock stamps of the first kTrTiles tiles of CTA 0 / group 0 -- epilogue thread 0 in
-// slots [0,16), the issuer's lane 0 in [16,24) -- read back with qs_debug_ws_trace (tools/ws_trace.py draws the timeline)
-#ifndef QS_WS_TRACE
-#define QS_WS_TRACE 0
-#endif
-#if QS_WS_TRACE
-constexpr int kTrTiles = 28, kTrSlots = 24;
-__device__ long long g_ws_trace[kTrTiles * kTrSlots];
-#define QS_TR(slot) do { if (trace_on && it < (uint32_t)kTrTiles) g_ws_trace[it * kTrSlots + (slot)] = clock64(); } while (0)
-#else
-#define QS_TR(slot) do { } while (0)
-#endif
 
 template <bool FUSED, int KIND>
 __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvStepArgs& ea) {
