@@ -299,8 +299,16 @@ typedef struct {
   float* per_sample;                      /* [batch,16] out, or NULL */
   float* col_sums;                        /* [16] out */
   float *g1, *g2, *g3;                    /* [128,32], [256,144], [256,16] out */
+  const void* packed_rows;                /* optional: the same rollout as ONE 128-byte record per row (qs_policy_pack_rollout);
+                                           * the kernels then gather a sample with one cache line instead of touching five arrays
+                                           * (1.1 GB -> 0.2 GB of DRAM reads per 1.7 M-sample minibatch).  NULL: the five arrays. */
 } qs_ppo_grad_t;
 int qs_policy_ppo_grad(qs_policy_t* p, const qs_ppo_grad_t* g, void* stream);
+/* Interleaves a flat rollout into 128-byte rows for qs_ppo_grad_t.packed_rows: floats [0,12) obs, [12,16) action, 16 return,
+ * 17 value, 18 neglogp, rest zero.  packed_out: rows * 128 bytes, 16-byte aligned.  Once per update (ppo2.py:340-362 runs
+ * noptepochs * nminibatches minibatch steps over the same rollout); the arrays stay the source of truth. */
+int qs_policy_pack_rollout(const float* obs, const float* actions, const float* returns, const float* values,
+                           const float* neglogp, int64_t rows, void* packed_out, void* stream);
 
 /* The optimiser step of the update in one launch: tf.clip_by_global_norm(grads, max_grad_norm) followed by
  * tf.train.AdamOptimizer(learning_rate, epsilon=1e-5).apply_gradients (rl_baselines/ppo2/ppo2.py:200-207), TensorFlow's

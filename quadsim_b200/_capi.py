@@ -22,7 +22,8 @@ SYMBOLS = ["qs_abi_version", "qs_last_error", "qs_create", "qs_destroy", "qs_obs
            "qs_import_state", "qs_get_stats", "qs_fn_apply", "qs_gae", "qs_policy_create", "qs_policy_destroy",
            "qs_policy_set_weights", "qs_policy_step", "qs_env_dtype", "qs_env_id0", "qs_rollout",
            "qs_step_range", "qs_expert_action", "qs_peek_state", "qs_policy_ppo_grad", "qs_step_n", "qs_default_params",
-           "qs_env_device", "qs_adam_step", "qs_permutation", "qs_policy_set_precision"]
+           "qs_env_device", "qs_adam_step", "qs_permutation", "qs_policy_set_precision",
+           "qs_policy_pack_rollout"]
 POLICY_BF16, POLICY_FP32 = 0, 1
 
 
@@ -74,7 +75,7 @@ class RolloutBuffers(C.Structure):
 class PPOGrad(C.Structure):
     _fields_ = ([(n, C.c_void_p) for n in ("obs", "actions", "returns", "values", "neglogp", "idx")] + [("batch", C.c_int64), ("adv_stats", C.c_void_p)]
                 + [(n, C.c_float) for n in ("cliprange", "cliprange_vf", "vf_coef")]
-                + [(n, C.c_void_p) for n in ("a1", "h", "hpv", "dz2", "dz1", "dout", "per_sample", "col_sums", "g1", "g2", "g3")])
+                + [(n, C.c_void_p) for n in ("a1", "h", "hpv", "dz2", "dz1", "dout", "per_sample", "col_sums", "g1", "g2", "g3", "packed_rows")])
 
 
 class AdamTensor(C.Structure):
@@ -139,6 +140,7 @@ def load():
     L.qs_step_n.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.qs_adam_step.argtypes = [C.POINTER(AdamTensor), C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp, C.c_float, vp, vp]
     L.qs_permutation.argtypes = [i64, u64, vp, vp]
+    L.qs_policy_pack_rollout.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp]
     L.qs_gae.argtypes = [i64, i64, vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp]
     if L.qs_abi_version() != ABI_VERSION:
         raise QuadSimError("libquadsim_b200.so ABI %d != expected %d; rebuild" % (L.qs_abi_version(), ABI_VERSION))

@@ -254,6 +254,7 @@ struct TrainArgs {
   uint4 *a1, *h, *hpv, *dz2, *dz1, *dout;
   float4* per_sample;                                  // [n,16] fp32 (optional: NULL skips the store)
   float* col_sums;                                     // [16] fp32: column sums of per_sample over the minibatch (atomics)
+  const float4* packed;                                // optional: 128-byte rows (obs | action | return, value, neglogp), see pack_rollout_kernel
 };
 // where the 16-byte chunk `b` of tile row `r` of an F-feature operand image lives (in uint4 units)
 __device__ __forceinline__ int64_t img_chunk(int64_t tile, int F, int r, int b) { return tile * (F * 16) + (b * 16 + (r >> 3)) * 8 + (r & 7); }
@@ -323,17 +324,32 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
   const int64_t i_first = (int64_t)tile0 * kTileRows + row, i_step = (int64_t)tile_stride * kTileRows;
   auto row_index = [&](int64_t i) -> int64_t { return i < a.n ? (idx ? __ldg(idx + i) : i) : 0; };
   struct Rec { float4 act; float ret, oldv, oldnlp; };  // TRAIN: a sample's rollout record (ppo2.py:244-262 feeds)
+  const float4* packed = TRAIN ? t.packed : nullptr;    // one 128-byte line per sample instead of five arrays (qs_policy_pack_rollout)
   auto load_rec = [&](int64_t src, bool valid) {
     Rec r = {make_float4(0.f, 0.f, 0.f, 0.f), 0.f, 0.f, 0.f};
     if (TRAIN && valid) {
-      r.act = __ldg(reinterpret_cast<const float4*>(t.actions) + src);
-      r.ret = __ldg(t.returns + src); r.oldv = __ldg(t.values + src); r.oldnlp = __ldg(t.neglogp + src);
+      if (packed) {
+        r.act = __ldg(packed + src * 8 + 3);
+        const float4 q = __ldg(packed + src * 8 + 4);
+        r.ret = q.x; r.oldv = q.y; r.oldnlp = q.z;
+      } else {
+        r.act = __ldg(reinterpret_cast<const float4*>(t.actions) + src);
+        r.ret = __ldg(t.returns + src); r.oldv = __ldg(t.values + src); r.oldnlp = __ldg(t.neglogp + src);
+      }
     }
     return r;
   };
+  auto load_row = [&](int64_t src, bool valid) {
+    if (packed && valid) {
+      ObsRow r;
+      r.a = __ldg(packed + src * 8); r.b = __ldg(packed + src * 8 + 1); r.c = __ldg(packed + src * 8 + 2);
+      return r;
+    }
+    return load_obs_at(a.obs, src, valid);
+  };
   const int64_t src_first = tile0 < tiles ? row_index(i_first) : 0;
   int64_t src_next = tile0 < tiles ? row_index(i_first + i_step) : 0;
-  ObsRow o = load_obs_at(a.obs, src_first, tile0 < tiles && i_first < a.n);  // in flight during the set-up
+  ObsRow o = load_row(src_first, tile0 < tiles && i_first < a.n);  // in flight during the set-up
   Rec rec_next = load_rec(src_first, tile0 < tiles && i_first < a.n);        // rows AND records run one tile ahead of their use
 
   if (tid == 0) {
@@ -411,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2) policy_kernel(const S
     // this sample's record was requested a tile ago; the next tile's row and record go out now, under this tile's work
     const float4 act4 = rec_next.act;
     const float ret = rec_next.ret, oldv = rec_next.oldv, oldnlp = rec_next.oldnlp;
-    o = load_obs_at(a.obs, src_next, i + i_step < a.n);
+    o = load_row(src_next, i + i_step < a.n);
     rec_next = load_rec(src_next, i + i_step < a.n);
     src_next = row_index(i + 2 * i_step);  // consumed a whole tile from now
     QS_TRT(3);
@@ -875,8 +891,21 @@ __global__ void adam_advance_kernel(long long* step_dev) { *step_dev += 1; }
 // block to finish (ticket counter) adds the partials in block order -- bit-reproducible -- writes the two floats the gradient
 // kernel reads, and re-arms the counter.  Replaces a gather, a Welford reduction and six elementwise launches of the caller.
 constexpr int kAdvBlocks = 1184;  // 8 per SM: the gathers are latency-bound, so many loads in flight
+__global__ void __launch_bounds__(256) pack_rollout_kernel(const float* __restrict__ obs, const float* __restrict__ act, const float* __restrict__ ret,
+                                                           const float* __restrict__ val, const float* __restrict__ nlp, int64_t rows, float4* __restrict__ out) {
+  // one 128-byte row per sample: [obs 12 | action 4 | return, value, neglogp, 0 | 0 x 12]; 8 consecutive threads write one row
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x, r = e >> 3;
+  const int c = (int)(e & 7);
+  if (r >= rows) return;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < 3) v = __ldg(reinterpret_cast<const float4*>(obs + r * kObs) + c);
+  else if (c == 3) v = __ldg(reinterpret_cast<const float4*>(act) + r);
+  else if (c == 4) v = make_float4(__ldg(ret + r), __ldg(val + r), __ldg(nlp + r), 0.f);
+  out[e] = v;
+}
+
 __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict__ ret, const float* __restrict__ val, const int64_t* __restrict__ idx,
-                                                        int64_t n, double* partial, unsigned int* ticket, float* stats) {
+                                                        int64_t n, double* partial, unsigned int* ticket, float* stats, const float4* __restrict__ packed) {
   double s = 0.0, q = 0.0;
   const int64_t stride = (int64_t)gridDim.x * 256;
   int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -886,13 +915,18 @@ __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict_
 #pragma unroll
     for (int u = 0; u < 4; u++) j[u] = idx ? idx[i + u * stride] : i + u * stride;
 #pragma unroll
-    for (int u = 0; u < 4; u++) a[u] = ret[j[u]] - val[j[u]];  // float32, as the reference forms it
+    for (int u = 0; u < 4; u++) {  // float32, as the reference forms it
+      if (packed) { const float4 q = __ldg(packed + j[u] * 8 + 4); a[u] = q.x - q.y; }
+      else a[u] = ret[j[u]] - val[j[u]];
+    }
 #pragma unroll
     for (int u = 0; u < 4; u++) { s += (double)a[u]; q += (double)a[u] * (double)a[u]; }
   }
   for (; i < n; i += stride) {
     const int64_t j = idx ? idx[i] : i;
-    const float a = ret[j] - val[j];
+    float a;
+    if (packed) { const float4 q = __ldg(packed + j * 8 + 4); a = q.x - q.y; }
+    else a = ret[j] - val[j];
     s += (double)a;
     q += (double)a * (double)a;
   }
@@ -1759,7 +1793,8 @@ int qs_policy_ppo_grad(qs_policy_t* p, const qs_ppo_grad_t* g, void* stream) {
   const float* adv_stats = g->adv_stats;
   if (e == cudaSuccess && !adv_stats) {  // the minibatch's advantage statistics, computed here (one launch)
     float* stats = reinterpret_cast<float*>(p->adv_ws + 2 * kAdvBlocks + 1);
-    adv_stats_kernel<<<kAdvBlocks, 256, 0, st>>>(g->returns, g->values, g->idx, g->batch, p->adv_ws, reinterpret_cast<unsigned int*>(p->adv_ws + 2 * kAdvBlocks), stats);
+    adv_stats_kernel<<<kAdvBlocks, 256, 0, st>>>(g->returns, g->values, g->idx, g->batch, p->adv_ws, reinterpret_cast<unsigned int*>(p->adv_ws + 2 * kAdvBlocks), stats,
+                                                 (const float4*)g->packed_rows);
     e = cudaGetLastError();
     adv_stats = stats;
   }
@@ -1767,7 +1802,7 @@ int qs_policy_ppo_grad(qs_policy_t* p, const qs_ppo_grad_t* g, void* stream) {
     StepArgs a = {p->packed, g->obs, g->batch, 0, 0, 0, 1, nullptr, nullptr, nullptr, nullptr};
     TrainArgs t = {g->actions, g->returns, g->values, g->neglogp, g->idx, adv_stats, g->cliprange, g->cliprange_vf, g->vf_coef,
                    (float)(1.0 / (double)g->batch), (uint4*)g->a1, (uint4*)g->h, (uint4*)g->hpv, (uint4*)g->dz2, (uint4*)g->dz1, (uint4*)g->dout,
-                   (float4*)g->per_sample, g->col_sums};
+                   (float4*)g->per_sample, g->col_sums, (const float4*)g->packed_rows};
     const int ctas = (tiles + kGroups - 1) / kGroups;
     policy_kernel<true><<<ctas < p->grid ? ctas : p->grid, kThreads, kSmemBytes, st>>>(a, t);
     e = cudaGetLastError();
@@ -1780,6 +1815,18 @@ int qs_policy_ppo_grad(qs_policy_t* p, const qs_ppo_grad_t* g, void* stream) {
   }
   cudaSetDevice(prev);
   if (e != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_policy_ppo_grad: %s", cudaGetErrorString(e));
+  return QS_OK;
+}
+
+int qs_policy_pack_rollout(const float* obs, const float* actions, const float* returns, const float* values, const float* neglogp, int64_t rows,
+                           void* packed_out, void* stream) {
+  if (!obs || !actions || !returns || !values || !neglogp || !packed_out) return qs_fail_(QS_ERR_INVALID, "qs_policy_pack_rollout: null argument");
+  if (rows <= 0) return qs_fail_(QS_ERR_INVALID, "qs_policy_pack_rollout: rows must be positive");
+  if (((uintptr_t)packed_out & 15) || ((uintptr_t)obs & 15) || ((uintptr_t)actions & 15)) return qs_fail_(QS_ERR_INVALID, "qs_policy_pack_rollout: obs, actions and packed_out must be 16-byte aligned");
+  const int64_t elems = rows * 8;
+  pack_rollout_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, (cudaStream_t)stream>>>(obs, actions, returns, values, neglogp, rows, (float4*)packed_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_policy_pack_rollout: %s", cudaGetErrorString(e));
   return QS_OK;
 }
 

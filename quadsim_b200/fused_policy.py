@@ -106,6 +106,9 @@ class FusedPolicy:
         m, B = self.module, int(idx.shape[0])
         ws = self._workspace(B)
         ret, val = batch["returns"], batch["values"]
+        packed = batch.get("packed_rows") if isinstance(batch, dict) else None
+        if packed is not None and (packed.dtype != torch.float32 or packed.shape != (batch["obs"].shape[0], 32) or not packed.is_contiguous()):
+            raise ValueError("packed_rows must be the [rows, 32] float32 tensor pack_rollout returned for this rollout")
         if adv_stats is not None and (adv_stats.dtype != torch.float32 or adv_stats.numel() != 2 or adv_stats.device != self.device):
             raise ValueError("adv_stats must be two float32 values on %s" % (self.device,))
         p = lambda t: t.data_ptr()
@@ -118,10 +121,29 @@ class FusedPolicy:
         g = _capi.PPOGrad(p(batch["obs"]), p(batch["actions"]), p(ret), p(val), p(batch["neglogp"]), p(idx), B, p(adv_stats) if adv_stats is not None else None,
                           float(cliprange), float(-1.0 if cliprange_vf is None or cliprange_vf < 0 else cliprange_vf), float(vf_coef),
                           p(ws["a1"]), p(ws["h"]), p(ws["hpv"]), p(ws["dz2"]), p(ws["dz1"]), p(ws["dout"]),
-                          p(ws["per_sample"]) if want_per_sample else None, p(ws["col"]), p(ws["g1"]), p(ws["g2"]), p(ws["g3"]))
+                          p(ws["per_sample"]) if want_per_sample else None, p(ws["col"]), p(ws["g1"]), p(ws["g2"]), p(ws["g3"]),
+                          p(packed) if packed is not None else None)
         with torch.cuda.device(self.device):
             _capi.check(self.lib.qs_policy_ppo_grad(self._h, C.byref(g), self._stream()))
         return self.grads_from_workspace(ent_coef, B)
+
+    @torch.no_grad()
+    def pack_rollout(self, batch, out=None):
+        """The flat rollout as ONE 128-byte row per sample (qs_policy_pack_rollout): `batch["packed_rows"] = pack_rollout(batch)`
+        makes every ppo_grad over that rollout gather a sample with one cache line instead of touching five arrays.  Once per
+        update; `out` reuses a previous [rows, 32] float32 tensor."""
+        rows = int(batch["obs"].shape[0])
+        for k in ("obs", "actions", "returns", "values", "neglogp"):
+            t = batch[k]
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+                raise ValueError("rollout tensor %r must be contiguous float32 on %s" % (k, self.device))
+        if out is None or out.shape != (rows, 32) or out.dtype != torch.float32 or out.device != self.device:
+            out = torch.empty((rows, 32), dtype=torch.float32, device=self.device)
+        p = lambda t: t.data_ptr()
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.qs_policy_pack_rollout(p(batch["obs"]), p(batch["actions"]), p(batch["returns"]), p(batch["values"]),
+                                                        p(batch["neglogp"]), rows, p(out), self._stream()))
+        return out
 
     def grads_from_workspace(self, ent_coef, B):
         """({param: grad}, logs) as views of the result buffers the gradient kernels filled (g1, g2, g3, column sums)."""

@@ -320,7 +320,7 @@ class PPO2:
     def _graph_step(self, batch, idx):
         """Replay the captured minibatch step on `idx` (copied into the graph's static index buffer)."""
         key = (batch["obs"].data_ptr(), batch["returns"].data_ptr(), batch["actions"].data_ptr(), batch["values"].data_ptr(),
-               batch["neglogp"].data_ptr(), idx.shape[0])
+               batch["neglogp"].data_ptr(), batch["packed_rows"].data_ptr() if "packed_rows" in batch else 0, idx.shape[0])
         if self._graph is None or self._graph[0] != key:
             if self.dist:
                 raise _capi.QuadSimError("graph_update is single-process: the gradient all-reduce is not captured")
@@ -365,6 +365,12 @@ class PPO2:
         mb_size = n_batch // self.nminibatches
         keys = ("obs", "returns", "actions", "values", "neglogp")
         logs = []
+        if self.fused_update or self.graph_update:
+            # the rollout as one 128-byte row per sample, once per update: the noptepochs * nminibatches gradient launches gather
+            # each sample with one cache line instead of touching five arrays (the buffer's address survives updates: a captured
+            # minibatch step reads it)
+            self._packed = self.fused.pack_rollout(batch, out=getattr(self, "_packed", None))
+            batch = dict(batch, packed_rows=self._packed)
         for _ in range(self.noptepochs):
             perm = self._shuffle(n_batch)
             for start in range(0, mb_size * self.nminibatches, mb_size):

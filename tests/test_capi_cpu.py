@@ -106,7 +106,7 @@ def test_invalid_arguments_return_status_not_crash():
     assert L.qs_gae(0, 4, None, None, None, None, None, 0.99, 0.95, None, None, None) == -1
     assert L.qs_env_dtype(None) == -1 and L.qs_env_id0(None) == 0 and L.qs_env_device(None) == -1
     assert C.sizeof(_capi.RolloutBuffers) == 7 * C.sizeof(C.c_void_p)
-    assert C.sizeof(_capi.PPOGrad) == 6 * 8 + 8 + 8 + 3 * 4 + 4 + 11 * 8  # 12-byte float block padded to the next pointer
+    assert C.sizeof(_capi.PPOGrad) == 6 * 8 + 8 + 8 + 3 * 4 + 4 + 12 * 8  # 12-byte float block padded to the next pointer
     assert L.qs_adam_step(None, 0, 3e-4, 0.9, 0.999, 1e-5, 1, None, 0.5, None, None) == -1 and b"qs_adam_step" in L.qs_last_error()
     assert L.qs_permutation(0, 1, None, None) == -1
 

@@ -85,6 +85,19 @@ def test_policy_step_and_ppo_grad_stay_in_bounds(n):
     for k, b in bufs.items():
         assert b.intact(), k
         assert b.written(), k
+    # the same through packed rows (qs_policy_pack_rollout): the pack stays inside its n * 128 bytes, and the statistics computed by
+    # the library (adv_stats = NULL) and the gather through the rows leave the per-sample block unchanged up to the statistics
+    packed = Guarded(n, 32, f32)
+    _capi.check(L.qs_policy_pack_rollout(p(obs), p(act.view), p(ret), p(oldv), p(oldnlp), n, packed.ptr, _stream()))
+    torch.cuda.synchronize()
+    assert packed.intact() and packed.written() and torch.equal(packed.view[:, :12], obs) and torch.equal(packed.view[:, 16], ret)
+    ps_arrays = bufs["per_sample"].view.clone()
+    g.packed_rows = packed.view.data_ptr()
+    _capi.check(L.qs_policy_ppo_grad(fused._h, C.byref(g), _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(ps_arrays, bufs["per_sample"].view)
+    for k, b in bufs.items():
+        assert b.intact(), k
     assert bool(torch.isfinite(bufs["per_sample"].view).all()) and bool(torch.isfinite(bufs["g2"].view).all())
     # every byte of every image is written (rows past the minibatch as zeros): nothing of the sentinel survives inside
     for k in ("a1", "h", "hpv", "dz2", "dz1", "dout"):

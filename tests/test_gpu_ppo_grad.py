@@ -135,6 +135,32 @@ def test_advantage_statistics_computed_by_the_library():
     env.close()
 
 
+def test_packed_rows_give_the_same_gradient():
+    """qs_policy_pack_rollout: one 128-byte row per sample (obs | action | return, value, neglogp); the gradient kernel and the
+    advantage statistics gather from it instead of the five arrays -- per-sample results bit-identical."""
+    env, algo, batch = _rollout()
+    M = batch["obs"].shape[0]
+    packed = algo.fused.pack_rollout(batch)
+    assert packed.shape == (M, 32)
+    assert torch.equal(packed[:, :12], batch["obs"]) and torch.equal(packed[:, 12:16], batch["actions"])
+    assert torch.equal(packed[:, 16], batch["returns"]) and torch.equal(packed[:, 17], batch["values"]) and torch.equal(packed[:, 18], batch["neglogp"])
+    assert float(packed[:, 19:].abs().max()) == 0.0
+    assert algo.fused.pack_rollout(batch, out=packed) is packed  # the buffer is reused
+    idx = torch.randperm(M, device="cuda")[:7001].contiguous()
+    args = (algo.cliprange, algo.cliprange_vf, algo.vf_coef, algo.ent_coef)
+    g_a, l_a = algo.fused.ppo_grad(batch, idx, *args)
+    g_a = {k: v.clone() for k, v in g_a.items()}
+    ps_a = algo.fused._ws["per_sample"][:7001].clone()
+    g_b, l_b = algo.fused.ppo_grad(dict(batch, packed_rows=packed), idx, *args)
+    assert torch.equal(ps_a, algo.fused._ws["per_sample"][:7001])
+    for prm in g_a:
+        scale = float(g_a[prm].abs().max()) + 1e-12
+        assert float((g_a[prm] - g_b[prm]).abs().max()) < 1e-5 * scale  # split-K adds land in any order
+    with pytest.raises(ValueError):
+        algo.fused.ppo_grad(dict(batch, packed_rows=packed[:-1]), idx, *args)
+    env.close()
+
+
 def _unpack_image(img, F, B):
     """An operand image of the weight-gradient contraction (include/quadsim_b200.h: per 128-sample tile, the 16-byte chunk b of
     row r at (b * 16 + (r >> 3)) * 128 + (r & 7) * 16) -> the [B, F] bf16 matrix it holds."""
