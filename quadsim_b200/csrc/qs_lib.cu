@@ -520,15 +520,36 @@ __global__ void __launch_bounds__(256) gae_kernel(int64_t T, int64_t n, const fl
   double lastgaelam = 0.0;
   const double gl = gamma * lam;
   const float gf = (float)gamma;
-  for (int64_t t = T - 1; t >= 0; t--) {
-    const float v = val[t * n + i];
-    const double delta = __dadd_rn(__dadd_rn((double)rew[t * n + i], __dmul_rn((double)__fmul_rn(gf, nextvalues), nextnonterminal)), -(double)v);
-    lastgaelam = __dadd_rn(delta, __dmul_rn(__dmul_rn(gl, nextnonterminal), lastgaelam));
-    const float a = (float)lastgaelam;
-    adv[t * n + i] = a;
-    ret[t * n + i] = __fadd_rn(a, v);
-    nextnonterminal = 1.0 - (double)dones[t * n + i];
-    nextvalues = v;
+  // The loads of a step do not depend on the recurrence: eight steps' worth are requested up front, then the recurrence (a dozen
+  // dependent fp64 operations per step) runs over the registers.  What the plain loop waited for were its three DRAM round trips
+  // per step.
+  int64_t t = T;
+  while (t > 0) {
+    const int m = t >= 8 ? 8 : (int)t;  // steps t-1, t-2, .., t-m
+    float vv[8], rr[8];
+    uint8_t dd[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (k < m) {
+        const int64_t o = (t - 1 - k) * n + i;
+        vv[k] = val[o]; rr[k] = rew[o]; dd[k] = dones[o];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (k < m) {
+        const int64_t o = (t - 1 - k) * n + i;
+        const float v = vv[k];
+        const double delta = __dadd_rn(__dadd_rn((double)rr[k], __dmul_rn((double)__fmul_rn(gf, nextvalues), nextnonterminal)), -(double)v);
+        lastgaelam = __dadd_rn(delta, __dmul_rn(__dmul_rn(gl, nextnonterminal), lastgaelam));
+        const float a = (float)lastgaelam;
+        adv[o] = a;
+        ret[o] = __fadd_rn(a, v);
+        nextnonterminal = 1.0 - (double)dd[k];
+        nextvalues = v;
+      }
+    }
+    t -= m;
   }
 }
 
