@@ -1058,11 +1058,15 @@ enum { kFullA1 = 0, kFullA2, kFullA3p, kFullA3v, kDone1, kDoneP, kDoneV, kDone3 
 // wait) and run the very device code of dock_step_kernel (dock_step_loaded, qs_env_kernels.cuh) on them.  One launch per
 // rollout step does model.step AND env.step; the env warps use the issue slots the policy's dependency chain leaves idle
 // (issue-active 28 % for the policy kernel alone), instead of a second kernel that can only share SMs by accident.
+#ifndef QS_FUSED_CHUNK
+#define QS_FUSED_CHUNK 32  // accumulator columns per read-out chunk of the fused kernel's policy half: at 64 the 96-register cap of the 576-thread CTA spills (2.49 vs 2.18 ms per rollout)
+#endif
 #ifndef QS_FUSED_ENV_SETS
 #define QS_FUSED_ENV_SETS 1   // env warp-sets (4 warps each) per group: set s serves action slot s, i.e. every kFuSets-th tile of the
-                              // group.  Two sets (measured with plain state loads: 2.80 vs 2.64 ms per 16-step rollout) lose
-                              // more to the 72-register cap of an 832-thread CTA than they gain, and their state stages do
-                              // not fit shared memory next to the policy's operands.
+                              // group.  Two sets (plain coalesced state loads: their stages would not fit) measure SLOWER in every
+                              // form tried -- 2.25 vs 2.18 ms per 16-step rollout at the uniform 72 registers of an 832-thread CTA,
+                              // 3.06 ms with the registers split by role through setmaxnreg: the step is not bound by how many env
+                              // tiles are in flight.
 #endif
 constexpr int kFuSets = QS_FUSED_ENV_SETS;
 static_assert(kFuSets == 1 || kFuSets == 2, "one or two env warp-sets per group (two action slots)");
@@ -1072,14 +1076,15 @@ constexpr int kFuOffAct = kWsSmemBytes;                       // [group][slot][1
 constexpr int kFuOffBar = kFuOffAct + kWsGroups * 2 * kTileRows * 16;  // [group][slot]{full, empty}, then [group][set] state-stage barrier
 constexpr int kFuStateBytes = (dock_words<float>() / 4) * kTileRows * 16;  // one tile's state rows: 20 KB, contiguous in HBM (tile-major layout)
 constexpr int kFuOffState = (kFuOffBar + kWsGroups * 2 * 16 + kWsGroups * 2 * 8 + 127) / 128 * 128;  // [group][set] stage
-constexpr int kFuSmemBytes = kFuOffState + kWsGroups * kFuSets * kFuStateBytes;
+constexpr bool kFuStage = kFuSets == 1;  // one set per group: bulk-copy state stage; two sets: plain coalesced loads (four stages do not fit)
+constexpr int kFuSmemBytes = kFuOffState + (kFuStage ? kWsGroups * kFuSets * kFuStateBytes : 0);
 constexpr bool kFuFits = kFuSmemBytes <= 227 * 1024;  // three groups' state stages do not fit: the fused step kernel is then unavailable
 static_assert(kFuFits || kWsGroups == 3, "shared memory budget");
 
 // programmatic dependent launch: pdl_prologue() of qs_env_kernels.cuh (stage the next kernel early, wait for the previous one)
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
-template <bool FUSED, int KIND>
+template <bool FUSED, int KIND, int CHUNK = kWsChunk>
 __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvStepArgs& ea) {
   pdl_prologue();
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -1150,7 +1155,7 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
   // layer 3 vf still uses: it is split into two N=64 halves, [0,64) (A3 pi, dead once layer 3 pi is in the pipe ahead of it)
   // and [192,256) (the read-out part of D2 vf); D3 moves to [112,128), the tail of the consumed D2 pi columns.
   constexpr bool kEarlyL1 = kWsGroups == 2 && kWsSides == 1 && QS_POLICY_WS_EARLY_L1;
-  static_assert(!kEarlyL1 || kWsChunk <= 64, "D1 is read in two 64-column pieces");
+  static_assert(!kEarlyL1 || CHUNK <= 64, "D1 is read in two 64-column pieces");
   constexpr uint32_t kColD3ws = kEarlyL1 ? 112 : (kWsGroups == 2 ? kWsCols / 2 : 128);
   auto d1_col = [](int c) -> uint32_t { return kEarlyL1 ? (uint32_t)(c < 64 ? c : 128 + c) : kColD1 + (uint32_t)c; };
   constexpr uint32_t idesc_n64 = umma_idesc(128, 64);
@@ -1174,18 +1179,22 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
         for (int off = 0; off < kFuStateBytes; off += 10240)
           bulk_g2s(st_dst + off, reinterpret_cast<const unsigned char*>(state_rows + (env0 / kTileRows) * (NR * kTileRows)) + off, 10240, st_bar);
       };
-      if (er == 0 && tile0 + (int64_t)env_set * tile_stride < tiles) request(env_set);
+      if (kFuStage && er == 0 && tile0 + (int64_t)env_set * tile_stride < tiles) request(env_set);
       uint32_t n_it = 0;
       for (uint32_t it = env_set; tile0 + (int64_t)it * tile_stride < tiles; it += kFuSets, n_it++) {  // this set's share of the group's tiles
         const int tile = tile0 + (int)it * tile_stride;
         const int64_t i = ea.first + (int64_t)tile * kTileRows + er;
         const bool active = i < ea.first + ea.n;
-        mbar_wait(st_bar, n_it & 1);
         float w[NW];
+        if constexpr (kFuStage) {
+          mbar_wait(st_bar, n_it & 1);
 #pragma unroll
-        for (int r = 0; r < NR; r++) unpack(st_buf[r * kTileRows + er], &w[r * 4]);
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + g * kFuSets + env_set), "n"(kTileRows) : "memory");  // the stage is drained
-        if (er == 0 && tile0 + (int64_t)(it + kFuSets) * tile_stride < tiles) request(it + kFuSets);
+          for (int r = 0; r < NR; r++) unpack(st_buf[r * kTileRows + er], &w[r * 4]);
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + g * kFuSets + env_set), "n"(kTileRows) : "memory");  // the stage is drained
+          if (er == 0 && tile0 + (int64_t)(it + kFuSets) * tile_stride < tiles) request(it + kFuSets);
+        } else {
+          if (active) load_words<float, NW>(ea.state, i, w);
+        }
         const uint32_t slot = it & 1, par = (it >> 1) & 1;
         mbar_wait(act_bar + slot * 16, par);
         const float4 c = act_buf[slot * kTileRows + er];
@@ -1355,13 +1364,13 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
       tc_fence_after();
       QS_TR(1);
 #pragma unroll 1
-      for (int c0 = kWsCols * side; c0 < kWsCols * (side + 1); c0 += kWsChunk) {
-        uint32_t r[kWsChunk];
+      for (int c0 = kWsCols * side; c0 < kWsCols * (side + 1); c0 += CHUNK) {
+        uint32_t r[CHUNK];
 #pragma unroll
-        for (int q = 0; q < kWsChunk; q += 32) tmem_ld32(trow + d1_col(c0) + q, r + q);
+        for (int q = 0; q < CHUNK; q += 32) tmem_ld32(trow + d1_col(c0) + q, r + q);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < kWsChunk / 8; j++) {
+        for (int j = 0; j < CHUNK / 8; j++) {
           uint4 w;
           w.x = relu_pack_bf16(r[8 * j + 0], r[8 * j + 1]);
           w.y = relu_pack_bf16(r[8 * j + 2], r[8 * j + 3]);
@@ -1391,15 +1400,15 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
         QS_TR(7 + 3 * half);
         const uint32_t base = trow + half * kColD2v + kWsCols * side;  // this side's columns; its packed A3 lands at their start
 #pragma unroll 1
-        for (int c0 = 0; c0 < kWsCols; c0 += kWsChunk) {
-          uint32_t r[kWsChunk], w[kWsChunk / 2];
+        for (int c0 = 0; c0 < kWsCols; c0 += CHUNK) {
+          uint32_t r[CHUNK], w[CHUNK / 2];
 #pragma unroll
-          for (int q = 0; q < kWsChunk; q += 32) tmem_ld32(base + c0 + q, r + q);
+          for (int q = 0; q < CHUNK; q += 32) tmem_ld32(base + c0 + q, r + q);
           tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < kWsChunk / 2; j++) w[j] = relu_pack_bf16(r[2 * j], r[2 * j + 1]);
+          for (int j = 0; j < CHUNK / 2; j++) w[j] = relu_pack_bf16(r[2 * j], r[2 * j + 1]);
 #pragma unroll
-          for (int q = 0; q < kWsChunk / 2; q += 16) tmem_st16(base + (c0 >> 1) + q, w + q);
+          for (int q = 0; q < CHUNK / 2; q += 16) tmem_st16(base + (c0 >> 1) + q, w + q);
         }
         QS_TR(8 + 3 * half);
         tmem_wait_st();
@@ -1439,10 +1448,14 @@ __device__ __forceinline__ void policy_fwd_ws_body(const StepArgs& a, const EnvS
   if (tid_hw < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
 }
 __global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel(const StepArgs a) { policy_fwd_ws_body<false, kDockV2>(a, EnvStepArgs{}); }
+// The same kernel reading its accumulators out in chunks of 32 columns: 96 registers instead of 128, 73 instead of 68 us per
+// 2^20 envs on its own -- but in a sliced rollout three env-step CTAs fit next to it on an SM instead of two, and the pair
+// overlaps better: 2.06 vs 2.12 ms per 16-step rollout.  qs_rollout launches this one when it runs more than one slice.
+__global__ void __launch_bounds__(kWsThreads, 1) policy_fwd_ws_kernel_lean(const StepArgs a) { policy_fwd_ws_body<false, kDockV2, 32>(a, EnvStepArgs{}); }
 // model.step + env.step of one rollout step in ONE launch (see the kFu* constants above): rl_baselines/ppo2/ppo2.py:472-482
 template <int KIND>
 __global__ void __launch_bounds__(kFuThreads, 1) policy_env_step_kernel(const StepArgs a, const __grid_constant__ EnvStepArgs ea) {
-  policy_fwd_ws_body<true, KIND>(a, ea);
+  policy_fwd_ws_body<true, KIND, QS_FUSED_CHUNK>(a, ea);
 }
 // Register-capped builds of the same kernel for the sliced rollout: a policy CTA at 128 registers x 320 threads leaves an SM
 // room for ONE 128-thread env CTA (80 registers) next to it, at 80 registers for three -- and it is the env kernel's occupancy
@@ -1637,6 +1650,7 @@ int qs_policy_create(qs_policy_t** out, int device) {
       (kFuFits && (err = cudaFuncSetAttribute(policy_env_step_kernel<kDockV0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes)) != cudaSuccess) ||
       (kFuFits && (err = cudaFuncSetAttribute(policy_env_step_kernel<kDockV2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemBytes)) != cudaSuccess) ||
       (err = cudaFuncSetAttribute(policy_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
+      (err = cudaFuncSetAttribute(policy_fwd_ws_kernel_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_fwd_ws_kernel_capped<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_fwd_ws_kernel_capped<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
       (err = cudaFuncSetAttribute(policy_fwd_ws_kernel_capped<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes)) != cudaSuccess ||
@@ -1707,8 +1721,11 @@ int qs_policy_set_weights(qs_policy_t* p, const qs_policy_weights_t* w, void* st
   return QS_OK;
 }
 
-int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, uint64_t env_id0, uint32_t step_idx, int deterministic,
-                   float* actions_out, float* clipped_out, float* values_out, float* neglogp_out, void* stream) {
+}  // extern "C"
+
+// lean: the 96-register build of the forward kernel (policy_fwd_ws_kernel_lean), for launches that share the SMs with env-step kernels
+static int policy_step_impl(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, uint64_t env_id0, uint32_t step_idx, int deterministic,
+                            float* actions_out, float* clipped_out, float* values_out, float* neglogp_out, void* stream, bool lean) {
   if (!p || !obs || !values_out) return qs_fail_(QS_ERR_INVALID, "qs_policy_step: null argument");
   if (!p->have_weights) return qs_fail_(QS_ERR_INVALID, "qs_policy_step: qs_policy_set_weights has not been called");
   if (n <= 0) return QS_OK;
@@ -1755,9 +1772,12 @@ int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, u
     cfg.stream = (cudaStream_t)stream; cfg.attrs = attr; cfg.numAttrs = na;
     // QUADSIM_B200_POLICY_REGS = 128 (uncapped build) | 96 | 80 | 72: see policy_fwd_ws_kernel_capped
     static const int regs = [] { const char* v = getenv("QUADSIM_B200_POLICY_REGS"); return v ? atoi(v) : kDefaultPolicyRegs; }();
+    static const int lean_env = [] { const char* v = getenv("QUADSIM_B200_POLICY_LEAN"); return v ? (v[0] == '0' ? 0 : 1) : -1; }();  // A/B: force either build
+    const bool use_lean = lean_env < 0 ? lean : lean_env == 1;
     cudaError_t le = regs == 96   ? cudaLaunchKernelEx(&cfg, policy_fwd_ws_kernel_capped<96>, a)
                      : regs == 80 ? cudaLaunchKernelEx(&cfg, policy_fwd_ws_kernel_capped<80>, a)
                      : regs == 72 ? cudaLaunchKernelEx(&cfg, policy_fwd_ws_kernel_capped<72>, a)
+                     : use_lean   ? cudaLaunchKernelEx(&cfg, policy_fwd_ws_kernel_lean, a)
                                   : cudaLaunchKernelEx(&cfg, policy_fwd_ws_kernel, a);
     if (le != cudaSuccess) { cudaSetDevice(prev); return qs_fail_(QS_ERR_CUDA, "qs_policy_step: %s", cudaGetErrorString(le)); }
   }
@@ -1765,6 +1785,13 @@ int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, u
   cudaSetDevice(prev);
   if (e != cudaSuccess) return qs_fail_(QS_ERR_CUDA, "qs_policy_step: %s", cudaGetErrorString(e));
   return QS_OK;
+}
+
+extern "C" {
+
+int qs_policy_step(qs_policy_t* p, int64_t n, const float* obs, uint64_t seed, uint64_t env_id0, uint32_t step_idx, int deterministic,
+                   float* actions_out, float* clipped_out, float* values_out, float* neglogp_out, void* stream) {
+  return policy_step_impl(p, n, obs, seed, env_id0, step_idx, deterministic, actions_out, clipped_out, values_out, neglogp_out, stream, false);
 }
 
 int qs_policy_ppo_grad(qs_policy_t* p, const qs_ppo_grad_t* g, void* stream) {
@@ -1941,12 +1968,12 @@ int qs_rollout(qs_env_t* env, qs_policy_t* pol, int64_t n_steps, const qs_rollou
       const int64_t f = first[k], m = first[k + 1] - first[k];
       if (t == n_steps) {
         // last_values = model.value(obs) (ppo2.py:510): deterministic pass, only the value head is stored
-        rc = qs_policy_step(pol, m, b->obs + (t * n + f) * kObs, seed, id0 + f, 0, 1, nullptr, nullptr, b->values + t * n + f, nullptr, st[k]);
+        rc = policy_step_impl(pol, m, b->obs + (t * n + f) * kObs, seed, id0 + f, 0, 1, nullptr, nullptr, b->values + t * n + f, nullptr, st[k], false);
         continue;
       }
       // model.step(obs) (ppo2.py:472) writes straight into the rollout's rows; np.clip to the Box (ppo2.py:478-481) -> clipped
-      rc = qs_policy_step(pol, m, b->obs + (t * n + f) * kObs, seed, id0 + f, step_idx0 + (uint32_t)t, 0, b->actions + (t * n + f) * kAct,
-                          b->clipped + f * kAct, b->values + t * n + f, b->neglogp + t * n + f, st[k]);
+      rc = policy_step_impl(pol, m, b->obs + (t * n + f) * kObs, seed, id0 + f, step_idx0 + (uint32_t)t, 0, b->actions + (t * n + f) * kAct,
+                            b->clipped + f * kAct, b->values + t * n + f, b->neglogp + t * n + f, st[k], n_slices > 1);
       // env.step(clipped_actions) (ppo2.py:482): the next observations / this step's rewards / the next row of dones
       if (rc == QS_OK)
         rc = qs_step_range(env, f, m, b->clipped, b->obs + (t + 1) * n * kObs, b->rewards + t * n, b->dones + (t + 1) * n, st[k]);
