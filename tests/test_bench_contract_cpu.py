@@ -75,9 +75,9 @@ def test_round2_line_is_self_contained_and_same_config():
 
 def test_round2_final_line_callers():
     """The round's last driver-style run (after the forward kernel's fix): the callers' numbers quoted in DESIGN.md section 9."""
-    d = _load("r2_bench_f_20steps.json")
+    d = _load("r2_bench_g_20steps.json")
     k = d["callers"]
-    assert k["rollout_env_steps_per_s"] >= 7.7e9 and k["update_epoch_ms"] <= 13.0 and k["gpu_launches_per_rollout"] == 67
+    assert k["rollout_env_steps_per_s"] >= 7.9e9 and k["update_epoch_ms"] <= 13.0 and k["gpu_launches_per_rollout"] == 67
     assert d["roofline"]["frac"] >= 0.99 and d["fp64"]["roofline"]["frac"] >= 0.95 and d["clocks"]["reasons"] == []
-    ref = _load("r2_bench_f_reference_arm.json")
+    ref = _load("r2_bench_g_reference_arm.json")
     assert ref["impl"] == "reference" and ref["timed_seconds"] >= 2.0 and abs(ref["value"] - d["cpu_baseline"]["port"]["value"]) < 0.15 * ref["value"]

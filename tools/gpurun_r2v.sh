@@ -1,7 +1,7 @@
 # final record of the round: full GPU suite, smoke, both bench arms (driver's invocation), launch list
 mkdir -p gpurun_out/r2v
 cd $GRAFT_REPO_ROOT
-(timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -15) > gpurun_out/r2v/pytest.log
+(timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -120) > gpurun_out/r2v/pytest.log
 tail -3 gpurun_out/r2v/pytest.log
 (timeout 300 python __graft_entry__.py smoke 2>&1 | tail -4) > gpurun_out/r2v/smoke.log
 tail -2 gpurun_out/r2v/smoke.log
